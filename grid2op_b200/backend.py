@@ -1,0 +1,423 @@
+"""``B200Backend`` — drop-in ``grid2op.Backend.Backend`` whose power flow runs on a B200.
+
+Boundary mirrored (reference, abstract API): grid2op/Backend/backend.py:419-760
+(``load_grid / apply_action / runpf / get_topo_vect / generators_info / loads_info /
+lines_or_info / lines_ex_info`` + optional ``shunt_info / storages_info / get_theta / copy /
+reset / _disconnect_line``).  Behavioural model: grid2op/Backend/pandaPowerBackend.py (cited per
+method).  The host side keeps what PandaPowerBackend keeps in its pandas tables as flat numpy
+arrays (set points in float64, per-element busbar + in-service flag); the solve is ONE call through
+the C ABI (``include/b200pf.h``) into the CUDA engine.  There is no CPU solver in this package:
+without ``libb200pf.so`` + a CUDA device ``load_grid`` raises.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import time
+import warnings
+from typing import Optional, Tuple, Union
+
+import numpy as np
+
+from ._bootstrap import ensure_grid2op, why_not
+
+if not ensure_grid2op():  # pragma: no cover
+    raise ImportError(f"grid2op (the host framework this backend plugs into) cannot be imported: {why_not()}")
+
+from grid2op.Backend.backend import Backend  # noqa: E402
+from grid2op.dtypes import dt_bool, dt_float, dt_int  # noqa: E402
+from grid2op.Exceptions import BackendError  # noqa: E402
+
+from .engine import STATUS_TEXT, PowerFlowEngine  # noqa: E402
+from .gridmodel import GridModel  # noqa: E402
+
+__all__ = ["B200Backend"]
+
+_K_LOAD, _K_GEN, _K_LOR, _K_LEX, _K_STO = 0, 1, 2, 3, 4
+
+
+class B200Backend(Backend):
+    shunts_data_available = True
+
+    def __init__(self, detailed_infos_for_cascading_failures: bool = False, can_be_copied: bool = True,
+                 max_iter: int = 10, tol_mva: float = 1e-8, device: int = 0):
+        Backend.__init__(self, detailed_infos_for_cascading_failures=detailed_infos_for_cascading_failures,
+                         can_be_copied=can_be_copied, max_iter=max_iter, tol_mva=tol_mva, device=device)
+        self._max_iter = int(max_iter)
+        self._tol_mva = float(tol_mva)
+        self._device = int(device)
+        self.can_output_theta = True
+        self._gm: Optional[GridModel] = None
+        self._engine = None
+        self._topo_vect: Optional[np.ndarray] = None
+        self.div_exception = None
+        self._last_status = 0
+        self._last_iters = 0
+        self._state0 = None
+
+    # ------------------------------------------------------------------------------------------
+    # engine factory (the only place that touches the device library)
+    # ------------------------------------------------------------------------------------------
+    def _make_engine(self, gm: GridModel):
+        return PowerFlowEngine(gm, max_batch=1, device=self._device)
+
+    # ------------------------------------------------------------------------------------------
+    # load_grid                                                      reference pPB:356-617, 670-874
+    # ------------------------------------------------------------------------------------------
+    def load_grid(self, path: Union[os.PathLike, str], filename: Optional[Union[os.PathLike, str]] = None) -> None:
+        self.can_handle_more_than_2_busbar()
+        self.can_handle_detachment()
+        full_path = self.make_complete_path(path, filename)
+        gm = GridModel(full_path, n_busbar=self.n_busbar_per_sub)
+        if gm.non_modeled:
+            warnings.warn(f"There are {gm.non_modeled} in the grid file. These elements are not modeled "
+                          "(neither by grid2op nor by this backend).")
+        self._gm = gm
+        self._engine = self._make_engine(gm)
+        # --- grid description expected by grid2op (docs/grid2op_extend/createbackend.rst:322-347)
+        self.n_line = gm.n_line
+        self.n_gen = gm.n_gen
+        self.n_load = gm.n_load
+        self.n_sub = gm.n_sub
+        self.name_line = gm.name_line.copy()
+        self.name_gen = gm.name_gen.copy()
+        self.name_load = gm.name_load.copy()
+        self.name_sub = gm.name_sub.copy()
+        self.n_storage = gm.n_storage
+        if gm.n_storage == 0:
+            self.set_no_storage()
+        else:
+            self.name_storage = gm.name_storage.copy()
+            self.storage_to_subid = gm.storage_sub.astype(dt_int)
+            self.storage_to_sub_pos = gm.storage_to_sub_pos.astype(dt_int)
+        self.sub_info = gm.sub_info.astype(dt_int)
+        self.dim_topo = int(gm.dim_topo)
+        self.load_to_subid = gm.load_sub.astype(dt_int)
+        self.gen_to_subid = gm.gen_sub.astype(dt_int)
+        self.line_or_to_subid = gm.line_or_sub.astype(dt_int)
+        self.line_ex_to_subid = gm.line_ex_sub.astype(dt_int)
+        self.load_to_sub_pos = gm.load_to_sub_pos.astype(dt_int)
+        self.gen_to_sub_pos = gm.gen_to_sub_pos.astype(dt_int)
+        self.line_or_to_sub_pos = gm.line_or_to_sub_pos.astype(dt_int)
+        self.line_ex_to_sub_pos = gm.line_ex_to_sub_pos.astype(dt_int)
+        self.n_shunt = gm.n_shunt
+        self.shunt_to_subid = gm.shunt_sub.astype(dt_int)
+        self.name_shunt = gm.name_shunt.copy()
+        self._sh_vnkv = gm.sh_vnkv.copy()
+        self._compute_pos_big_topo()
+        self.thermal_limit_a = gm.thermal_limit_a.astype(dt_float)
+
+        # position -> (kind, element) dispatch for apply_action               pPB:630-653
+        kind = np.full(gm.dim_topo, -1, dtype=np.int8)
+        idx = np.zeros(gm.dim_topo, dtype=np.int32)
+        kind[gm.load_pos] = _K_LOAD; idx[gm.load_pos] = np.arange(gm.n_load)
+        kind[gm.gen_pos] = _K_GEN; idx[gm.gen_pos] = np.arange(gm.n_gen)
+        kind[gm.line_or_pos] = _K_LOR; idx[gm.line_or_pos] = np.arange(gm.n_line)
+        kind[gm.line_ex_pos] = _K_LEX; idx[gm.line_ex_pos] = np.arange(gm.n_line)
+        if gm.n_storage:
+            kind[gm.storage_pos] = _K_STO; idx[gm.storage_pos] = np.arange(gm.n_storage)
+        self._pos_kind, self._pos_idx = kind, idx
+
+        # --- mutable state (what PandaPowerBackend keeps in its DataFrames)
+        self._gen_p = gm.gen_p0.copy()
+        self._gen_vm = gm.gen_vm0.copy()
+        self._hid_vm = gm.hidden_vm0.copy()
+        self._load_p = gm.load_p0.copy()
+        self._load_q = gm.load_q0.copy()
+        self._sto_p = gm.storage_p0.copy()
+        self._sh_p = gm.shunt_p0.copy()
+        self._sh_q = gm.shunt_q0.copy()
+        self._line_on = gm.line_in_service0.copy()
+        self._lor_bus = np.ones(gm.n_line, dtype=np.int8)
+        self._lex_bus = np.ones(gm.n_line, dtype=np.int8)
+        self._gen_on = gm.gen_on0.copy()
+        self._gen_bus = np.ones(gm.n_gen, dtype=np.int8)
+        self._load_on = gm.load_on0.copy()
+        self._load_bus = np.ones(gm.n_load, dtype=np.int8)
+        self._sto_on = gm.storage_on0.copy()
+        self._sto_bus = np.ones(gm.n_storage, dtype=np.int8)
+        self._sh_on = gm.shunt_on0.copy()
+        self._sh_bus = np.ones(gm.n_shunt, dtype=np.int8)
+        self._hid_on = gm.hidden_on0.copy()
+        self._hid_bus = np.ones(gm.n_hidden, dtype=np.int8)
+
+        # --- result buffers                                                   pPB:815-860
+        def buf(n):
+            return np.full(n, np.nan, dtype=dt_float)
+
+        self.p_or, self.q_or, self.v_or, self.a_or = buf(gm.n_line), buf(gm.n_line), buf(gm.n_line), buf(gm.n_line)
+        self.p_ex, self.q_ex, self.v_ex, self.a_ex = buf(gm.n_line), buf(gm.n_line), buf(gm.n_line), buf(gm.n_line)
+        self.theta_or, self.theta_ex = buf(gm.n_line), buf(gm.n_line)
+        self.prod_p, self.prod_q, self.prod_v, self.gen_theta = buf(gm.n_gen), buf(gm.n_gen), buf(gm.n_gen), buf(gm.n_gen)
+        self.load_p, self.load_q, self.load_v, self.load_theta = buf(gm.n_load), buf(gm.n_load), buf(gm.n_load), buf(gm.n_load)
+        self.storage_p, self.storage_q, self.storage_v, self.storage_theta = (buf(gm.n_storage), buf(gm.n_storage),
+                                                                              buf(gm.n_storage), buf(gm.n_storage))
+        self._shunt_p, self._shunt_q, self._shunt_v = buf(gm.n_shunt), buf(gm.n_shunt), buf(gm.n_shunt)
+        self.line_status = np.zeros(gm.n_line, dtype=dt_bool)
+        self._topo_vect = np.full(gm.dim_topo, -1, dtype=dt_int)
+        self._refresh_status_topo()
+        self.comp_time = 0.0
+
+        # initial power flow (the reference runs it when loading, pPB:386/455/577, AC then DC on failure)
+        ok, _ = self.runpf(is_dc=False)
+        if not ok:
+            ok, _ = self.runpf(is_dc=True)
+        if ok and gm.id_gen_added is not None:
+            self._gen_p[gm.id_gen_added] = float(self.prod_p[gm.id_gen_added])   # pPB:422
+        self._refresh_status_topo()
+        self.comp_time = 0.0
+        self._state0 = self._snapshot()
+
+    # ------------------------------------------------------------------------------------------
+    def _snapshot(self):
+        names = ("_gen_p", "_gen_vm", "_hid_vm", "_load_p", "_load_q", "_sto_p", "_sh_p", "_sh_q", "_line_on",
+                 "_lor_bus", "_lex_bus", "_gen_on", "_gen_bus", "_load_on", "_load_bus", "_sto_on", "_sto_bus",
+                 "_sh_on", "_sh_bus", "_hid_on", "_hid_bus",
+                 "p_or", "q_or", "v_or", "a_or", "p_ex", "q_ex", "v_ex", "a_ex", "theta_or", "theta_ex",
+                 "prod_p", "prod_q", "prod_v", "gen_theta", "load_p", "load_q", "load_v", "load_theta",
+                 "storage_p", "storage_q", "storage_v", "storage_theta", "_shunt_p", "_shunt_q", "_shunt_v")
+        return {k: getattr(self, k).copy() for k in names}
+
+    def _restore(self, snap):
+        for k, v in snap.items():
+            setattr(self, k, v.copy())
+
+    # pPB:1450-1459 and 1489-1524
+    def _refresh_status_topo(self):
+        gm = self._gm
+        self.line_status = self._line_on.astype(dt_bool)
+        tv = np.full(gm.dim_topo, -1, dtype=dt_int)
+        tv[gm.line_or_pos] = np.where(self._line_on, self._lor_bus, -1)
+        tv[gm.line_ex_pos] = np.where(self._line_on, self._lex_bus, -1)
+        tv[gm.load_pos] = np.where(self._load_on, self._load_bus, -1)
+        tv[gm.gen_pos] = np.where(self._gen_on, self._gen_bus, -1)
+        if gm.n_storage:
+            tv[gm.storage_pos] = np.where(self._sto_on, self._sto_bus, -1)
+        self._topo_vect = tv
+
+    # ------------------------------------------------------------------------------------------
+    # apply_action                                                           reference pPB:902-1067
+    # ------------------------------------------------------------------------------------------
+    def apply_action(self, backend_action) -> None:
+        if backend_action is None:
+            return
+        gm = self._gm
+        _, (prod_p, prod_v, load_p, load_q, storage), topo__, shunts__ = backend_action()
+        ch = prod_p.changed
+        self._gen_p[ch] = prod_p.values[ch]
+        ch = prod_v.changed
+        # float32 / float32 like the reference (pPB:927); stored in float64
+        self._gen_vm[ch] = prod_v.values[ch] / gm.prod_pu_to_kv[ch]
+        if gm.id_gen_added is not None and gm.n_hidden and prod_v.changed[gm.id_gen_added]:
+            self._hid_vm[:] = self._gen_vm[gm.id_gen_added]                    # pPB:929-931
+        ch = load_p.changed
+        self._load_p[ch] = load_p.values[ch]
+        ch = load_q.changed
+        self._load_q[ch] = load_q.values[ch]
+        if gm.n_storage > 0:
+            ch = storage.changed
+            self._sto_p[ch] = storage.values[ch]
+            stor_bus = backend_action.get_storages_bus()                        # pPB:941-951
+            for i in np.flatnonzero(stor_bus.changed):
+                b = int(stor_bus.values[i])
+                if b <= -1:
+                    self._sto_on[i] = False
+                    self._sto_bus[i] = 1
+                else:
+                    self._sto_on[i] = True
+                    self._sto_bus[i] = b
+        if type(self).shunts_data_available and shunts__ is not None:
+            shunt_p, shunt_q, shunt_bus = shunts__
+            ch = shunt_p.changed
+            self._sh_p[ch] = shunt_p.values[ch]
+            ch = shunt_q.changed
+            self._sh_q[ch] = shunt_q.values[ch]
+            for i in np.flatnonzero(shunt_bus.changed):
+                b = int(shunt_bus.values[i])
+                if b == -1:
+                    self._sh_on[i] = False
+                else:
+                    self._sh_on[i] = True
+                    self._sh_bus[i] = b
+        kind, idx = self._pos_kind, self._pos_idx
+        for pos, new_bus in topo__:                                             # pPB:971-975
+            k = kind[pos]
+            i = idx[pos]
+            new_bus = int(new_bus)
+            if k == _K_LOAD:
+                if new_bus >= 1:
+                    self._load_on[i] = True; self._load_bus[i] = new_bus
+                else:
+                    self._load_on[i] = False
+            elif k == _K_GEN:
+                if new_bus >= 1:
+                    self._gen_on[i] = True; self._gen_bus[i] = new_bus
+                    if gm.id_gen_added is not None and gm.n_hidden and i == gm.n_gen - 1:
+                        self._hid_bus[0] = new_bus                              # pPB:997-1003
+                else:
+                    self._gen_on[i] = False
+            elif k == _K_LOR:
+                if new_bus >= 1:
+                    self._line_on[i] = True; self._lor_bus[i] = new_bus
+                else:
+                    self._line_on[i] = False
+            elif k == _K_LEX:
+                if new_bus >= 1:
+                    self._line_on[i] = True; self._lex_bus[i] = new_bus
+                else:
+                    self._line_on[i] = False
+
+    # ------------------------------------------------------------------------------------------
+    # runpf                                                        reference pPB:1078-1120, 1220-1255
+    # ------------------------------------------------------------------------------------------
+    def _device_records(self):
+        gm = self._gm
+        topo = np.empty(gm.n_topo_in, dtype=np.int8)
+        topo[:gm.dim_topo] = self._topo_vect
+        topo[gm.dim_topo:gm.dim_topo + gm.n_shunt] = np.where(self._sh_on, self._sh_bus, -1)
+        topo[gm.dim_topo + gm.n_shunt:] = np.where(self._hid_on, self._hid_bus, -1)
+        inj = np.concatenate([self._gen_p, self._hid_vm, self._gen_vm, self._load_p, self._load_q,
+                              self._sto_p, self._sh_p, self._sh_q])
+        return topo, inj
+
+    def runpf(self, is_dc: bool = False) -> Tuple[bool, Union[Exception, None]]:
+        gm = self._gm
+        t0 = time.perf_counter()
+        self._refresh_status_topo()                                             # pPB:1236-1237
+        topo, inj = self._device_records()
+        nb_cap = int(min(gm.n_slot, np.unique(self._active_slots(topo)).size)) if gm.n_slot > 64 else 0
+        out, status, iters, _ = self._engine.run(topo[None, :], inj[None, :], is_dc=is_dc, max_iter=self._max_iter,
+                                                 tol_mva=self._tol_mva, nb_cap=nb_cap)
+        self.comp_time += time.perf_counter() - t0
+        st = int(status[0])
+        self._last_status, self._last_iters = st, int(iters[0])
+        if st != 0:
+            msg = STATUS_TEXT.get(st, f"status {st}")
+            self.div_exception = BackendError(msg)
+            self._reset_all_nan()
+            return False, BackendError(f'powerflow diverged with error :"{msg}"')
+        self._fetch(out, is_dc)
+        self.div_exception = None
+        return True, None
+
+    def _active_slots(self, topo):
+        gm = self._gm
+        subs = np.concatenate([gm.line_or_sub, gm.line_ex_sub, gm.gen_sub, gm.load_sub, gm.storage_sub,
+                               gm.shunt_sub, gm.hidden_sub])
+        pos = np.concatenate([gm.line_or_pos, gm.line_ex_pos, gm.gen_pos, gm.load_pos, gm.storage_pos,
+                              gm.dim_topo + np.arange(gm.n_shunt), gm.dim_topo + gm.n_shunt + np.arange(gm.n_hidden)])
+        b = topo[pos].astype(np.int64)
+        ok = b > 0
+        return subs[ok].astype(np.int64) + (b[ok] - 1) * gm.n_sub
+
+    # pPB:1122-1218 (+ 1526-1564, 1596-1612, 1621-1647)
+    def _fetch(self, out, is_dc):
+        gm = self._gm
+        v = self._engine.view(out)
+        nh = gm.n_hidden
+        self.p_or[:] = v.p_or[0]; self.q_or[:] = v.q_or[0]; self.v_or[:] = v.v_or[0]; self.a_or[:] = v.a_or[0]
+        self.p_ex[:] = v.p_ex[0]; self.q_ex[:] = v.q_ex[0]; self.v_ex[:] = v.v_ex[0]; self.a_ex[:] = v.a_ex[0]
+        self.theta_or[:] = v.theta_or[0]; self.theta_ex[:] = v.theta_ex[0]
+        self.prod_p[:] = v.unit_p[0, nh:]; self.prod_q[:] = v.unit_q[0, nh:]
+        self.prod_v[:] = v.unit_v[0, nh:]; self.gen_theta[:] = v.unit_theta[0, nh:]
+        if gm.id_gen_added is not None and nh:
+            # the created generator carries the power of the ext_grid it stands for     pPB:1536-1546
+            self.prod_p[gm.id_gen_added] += v.unit_p[0, 0]
+            self.prod_q[gm.id_gen_added] += v.unit_q[0, 0]
+        self.load_p[:] = np.where(self._load_on, self._load_p, 0.0)
+        self.load_q[:] = np.where(self._load_on, self._load_q, 0.0)
+        self.load_v[:] = v.load_v[0]; self.load_theta[:] = v.load_theta[0]
+        if gm.n_storage:
+            self.storage_p[:] = self._sto_p                                    # set point table, pPB:1627
+            self.storage_q[:] = gm.storage_q
+            self.storage_v[:] = v.storage_v[0]
+            self.storage_theta[:] = v.storage_v[0]                              # sic, pPB:1635-1640
+            if is_dc:
+                # res_bus.vm_pu is NaN in DC -> the reference zeroes p, q, v        pPB:1203-1206
+                # (only for connected units: a disconnected one already has v = 0, keeps its set point)
+                on = self._sto_on
+                self.storage_p[on] = 0.0; self.storage_q[on] = 0.0; self.storage_v[:] = 0.0
+                self.storage_theta[:] = np.nan
+        self._shunt_p[:] = v.shunt_p[0]; self._shunt_q[:] = v.shunt_q[0]; self._shunt_v[:] = v.shunt_v[0]
+        if is_dc:                                                               # pPB:1212-1218
+            self.prod_q[:] = 0.0; self.load_q[:] = 0.0; self.storage_q[:] = 0.0
+            self.q_or[:] = 0.0; self.q_ex[:] = 0.0
+
+    # pPB:1257-1287
+    def _reset_all_nan(self):
+        for nm in ("p_or", "q_or", "v_or", "a_or", "p_ex", "q_ex", "v_ex", "a_ex", "prod_p", "prod_q", "prod_v",
+                   "load_p", "load_q", "load_v", "storage_p", "storage_q", "storage_v", "theta_or", "theta_ex",
+                   "load_theta", "gen_theta", "storage_theta", "_shunt_p", "_shunt_q", "_shunt_v"):
+            getattr(self, nm)[:] = np.nan
+        self._topo_vect = np.full(self._gm.dim_topo, -1, dtype=dt_int)
+        self.line_status = np.zeros(self._gm.n_line, dtype=dt_bool)
+
+    # ------------------------------------------------------------------------------------------
+    # read-back                                                              reference pPB:1439-1647
+    # ------------------------------------------------------------------------------------------
+    def get_line_status(self) -> np.ndarray:
+        return self.line_status
+
+    def get_line_flow(self) -> np.ndarray:
+        return self.a_or
+
+    def get_topo_vect(self) -> np.ndarray:
+        return self._topo_vect.copy()
+
+    def generators_info(self):
+        return self.prod_p.copy(), self.prod_q.copy(), self.prod_v.copy()
+
+    def loads_info(self):
+        return self.load_p.copy(), self.load_q.copy(), self.load_v.copy()
+
+    def lines_or_info(self):
+        return self.p_or.copy(), self.q_or.copy(), self.v_or.copy(), self.a_or.copy()
+
+    def lines_ex_info(self):
+        return self.p_ex.copy(), self.q_ex.copy(), self.v_ex.copy(), self.a_ex.copy()
+
+    def storages_info(self):
+        return self.storage_p.copy(), self.storage_q.copy(), self.storage_v.copy()
+
+    def shunt_info(self):
+        bus = np.where(self._sh_on, self._sh_bus, -1).astype(dt_int)
+        return self._shunt_p.copy(), self._shunt_q.copy(), self._shunt_v.copy(), bus
+
+    def get_theta(self):
+        return (1.0 * self.theta_or, 1.0 * self.theta_ex, 1.0 * self.load_theta, 1.0 * self.gen_theta,
+                1.0 * self.storage_theta)
+
+    def sub_from_bus_id(self, bus_id: int) -> int:
+        n = self._gm.n_sub
+        return bus_id - n * (bus_id // n)
+
+    # ------------------------------------------------------------------------------------------
+    # life cycle
+    # ------------------------------------------------------------------------------------------
+    def _disconnect_line(self, id_: int) -> None:                               # pPB:1464-1475
+        self._line_on[id_] = False
+        self._topo_vect[type(self).line_or_pos_topo_vect[id_]] = -1
+        self._topo_vect[type(self).line_ex_pos_topo_vect[id_]] = -1
+        self.line_status[id_] = False
+
+    def reset(self, path=None, grid_filename=None) -> None:                     # pPB:334-354
+        self._restore(self._state0)
+        self._refresh_status_topo()
+        self.comp_time = 0.0
+
+    def copy(self) -> "B200Backend":                                            # pPB:1289-1409
+        gm, eng, st0 = self._gm, self._engine, self._state0
+        self._gm = self._engine = self._state0 = None
+        try:
+            res = copy.deepcopy(self)
+        finally:
+            self._gm, self._engine, self._state0 = gm, eng, st0
+        res._gm, res._engine, res._state0 = gm, eng, st0      # immutable / shared device handle
+        return res
+
+    def close(self) -> None:
+        self._engine = None
+        self._gm = None
+
+    def save_file(self, full_path) -> None:
+        raise NotImplementedError("B200Backend does not write pandapower json files")

@@ -1,0 +1,374 @@
+// b200pf.cu — C-ABI of the B200 batched power-flow engine (see include/b200pf.h).
+// Host side: owns the device copy of the static grid description, the staging buffers, one CUDA
+// stream per handle, and picks the thread-group size / shared-memory budget per launch.
+#include "b200pf_kernel.cuh"
+#include "../../include/b200pf.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace b200pf;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(B200PF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+    } while (0)
+
+struct b200pf_handle {
+    int device = 0;
+    int max_batch = 0;
+    cudaStream_t stream = nullptr;
+    DevGrid g{};
+    std::vector<void *> dev_allocs;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    // staging (run_host)
+    int8_t *d_topo = nullptr; double *d_inj = nullptr; float *d_out = nullptr; int *d_status = nullptr;
+    int *d_iters = nullptr; double *d_busv = nullptr;
+    int8_t *h_topo = nullptr; double *h_inj = nullptr; float *h_out = nullptr; int *h_status = nullptr;
+    int *h_iters = nullptr; double *h_busv = nullptr;
+    // series
+    float *d_chron = nullptr; int *d_scen = nullptr; int *d_t = nullptr; double *d_static_inj = nullptr;
+    float *d_thlim = nullptr; float *d_rho = nullptr; int8_t *d_series_topo = nullptr;
+    int series_batch = 0, n_scen = 0, n_rows = 0;
+    int64_t launches = 0;
+    int last_smem = 0, last_T = 0, last_grid = 0, last_block = 0;
+};
+
+template <typename Tp>
+static int upload(b200pf_handle *h, const Tp *src, size_t n, const Tp **dst) {
+    Tp *d = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(Tp);
+    CU(cudaMalloc(&d, bytes));
+    h->dev_allocs.push_back(d);
+    if (n) CU(cudaMemcpy(d, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+    *dst = d;
+    return 0;
+}
+
+extern "C" const char *b200pf_last_error(void) { return g_err.c_str(); }
+extern "C" int b200pf_abi_version(void) { return B200PF_ABI_VERSION; }
+extern "C" int b200pf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int device, b200pf_handle **out) {
+    if (!gd || !out || max_batch <= 0) return fail(B200PF_E_ARG, "null argument or max_batch <= 0");
+    if (gd->abi_version != B200PF_ABI_VERSION) return fail(B200PF_E_ARG, "ABI version mismatch");
+    if (gd->n_sub <= 0 || gd->n_busbar <= 0 || gd->n_line < 0) return fail(B200PF_E_ARG, "bad grid sizes");
+    if ((long)gd->n_sub * gd->n_busbar > 30000) return fail(B200PF_E_ARG, "too many bus slots");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B200PF_E_CUDA, "no CUDA device available: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(B200PF_E_ARG, "bad device index");
+    CU(cudaSetDevice(device));
+    b200pf_handle *h = new b200pf_handle();
+    h->device = device;
+    h->max_batch = max_batch;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    DevGrid &g = h->g;
+    g.n_sub = gd->n_sub; g.n_busbar = gd->n_busbar; g.n_slot = gd->n_sub * gd->n_busbar;
+    g.n_line = gd->n_line; g.n_gen = gd->n_gen; g.n_hidden = gd->n_hidden; g.n_unit = gd->n_gen + gd->n_hidden;
+    g.n_load = gd->n_load; g.n_sto = gd->n_storage; g.n_shunt = gd->n_shunt; g.dim_topo = gd->dim_topo;
+    g.n_topo_in = g.dim_topo + g.n_shunt + g.n_hidden;
+    g.n_inj = g.n_gen + g.n_unit + 2 * g.n_load + g.n_sto + 2 * g.n_shunt;
+    g.n_out = 10 * g.n_line + 4 * g.n_unit + 2 * g.n_load + g.n_sto + 3 * g.n_shunt;
+    g.base_mva = gd->sn_mva;
+    int rc = 0;
+#define UP(field, src, n) if ((rc = upload(h, src, (size_t)(n), &g.field)) != 0) { b200pf_destroy(h); return rc; }
+    UP(line_or_sub, gd->line_or_sub, g.n_line) UP(line_ex_sub, gd->line_ex_sub, g.n_line)
+    UP(line_or_pos, gd->line_or_pos, g.n_line) UP(line_ex_pos, gd->line_ex_pos, g.n_line)
+    UP(line_y, gd->line_y, 8 * g.n_line) UP(line_bdc, gd->line_bdc, g.n_line) UP(line_pshift, gd->line_pshift, g.n_line)
+    UP(line_or_vn, gd->line_or_vn, g.n_line) UP(line_ex_vn, gd->line_ex_vn, g.n_line)
+    UP(unit_sub, gd->unit_sub, g.n_unit) UP(unit_pos, gd->unit_pos, g.n_unit) UP(unit_is_ref, gd->unit_is_ref, g.n_unit)
+    UP(unit_qmin, gd->unit_qmin, g.n_unit) UP(unit_qmax, gd->unit_qmax, g.n_unit) UP(unit_vn, gd->unit_vn, g.n_unit)
+    UP(load_sub, gd->load_sub, g.n_load) UP(load_pos, gd->load_pos, g.n_load) UP(load_vn, gd->load_vn, g.n_load)
+    UP(sto_sub, gd->storage_sub, g.n_sto) UP(sto_pos, gd->storage_pos, g.n_sto) UP(sto_vn, gd->storage_vn, g.n_sto)
+    UP(sto_q, gd->storage_q, g.n_sto)
+    UP(sh_sub, gd->shunt_sub, g.n_shunt) UP(sh_vn, gd->shunt_vn, g.n_shunt) UP(sh_vratio, gd->shunt_vratio, g.n_shunt)
+    // static incidence lists: line ends per substation, in line order (deterministic summation order)
+    {
+        std::vector<int> ptr(g.n_sub + 1, 0), ends(2 * (size_t)g.n_line);
+        for (int l = 0; l < g.n_line; ++l) {
+            if (gd->line_or_sub[l] < 0 || gd->line_or_sub[l] >= g.n_sub || gd->line_ex_sub[l] < 0 || gd->line_ex_sub[l] >= g.n_sub) {
+                b200pf_destroy(h);
+                return fail(B200PF_E_ARG, "line substation id out of range");
+            }
+            ptr[gd->line_or_sub[l] + 1]++; ptr[gd->line_ex_sub[l] + 1]++;
+        }
+        for (int s = 0; s < g.n_sub; ++s) ptr[s + 1] += ptr[s];
+        std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+        for (int l = 0; l < g.n_line; ++l) {
+            ends[fill[gd->line_or_sub[l]]++] = 2 * l;
+            ends[fill[gd->line_ex_sub[l]]++] = 2 * l + 1;
+        }
+        UP(sub_end_ptr, ptr.data(), ptr.size()) UP(sub_end, ends.data(), ends.size())
+    }
+#undef UP
+    size_t B = (size_t)max_batch;
+    auto dmal = [&](void **p, size_t bytes) -> int { CU(cudaMalloc(p, bytes ? bytes : 1)); h->dev_allocs.push_back(*p); return 0; };
+    if ((rc = dmal((void **)&h->d_topo, B * g.n_topo_in)) || (rc = dmal((void **)&h->d_inj, B * g.n_inj * 8)) ||
+        (rc = dmal((void **)&h->d_out, B * g.n_out * 4)) || (rc = dmal((void **)&h->d_status, B * 4)) ||
+        (rc = dmal((void **)&h->d_iters, B * 4)) || (rc = dmal((void **)&h->d_busv, B * 2 * g.n_slot * 8))) {
+        b200pf_destroy(h);
+        return rc;
+    }
+    if (cudaMallocHost(&h->h_topo, B * g.n_topo_in + 1) != cudaSuccess || cudaMallocHost(&h->h_inj, B * g.n_inj * 8 + 8) != cudaSuccess ||
+        cudaMallocHost(&h->h_out, B * g.n_out * 4 + 4) != cudaSuccess || cudaMallocHost(&h->h_status, B * 4) != cudaSuccess ||
+        cudaMallocHost(&h->h_iters, B * 4) != cudaSuccess || cudaMallocHost(&h->h_busv, B * 2 * g.n_slot * 8 + 8) != cudaSuccess) {
+        b200pf_destroy(h);
+        return fail(B200PF_E_CUDA, "pinned host allocation failed");
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int b200pf_destroy(b200pf_handle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->dev_allocs) cudaFree(p);
+    void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv};
+    for (void *p : pinned) if (p) cudaFreeHost(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int b200pf_sizes(const b200pf_handle *h, int *n_topo_in, int *n_inj, int *n_out, int *n_slot) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (n_topo_in) *n_topo_in = h->g.n_topo_in;
+    if (n_inj) *n_inj = h->g.n_inj;
+    if (n_out) *n_out = h->g.n_out;
+    if (n_slot) *n_slot = h->g.n_slot;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch configuration
+// ------------------------------------------------------------------------------------------------
+template <int T, typename JT>
+static int launch_t(b200pf_handle *h, const RunArgs &a) {
+    const DevGrid &g = h->g;
+    constexpr int BLOCK = (T == 32) ? 128 : T;
+    constexpr int GPB = BLOCK / T;
+    WsLayout L = ws_layout(a.nb_cap, g.n_slot, g.n_line, g.n_inj, (size_t)a.mat_bytes);
+    const int ws_bytes = (int)L.total;
+    const size_t smem = (size_t)ws_bytes * GPB;
+    if (smem > (size_t)h->max_smem_optin)
+        return fail(B200PF_E_CAPACITY, "workspace does not fit in shared memory");
+    auto kern = pf_kernel<T, JT>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+    if (occ < 1) occ = 1;
+    int need = (a.batch + GPB - 1) / GPB;
+    int grid = h->sm_count * occ;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<grid, BLOCK, smem, h->stream>>>(g, a, ws_bytes);
+    CU(cudaGetLastError());
+    h->launches++;
+    h->last_smem = (int)smem; h->last_T = T; h->last_grid = grid; h->last_block = BLOCK;
+    return 0;
+}
+
+// Sizing policy.  nb_cap (bus arrays) = the caller's bound or every slot.  The matrix region gets
+// what the worst case of nb_cap buses needs, clipped to what is left on chip; the kernel checks the
+// ACTUAL system size of each instance against it (B200PF_ST_TOO_LARGE), so e.g. the 118-substation
+// grid (236 slots) runs as long as its Newton system (191 unknowns + splits) fits.
+static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
+    const DevGrid &g = h->g;
+    const char *f64 = getenv("B200PF_JACOBIAN_FP64");
+    const bool jd = f64 && f64[0] == '1';
+    const int jt = jd ? 8 : 4;
+    int cap = nb_cap_req;
+    if (cap <= 0 || cap > g.n_slot) cap = g.n_slot;
+    const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
+    size_t want = ws_mat_worst(cap, jt);
+    int T = 32;
+    {
+        size_t d = 2 * (size_t)cap;
+        T = d <= 64 ? 32 : (d <= 128 ? 64 : (d <= 256 ? 128 : 256));
+    }
+    int gpb = (T == 32) ? 4 : 1;
+    if ((fixed + want) * gpb > (size_t)h->max_smem_optin) {
+        // does not fit with 4 warps per CTA / worst case: one group per CTA, clipped matrix
+        if (T == 32) { T = 64; }
+        gpb = 1;
+        if (fixed + 1024 > (size_t)h->max_smem_optin) return fail(B200PF_E_CAPACITY, "grid too large for the on-chip workspace");
+        size_t avail = ((size_t)h->max_smem_optin - fixed) & ~size_t(15);
+        if (want > avail) want = avail;
+        size_t dmax = 1;
+        while ((dmax + 1) * (dmax + 3) * jt <= want) ++dmax;
+        T = dmax <= 128 ? 64 : (dmax <= 256 ? 128 : 256);
+    }
+    a.nb_cap = cap;
+    a.mat_bytes = (int)want;
+    if (jd) {
+        switch (T) {
+            case 32: return launch_t<32, double>(h, a);
+            case 64: return launch_t<64, double>(h, a);
+            case 128: return launch_t<128, double>(h, a);
+            default: return launch_t<256, double>(h, a);
+        }
+    }
+    switch (T) {
+        case 32: return launch_t<32, float>(h, a);
+        case 64: return launch_t<64, float>(h, a);
+        case 128: return launch_t<128, float>(h, a);
+        default: return launch_t<256, float>(h, a);
+    }
+}
+
+static RunArgs base_args(const b200pf_handle *h, int batch, int is_dc, int max_iter, double tol_mva) {
+    RunArgs a{};
+    a.batch = batch; a.is_dc = is_dc; a.max_iter = max_iter;
+    a.tol_pu = tol_mva / h->g.base_mva;
+    return a;
+}
+
+extern "C" int b200pf_run_device(b200pf_handle *h, int batch, const int8_t *d_topo, const double *d_inj, int is_dc,
+                                 int max_iter, double tol_mva, int nb_cap, float *d_out, int32_t *d_status,
+                                 int32_t *d_iters, double *d_busv) {
+    if (!h || !d_topo || !d_inj || !d_out || !d_status || !d_iters) return fail(B200PF_E_ARG, "null pointer");
+    if (batch <= 0) return fail(B200PF_E_ARG, "batch <= 0");
+    CU(cudaSetDevice(h->device));
+    RunArgs a = base_args(h, batch, is_dc, max_iter, tol_mva);
+    a.topo = d_topo; a.inj = d_inj; a.out = d_out; a.status = d_status; a.iters = d_iters; a.busv = d_busv;
+    return launch(h, a, nb_cap);
+}
+
+extern "C" int b200pf_run_host(b200pf_handle *h, int batch, const int8_t *topo, const double *inj, int is_dc,
+                               int max_iter, double tol_mva, int nb_cap, float *out, int32_t *status,
+                               int32_t *iters, double *busv) {
+    if (!h || !topo || !inj || !out || !status || !iters) return fail(B200PF_E_ARG, "null pointer");
+    if (batch <= 0 || batch > h->max_batch) return fail(B200PF_E_ARG, "batch out of range (max_batch)");
+    CU(cudaSetDevice(h->device));
+    const DevGrid &g = h->g;
+    const size_t B = (size_t)batch;
+    memcpy(h->h_topo, topo, B * g.n_topo_in);
+    memcpy(h->h_inj, inj, B * g.n_inj * 8);
+    CU(cudaMemcpyAsync(h->d_topo, h->h_topo, B * g.n_topo_in, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_inj, h->h_inj, B * g.n_inj * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = b200pf_run_device(h, batch, h->d_topo, h->d_inj, is_dc, max_iter, tol_mva, nb_cap, h->d_out, h->d_status,
+                               h->d_iters, busv ? h->d_busv : nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->h_out, h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (busv) CU(cudaMemcpyAsync(h->h_busv, h->d_busv, B * 2 * g.n_slot * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->h_out, B * g.n_out * 4);
+    memcpy(status, h->h_status, B * 4);
+    memcpy(iters, h->h_iters, B * 4);
+    if (busv) memcpy(busv, h->h_busv, B * 2 * g.n_slot * 8);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// time-series stepping
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int n_scen, int n_rows, const int32_t *scen,
+                                  const int32_t *t0, int batch, const double *static_inj, const float *thermal_limit_a) {
+    if (!h || !chron_host || !scen || !t0 || !static_inj || !thermal_limit_a) return fail(B200PF_E_ARG, "null pointer");
+    if (batch <= 0 || batch > h->max_batch || n_scen <= 0 || n_rows <= 0) return fail(B200PF_E_ARG, "bad sizes");
+    CU(cudaSetDevice(h->device));
+    const DevGrid &g = h->g;
+    for (int i = 0; i < batch; ++i)
+        if (scen[i] < 0 || scen[i] >= n_scen || t0[i] < 0 || t0[i] >= n_rows) return fail(B200PF_E_ARG, "scenario / row index out of range");
+    const size_t ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
+    auto dmal = [&](void **p, size_t bytes) -> int { CU(cudaMalloc(p, bytes ? bytes : 1)); h->dev_allocs.push_back(*p); return 0; };
+    int rc;
+    if ((rc = dmal((void **)&h->d_chron, (size_t)n_scen * n_rows * ncol * 4)) || (rc = dmal((void **)&h->d_scen, (size_t)batch * 4)) ||
+        (rc = dmal((void **)&h->d_t, (size_t)batch * 4)) || (rc = dmal((void **)&h->d_static_inj, (size_t)g.n_inj * 8)) ||
+        (rc = dmal((void **)&h->d_thlim, (size_t)g.n_line * 4)) || (rc = dmal((void **)&h->d_rho, (size_t)batch * g.n_line * 4)) ||
+        (rc = dmal((void **)&h->d_series_topo, (size_t)batch * g.n_topo_in)))
+        return rc;
+    CU(cudaMemcpy(h->d_chron, chron_host, (size_t)n_scen * n_rows * ncol * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_scen, scen, (size_t)batch * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_t, t0, (size_t)batch * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_static_inj, static_inj, (size_t)g.n_inj * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_thlim, thermal_limit_a, (size_t)g.n_line * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->d_series_topo, 1, (size_t)batch * g.n_topo_in));
+    h->series_batch = batch; h->n_scen = n_scen; h->n_rows = n_rows;
+    return 0;
+}
+
+extern "C" int b200pf_series_set_topo(b200pf_handle *h, const int8_t *topo) {
+    if (!h || !topo) return fail(B200PF_E_ARG, "null pointer");
+    if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(h->d_series_topo, topo, (size_t)h->series_batch * h->g.n_topo_in, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, double tol_mva, int nb_cap) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
+    CU(cudaSetDevice(h->device));
+    RunArgs a = base_args(h, h->series_batch, is_dc, max_iter, tol_mva);
+    a.topo = h->d_series_topo; a.inj = nullptr; a.out = h->d_out; a.status = h->d_status; a.iters = h->d_iters; a.busv = nullptr;
+    a.series = 1; a.chron = h->d_chron; a.n_scen = h->n_scen; a.n_rows = h->n_rows; a.scen = h->d_scen; a.t = h->d_t;
+    a.static_inj = h->d_static_inj; a.th_lim = h->d_thlim; a.rho = h->d_rho;
+    return launch(h, a, nb_cap);
+}
+
+extern "C" int b200pf_series_results(b200pf_handle *h, float **d_out, int32_t **d_status, int32_t **d_iters, float **d_rho, int32_t **d_t) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (d_out) *d_out = h->d_out;
+    if (d_status) *d_status = h->d_status;
+    if (d_iters) *d_iters = h->d_iters;
+    if (d_rho) *d_rho = h->d_rho;
+    if (d_t) *d_t = h->d_t;
+    return 0;
+}
+
+extern "C" int b200pf_series_fetch(b200pf_handle *h, float *out, int32_t *status, int32_t *iters, float *rho) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
+    CU(cudaSetDevice(h->device));
+    const size_t B = (size_t)h->series_batch;
+    const DevGrid &g = h->g;
+    CU(cudaStreamSynchronize(h->stream));
+    if (out) CU(cudaMemcpy(out, h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost));
+    if (status) CU(cudaMemcpy(status, h->d_status, B * 4, cudaMemcpyDeviceToHost));
+    if (iters) CU(cudaMemcpy(iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost));
+    if (rho) CU(cudaMemcpy(rho, h->d_rho, B * g.n_line * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int b200pf_sync(b200pf_handle *h) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" uint64_t b200pf_stream(b200pf_handle *h) { return h ? (uint64_t)(uintptr_t)h->stream : 0; }
+extern "C" int64_t b200pf_launch_count(const b200pf_handle *h) { return h ? h->launches : 0; }
+extern "C" int b200pf_last_launch_info(const b200pf_handle *h, int *smem_bytes, int *threads_per_instance, int *grid_blocks,
+                                       int *block_threads) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (smem_bytes) *smem_bytes = h->last_smem;
+    if (threads_per_instance) *threads_per_instance = h->last_T;
+    if (grid_blocks) *grid_blocks = h->last_grid;
+    if (block_threads) *block_threads = h->last_block;
+    return 0;
+}

@@ -1,0 +1,268 @@
+"""ctypes binding of ``libb200pf.so`` (C ABI declared in ``include/b200pf.h``).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible,
+:class:`PowerFlowEngine` raises :class:`EngineUnavailable`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .gridmodel import GridModel
+
+__all__ = ["PowerFlowEngine", "EngineUnavailable", "lib_path", "load_library",
+           "ST_CONVERGED", "ST_DIVERGED", "ST_UNSUPPLIED", "ST_NO_REF", "ST_TOO_LARGE", "ABI_SYMBOLS"]
+
+ST_CONVERGED, ST_DIVERGED, ST_UNSUPPLIED, ST_NO_REF, ST_TOO_LARGE = 0, 1, 2, 3, 4
+STATUS_TEXT = {
+    ST_DIVERGED: "Newton-Raphson did not converge (or singular system)",
+    ST_UNSUPPLIED: "an in-service bus is not connected to a reference bus (isolated element / islanded grid)",
+    ST_NO_REF: "no reference (slack) unit is in service",
+    ST_TOO_LARGE: "more active buses than the launch was sized for",
+}
+
+ABI_SYMBOLS = (
+    "b200pf_last_error", "b200pf_abi_version", "b200pf_device_count", "b200pf_create", "b200pf_destroy",
+    "b200pf_sizes", "b200pf_run_host", "b200pf_run_device", "b200pf_series_bind", "b200pf_series_set_topo",
+    "b200pf_series_step", "b200pf_series_results", "b200pf_series_fetch", "b200pf_sync", "b200pf_stream",
+    "b200pf_launch_count", "b200pf_last_launch_info",
+)
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class _GridDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("n_sub", C.c_int32), ("n_busbar", C.c_int32),
+        ("n_line", C.c_int32), ("n_gen", C.c_int32), ("n_hidden", C.c_int32), ("n_load", C.c_int32),
+        ("n_storage", C.c_int32), ("n_shunt", C.c_int32), ("dim_topo", C.c_int32),
+        ("sn_mva", C.c_double),
+        ("line_or_sub", C.c_void_p), ("line_ex_sub", C.c_void_p), ("line_or_pos", C.c_void_p), ("line_ex_pos", C.c_void_p),
+        ("line_y", C.c_void_p), ("line_bdc", C.c_void_p), ("line_pshift", C.c_void_p),
+        ("line_or_vn", C.c_void_p), ("line_ex_vn", C.c_void_p),
+        ("unit_sub", C.c_void_p), ("unit_pos", C.c_void_p), ("unit_is_ref", C.c_void_p),
+        ("unit_qmin", C.c_void_p), ("unit_qmax", C.c_void_p), ("unit_vn", C.c_void_p),
+        ("load_sub", C.c_void_p), ("load_pos", C.c_void_p), ("load_vn", C.c_void_p),
+        ("storage_sub", C.c_void_p), ("storage_pos", C.c_void_p), ("storage_vn", C.c_void_p), ("storage_q", C.c_void_p),
+        ("shunt_sub", C.c_void_p), ("shunt_vn", C.c_void_p), ("shunt_vratio", C.c_void_p),
+    ]
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200pf.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen the engine and declare the prototypes of include/b200pf.h."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise EngineUnavailable(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(p)
+    vp, i32, f64 = C.c_void_p, C.c_int, C.c_double
+    lib.b200pf_last_error.restype = C.c_char_p
+    lib.b200pf_abi_version.restype = i32
+    lib.b200pf_device_count.restype = i32
+    lib.b200pf_create.argtypes = [C.POINTER(_GridDesc), i32, i32, C.POINTER(vp)]
+    lib.b200pf_destroy.argtypes = [vp]
+    lib.b200pf_sizes.argtypes = [vp] + [C.POINTER(i32)] * 4
+    lib.b200pf_run_host.argtypes = [vp, i32, vp, vp, i32, i32, f64, i32, vp, vp, vp, vp]
+    lib.b200pf_run_device.argtypes = [vp, i32, vp, vp, i32, i32, f64, i32, vp, vp, vp, vp]
+    lib.b200pf_series_bind.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, vp]
+    lib.b200pf_series_set_topo.argtypes = [vp, vp]
+    lib.b200pf_series_step.argtypes = [vp, i32, i32, f64, i32]
+    lib.b200pf_series_results.argtypes = [vp] + [C.POINTER(vp)] * 5
+    lib.b200pf_series_fetch.argtypes = [vp, vp, vp, vp, vp]
+    lib.b200pf_sync.argtypes = [vp]
+    lib.b200pf_stream.argtypes = [vp]
+    lib.b200pf_stream.restype = C.c_uint64
+    lib.b200pf_launch_count.argtypes = [vp]
+    lib.b200pf_launch_count.restype = C.c_int64
+    lib.b200pf_last_launch_info.argtypes = [vp] + [C.POINTER(i32)] * 4
+    for nm in ("b200pf_create", "b200pf_destroy", "b200pf_sizes", "b200pf_run_host", "b200pf_run_device",
+               "b200pf_series_bind", "b200pf_series_set_topo", "b200pf_series_step", "b200pf_series_results",
+               "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info"):
+        getattr(lib, nm).restype = i32
+    _LIB = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OutputView:
+    """Named float32 views into the packed result record ``out[batch, n_out]`` (include/b200pf.h)."""
+
+    def __init__(self, gm: GridModel, out: np.ndarray):
+        nl, nu, nld, ns, nsh = gm.n_line, gm.n_unit, gm.n_load, gm.n_storage, gm.n_shunt
+        o = 0
+
+        def take(n):
+            nonlocal o
+            v = out[:, o:o + n]
+            o += n
+            return v
+
+        (self.p_or, self.q_or, self.v_or, self.a_or, self.theta_or,
+         self.p_ex, self.q_ex, self.v_ex, self.a_ex, self.theta_ex) = [take(nl) for _ in range(10)]
+        self.unit_p, self.unit_q, self.unit_v, self.unit_theta = [take(nu) for _ in range(4)]
+        self.load_v, self.load_theta = take(nld), take(nld)
+        self.storage_v = take(ns)
+        self.shunt_p, self.shunt_q, self.shunt_v = take(nsh), take(nsh), take(nsh)
+        assert o == gm.n_out
+
+
+class PowerFlowEngine:
+    """One device handle: static grid on the GPU + staging for up to ``max_batch`` instances."""
+
+    def __init__(self, gm: GridModel, max_batch: int = 1, device: int = 0):
+        self.gm = gm
+        self.lib = load_library()
+        if self.lib.b200pf_abi_version() != 1:
+            raise EngineUnavailable("libb200pf ABI version mismatch")
+        self.max_batch = int(max_batch)
+        self._keep = []
+        d = _GridDesc()
+        d.abi_version = 1
+        d.n_sub, d.n_busbar = gm.n_sub, gm.n_busbar
+        d.n_line, d.n_gen, d.n_hidden, d.n_load = gm.n_line, gm.n_gen, gm.n_hidden, gm.n_load
+        d.n_storage, d.n_shunt, d.dim_topo = gm.n_storage, gm.n_shunt, gm.dim_topo
+        d.sn_mva = gm.sn_mva
+
+        def put(name, arr, dtype):
+            a = np.ascontiguousarray(arr, dtype=dtype)
+            if a.size == 0:
+                a = np.zeros(1, dtype=dtype)
+            self._keep.append(a)
+            setattr(d, name, a.ctypes.data)
+
+        i32, f64, f32 = np.int32, np.float64, np.float32
+        put("line_or_sub", gm.line_or_sub, i32); put("line_ex_sub", gm.line_ex_sub, i32)
+        put("line_or_pos", gm.line_or_pos, i32); put("line_ex_pos", gm.line_ex_pos, i32)
+        put("line_y", gm.line_y, f64); put("line_bdc", gm.line_bdc, f64); put("line_pshift", gm.line_pshift, f64)
+        put("line_or_vn", gm.line_or_vn, f32); put("line_ex_vn", gm.line_ex_vn, f32)
+        put("unit_sub", gm.unit_sub, i32); put("unit_pos", gm.unit_pos, i32); put("unit_is_ref", gm.unit_is_ref, i32)
+        put("unit_qmin", gm.unit_qmin, f64); put("unit_qmax", gm.unit_qmax, f64); put("unit_vn", gm.unit_vn, f32)
+        put("load_sub", gm.load_sub, i32); put("load_pos", gm.load_pos, i32); put("load_vn", gm.load_vn, f32)
+        put("storage_sub", gm.storage_sub, i32); put("storage_pos", gm.storage_pos, i32)
+        put("storage_vn", gm.storage_vn, f32); put("storage_q", gm.storage_q, f64)
+        put("shunt_sub", gm.shunt_sub, i32); put("shunt_vn", gm.shunt_vn, f32); put("shunt_vratio", gm.shunt_vratio, f64)
+        h = C.c_void_p()
+        rc = self.lib.b200pf_create(C.byref(d), self.max_batch, int(device), C.byref(h))
+        if rc != 0:
+            raise EngineUnavailable(f"b200pf_create failed ({rc}): {self.lib.b200pf_last_error().decode()}")
+        self.h = h
+        n = [C.c_int() for _ in range(4)]
+        self.lib.b200pf_sizes(self.h, *[C.byref(v) for v in n])
+        assert (n[0].value, n[1].value, n[2].value, n[3].value) == (gm.n_topo_in, gm.n_inj, gm.n_out, gm.n_slot)
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.b200pf_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.b200pf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, topo: np.ndarray, inj: np.ndarray, is_dc: bool = False, max_iter: int = 10,
+            tol_mva: float = 1e-8, nb_cap: int = 0, want_busv: bool = False
+            ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, Optional[np.ndarray]]:
+        """Host-buffer entry point (H2D + kernel + D2H).  ``topo`` int8 [B, n_topo_in], ``inj`` f64 [B, n_inj]."""
+        gm = self.gm
+        topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(-1, gm.n_topo_in)
+        inj = np.ascontiguousarray(inj, dtype=np.float64).reshape(-1, gm.n_inj)
+        B = topo.shape[0]
+        if inj.shape[0] != B:
+            raise ValueError("topo / inj batch mismatch")
+        out = np.empty((B, gm.n_out), dtype=np.float32)
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty(B, dtype=np.int32)
+        busv = np.empty((B, 2 * gm.n_slot), dtype=np.float64) if want_busv else None
+        rc = self.lib.b200pf_run_host(self.h, B, _ptr(topo), _ptr(inj), int(bool(is_dc)), int(max_iter), float(tol_mva),
+                                      int(nb_cap), _ptr(out), _ptr(status), _ptr(iters), _ptr(busv))
+        self._check(rc, "b200pf_run_host")
+        return out, status, iters, busv
+
+    def run_device(self, batch: int, d_topo: int, d_inj: int, d_out: int, d_status: int, d_iters: int,
+                   d_busv: int = 0, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0):
+        """Device-pointer entry point (asynchronous on the handle's stream)."""
+        rc = self.lib.b200pf_run_device(self.h, int(batch), C.c_void_p(d_topo), C.c_void_p(d_inj), int(bool(is_dc)),
+                                        int(max_iter), float(tol_mva), int(nb_cap), C.c_void_p(d_out),
+                                        C.c_void_p(d_status), C.c_void_p(d_iters), C.c_void_p(d_busv) if d_busv else None)
+        self._check(rc, "b200pf_run_device")
+
+    # ---- time series -------------------------------------------------------------------------
+    def series_bind(self, chron: np.ndarray, scen: np.ndarray, t0: np.ndarray, static_inj: np.ndarray,
+                    thermal_limit_a: np.ndarray):
+        gm = self.gm
+        chron = np.ascontiguousarray(chron, dtype=np.float32)
+        assert chron.ndim == 3 and chron.shape[2] == 2 * gm.n_load + 2 * gm.n_gen
+        scen = np.ascontiguousarray(scen, dtype=np.int32)
+        t0 = np.ascontiguousarray(t0, dtype=np.int32)
+        static_inj = np.ascontiguousarray(static_inj, dtype=np.float64)
+        th = np.ascontiguousarray(thermal_limit_a, dtype=np.float32)
+        assert static_inj.shape == (gm.n_inj,) and th.shape == (gm.n_line,)
+        self._series_batch = int(scen.shape[0])
+        rc = self.lib.b200pf_series_bind(self.h, _ptr(chron), chron.shape[0], chron.shape[1], _ptr(scen), _ptr(t0),
+                                         self._series_batch, _ptr(static_inj), _ptr(th))
+        self._check(rc, "b200pf_series_bind")
+
+    def series_set_topo(self, topo: np.ndarray):
+        topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(self._series_batch, self.gm.n_topo_in)
+        self._check(self.lib.b200pf_series_set_topo(self.h, _ptr(topo)), "b200pf_series_set_topo")
+
+    def series_step(self, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0):
+        self._check(self.lib.b200pf_series_step(self.h, int(bool(is_dc)), int(max_iter), float(tol_mva), int(nb_cap)),
+                    "b200pf_series_step")
+
+    def series_fetch(self, want_out=True, want_rho=True):
+        gm, B = self.gm, self._series_batch
+        out = np.empty((B, gm.n_out), dtype=np.float32) if want_out else None
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty(B, dtype=np.int32)
+        rho = np.empty((B, gm.n_line), dtype=np.float32) if want_rho else None
+        self._check(self.lib.b200pf_series_fetch(self.h, _ptr(out), _ptr(status), _ptr(iters), _ptr(rho)), "b200pf_series_fetch")
+        return out, status, iters, rho
+
+    def series_device_pointers(self):
+        p = [C.c_void_p() for _ in range(5)]
+        self._check(self.lib.b200pf_series_results(self.h, *[C.byref(v) for v in p]), "b200pf_series_results")
+        return dict(out=p[0].value, status=p[1].value, iters=p[2].value, rho=p[3].value, t=p[4].value)
+
+    def sync(self):
+        self._check(self.lib.b200pf_sync(self.h), "b200pf_sync")
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.b200pf_stream(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b200pf_launch_count(self.h))
+
+    def last_launch_info(self):
+        v = [C.c_int() for _ in range(4)]
+        self.lib.b200pf_last_launch_info(self.h, *[C.byref(x) for x in v])
+        return dict(smem_bytes=v[0].value, threads_per_instance=v[1].value, grid=v[2].value, block=v[3].value)
+
+    def view(self, out: np.ndarray) -> OutputView:
+        return OutputView(self.gm, out)

@@ -1,0 +1,148 @@
+/*
+ * b200pf.h — C ABI of the B200-native batched power-flow engine (libb200pf.so).
+ *
+ * This is the drop-in boundary for ONE path of Grid2Op: what
+ * grid2op.Backend.PandaPowerBackend delegates to pandapower in
+ *   runpf()                     reference grid2op/Backend/pandaPowerBackend.py:1220-1255
+ *     -> pp.runpp(init="dc", max_iteration=10, check_connectivity=False)   pPB:1097-1105
+ *     -> pp.rundcpp(check_connectivity=True)                               pPB:1090
+ *   _fetch_data_pf_converged()  pPB:1122-1218 (+ _gens_info :1526, _loads_info :1549,
+ *                               _storages_info :1621, shunt_info :1596)
+ * for a *batch* of independent grid instances that share one static grid description.
+ *
+ * Plain C: pointers and sizes only, no torch types.  Every function returns 0 on success or a
+ * negative B200PF_E_* code; b200pf_last_error() gives the message.  A handle is not thread safe;
+ * different handles are independent (one CUDA stream each).  No CPU fallback exists: with no
+ * CUDA device b200pf_create() fails with B200PF_E_CUDA.
+ *
+ * Data layout (all row-major, instance-major so that one warp/CTA reads one contiguous record):
+ *   topo   int8  [batch][n_topo_in]   n_topo_in = dim_topo + n_shunt + n_hidden
+ *            [0, dim_topo)            local busbar of every element, grid2op topo_vect order,
+ *                                     -1 = disconnected, 1..n_busbar        (pPB:1489-1524)
+ *            [dim_topo, +n_shunt)     local busbar of every shunt (-1 = off) (pPB:1609-1611)
+ *            [.., +n_hidden)          local busbar of every hidden reference unit (ext_grid kept
+ *                                     next to the generator the reference creates, pPB:394-453)
+ *   inj    f64   [batch][n_inj]       n_inj = n_gen + n_unit + 2 n_load + n_storage + 2 n_shunt
+ *            gen_p[n_gen] MW | unit_vm[n_unit] p.u. (hidden units first) | load_p | load_q |
+ *            storage_p | shunt_p | shunt_q        (what pPB:926-969 writes into its tables)
+ *   out    f32   [batch][n_out]       n_out = 10 n_line + 4 n_unit + 2 n_load + n_storage + 3 n_shunt
+ *            p_or q_or v_or a_or theta_or p_ex q_ex v_ex a_ex theta_ex   (each n_line)
+ *            unit_p unit_q unit_v unit_theta (each n_unit, hidden units first)
+ *            load_v load_theta (n_load) | storage_v (n_storage) | shunt_p shunt_q shunt_v (n_shunt)
+ *            units: MW, MVAr, kV, A, degrees — the float32 values PandaPowerBackend returns.
+ *   status int32 [batch]              B200PF_ST_*
+ *   iters  int32 [batch]              Newton iterations used (0 in DC mode)
+ *   busv   f64   [batch][2*n_slot]    optional: |V| p.u. then angle rad per bus slot
+ *                                     (slot = sub + (busbar-1)*n_sub, NaN when unused)
+ */
+#ifndef B200PF_H
+#define B200PF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PF_ABI_VERSION 1
+
+enum {
+    B200PF_OK = 0,
+    B200PF_E_ARG = -1,      /* bad argument */
+    B200PF_E_CUDA = -2,     /* CUDA runtime error / no device */
+    B200PF_E_CAPACITY = -3, /* grid does not fit the on-chip budget of this build */
+    B200PF_E_STATE = -4     /* call sequence error */
+};
+
+/* per-instance solver status (what runpf() turns into (bool, exception), pPB:1248-1255) */
+enum {
+    B200PF_ST_CONVERGED = 0,
+    B200PF_ST_DIVERGED = 1,   /* Newton did not reach the tolerance / singular matrix / NaN */
+    B200PF_ST_UNSUPPLIED = 2, /* an in-service bus is not connected to a reference bus */
+    B200PF_ST_NO_REF = 3,     /* no reference unit in service */
+    B200PF_ST_TOO_LARGE = 4   /* more active buses than the launch was sized for (nb_cap) */
+};
+
+/* Static grid description (host pointers, copied at create).  Element order = the reference's
+ * (lines then trafos = "lines"; pPB:481-483).  Sub ids are substation indices 0..n_sub-1. */
+typedef struct b200pf_grid_desc {
+    int32_t abi_version; /* B200PF_ABI_VERSION */
+    int32_t n_sub, n_busbar;
+    int32_t n_line, n_gen, n_hidden, n_load, n_storage, n_shunt, dim_topo;
+    double sn_mva;
+    /* lines (n_line) */
+    const int32_t *line_or_sub, *line_ex_sub, *line_or_pos, *line_ex_pos;
+    const double *line_y;     /* [n_line][8]: yff.re yff.im yft.re yft.im ytf.re ytf.im ytt.re ytt.im (p.u.) */
+    const double *line_bdc;   /* [n_line] 1/(x*ratio) */
+    const double *line_pshift;/* [n_line] DC phase-shift injection  b*(-shift_rad) */
+    const float *line_or_vn, *line_ex_vn; /* kV (float32 like pPB:796-801) */
+    /* units (n_unit = n_hidden + n_gen; hidden reference units first, like the ppc gen table) */
+    const int32_t *unit_sub;  /* [n_unit] */
+    const int32_t *unit_pos;  /* [n_unit] topo_vect position; hidden unit h: dim_topo + n_shunt + h */
+    const int32_t *unit_is_ref; /* [n_unit] ext_grid or gen.slack */
+    const double *unit_qmin, *unit_qmax; /* [n_unit] MVAr (reactive sharing, PYPOWER pfsoln) */
+    const float *unit_vn;     /* [n_unit] kV */
+    /* loads / storages / shunts */
+    const int32_t *load_sub, *load_pos;        const float *load_vn;
+    const int32_t *storage_sub, *storage_pos;  const float *storage_vn;  const double *storage_q;
+    const int32_t *shunt_sub;                  const float *shunt_vn;    const double *shunt_vratio; /* (vn_bus/vn_shunt)^2*step */
+} b200pf_grid_desc;
+
+typedef struct b200pf_handle b200pf_handle;
+
+const char *b200pf_last_error(void);
+int b200pf_abi_version(void);
+int b200pf_device_count(void);
+
+/* create / destroy.  max_batch sizes the device and pinned staging buffers. */
+int b200pf_create(const b200pf_grid_desc *grid, int max_batch, int device, b200pf_handle **out);
+int b200pf_destroy(b200pf_handle *h);
+
+/* sizes derived from the grid description */
+int b200pf_sizes(const b200pf_handle *h, int *n_topo_in, int *n_inj, int *n_out, int *n_slot);
+
+/* One batched power flow from HOST buffers: H2D copies, kernel, D2H copies, synchronised on return.
+ * busv may be NULL.  nb_cap = upper bound of active buses per instance the launch is sized for
+ * (<= 0: all n_sub*n_busbar slots, or the largest size that fits on chip).
+ * tol_mva: 1e-8 reproduces pandapower's default tolerance_mva; max_iter 10 = pPB:124. */
+int b200pf_run_host(b200pf_handle *h, int batch, const int8_t *topo, const double *inj, int is_dc,
+                    int max_iter, double tol_mva, int nb_cap, float *out, int32_t *status,
+                    int32_t *iters, double *busv);
+
+/* Same with DEVICE pointers, asynchronous on the handle's stream (b200pf_sync to wait). */
+int b200pf_run_device(b200pf_handle *h, int batch, const int8_t *d_topo, const double *d_inj,
+                      int is_dc, int max_iter, double tol_mva, int nb_cap, float *d_out,
+                      int32_t *d_status, int32_t *d_iters, double *d_busv);
+
+/* Batched time-series stepping (the DoNothing subset of BaseEnv.step, reference
+ * grid2op/Environment/baseEnv.py:3778-3872 with NO_OVERFLOW_DISCONNECTION): the chronics
+ * (grid2op/Chronics/gridStateFromFile.py:749-808 rows: load_p, load_q, prod_p, prod_v[kV] in
+ * BACKEND element order) live in HBM as float32 [n_scen][n_rows][2 n_load + 2 n_gen]; instance i
+ * replays scenario scen[i] from row t0[i], wrapping around.  Every call advances all instances by
+ * one row, solves, and writes out/status/iters plus rho = a_or / thermal_limit (f32 [batch][n_line]).
+ * topo is device state owned by the handle (set with b200pf_series_set_topo). */
+int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int n_scen, int n_rows,
+                       const int32_t *scen, const int32_t *t0, int batch,
+                       const double *static_inj /* [n_inj] defaults for storage / shunt / hidden vm */,
+                       const float *thermal_limit_a /* [n_line] */);
+int b200pf_series_set_topo(b200pf_handle *h, const int8_t *topo /* [batch][n_topo_in] host */);
+int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, double tol_mva, int nb_cap);
+/* device pointers of the resident results of the last series step (valid until destroy) */
+int b200pf_series_results(b200pf_handle *h, float **d_out, int32_t **d_status, int32_t **d_iters,
+                          float **d_rho, int32_t **d_t);
+/* copy results of the last series step to host buffers (any pointer may be NULL) */
+int b200pf_series_fetch(b200pf_handle *h, float *out, int32_t *status, int32_t *iters, float *rho);
+
+int b200pf_sync(b200pf_handle *h);
+/* cudaStream_t of the handle as an integer (for event timing by the caller) */
+uint64_t b200pf_stream(b200pf_handle *h);
+/* number of kernels launched by this handle so far */
+int64_t b200pf_launch_count(const b200pf_handle *h);
+/* dynamic shared memory bytes and threads-per-instance the last launch used (diagnostics) */
+int b200pf_last_launch_info(const b200pf_handle *h, int *smem_bytes, int *threads_per_instance,
+                            int *grid_blocks, int *block_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PF_H */

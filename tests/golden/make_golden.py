@@ -1,0 +1,72 @@
+"""Generates the committed golden fixtures from the reference tree (run once, here, where
+/root/reference exists):
+
+  pp_results_<env>.json   the res_* tables real pandapower stored in grid2op/data/<env>/grid.json
+  case14_sandbox_chronics.npz   float32 load_p/load_q/prod_p/prod_v rows of the 3 bundled scenarios of
+                          l2rpn_case14_sandbox re-ordered to BACKEND element order (bench / series tests)
+  oracle_case14_steps.npz  oracle (fp64) results on 64 chronics rows of l2rpn_case14_sandbox
+"""
+import bz2
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import pandapower_ref as ppr  # noqa: E402
+from grid2op_b200.gridmodel import GridModel  # noqa: E402
+
+REF = os.environ.get("GRID2OP_REF_DATA", "/root/reference/grid2op/data")
+COLS = {
+    "bus": ["vm_pu", "va_degree"],
+    "line": ["p_from_mw", "q_from_mvar", "p_to_mw", "q_to_mvar", "i_from_ka", "i_to_ka", "vm_from_pu", "va_from_degree",
+             "vm_to_pu", "va_to_degree"],
+    "trafo": ["p_hv_mw", "q_hv_mvar", "p_lv_mw", "q_lv_mvar", "i_hv_ka", "i_lv_ka"],
+    "gen": ["p_mw", "q_mvar", "vm_pu", "va_degree"],
+}
+
+
+def stored_results():
+    for env in ("rte_case5_example", "l2rpn_neurips_2020_track1", "l2rpn_wcci_2022_dev"):
+        net = ppr.from_json(os.path.join(REF, env, "grid.json"))
+        out = {"env": env, "res": {}}
+        for tab, cols in COLS.items():
+            st = net.stored_res.get("res_" + tab)
+            if st is None or len(st) == 0:
+                continue
+            out["res"][tab] = {c: [None if not np.isfinite(v) else float(v) for v in st.num(c, np.nan)] for c in cols if c in st}
+        with open(os.path.join(HERE, f"pp_results_{env}.json"), "w") as f:
+            json.dump(out, f)
+
+
+def read_csv_bz2(path):
+    with bz2.open(path, "rt") as f:
+        header = f.readline().strip().split(";")
+        rows = [[float(x) for x in line.strip().split(";")] for line in f if line.strip()]
+    return header, np.array(rows, dtype=np.float64)
+
+
+def case14_chronics():
+    env = "l2rpn_case14_sandbox"
+    gm = GridModel(os.path.join(REF, env, "grid.json"))
+    scen = []
+    for sc in ("0000", "0001", "0002"):
+        d = os.path.join(REF, env, "chronics", sc)
+        cols = []
+        for fn, names in (("load_p", gm.name_load), ("load_q", gm.name_load), ("prod_p", gm.name_gen), ("prod_v", gm.name_gen)):
+            hdr, arr = read_csv_bz2(os.path.join(d, fn + ".csv.bz2"))
+            order = [hdr.index(n) for n in names]            # chronics columns are matched by NAME
+            cols.append(arr[:, order])
+        scen.append(np.concatenate(cols, axis=1).astype(np.float32))
+    chron = np.stack(scen)                                    # [3, 576, 2*n_load + 2*n_gen]
+    np.savez_compressed(os.path.join(HERE, "case14_sandbox_chronics.npz"), chron=chron,
+                        name_load=gm.name_load, name_gen=gm.name_gen)
+    return gm, chron
+
+
+if __name__ == "__main__":
+    stored_results()
+    gm, chron = case14_chronics()
+    print("chronics", chron.shape, chron.dtype)

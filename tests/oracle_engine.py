@@ -1,0 +1,204 @@
+"""TEST INFRASTRUCTURE: an engine-shaped adapter around the fp64 oracle.
+
+It has the call signature of ``grid2op_b200.engine.PowerFlowEngine.run`` (same packed records as
+``include/b200pf.h``) but computes with ``oracle/pandapower_ref.py``.  Uses:
+  * ``-m "not gpu"`` tests monkeypatch it into ``B200Backend._make_engine`` to exercise the HOST
+    logic of the backend (apply_action, topology bookkeeping, read-back conventions) on the CPU;
+  * gpu tests call it next to the CUDA engine on the same records and compare.
+It is never importable from the product package.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from grid2op_b200.engine import OutputView
+from grid2op_b200.gridmodel import GridModel
+from oracle import pandapower_ref as ppr
+
+
+class OracleEngine:
+    def __init__(self, gm: GridModel, max_batch: int = 1, device: int = 0):
+        self.gm = gm
+        net = ppr.from_json(gm.path)
+        # same reference-unit normalisation as the backend under test (pPB:394-453)
+        if gm.id_gen_added is not None:
+            n_file = len(net.gen)
+            eg = net.ext_grid
+            for k in range(gm.n_gen - n_file):
+                net.gen.append_row((int(net.gen.index.max()) + 1) if len(net.gen) else 0,
+                                   bus=int(gm.gen_sub[n_file + k]), p_mw=0.0, vm_pu=float(gm.gen_vm0[n_file + k]),
+                                   min_q_mvar=float(gm.unit_qmin[gm.n_hidden + n_file + k]),
+                                   max_q_mvar=float(gm.unit_qmax[gm.n_hidden + n_file + k]),
+                                   scaling=1.0, slack=bool(gm.gen_slack[n_file + k]), in_service=True)
+            net.tables["ext_grid"] = ppr.Frame(eg.index[:gm.n_hidden], {c: v[:gm.n_hidden] for c, v in eg.cols.items()})
+        elif len(net.ext_grid) > gm.n_hidden:
+            eg = net.ext_grid
+            net.tables["ext_grid"] = ppr.Frame(eg.index[:gm.n_hidden], {c: v[:gm.n_hidden] for c, v in eg.cols.items()})
+        if len(net.ext_grid):
+            net.ext_grid["va_degree"] = np.array([0.0] * len(net.ext_grid), dtype=object)
+        base = net.bus.copy()
+        n_sub = gm.n_sub
+        for k in range(1, gm.n_busbar):
+            for i in range(n_sub):
+                vals = {c: base.cols[c][i] for c in base.cols}
+                vals["in_service"] = False
+                net.bus.append_row(int(base.index[i]) + k * n_sub, **vals)
+        self.net0 = net
+        self.launch_count = 0
+
+    def close(self):
+        pass
+
+    def view(self, out):
+        return OutputView(self.gm, out)
+
+    def last_launch_info(self):
+        return {}
+
+    def _one(self, tv, inj, is_dc, max_iter, tol_mva):
+        gm = self.gm
+        net = self.net0.deepcopy()
+        sl = gm.inj_slices()
+        n_sub = gm.n_sub
+
+        def glob(sub, b):
+            return int(sub) + (int(b) - 1) * n_sub
+
+        active = np.zeros(gm.n_slot, dtype=bool)
+
+        def setcol(tbl, col, i, val):
+            tbl[col][i] = val
+
+        nl = gm.n_powerline
+        for l in range(gm.n_line):
+            bo, be = int(tv[gm.line_or_pos[l]]), int(tv[gm.line_ex_pos[l]])
+            on = bo > 0 and be > 0
+            tbl, i = (net.line, l) if l < nl else (net.trafo, l - nl)
+            cf, ct = ("from_bus", "to_bus") if l < nl else ("hv_bus", "lv_bus")
+            setcol(tbl, "in_service", i, on)
+            if on:
+                setcol(tbl, cf, i, glob(gm.line_or_sub[l], bo)); setcol(tbl, ct, i, glob(gm.line_ex_sub[l], be))
+            if bo > 0:
+                active[glob(gm.line_or_sub[l], bo)] = True
+            if be > 0:
+                active[glob(gm.line_ex_sub[l], be)] = True
+        for g in range(gm.n_gen):
+            b = int(tv[gm.gen_pos[g]])
+            setcol(net.gen, "in_service", g, b > 0)
+            if b > 0:
+                setcol(net.gen, "bus", g, glob(gm.gen_sub[g], b)); active[glob(gm.gen_sub[g], b)] = True
+            setcol(net.gen, "p_mw", g, float(inj[sl["gen_p"]][g]))
+            setcol(net.gen, "vm_pu", g, float(inj[sl["gen_vm"]][g]))
+            if "scaling" in net.gen:
+                setcol(net.gen, "scaling", g, 1.0)
+        for h in range(gm.n_hidden):
+            b = int(tv[gm.dim_topo + gm.n_shunt + h])
+            setcol(net.ext_grid, "in_service", h, b > 0)
+            if b > 0:
+                setcol(net.ext_grid, "bus", h, glob(gm.hidden_sub[h], b)); active[glob(gm.hidden_sub[h], b)] = True
+            setcol(net.ext_grid, "vm_pu", h, float(inj[sl["hidden_vm"]][h]))
+        for k in range(gm.n_load):
+            b = int(tv[gm.load_pos[k]])
+            setcol(net.load, "in_service", k, b > 0)
+            if b > 0:
+                setcol(net.load, "bus", k, glob(gm.load_sub[k], b)); active[glob(gm.load_sub[k], b)] = True
+            setcol(net.load, "p_mw", k, float(inj[sl["load_p"]][k])); setcol(net.load, "q_mvar", k, float(inj[sl["load_q"]][k]))
+            if "scaling" in net.load:
+                setcol(net.load, "scaling", k, 1.0)
+        for k in range(gm.n_storage):
+            b = int(tv[gm.storage_pos[k]])
+            setcol(net.storage, "in_service", k, b > 0)
+            if b > 0:
+                setcol(net.storage, "bus", k, glob(gm.storage_sub[k], b)); active[glob(gm.storage_sub[k], b)] = True
+            setcol(net.storage, "p_mw", k, float(inj[sl["storage_p"]][k]))
+        for k in range(gm.n_shunt):
+            b = int(tv[gm.dim_topo + k])
+            setcol(net.shunt, "in_service", k, b > 0)
+            if b > 0:
+                setcol(net.shunt, "bus", k, glob(gm.shunt_sub[k], b)); active[glob(gm.shunt_sub[k], b)] = True
+            setcol(net.shunt, "p_mw", k, float(inj[sl["shunt_p"]][k])); setcol(net.shunt, "q_mvar", k, float(inj[sl["shunt_q"]][k]))
+        net.bus["in_service"] = np.array([bool(active[int(l)]) for l in net.bus.index], dtype=object)
+        out = np.full(gm.n_out, np.nan, dtype=np.float32)
+        busv = np.full(2 * gm.n_slot, np.nan)
+        try:
+            if is_dc:
+                ppr.rundcpp(net, check_connectivity=True)
+            else:
+                ppr.runpp(net, max_iteration=max_iter, tolerance_mva=tol_mva, check_connectivity=False)
+            bus_ok = net.bus.flag("in_service")
+            if np.isnan(net.res["bus"]["va_degree"][bus_ok]).any():
+                raise ppr.LoadflowNotConverged("unsupplied")
+        except ppr.LoadflowNotConverged as exc:
+            msg = str(exc)
+            st = 2 if ("not connected" in msg or "unsupplied" in msg) else (3 if "no reference" in msg else 1)
+            return out, st, 0, busv
+        r = net.res
+        v = OutputView(gm, out[None, :])
+        lab = {int(l): i for i, l in enumerate(net.bus.index)}
+        f32 = np.float32
+
+        def cat(a, b):
+            return np.concatenate([r["line"][a], r["trafo"][b]])
+
+        on = np.array([tv[gm.line_or_pos[l]] > 0 and tv[gm.line_ex_pos[l]] > 0 for l in range(gm.n_line)])
+        v.p_or[0] = cat("p_from_mw", "p_hv_mw"); v.q_or[0] = cat("q_from_mvar", "q_hv_mvar")
+        v.p_ex[0] = cat("p_to_mw", "p_lv_mw"); v.q_ex[0] = cat("q_to_mvar", "q_lv_mvar")
+        a1 = (cat("i_from_ka", "i_hv_ka") * 1000.0).astype(f32); a2 = (cat("i_to_ka", "i_lv_ka") * 1000.0).astype(f32)
+        a1[~np.isfinite(a1)] = 0; a2[~np.isfinite(a2)] = 0
+        v.a_or[0] = np.where(on, a1, 0); v.a_ex[0] = np.where(on, a2, 0)
+        vm1 = cat("vm_from_pu", "vm_hv_pu").astype(f32); vm2 = cat("vm_to_pu", "vm_lv_pu").astype(f32)
+        vm1[~np.isfinite(vm1)] = 0; vm2[~np.isfinite(vm2)] = 0
+        v.v_or[0] = np.where(on, vm1 * gm.line_or_vn, 0); v.v_ex[0] = np.where(on, vm2 * gm.line_ex_vn, 0)
+        t1 = cat("va_from_degree", "va_hv_degree").astype(f32); t2 = cat("va_to_degree", "va_lv_degree").astype(f32)
+        t1[~np.isfinite(t1)] = 0; t2[~np.isfinite(t2)] = 0
+        v.theta_or[0] = np.where(on, t1, 0); v.theta_ex[0] = np.where(on, t2, 0)
+        nh = gm.n_hidden
+        # ext_grid voltage = its bus voltage
+        for h in range(nh):
+            b = int(tv[gm.dim_topo + gm.n_shunt + h])
+            if b > 0:
+                i = lab[glob(gm.hidden_sub[h], b)]
+                vmh = net.res["line"]["vm_from_pu"] if False else None
+            v.unit_p[0, h] = r["ext_grid"]["p_mw"][h]; v.unit_q[0, h] = r["ext_grid"]["q_mvar"][h]
+            if b > 0:
+                pbus = ppr.pd2ppc(net)
+                vm_b = (r["bus"]["vm_pu"][i] if not is_dc else pbus.vm0[i])
+                v.unit_v[0, h] = f32(vm_b) * gm.unit_vn[h]; v.unit_theta[0, h] = r["bus"]["va_degree"][i]
+            else:
+                v.unit_v[0, h] = 0; v.unit_theta[0, h] = 0
+        v.unit_p[0, nh:] = r["gen"]["p_mw"]; v.unit_q[0, nh:] = r["gen"]["q_mvar"]
+        v.unit_v[0, nh:] = r["gen"]["vm_pu"].astype(f32) * gm.unit_vn[nh:]; v.unit_theta[0, nh:] = r["gen"]["va_degree"]
+        vm_bus = r["bus"]["vm_pu"] if not is_dc else ppr.pd2ppc(net).vm0
+        for k in range(gm.n_load):
+            b = int(tv[gm.load_pos[k]])
+            if b > 0:
+                i = lab[glob(gm.load_sub[k], b)]
+                v.load_v[0, k] = f32(vm_bus[i]) * gm.load_vn[k]; v.load_theta[0, k] = r["bus"]["va_degree"][i]
+            else:
+                v.load_v[0, k] = 0; v.load_theta[0, k] = 0
+        for k in range(gm.n_storage):
+            b = int(tv[gm.storage_pos[k]])
+            v.storage_v[0, k] = f32(vm_bus[lab[glob(gm.storage_sub[k], b)]]) * gm.storage_vn[k] if b > 0 else 0
+        for k in range(gm.n_shunt):
+            b = int(tv[gm.dim_topo + k])
+            v.shunt_p[0, k] = r["shunt"]["p_mw"][k]; v.shunt_q[0, k] = r["shunt"]["q_mvar"][k]
+            v.shunt_v[0, k] = f32(vm_bus[lab[glob(gm.shunt_sub[k], b)]]) * gm.shunt_vn[k] if b > 0 else 0
+        for s in range(gm.n_slot):
+            i = lab[s]
+            if active[s]:
+                busv[s] = vm_bus[i]; busv[gm.n_slot + s] = np.deg2rad(r["bus"]["va_degree"][i])
+        return out, 0, int(getattr(net, "iterations", 0)), busv
+
+    def run(self, topo, inj, is_dc=False, max_iter=10, tol_mva=1e-8, nb_cap=0, want_busv=False):
+        gm = self.gm
+        topo = np.asarray(topo, dtype=np.int8).reshape(-1, gm.n_topo_in)
+        inj = np.asarray(inj, dtype=np.float64).reshape(-1, gm.n_inj)
+        B = topo.shape[0]
+        out = np.empty((B, gm.n_out), dtype=np.float32)
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty(B, dtype=np.int32)
+        busv = np.empty((B, 2 * gm.n_slot))
+        for b in range(B):
+            out[b], status[b], iters[b], busv[b] = self._one(topo[b], inj[b], is_dc, max_iter, tol_mva)
+        self.launch_count += 1
+        return out, status, iters, (busv if want_busv else None)
