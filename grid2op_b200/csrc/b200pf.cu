@@ -26,6 +26,8 @@ struct b200pf_handle {
     int device = 0;
     int max_batch = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    float *x_out = nullptr; int *x_status = nullptr; int *x_iters = nullptr; float *x_rho = nullptr;
     DevGrid g{};
     std::vector<void *> dev_allocs;
     int sm_count = 148;
@@ -81,7 +83,8 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
     CU(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
     DevGrid &g = h->g;
     g.n_sub = gd->n_sub; g.n_busbar = gd->n_busbar; g.n_slot = gd->n_sub * gd->n_busbar;
     g.n_line = gd->n_line; g.n_gen = gd->n_gen; g.n_hidden = gd->n_hidden; g.n_unit = gd->n_gen + gd->n_hidden;
@@ -142,11 +145,11 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
 extern "C" int b200pf_destroy(b200pf_handle *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (void *p : h->dev_allocs) cudaFree(p);
     void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv};
     for (void *p : pinned) if (p) cudaFreeHost(p);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
 }
@@ -166,8 +169,8 @@ extern "C" int b200pf_sizes(const b200pf_handle *h, int *n_topo_in, int *n_inj, 
 template <int T, typename JT>
 static int launch_t(b200pf_handle *h, const RunArgs &a) {
     const DevGrid &g = h->g;
-    constexpr int BLOCK = (T == 32) ? 128 : T;
-    constexpr int GPB = BLOCK / T;
+    constexpr int BLOCK = T;
+    constexpr int GPB = 1;
     WsLayout L = ws_layout(a.nb_cap, g.n_slot, g.n_line, g.n_inj, (size_t)a.mat_bytes);
     const int ws_bytes = (int)L.total;
     const size_t smem = (size_t)ws_bytes * GPB;
@@ -178,9 +181,12 @@ static int launch_t(b200pf_handle *h, const RunArgs &a) {
     int occ = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
     if (occ < 1) occ = 1;
+    // persistent groups; size the grid so that every group gets the same number of instances (no
+    // ragged last wave): rounds = ceil(batch / resident groups), grid = ceil(batch / rounds)
     int need = (a.batch + GPB - 1) / GPB;
-    int grid = h->sm_count * occ;
-    if (grid > need) grid = need;
+    int resident = h->sm_count * occ;
+    int rounds = (need + resident - 1) / resident;
+    int grid = (need + rounds - 1) / rounds;
     if (grid < 1) grid = 1;
     kern<<<grid, BLOCK, smem, h->stream>>>(g, a, ws_bytes);
     CU(cudaGetLastError());
@@ -207,7 +213,7 @@ static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
         size_t d = 2 * (size_t)cap;
         T = d <= 64 ? 32 : (d <= 128 ? 64 : (d <= 256 ? 128 : 256));
     }
-    int gpb = (T == 32) ? 4 : 1;
+    int gpb = 1;
     if ((fixed + want) * gpb > (size_t)h->max_smem_optin) {
         // does not fit with 4 warps per CTA / worst case: one group per CTA, clipped matrix
         if (T == 32) { T = 64; }
@@ -324,18 +330,19 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
     if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
     CU(cudaSetDevice(h->device));
     RunArgs a = base_args(h, h->series_batch, is_dc, max_iter, tol_mva);
-    a.topo = h->d_series_topo; a.inj = nullptr; a.out = h->d_out; a.status = h->d_status; a.iters = h->d_iters; a.busv = nullptr;
+    a.topo = h->d_series_topo; a.inj = nullptr; a.out = h->x_out ? h->x_out : h->d_out; a.status = h->x_status ? h->x_status : h->d_status;
+    a.iters = h->x_iters ? h->x_iters : h->d_iters; a.busv = nullptr;
     a.series = 1; a.chron = h->d_chron; a.n_scen = h->n_scen; a.n_rows = h->n_rows; a.scen = h->d_scen; a.t = h->d_t;
-    a.static_inj = h->d_static_inj; a.th_lim = h->d_thlim; a.rho = h->d_rho;
+    a.static_inj = h->d_static_inj; a.th_lim = h->d_thlim; a.rho = h->x_rho ? h->x_rho : h->d_rho;
     return launch(h, a, nb_cap);
 }
 
 extern "C" int b200pf_series_results(b200pf_handle *h, float **d_out, int32_t **d_status, int32_t **d_iters, float **d_rho, int32_t **d_t) {
     if (!h) return fail(B200PF_E_ARG, "null handle");
-    if (d_out) *d_out = h->d_out;
-    if (d_status) *d_status = h->d_status;
-    if (d_iters) *d_iters = h->d_iters;
-    if (d_rho) *d_rho = h->d_rho;
+    if (d_out) *d_out = h->x_out ? h->x_out : h->d_out;
+    if (d_status) *d_status = h->x_status ? h->x_status : h->d_status;
+    if (d_iters) *d_iters = h->x_iters ? h->x_iters : h->d_iters;
+    if (d_rho) *d_rho = h->x_rho ? h->x_rho : h->d_rho;
     if (d_t) *d_t = h->d_t;
     return 0;
 }
@@ -347,10 +354,55 @@ extern "C" int b200pf_series_fetch(b200pf_handle *h, float *out, int32_t *status
     const size_t B = (size_t)h->series_batch;
     const DevGrid &g = h->g;
     CU(cudaStreamSynchronize(h->stream));
-    if (out) CU(cudaMemcpy(out, h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost));
-    if (status) CU(cudaMemcpy(status, h->d_status, B * 4, cudaMemcpyDeviceToHost));
-    if (iters) CU(cudaMemcpy(iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost));
-    if (rho) CU(cudaMemcpy(rho, h->d_rho, B * g.n_line * 4, cudaMemcpyDeviceToHost));
+    if (out) CU(cudaMemcpy(out, h->x_out ? h->x_out : h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost));
+    if (status) CU(cudaMemcpy(status, h->x_status ? h->x_status : h->d_status, B * 4, cudaMemcpyDeviceToHost));
+    if (iters) CU(cudaMemcpy(iters, h->x_iters ? h->x_iters : h->d_iters, B * 4, cudaMemcpyDeviceToHost));
+    if (rho) CU(cudaMemcpy(rho, h->x_rho ? h->x_rho : h->d_rho, B * g.n_line * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int b200pf_staging(b200pf_handle *h, int8_t **topo, double **inj, float **out, int32_t **status, int32_t **iters,
+                              double **busv) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (topo) *topo = h->h_topo;
+    if (inj) *inj = h->h_inj;
+    if (out) *out = h->h_out;
+    if (status) *status = h->h_status;
+    if (iters) *iters = h->h_iters;
+    if (busv) *busv = h->h_busv;
+    return 0;
+}
+
+extern "C" int b200pf_run_staged(b200pf_handle *h, int batch, int is_dc, int max_iter, double tol_mva, int nb_cap, int want_busv) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (batch <= 0 || batch > h->max_batch) return fail(B200PF_E_ARG, "batch out of range (max_batch)");
+    CU(cudaSetDevice(h->device));
+    const DevGrid &g = h->g;
+    const size_t B = (size_t)batch;
+    CU(cudaMemcpyAsync(h->d_topo, h->h_topo, B * g.n_topo_in, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_inj, h->h_inj, B * g.n_inj * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = b200pf_run_device(h, batch, h->d_topo, h->d_inj, is_dc, max_iter, tol_mva, nb_cap, h->d_out, h->d_status,
+                               h->d_iters, want_busv ? h->d_busv : nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->h_out, h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (want_busv) CU(cudaMemcpyAsync(h->h_busv, h->d_busv, B * 2 * g.n_slot * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200pf_series_bind_outputs(b200pf_handle *h, float *d_out, int32_t *d_status, int32_t *d_iters, float *d_rho) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    h->x_out = d_out; h->x_status = d_status; h->x_iters = d_iters; h->x_rho = d_rho;
+    return 0;
+}
+
+extern "C" int b200pf_set_stream(b200pf_handle *h, uint64_t stream) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = stream ? (cudaStream_t)(uintptr_t)stream : h->own_stream;
     return 0;
 }
 

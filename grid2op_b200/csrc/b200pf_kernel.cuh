@@ -13,6 +13,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef B200PF_MIN_WARP_CTAS
+#define B200PF_MIN_WARP_CTAS 28   // register budget: 65536 / (28 * 32) = 73 per thread
+#endif
+
 namespace b200pf {
 
 struct DevGrid {
@@ -75,7 +79,7 @@ struct WsLayout {
     size_t off_vf32;     // float [2 nbc]
     size_t off_short;    // shorts: cidx[n_slot] colth[nbc] colv[nbc] bsub[nbc] cntu[nbc] nrefu[nbc] rowbus[2nbc] used[2nbc] prow[2nbc] brf[n_line] brt[n_line]
     size_t off_byte;     // bytes: btype[nbc] reach[nbc] mark[n_slot]
-    size_t off_red;      // reduction scratch 64 B * 2
+    size_t off_red;      // reduction scratch (256 B) + pivot-row buffers of the register Gauss-Jordan (768 B)
     size_t off_mat;      // matrix region
     size_t total;
 };
@@ -88,7 +92,7 @@ __host__ __device__ inline size_t ws_fixed_bytes(int nbc, int n_slot, int n_line
     o += align16(size_t(2) * nbc * 4);
     o += align16(size_t(n_slot + 5 * nbc + 6 * nbc + 2 * n_line) * 2);
     o += align16(size_t(2 * nbc + n_slot));
-    o += 256;
+    o += 576;
     return o;
 }
 
@@ -109,7 +113,7 @@ __host__ __device__ inline WsLayout ws_layout(int nbc, int n_slot, int n_line, i
     L.off_vf32 = o;  o += align16(size_t(2) * nbc * 4);
     L.off_short = o; o += align16(size_t(n_slot + 5 * nbc + 6 * nbc + 2 * n_line) * 2);
     L.off_byte = o;  o += align16(size_t(2 * nbc + n_slot));
-    L.off_red = o;   o += 256;
+    L.off_red = o;   o += 576;
     L.off_mat = o;
     o += align16(mat_bytes);
     L.total = o;
@@ -124,6 +128,7 @@ struct Ws {
     unsigned char *btype, *reach, *mark;
     float *redf;
     int *redi;
+    double *pivbuf;   // 2 x 36 scalars (float or double) for gj_warp_reg
     void *mat;
 };
 
@@ -148,6 +153,7 @@ __device__ inline Ws ws_bind(unsigned char *base, int nbc, int n_slot, int n_lin
     w.btype = b; w.reach = b + nbc; w.mark = b + 2 * nbc;
     w.redf = reinterpret_cast<float *>(base + L.off_red);
     w.redi = reinterpret_cast<int *>(base + L.off_red + 128);
+    w.pivbuf = reinterpret_cast<double *>(base + L.off_red + 256);
     w.mat = base + L.off_mat;
     return w;
 }
@@ -201,6 +207,65 @@ template <int T> __device__ __forceinline__ void gargmax(float &val, int &row, W
         if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; }
     }
     val = bv; row = br;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp Gauss-Jordan with the matrix in REGISTERS (n <= DMAX <= 32): lane r owns row r (DMAX columns +
+// right-hand side), everything statically unrolled so that column indices are register names.  Per
+// elimination step: pivot = max |a[r][k]| over unused rows via one REDUX (IEEE bit pattern of a
+// non-negative float is monotonic) + ballot; the pivot lane publishes its row tail to shared memory
+// (STS.128), all lanes read it back as broadcast LDS.128 and do DMAX-k FFMAs.  Two alternating
+// row buffers -> one __syncwarp per step.  `prow` : 2*(DMAX+4) scalars of per-warp scratch.
+// ---------------------------------------------------------------------------------------------
+template <int DMAX, typename S>
+__device__ __forceinline__ bool gj_warp_reg(const S *M, int n, int pitch, S *xs, S *prow, int lane) {
+    static_assert(DMAX % 4 == 0 && DMAX <= 32, "DMAX");
+    constexpr int W = DMAX + 4;          // buffer stride (rhs lives at index DMAX)
+    S a[DMAX + 1];
+    const bool mine = lane < n;
+    const S *Mr = M + lane * pitch;
+#pragma unroll
+    for (int c = 0; c < DMAX; ++c) a[c] = (mine && c < n) ? Mr[c] : S(0);
+    a[DMAX] = mine ? Mr[n] : S(0);
+    bool used = !mine;
+    int mycol = -1;
+    S pivval = S(1);
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) {
+        if (k >= n) break;                                   // warp-uniform
+        const float mag = fabsf((float)a[k]);
+        const unsigned bits = (used || !(mag == mag)) ? 0u : __float_as_uint(mag);
+        const unsigned mx = __reduce_max_sync(0xffffffffu, bits);
+        if (mx < 0x00800000u) return false;                  // below the smallest normal: singular / NaN
+        const unsigned who = __ballot_sync(0xffffffffu, bits == mx && !used);
+        const int p = __ffs(who) - 1;
+        S *buf = prow + (k & 1) * W;
+        if (lane == p) {
+#pragma unroll
+            for (int c = (k & ~3); c < DMAX + 1; ++c) buf[c] = a[c];
+            used = true; mycol = k; pivval = a[k];
+        }
+        __syncwarp();
+        const S piv = buf[k];
+        S inv;
+        if (sizeof(S) == 4) inv = (S)__frcp_rn((float)piv); else inv = S(1) / piv;
+        const S m = (lane == p) ? S(0) : a[k] * inv;
+#pragma unroll
+        for (int c = k + 1; c < DMAX + 1; ++c) a[c] -= m * buf[c];
+    }
+    if (mycol >= 0) xs[mycol] = a[DMAX] / pivval;
+    __syncwarp();
+    return true;
+}
+
+// pick the smallest unrolled variant that holds n
+template <typename S>
+__device__ __forceinline__ bool gj_warp_dispatch(const S *M, int n, int pitch, S *xs, S *prow, int lane) {
+    if (n <= 8) return gj_warp_reg<8, S>(M, n, pitch, xs, prow, lane);
+    if (n <= 16) return gj_warp_reg<16, S>(M, n, pitch, xs, prow, lane);
+    if (sizeof(S) == 8) return false;     // fp64 rows wider than 16 would blow the register budget (caller falls back)
+    if (n <= 24) return gj_warp_reg<24, S>(M, n, pitch, xs, prow, lane);
+    return gj_warp_reg<32, S>(M, n, pitch, xs, prow, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -507,7 +572,9 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             }
             gsync<T>();
             double *th = w.pcalc;   // scratch
-            bool ok = gauss_jordan_d<T>(M, n1, pitch, th, w, tid);
+            bool ok;
+            if (T == 32 && n1 <= 16) ok = gj_warp_dispatch<double>(M, n1, pitch, th, w.pivbuf, tid);
+            else ok = gauss_jordan_d<T>(M, n1, pitch, th, w, tid);
             if (!ok) status = ST_DIV;
             else {
                 for (int r = tid; r < n1; r += T) w.va[w.rowbus[r]] = th[r];
@@ -605,7 +672,11 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             }
             gsync<T>();
             // (c) solve J dx = -F
-            if (!gauss_jordan<T, JT>(J, d, pitch, w.x, w, tid)) { iters = it + 1; break; }
+            bool solved;
+            if (T == 32 && d <= 32 && sizeof(JT) == 4)
+                solved = gj_warp_dispatch<float>(reinterpret_cast<float *>(J), d, pitch, w.x, reinterpret_cast<float *>(w.pivbuf), tid);
+            else solved = gauss_jordan<T, JT>(J, d, pitch, w.x, w, tid);
+            if (!solved) { iters = it + 1; break; }
             // (d) fp64 state update; |V| unknown is relative (dV/V)
             for (int i = tid; i < nb; i += T) {
                 double vm = w.vm[i], va = w.va[i];
@@ -753,11 +824,11 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
 
 // persistent kernel: each group (warp / CTA) strides over the instances of the batch
 template <int T, typename JT>
-__global__ void __launch_bounds__((T == 32) ? 128 : T)
+__global__ void __launch_bounds__(T, (T == 32) ? B200PF_MIN_WARP_CTAS : 1)
 pf_kernel(const DevGrid g, const RunArgs a, const int ws_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int BLOCK = (T == 32) ? 128 : T;
-    constexpr int GPB = BLOCK / T;          // groups per block
+    constexpr int BLOCK = T;                // one group per CTA (a warp-CTA for the small grids: finest SM balance)
+    constexpr int GPB = 1;
     const int gid = threadIdx.x / T;
     const int tid = threadIdx.x % T;
     unsigned char *wsbase = smem + (size_t)gid * ws_bytes;

@@ -28,7 +28,8 @@ ABI_SYMBOLS = (
     "b200pf_last_error", "b200pf_abi_version", "b200pf_device_count", "b200pf_create", "b200pf_destroy",
     "b200pf_sizes", "b200pf_run_host", "b200pf_run_device", "b200pf_series_bind", "b200pf_series_set_topo",
     "b200pf_series_step", "b200pf_series_results", "b200pf_series_fetch", "b200pf_sync", "b200pf_stream",
-    "b200pf_launch_count", "b200pf_last_launch_info",
+    "b200pf_launch_count", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
+    "b200pf_series_bind_outputs", "b200pf_set_stream",
 )
 
 
@@ -84,6 +85,10 @@ def load_library():
     lib.b200pf_series_results.argtypes = [vp] + [C.POINTER(vp)] * 5
     lib.b200pf_series_fetch.argtypes = [vp, vp, vp, vp, vp]
     lib.b200pf_sync.argtypes = [vp]
+    lib.b200pf_staging.argtypes = [vp] + [C.POINTER(vp)] * 6
+    lib.b200pf_run_staged.argtypes = [vp, i32, i32, i32, f64, i32, i32]
+    lib.b200pf_series_bind_outputs.argtypes = [vp, vp, vp, vp, vp]
+    lib.b200pf_set_stream.argtypes = [vp, C.c_uint64]
     lib.b200pf_stream.argtypes = [vp]
     lib.b200pf_stream.restype = C.c_uint64
     lib.b200pf_launch_count.argtypes = [vp]
@@ -91,7 +96,8 @@ def load_library():
     lib.b200pf_last_launch_info.argtypes = [vp] + [C.POINTER(i32)] * 4
     for nm in ("b200pf_create", "b200pf_destroy", "b200pf_sizes", "b200pf_run_host", "b200pf_run_device",
                "b200pf_series_bind", "b200pf_series_set_topo", "b200pf_series_step", "b200pf_series_results",
-               "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info"):
+               "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
+               "b200pf_series_bind_outputs", "b200pf_set_stream"):
         getattr(lib, nm).restype = i32
     _LIB = lib
     return lib
@@ -209,6 +215,34 @@ class PowerFlowEngine:
                                         int(max_iter), float(tol_mva), int(nb_cap), C.c_void_p(d_out),
                                         C.c_void_p(d_status), C.c_void_p(d_iters), C.c_void_p(d_busv) if d_busv else None)
         self._check(rc, "b200pf_run_device")
+
+    # ---- zero-copy host path ------------------------------------------------------------------
+    def staging(self):
+        """numpy views of the handle's pinned staging buffers (topo, inj, out, status, iters)."""
+        gm, B = self.gm, self.max_batch
+        p = [C.c_void_p() for _ in range(6)]
+        self._check(self.lib.b200pf_staging(self.h, *[C.byref(v) for v in p]), "b200pf_staging")
+
+        def view(ptr, ctype, shape):
+            n = int(np.prod(shape))
+            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+            return arr.reshape(shape)
+
+        return dict(topo=view(p[0], C.c_int8, (B, gm.n_topo_in)), inj=view(p[1], C.c_double, (B, gm.n_inj)),
+                    out=view(p[2], C.c_float, (B, gm.n_out)), status=view(p[3], C.c_int32, (B,)),
+                    iters=view(p[4], C.c_int32, (B,)))
+
+    def run_staged(self, batch: int, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0):
+        self._check(self.lib.b200pf_run_staged(self.h, int(batch), int(bool(is_dc)), int(max_iter), float(tol_mva),
+                                               int(nb_cap), 0), "b200pf_run_staged")
+
+    def set_stream(self, stream: int):
+        self._check(self.lib.b200pf_set_stream(self.h, C.c_uint64(int(stream))), "b200pf_set_stream")
+
+    def series_bind_outputs(self, d_out: int = 0, d_status: int = 0, d_iters: int = 0, d_rho: int = 0):
+        self._check(self.lib.b200pf_series_bind_outputs(self.h, C.c_void_p(d_out or None), C.c_void_p(d_status or None),
+                                                        C.c_void_p(d_iters or None), C.c_void_p(d_rho or None)),
+                    "b200pf_series_bind_outputs")
 
     # ---- time series -------------------------------------------------------------------------
     def series_bind(self, chron: np.ndarray, scen: np.ndarray, t0: np.ndarray, static_inj: np.ndarray,

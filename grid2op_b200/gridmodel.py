@@ -306,3 +306,30 @@ class GridModel:
             o += n
         assert o == self.n_inj
         return res
+
+    # ---------------------------------------------------------------------------------------------
+    # compact (de)serialisation: lets the batched driver / bench run without the grid2op data tree
+    # ---------------------------------------------------------------------------------------------
+    def to_npz(self, path: str) -> None:
+        blob = {}
+        for k, v in self.__dict__.items():
+            if isinstance(v, np.ndarray):
+                blob["a__" + k] = v
+            elif isinstance(v, (int, float, str, bool)) or v is None:
+                blob["s__" + k] = np.array([repr(v)])
+            elif isinstance(v, list):
+                blob["s__" + k] = np.array([repr(v)])
+        np.savez_compressed(path, **blob)
+
+    @classmethod
+    def from_npz(cls, path: str) -> "GridModel":
+        import ast
+
+        self = object.__new__(cls)
+        with np.load(path, allow_pickle=False) as z:
+            for key in z.files:
+                if key.startswith("a__"):
+                    setattr(self, key[3:], z[key])
+                else:
+                    setattr(self, key[3:], ast.literal_eval(str(z[key][0])))
+        return self

@@ -1,0 +1,97 @@
+"""Batched DoNothing stepping over chronics: the throughput driver next to the drop-in Backend.
+
+What one ``step`` restates for a whole batch of independent environments (reference, per env):
+``BaseEnv.step`` grid2op/Environment/baseEnv.py:3778-3872 restricted to the DoNothing agent with
+``NO_OVERFLOW_DISCONNECTION`` (the setting of the reference's own profiling script,
+``_profiling/profiler_do_nothing.py:52``): next chronics row (gridStateFromFile.py:766-776) ->
+``apply_action`` -> ``runpf`` -> read-back + ``rho = a_or / thermal_limit``
+(``Backend.get_relative_flow`` backend.py:1145-1168).  An instance whose power flow fails is "done".
+
+Two ways to drive it:
+* :meth:`step_device` - chronics resident in HBM, nothing crosses PCIe (``value`` in bench.py);
+* :meth:`step_host`   - host buffers in, host buffers out through the C ABI (``e2e`` in bench.py).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from .engine import PowerFlowEngine
+from .gridmodel import GridModel
+
+__all__ = ["BatchedDoNothing", "instance_schedule"]
+
+
+def instance_schedule(n: int, n_scen: int, n_rows: int, offset: int = 0):
+    """Deterministic, seed-free assignment used by the benchmarks:
+    instance i replays scenario ``i mod n_scen`` starting at row ``(i*37) mod n_rows``."""
+    i = np.arange(offset, offset + n, dtype=np.int64)
+    return (i % n_scen).astype(np.int32), ((i * 37) % n_rows).astype(np.int32)
+
+
+class BatchedDoNothing:
+    def __init__(self, gm: GridModel, chron: np.ndarray, batch: int, device: int = 0, offset: int = 0,
+                 max_iter: int = 10, tol_mva: float = 1e-8, is_dc: bool = False):
+        self.gm = gm
+        self.batch = int(batch)
+        self.chron = np.ascontiguousarray(chron, dtype=np.float32)
+        assert self.chron.ndim == 3 and self.chron.shape[2] == 2 * gm.n_load + 2 * gm.n_gen
+        self.scen, self.t0 = instance_schedule(self.batch, self.chron.shape[0], self.chron.shape[1], offset)
+        self.engine = PowerFlowEngine(gm, max_batch=self.batch, device=device)
+        self.max_iter, self.tol_mva, self.is_dc = int(max_iter), float(tol_mva), bool(is_dc)
+        self.topo0 = np.tile(gm.default_topo(), (self.batch, 1))
+        self.nb_cap = int(np.count_nonzero(np.bincount(self._slots(gm.default_topo()), minlength=gm.n_slot)))
+        self.engine.series_bind(self.chron, self.scen, self.t0, gm.default_inj(), gm.thermal_limit_a)
+        self.engine.series_set_topo(self.topo0)
+        # host path state
+        self._t_host = self.t0.astype(np.int64).copy()
+        self._stage = None
+        self._sl = gm.inj_slices()
+        self._inj0 = gm.default_inj()
+
+    def _slots(self, tv):
+        gm = self.gm
+        subs = np.concatenate([gm.line_or_sub, gm.line_ex_sub, gm.gen_sub, gm.load_sub, gm.storage_sub, gm.shunt_sub, gm.hidden_sub])
+        pos = np.concatenate([gm.line_or_pos, gm.line_ex_pos, gm.gen_pos, gm.load_pos, gm.storage_pos,
+                              gm.dim_topo + np.arange(gm.n_shunt), gm.dim_topo + gm.n_shunt + np.arange(gm.n_hidden)])
+        b = tv[pos].astype(np.int64)
+        ok = b > 0
+        return subs[ok].astype(np.int64) + (b[ok] - 1) * gm.n_sub
+
+    # ---- device-resident ------------------------------------------------------------------------
+    def step_device(self) -> None:
+        """Asynchronous: one fused kernel for the whole batch; results stay in HBM."""
+        self.engine.series_step(is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva, nb_cap=self.nb_cap)
+
+    def fetch(self):
+        return self.engine.series_fetch()
+
+    # ---- host buffers in / out --------------------------------------------------------------------
+    def step_host(self):
+        """Next chronics row of every instance gathered on the host, written into the pinned staging
+        records, H2D, kernel, D2H; returns (out view, status view) living in the staging buffers."""
+        gm = self.gm
+        if self._stage is None:
+            self._stage = self.engine.staging()
+            self._stage["topo"][:self.batch] = self.topo0
+            self._stage["inj"][:self.batch] = self._inj0[None, :]
+        st = self._stage
+        rows = self.chron[self.scen, self._t_host]
+        nl, ng = gm.n_load, gm.n_gen
+        inj = st["inj"][:self.batch]
+        sl = self._sl
+        inj[:, sl["load_p"]] = rows[:, :nl]
+        inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
+        inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
+        inj[:, sl["gen_vm"]] = rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]     # float32 / float32 (pPB:927)
+        self._t_host = (self._t_host + 1) % self.chron.shape[1]
+        self.engine.run_staged(self.batch, is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva, nb_cap=self.nb_cap)
+        return st["out"][:self.batch], st["status"][:self.batch]
+
+    def bytes_per_step_host(self):
+        gm = self.gm
+        return self.batch * (gm.n_topo_in + 8 * gm.n_inj), self.batch * (4 * gm.n_out + 8)
+
+    def close(self):
+        self.engine.close()

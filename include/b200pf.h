@@ -133,6 +133,20 @@ int b200pf_series_results(b200pf_handle *h, float **d_out, int32_t **d_status, i
 /* copy results of the last series step to host buffers (any pointer may be NULL) */
 int b200pf_series_fetch(b200pf_handle *h, float *out, int32_t *status, int32_t *iters, float *rho);
 
+/* Pinned host staging buffers owned by the handle (sized for max_batch): a caller that fills topo /
+ * inj in place and reads out / status / iters in place avoids one host copy in each direction. */
+int b200pf_staging(b200pf_handle *h, int8_t **topo, double **inj, float **out, int32_t **status,
+                   int32_t **iters, double **busv);
+/* b200pf_run_host on the staging buffers (H2D, kernel, D2H, synchronised on return) */
+int b200pf_run_staged(b200pf_handle *h, int batch, int is_dc, int max_iter, double tol_mva, int nb_cap,
+                      int want_busv);
+/* let the series results land in caller-owned DEVICE buffers (e.g. torch tensors); NULL keeps the
+ * handle's own buffer for that array */
+int b200pf_series_bind_outputs(b200pf_handle *h, float *d_out, int32_t *d_status, int32_t *d_iters,
+                               float *d_rho);
+/* run all work of this handle on the caller's stream (cudaStream_t as integer; 0 = the handle's own) */
+int b200pf_set_stream(b200pf_handle *h, uint64_t stream);
+
 int b200pf_sync(b200pf_handle *h);
 /* cudaStream_t of the handle as an integer (for event timing by the caller) */
 uint64_t b200pf_stream(b200pf_handle *h);

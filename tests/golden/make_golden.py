@@ -66,7 +66,42 @@ def case14_chronics():
     return gm, chron
 
 
+def grid_models():
+    for env in ("l2rpn_case14_sandbox", "rte_case5_example", "l2rpn_neurips_2020_track1", "l2rpn_wcci_2022_dev"):
+        gm = GridModel(os.path.join(REF, env, "grid.json"))
+        gm.path = env            # no absolute paths in fixtures
+        gm.to_npz(os.path.join(HERE, f"gridmodel_{env}.npz"))
+
+
+def oracle_steps(gm, chron, n=48):
+    """fp64 oracle results for n (scenario,row) pairs of the case14 chronics: the parity fixture the GPU
+    box checks the CUDA path against when the reference tree is absent."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE)))
+    from oracle_engine import OracleEngine
+    gm_full = GridModel(os.path.join(REF, "l2rpn_case14_sandbox", "grid.json"))
+    eng = OracleEngine(gm_full)
+    sl = gm_full.inj_slices()
+    rng = np.random.default_rng(0)
+    scen = rng.integers(0, chron.shape[0], n)
+    rows = rng.integers(0, chron.shape[1], n)
+    inj = np.tile(gm_full.default_inj(), (n, 1))
+    nl, ng = gm_full.n_load, gm_full.n_gen
+    for i in range(n):
+        r = chron[scen[i], rows[i]]
+        inj[i, sl["load_p"]] = r[:nl]
+        inj[i, sl["load_q"]] = r[nl:2 * nl]
+        inj[i, sl["gen_p"]] = r[2 * nl:2 * nl + ng]
+        inj[i, sl["gen_vm"]] = (r[2 * nl + ng:] / gm_full.prod_pu_to_kv).astype(np.float32)   # float32 division, pPB:927
+    topo = np.tile(gm_full.default_topo(), (n, 1))
+    out, status, iters, busv = eng.run(topo, inj, want_busv=True)
+    assert (status == 0).all()
+    np.savez_compressed(os.path.join(HERE, "oracle_case14_steps.npz"), scen=scen, rows=rows, inj=inj, topo=topo,
+                        out=out, busv=busv, iters=iters)
+
+
 if __name__ == "__main__":
     stored_results()
     gm, chron = case14_chronics()
     print("chronics", chron.shape, chron.dtype)
+    grid_models()
+    oracle_steps(gm, chron)

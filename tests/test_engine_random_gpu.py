@@ -1,0 +1,105 @@
+"""GPU parity on perturbed states: random bus splits, line outages and injection changes (converging and
+diverging), CUDA engine through the C ABI vs the fp64 oracle (C restatement, itself checked against the
+numpy oracle in tests/test_c_oracle.py).  Tolerance: 1e-4 p.u. (north_star) on flows and voltages."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import env_grid
+
+from grid2op_b200.gridmodel import GridModel
+from oracle.c_oracle import COracle
+from test_c_oracle import random_cases
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _compare(gm, out, ref, ok):
+    from grid2op_b200.engine import OutputView
+    a, b = OutputView(gm, out[ok]), OutputView(gm, ref[ok])
+    tol_mw = 1e-4 * gm.sn_mva
+    for k in ("p_or", "q_or", "p_ex", "q_ex", "unit_p", "unit_q", "shunt_p", "shunt_q"):
+        x, y = getattr(a, k), getattr(b, k)
+        assert np.max(np.abs(x - y) - 4e-7 * np.abs(y), initial=0.0) <= tol_mw, k          # + float32 record rounding
+    for k, vn in (("v_or", gm.line_or_vn), ("v_ex", gm.line_ex_vn), ("load_v", gm.load_vn)):
+        x, y = getattr(a, k), getattr(b, k)
+        assert np.max(np.abs(x - y) / vn, initial=0.0) <= 1e-4, k                            # p.u.
+    for k in ("theta_or", "theta_ex", "load_theta", "unit_theta"):
+        assert np.max(np.abs(getattr(a, k) - getattr(b, k)), initial=0.0) <= 1e-3, k         # degrees
+    x, y = a.a_or, b.a_or
+    assert np.max(np.abs(x - y) - 1e-5 * np.abs(y), initial=0.0) <= 1e-2
+
+
+@pytest.mark.parametrize("name,n", [("rte_case5_example", 256), ("l2rpn_case14_sandbox", 512), ("educ_case14_storage", 256),
+                                    ("l2rpn_2019", 128), ("l2rpn_neurips_2020_track1", 128), ("l2rpn_wcci_2022_dev", 16)])
+@pytest.mark.parametrize("dc", [False, True])
+def test_random_states(cuda_required, name, n, dc):
+    from grid2op_b200.engine import PowerFlowEngine
+    path = env_grid(name)
+    if path is None:
+        pytest.skip("reference grid files not available")
+    gm = GridModel(path)
+    topo, inj = random_cases(gm, n, seed=11)
+    eng = PowerFlowEngine(gm, max_batch=n)
+    out, status, iters, _ = eng.run(topo, inj, is_dc=dc)
+    ref, rstatus, riters, _ = COracle(gm).run(topo, inj, is_dc=dc)
+    # integers: convergence / failure class must agree exactly
+    assert np.array_equal(status == 0, rstatus == 0)
+    bad = status != 0
+    assert np.array_equal(status[bad], rstatus[bad])
+    assert np.isnan(out[bad]).all()
+    ok = ~bad
+    assert ok.sum() >= n // 4
+    _compare(gm, out, ref, ok)
+    if not dc:
+        # fp32 Jacobian + fp64 residual: same iteration count as the fp64 Newton, at most one more
+        assert np.all(iters[ok] >= riters[ok]) and np.all(iters[ok] <= riters[ok] + 1)
+    eng.close()
+
+
+def test_golden_fixture_case14(cuda_required):
+    """Committed oracle fixture (tests/golden/oracle_case14_steps.npz, made by make_golden.py): runs without
+    any reference file, e.g. on a GPU box that only has this repository."""
+    from grid2op_b200.engine import PowerFlowEngine
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    z = np.load(os.path.join(GOLD, "oracle_case14_steps.npz"))
+    eng = PowerFlowEngine(gm, max_batch=len(z["topo"]))
+    out, status, iters, busv = eng.run(z["topo"], z["inj"], want_busv=True)
+    assert (status == 0).all()
+    _compare(gm, out, z["out"], np.ones(len(out), dtype=bool))
+    m = np.isfinite(z["busv"])
+    assert np.max(np.abs(busv[m] - z["busv"][m])) <= 1e-7          # p.u. / rad, fp64 state
+    assert np.array_equal(iters, z["iters"])
+    eng.close()
+
+
+def test_series_mode_matches_explicit_records(cuda_required):
+    """Device-resident chronics stepping == the same rows fed through the host-record entry point."""
+    from grid2op_b200.engine import PowerFlowEngine
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"]
+    B = 300
+    scen = (np.arange(B) % 3).astype(np.int32)
+    t0 = ((np.arange(B) * 37) % chron.shape[1]).astype(np.int32)
+    eng = PowerFlowEngine(gm, max_batch=B)
+    eng.series_bind(chron, scen, t0, gm.default_inj(), gm.thermal_limit_a)
+    eng.series_set_topo(np.tile(gm.default_topo(), (B, 1)))
+    sl = gm.inj_slices()
+    nl, ng = gm.n_load, gm.n_gen
+    for step in range(3):
+        eng.series_step(nb_cap=gm.n_sub)
+        out, status, iters, rho = eng.series_fetch()
+        rows = chron[scen, (t0 + step) % chron.shape[1]]
+        inj = np.tile(gm.default_inj(), (B, 1))
+        inj[:, sl["load_p"]] = rows[:, :nl]
+        inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
+        inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
+        inj[:, sl["gen_vm"]] = (rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]).astype(np.float32)
+        out2, status2, iters2, _ = eng.run(np.tile(gm.default_topo(), (B, 1)), inj)
+        assert (status == 0).all() and (status2 == 0).all()
+        assert np.array_equal(out, out2) and np.array_equal(iters, iters2)       # bit-exact: same kernel, same inputs
+        v = eng.view(out)
+        assert np.allclose(rho, v.a_or / gm.thermal_limit_a[None, :], rtol=1e-6)
+    eng.close()
