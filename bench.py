@@ -135,10 +135,20 @@ def run_reference(args):
     batch = args.batch
     from oracle.c_oracle import COracle
     from grid2op_b200.rollout import instance_schedule
-    orc = COracle(gm)
     scen, t0 = instance_schedule(batch, chron.shape[0], chron.shape[1])
     sl = gm.inj_slices(); nl, ng = gm.n_load, gm.n_gen
     topo = np.tile(gm.default_topo(), (batch, 1)); inj = np.tile(gm.default_inj(), (batch, 1))
+    # "all the host threads it can use": try the logical and the physical core count, keep the faster
+    ncpu = os.cpu_count() or 1
+    best = None
+    for nt in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
+        o = COracle(gm, nthreads=nt)
+        o.run(topo, inj)
+        t = time.perf_counter(); o.run(topo, inj); dt_ = time.perf_counter() - t
+        if best is None or dt_ < best[0]:
+            best = (dt_, nt, o)
+    orc = best[2]
+    n_threads = best[1]
 
     def step(k):
         rows = chron[scen, (t0 + k) % chron.shape[1]]
@@ -161,8 +171,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (bundled l2rpn_case14_sandbox chronics rows replayed, DoNothing)",
         "config": {"workload": f"l2rpn_case14_sandbox AC Newton-Raphson, batch {batch}, DoNothing rollout, host CPU",
                    "batch_per_step": batch},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.max_threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {batch} instances (whole batch per step), oracle/pf_oracle.c, OpenMP"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {batch} instances (whole batch per step), oracle/pf_oracle.c, OpenMP x{n_threads}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -285,7 +285,7 @@ class B200Backend(Backend):
         t0 = time.perf_counter()
         self._refresh_status_topo()                                             # pPB:1236-1237
         topo, inj = self._device_records()
-        nb_cap = int(min(gm.n_slot, np.unique(self._active_slots(topo)).size)) if gm.n_slot > 64 else 0
+        nb_cap = int(min(gm.n_slot, np.unique(self._active_slots(topo)).size))     # exact number of active buses
         out, status, iters, _ = self._engine.run(topo[None, :], inj[None, :], is_dc=is_dc, max_iter=self._max_iter,
                                                  tol_mva=self._tol_mva, nb_cap=nb_cap)
         self.comp_time += time.perf_counter() - t0

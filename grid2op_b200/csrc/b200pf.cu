@@ -2,6 +2,7 @@
 // Host side: owns the device copy of the static grid description, the staging buffers, one CUDA
 // stream per handle, and picks the thread-group size / shared-memory budget per launch.
 #include "b200pf_kernel.cuh"
+#include "b200pf_small.cuh"
 #include "../../include/b200pf.h"
 
 #include <cstdio>
@@ -37,6 +38,7 @@ struct b200pf_handle {
     int *d_iters = nullptr; double *d_busv = nullptr;
     int8_t *h_topo = nullptr; double *h_inj = nullptr; float *h_out = nullptr; int *h_status = nullptr;
     int *h_iters = nullptr; double *h_busv = nullptr;
+    float *h_rows = nullptr; float *d_rows = nullptr;
     // series
     float *d_chron = nullptr; int *d_scen = nullptr; int *d_t = nullptr; double *d_static_inj = nullptr;
     float *d_thlim = nullptr; float *d_rho = nullptr; int8_t *d_series_topo = nullptr;
@@ -138,6 +140,11 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         b200pf_destroy(h);
         return fail(B200PF_E_CUDA, "pinned host allocation failed");
     }
+    {
+        const size_t ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
+        if ((rc = dmal((void **)&h->d_rows, B * ncol * 4)) || (rc = dmal((void **)&h->d_static_inj, (size_t)g.n_inj * 8))) { b200pf_destroy(h); return rc; }
+        if (cudaMallocHost(&h->h_rows, B * ncol * 4 + 4) != cudaSuccess) { b200pf_destroy(h); return fail(B200PF_E_CUDA, "pinned host allocation failed"); }
+    }
     *out = h;
     return 0;
 }
@@ -147,7 +154,7 @@ extern "C" int b200pf_destroy(b200pf_handle *h) {
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (void *p : h->dev_allocs) cudaFree(p);
-    void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv};
+    void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv, h->h_rows};
     for (void *p : pinned) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -199,6 +206,28 @@ static int launch_t(b200pf_handle *h, const RunArgs &a) {
 // what the worst case of nb_cap buses needs, clipped to what is left on chip; the kernel checks the
 // ACTUAL system size of each instance against it (B200PF_ST_TOO_LARGE), so e.g. the 118-substation
 // grid (236 slots) runs as long as its Newton system (191 unknowns + splits) fits.
+static int launch_small(b200pf_handle *h, RunArgs a, int cap) {
+    const DevGrid &g = h->g;
+    a.nb_cap = cap;
+    SmallLayout L = small_layout(cap);
+    a.mat_bytes = L.total - L.off_mat;
+    auto kern = pf_kernel_small;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, (size_t)L.total));
+    if (occ < 1) occ = 1;
+    const int resident = h->sm_count * occ;
+    const int rounds = (a.batch + resident - 1) / resident;
+    int grid = (a.batch + rounds - 1) / rounds;
+    if (grid < 1) grid = 1;
+    kern<<<grid, 32, L.total, h->stream>>>(g, a, L);
+    CU(cudaGetLastError());
+    h->launches++;
+    h->last_smem = L.total; h->last_T = 32; h->last_grid = grid; h->last_block = 32;
+    (void)g;
+    return 0;
+}
+
 static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
     const DevGrid &g = h->g;
     const char *f64 = getenv("B200PF_JACOBIAN_FP64");
@@ -206,6 +235,12 @@ static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
     const int jt = jd ? 8 : 4;
     int cap = nb_cap_req;
     if (cap <= 0 || cap > g.n_slot) cap = g.n_slot;
+    // warp-per-instance fast path: every element class fits one warp and the caller bounds the number
+    // of active buses so that the Newton system has <= 32 unknowns (see b200pf_small.cuh)
+    const char *nos = getenv("B200PF_NO_SMALL_KERNEL");
+    if (!jd && !(nos && nos[0] == '1') && g.n_slot <= 32 && g.n_line <= 32 && g.n_unit <= 32 && g.n_load <= 32 &&
+        g.n_sto <= 32 && g.n_shunt <= 32 && cap <= 17)
+        return launch_small(h, a, cap);
     const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
     size_t want = ws_mat_worst(cap, jt);
     int T = 32;
@@ -303,7 +338,7 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
     auto dmal = [&](void **p, size_t bytes) -> int { CU(cudaMalloc(p, bytes ? bytes : 1)); h->dev_allocs.push_back(*p); return 0; };
     int rc;
     if ((rc = dmal((void **)&h->d_chron, (size_t)n_scen * n_rows * ncol * 4)) || (rc = dmal((void **)&h->d_scen, (size_t)batch * 4)) ||
-        (rc = dmal((void **)&h->d_t, (size_t)batch * 4)) || (rc = dmal((void **)&h->d_static_inj, (size_t)g.n_inj * 8)) ||
+        (rc = dmal((void **)&h->d_t, (size_t)batch * 4)) ||
         (rc = dmal((void **)&h->d_thlim, (size_t)g.n_line * 4)) || (rc = dmal((void **)&h->d_rho, (size_t)batch * g.n_line * 4)) ||
         (rc = dmal((void **)&h->d_series_topo, (size_t)batch * g.n_topo_in)))
         return rc;
@@ -388,6 +423,39 @@ extern "C" int b200pf_run_staged(b200pf_handle *h, int batch, int is_dc, int max
     CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
     if (want_busv) CU(cudaMemcpyAsync(h->h_busv, h->d_busv, B * 2 * g.n_slot * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200pf_set_static_inj(b200pf_handle *h, const double *static_inj) {
+    if (!h || !static_inj) return fail(B200PF_E_ARG, "null pointer");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(h->d_static_inj, static_inj, (size_t)h->g.n_inj * 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int b200pf_rows_staging(b200pf_handle *h, float **rows) {
+    if (!h || !rows) return fail(B200PF_E_ARG, "null pointer");
+    *rows = h->h_rows;
+    return 0;
+}
+
+extern "C" int b200pf_run_rows_staged(b200pf_handle *h, int batch, int is_dc, int max_iter, double tol_mva, int nb_cap) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (batch <= 0 || batch > h->max_batch) return fail(B200PF_E_ARG, "batch out of range (max_batch)");
+    CU(cudaSetDevice(h->device));
+    const DevGrid &g = h->g;
+    const size_t B = (size_t)batch, ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
+    CU(cudaMemcpyAsync(h->d_topo, h->h_topo, B * g.n_topo_in, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_rows, h->h_rows, B * ncol * 4, cudaMemcpyHostToDevice, h->stream));
+    RunArgs a = base_args(h, batch, is_dc, max_iter, tol_mva);
+    a.topo = h->d_topo; a.inj = nullptr; a.out = h->d_out; a.status = h->d_status; a.iters = h->d_iters; a.busv = nullptr;
+    a.series = 1; a.rows = h->d_rows; a.static_inj = h->d_static_inj;
+    int rc = launch(h, a, nb_cap);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->h_out, h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -56,6 +56,7 @@ struct RunArgs {
     // time-series mode
     int series;
     const float *chron;
+    const float *rows;      // rows mode: float32 [batch][2 n_load + 2 n_gen] for this very step (overrides chron)
     int n_scen, n_rows;
     const int *scen;
     int *t;
@@ -363,9 +364,10 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
 
     // ---- 0. stage the injection record -----------------------------------------------------
     if (a.series) {
-        const int sc = a.scen[inst];
-        const int trow = a.t[inst];
-        const float *row = a.chron + ((size_t)sc * a.n_rows + trow) * (size_t)(2 * g.n_load + 2 * g.n_gen);
+        const int sc = a.rows ? 0 : a.scen[inst];
+        const int trow = a.rows ? 0 : a.t[inst];
+        const float *row = a.rows ? a.rows + (size_t)inst * (size_t)(2 * g.n_load + 2 * g.n_gen)
+                                  : a.chron + ((size_t)sc * a.n_rows + trow) * (size_t)(2 * g.n_load + 2 * g.n_gen);
         for (int k = tid; k < g.n_inj; k += T) w.inj[k] = a.static_inj[k];
         gsync<T>();
         for (int k = tid; k < g.n_load; k += T) {
@@ -378,7 +380,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             w.inj[g.n_gen + g.n_hidden + k] = (double)__fdiv_rn(row[2 * g.n_load + g.n_gen + k], g.unit_vn[g.n_hidden + k]);
         }
         gsync<T>();
-        if (tid == 0) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1;
+        if (tid == 0 && !a.rows) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1;
     } else {
         const double *src = a.inj + (size_t)inst * g.n_inj;
         for (int k = tid; k < g.n_inj; k += T) w.inj[k] = src[k];

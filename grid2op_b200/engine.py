@@ -29,7 +29,8 @@ ABI_SYMBOLS = (
     "b200pf_sizes", "b200pf_run_host", "b200pf_run_device", "b200pf_series_bind", "b200pf_series_set_topo",
     "b200pf_series_step", "b200pf_series_results", "b200pf_series_fetch", "b200pf_sync", "b200pf_stream",
     "b200pf_launch_count", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
-    "b200pf_series_bind_outputs", "b200pf_set_stream",
+    "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
+    "b200pf_run_rows_staged",
 )
 
 
@@ -89,6 +90,9 @@ def load_library():
     lib.b200pf_run_staged.argtypes = [vp, i32, i32, i32, f64, i32, i32]
     lib.b200pf_series_bind_outputs.argtypes = [vp, vp, vp, vp, vp]
     lib.b200pf_set_stream.argtypes = [vp, C.c_uint64]
+    lib.b200pf_set_static_inj.argtypes = [vp, vp]
+    lib.b200pf_rows_staging.argtypes = [vp, C.POINTER(vp)]
+    lib.b200pf_run_rows_staged.argtypes = [vp, i32, i32, i32, f64, i32]
     lib.b200pf_stream.argtypes = [vp]
     lib.b200pf_stream.restype = C.c_uint64
     lib.b200pf_launch_count.argtypes = [vp]
@@ -97,7 +101,8 @@ def load_library():
     for nm in ("b200pf_create", "b200pf_destroy", "b200pf_sizes", "b200pf_run_host", "b200pf_run_device",
                "b200pf_series_bind", "b200pf_series_set_topo", "b200pf_series_step", "b200pf_series_results",
                "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
-               "b200pf_series_bind_outputs", "b200pf_set_stream"):
+               "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
+               "b200pf_run_rows_staged"):
         getattr(lib, nm).restype = i32
     _LIB = lib
     return lib
@@ -189,14 +194,41 @@ class PowerFlowEngine:
         except Exception:
             pass
 
+    def max_active_buses(self, topo: np.ndarray) -> int:
+        """Largest number of active buses (bus slots with at least one connected element) over a batch
+        of topology records: the tight ``nb_cap`` for a launch (0 = unknown -> size for every slot)."""
+        gm = self.gm
+        if gm.n_slot > 64:
+            return 0
+        if getattr(self, "_slot_tbl", None) is None:
+            sub = np.zeros(gm.n_topo_in, dtype=np.int64)
+            sub[gm.line_or_pos] = gm.line_or_sub; sub[gm.line_ex_pos] = gm.line_ex_sub
+            sub[gm.gen_pos] = gm.gen_sub; sub[gm.load_pos] = gm.load_sub
+            if gm.n_storage:
+                sub[gm.storage_pos] = gm.storage_sub
+            sub[gm.dim_topo:gm.dim_topo + gm.n_shunt] = gm.shunt_sub
+            sub[gm.dim_topo + gm.n_shunt:] = gm.hidden_sub
+            self._slot_tbl = sub
+        topo = np.asarray(topo).reshape(-1, gm.n_topo_in).astype(np.int64)
+        slot = self._slot_tbl[None, :] + (topo - 1) * gm.n_sub
+        bits = np.where(topo > 0, np.left_shift(np.uint64(1), slot.clip(0, 63).astype(np.uint64)), np.uint64(0))
+        mask = np.bitwise_or.reduce(bits, axis=1)
+        cnt = np.zeros(mask.shape[0], dtype=np.int64)
+        for k in range(gm.n_slot):
+            cnt += ((mask >> np.uint64(k)) & np.uint64(1)).astype(np.int64)
+        return int(cnt.max()) if cnt.size else 0
+
     def run(self, topo: np.ndarray, inj: np.ndarray, is_dc: bool = False, max_iter: int = 10,
-            tol_mva: float = 1e-8, nb_cap: int = 0, want_busv: bool = False
+            tol_mva: float = 1e-8, nb_cap: int = -1, want_busv: bool = False
             ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, Optional[np.ndarray]]:
-        """Host-buffer entry point (H2D + kernel + D2H).  ``topo`` int8 [B, n_topo_in], ``inj`` f64 [B, n_inj]."""
+        """Host-buffer entry point (H2D + kernel + D2H).  ``topo`` int8 [B, n_topo_in], ``inj`` f64 [B, n_inj].
+        ``nb_cap`` < 0: computed from ``topo`` (tight bound -> the warp-per-instance kernel when it applies)."""
         gm = self.gm
         topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(-1, gm.n_topo_in)
         inj = np.ascontiguousarray(inj, dtype=np.float64).reshape(-1, gm.n_inj)
         B = topo.shape[0]
+        if nb_cap < 0:
+            nb_cap = self.max_active_buses(topo)
         if inj.shape[0] != B:
             raise ValueError("topo / inj batch mismatch")
         out = np.empty((B, gm.n_out), dtype=np.float32)
@@ -235,6 +267,24 @@ class PowerFlowEngine:
     def run_staged(self, batch: int, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0):
         self._check(self.lib.b200pf_run_staged(self.h, int(batch), int(bool(is_dc)), int(max_iter), float(tol_mva),
                                                int(nb_cap), 0), "b200pf_run_staged")
+
+    def rows_staging(self) -> np.ndarray:
+        """numpy view of the pinned float32 rows buffer [max_batch, 2 n_load + 2 n_gen]."""
+        gm, B = self.gm, self.max_batch
+        p = C.c_void_p()
+        self._check(self.lib.b200pf_rows_staging(self.h, C.byref(p)), "b200pf_rows_staging")
+        ncol = 2 * gm.n_load + 2 * gm.n_gen
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(B * ncol,))
+        return arr.reshape(B, ncol)
+
+    def set_static_inj(self, static_inj: np.ndarray):
+        a = np.ascontiguousarray(static_inj, dtype=np.float64)
+        assert a.shape == (self.gm.n_inj,)
+        self._check(self.lib.b200pf_set_static_inj(self.h, _ptr(a)), "b200pf_set_static_inj")
+
+    def run_rows_staged(self, batch: int, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0):
+        self._check(self.lib.b200pf_run_rows_staged(self.h, int(batch), int(bool(is_dc)), int(max_iter), float(tol_mva),
+                                                    int(nb_cap)), "b200pf_run_rows_staged")
 
     def set_stream(self, stream: int):
         self._check(self.lib.b200pf_set_stream(self.h, C.c_uint64(int(stream))), "b200pf_set_stream")

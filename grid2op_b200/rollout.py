@@ -69,29 +69,26 @@ class BatchedDoNothing:
 
     # ---- host buffers in / out --------------------------------------------------------------------
     def step_host(self):
-        """Next chronics row of every instance gathered on the host, written into the pinned staging
-        records, H2D, kernel, D2H; returns (out view, status view) living in the staging buffers."""
-        gm = self.gm
+        """Next chronics row of every instance gathered on the host straight into the pinned float32 rows
+        buffer, H2D (topology record + rows), kernel, D2H; returns (out view, status view) living in the
+        pinned staging buffers."""
         if self._stage is None:
             self._stage = self.engine.staging()
+            self._rows = self.engine.rows_staging()
             self._stage["topo"][:self.batch] = self.topo0
-            self._stage["inj"][:self.batch] = self._inj0[None, :]
+            self.engine.set_static_inj(self._inj0)
+            n_rows = self.chron.shape[1]
+            self._chron_flat = self.chron.reshape(-1, self.chron.shape[2])
+            self._row_base = self.scen.astype(np.int64) * n_rows
         st = self._stage
-        rows = self.chron[self.scen, self._t_host]
-        nl, ng = gm.n_load, gm.n_gen
-        inj = st["inj"][:self.batch]
-        sl = self._sl
-        inj[:, sl["load_p"]] = rows[:, :nl]
-        inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
-        inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
-        inj[:, sl["gen_vm"]] = rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]     # float32 / float32 (pPB:927)
+        np.take(self._chron_flat, self._row_base + self._t_host, axis=0, out=self._rows[:self.batch])
         self._t_host = (self._t_host + 1) % self.chron.shape[1]
-        self.engine.run_staged(self.batch, is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva, nb_cap=self.nb_cap)
+        self.engine.run_rows_staged(self.batch, is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva, nb_cap=self.nb_cap)
         return st["out"][:self.batch], st["status"][:self.batch]
 
     def bytes_per_step_host(self):
         gm = self.gm
-        return self.batch * (gm.n_topo_in + 8 * gm.n_inj), self.batch * (4 * gm.n_out + 8)
+        return self.batch * (gm.n_topo_in + 4 * (2 * gm.n_load + 2 * gm.n_gen)), self.batch * (4 * gm.n_out + 8)
 
     def close(self):
         self.engine.close()

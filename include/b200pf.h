@@ -144,6 +144,14 @@ int b200pf_run_staged(b200pf_handle *h, int batch, int is_dc, int max_iter, doub
  * handle's own buffer for that array */
 int b200pf_series_bind_outputs(b200pf_handle *h, float *d_out, int32_t *d_status, int32_t *d_iters,
                                float *d_rho);
+/* "rows" entry point: like b200pf_run_staged but the injections of this step come as the float32
+ * chronics ROW of every instance (load_p, load_q, prod_p, prod_v[kV]; 2 n_load + 2 n_gen values, backend
+ * element order) written by the caller into the pinned rows staging buffer (b200pf_rows_staging);
+ * storage / shunt / hidden-unit values come from static_inj (b200pf_set_static_inj).  Less than half
+ * the host->device bytes of the f64 record, and no host-side float64 packing. */
+int b200pf_set_static_inj(b200pf_handle *h, const double *static_inj /* [n_inj] */);
+int b200pf_rows_staging(b200pf_handle *h, float **rows);
+int b200pf_run_rows_staged(b200pf_handle *h, int batch, int is_dc, int max_iter, double tol_mva, int nb_cap);
 /* run all work of this handle on the caller's stream (cudaStream_t as integer; 0 = the handle's own) */
 int b200pf_set_stream(b200pf_handle *h, uint64_t stream);
 

@@ -36,19 +36,16 @@ def random_cases(gm, n, seed, p_split=0.15, p_disc=0.03):
     return topo, inj
 
 
-_SUB_CACHE = {}
-
-
 def _sub_of(gm, p):
-    key = id(gm)
-    if key not in _SUB_CACHE:
+    m = getattr(gm, "_test_sub_of_pos", None)
+    if m is None:
         m = np.zeros(gm.dim_topo, dtype=np.int64)
         m[gm.line_or_pos] = gm.line_or_sub; m[gm.line_ex_pos] = gm.line_ex_sub
         m[gm.gen_pos] = gm.gen_sub; m[gm.load_pos] = gm.load_sub
         if gm.n_storage:
             m[gm.storage_pos] = gm.storage_sub
-        _SUB_CACHE[key] = m
-    return _SUB_CACHE[key][p]
+        gm._test_sub_of_pos = m
+    return m[p]
 
 
 @pytest.mark.parametrize("name", GRIDS)

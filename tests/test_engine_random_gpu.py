@@ -103,3 +103,18 @@ def test_series_mode_matches_explicit_records(cuda_required):
         v = eng.view(out)
         assert np.allclose(rho, v.a_or / gm.thermal_limit_a[None, :], rtol=1e-6)
     eng.close()
+
+
+def test_rows_mode_matches_series_mode(cuda_required):
+    """b200pf_run_rows_staged (float32 rows from pinned host memory) == device-resident series stepping."""
+    from grid2op_b200.rollout import BatchedDoNothing
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"]
+    env = BatchedDoNothing(gm, chron, 200)
+    for _ in range(3):
+        env.step_device()
+        o1, s1, i1, _ = env.fetch()
+        o2, s2 = env.step_host()
+        assert (s1 == 0).all() and np.array_equal(s1, s2)
+        assert np.array_equal(o1, o2)
+    env.close()
