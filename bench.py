@@ -8,7 +8,8 @@ Workload at N=1 (BASELINE.json configs[1]): l2rpn_case14_sandbox, AC Newton-Raph
 GPU, DoNothing rollout over the bundled chronics (instance i -> scenario i mod 3, start row (i*37) mod
 576), NO_OVERFLOW_DISCONNECTION like the reference's own profiling script.  A "step" is
 one pass of the hot path over the whole batch = batch env.step() calls.  N>1: weak scaling (4096 per
-GPU), no data-path collective inside the solve, one NCCL gather of rho per step to rank 0.
+GPU), no data-path collective inside the solve, one NCCL gather of rho per step to rank 0
+(asynchronous, overlapped with the next step's solve).
 
 One JSON line on stdout (rank 0).  Keys documented in DESIGN.md section "Measurement".
 """
@@ -198,21 +199,34 @@ def run_ours(args):
     stream = torch.cuda.Stream()            # a real (non-default) stream shared by torch events and the engine
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
-    # results land in torch tensors (so NCCL can gather them)
-    rho = torch.empty((batch, gm.n_line), dtype=torch.float32, device="cuda")
+    # results land in torch tensors (so NCCL can gather them); rho is double-buffered so that the gather of
+    # step k (NCCL stream) overlaps the solve of step k+1 (compute stream)
+    rho_bufs = [torch.empty((batch, gm.n_line), dtype=torch.float32, device="cuda") for _ in range(2)]
     status = torch.empty((batch,), dtype=torch.int32, device="cuda")
     iters = torch.empty((batch,), dtype=torch.int32, device="cuda")
-    eng.series_bind_outputs(0, status.data_ptr(), iters.data_ptr(), rho.data_ptr())
-    gather_list = [torch.empty_like(rho) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gather_lists = [[torch.empty_like(rho_bufs[0]) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    state = {"k": 0, "pending": None}
 
     def one_step():
+        k = state["k"]
+        buf = rho_bufs[k % 2]
+        eng.series_bind_outputs(0, status.data_ptr(), iters.data_ptr(), buf.data_ptr())
         env.step_device()
         if world > 1:
-            dist.gather(rho, gather_list, dst=0)
+            if state["pending"] is not None:
+                state["pending"].wait()                 # gather of step k-1 overlapped this step's kernel
+            state["pending"] = dist.gather(buf, gather_lists[k % 2], dst=0, async_op=True)
+        state["k"] = k + 1
+
+    def drain():
+        if state["pending"] is not None:
+            state["pending"].wait()
+            state["pending"] = None
 
     for _ in range(max(args.warmup, 3)):
         one_step()
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -229,13 +243,17 @@ def run_ours(args):
         a.record()
         one_step()
         b.record()
+    tail_a, tail_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tail_a.record()
+    drain()                                 # the last gather is timed too
+    tail_b.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
     launches = eng.launch_count - launches0
-    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs)) + float(tail_a.elapsed_time(tail_b))
     n_bad = int((status != 0).sum().item())
     mean_iters = float(iters.float().mean().item())
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")

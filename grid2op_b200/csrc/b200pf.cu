@@ -142,7 +142,8 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
     }
     {
         const size_t ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
-        if ((rc = dmal((void **)&h->d_rows, B * ncol * 4)) || (rc = dmal((void **)&h->d_static_inj, (size_t)g.n_inj * 8))) { b200pf_destroy(h); return rc; }
+        if ((rc = dmal((void **)&h->d_rows, B * ncol * 4)) || (rc = dmal((void **)&h->d_static_inj, (size_t)g.n_inj * 8)) ||
+            (rc = dmal((void **)&h->d_thlim, (size_t)g.n_line * 4)) || (rc = dmal((void **)&h->d_rho, B * g.n_line * 4))) { b200pf_destroy(h); return rc; }
         if (cudaMallocHost(&h->h_rows, B * ncol * 4 + 4) != cudaSuccess) { b200pf_destroy(h); return fail(B200PF_E_CUDA, "pinned host allocation failed"); }
     }
     *out = h;
@@ -339,7 +340,6 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
     int rc;
     if ((rc = dmal((void **)&h->d_chron, (size_t)n_scen * n_rows * ncol * 4)) || (rc = dmal((void **)&h->d_scen, (size_t)batch * 4)) ||
         (rc = dmal((void **)&h->d_t, (size_t)batch * 4)) ||
-        (rc = dmal((void **)&h->d_thlim, (size_t)g.n_line * 4)) || (rc = dmal((void **)&h->d_rho, (size_t)batch * g.n_line * 4)) ||
         (rc = dmal((void **)&h->d_series_topo, (size_t)batch * g.n_topo_in)))
         return rc;
     CU(cudaMemcpy(h->d_chron, chron_host, (size_t)n_scen * n_rows * ncol * 4, cudaMemcpyHostToDevice));
@@ -423,6 +423,33 @@ extern "C" int b200pf_run_staged(b200pf_handle *h, int batch, int is_dc, int max
     CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
     if (want_busv) CU(cudaMemcpyAsync(h->h_busv, h->d_busv, B * 2 * g.n_slot * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200pf_set_thermal_limit(b200pf_handle *h, const float *thermal_limit_a) {
+    if (!h || !thermal_limit_a) return fail(B200PF_E_ARG, "null pointer");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(h->d_thlim, thermal_limit_a, (size_t)h->g.n_line * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int b200pf_n1_host(b200pf_handle *h, int batch, const int8_t *topo, const double *inj, int max_iter, double tol_mva,
+                              int nb_cap, float *rho, int32_t *status) {
+    if (!h || !topo || !inj || !rho || !status) return fail(B200PF_E_ARG, "null pointer");
+    const DevGrid &g = h->g;
+    if (batch <= 0 || (long)batch * g.n_line > h->max_batch) return fail(B200PF_E_ARG, "batch * n_line exceeds max_batch");
+    CU(cudaSetDevice(h->device));
+    const size_t B = (size_t)batch, N = B * g.n_line;
+    CU(cudaMemcpyAsync(h->d_topo, topo, B * g.n_topo_in, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_inj, inj, B * g.n_inj * 8, cudaMemcpyHostToDevice, h->stream));
+    RunArgs a = base_args(h, (int)N, 0, max_iter, tol_mva);
+    a.topo = h->d_topo; a.inj = h->d_inj; a.out = nullptr; a.status = h->d_status; a.iters = h->d_iters; a.busv = nullptr;
+    a.n1_lines = g.n_line; a.th_lim = h->d_thlim; a.rho = h->d_rho;
+    int rc = launch(h, a, nb_cap);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(rho, h->d_rho, N * g.n_line * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(status, h->d_status, N * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -56,6 +56,7 @@ struct RunArgs {
     // time-series mode
     int series;
     const float *chron;
+    int n1_lines;           // > 0: contingency mode, instance = (base state, outage line) pair, base = inst / n1_lines
     const float *rows;      // rows mode: float32 [batch][2 n_load + 2 n_gen] for this very step (overrides chron)
     int n_scen, n_rows;
     const int *scen;
@@ -357,16 +358,18 @@ template <int T, typename JT>
 __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, unsigned char *wsbase, int tid) {
     const int nbc = a.nb_cap;
     Ws w = ws_bind(wsbase, nbc, g.n_slot, g.n_line, g.n_inj, (size_t)a.mat_bytes);
-    const int8_t *tv = a.topo + (size_t)inst * g.n_topo_in;
-    float *out = a.out + (size_t)inst * g.n_out;
+    const int src = a.n1_lines > 0 ? inst / a.n1_lines : inst;          // record the inputs come from
+    const int outage = a.n1_lines > 0 ? inst % a.n1_lines : -1;         // line forced out of service (N-1 sweep)
+    const int8_t *tv = a.topo + (size_t)src * g.n_topo_in;
+    float *out = a.out ? a.out + (size_t)inst * g.n_out : nullptr;
     const double base = g.base_mva;
     const int nl = g.n_line;
 
     // ---- 0. stage the injection record -----------------------------------------------------
     if (a.series) {
-        const int sc = a.rows ? 0 : a.scen[inst];
-        const int trow = a.rows ? 0 : a.t[inst];
-        const float *row = a.rows ? a.rows + (size_t)inst * (size_t)(2 * g.n_load + 2 * g.n_gen)
+        const int sc = a.rows ? 0 : a.scen[src];
+        const int trow = a.rows ? 0 : a.t[src];
+        const float *row = a.rows ? a.rows + (size_t)src * (size_t)(2 * g.n_load + 2 * g.n_gen)
                                   : a.chron + ((size_t)sc * a.n_rows + trow) * (size_t)(2 * g.n_load + 2 * g.n_gen);
         for (int k = tid; k < g.n_inj; k += T) w.inj[k] = a.static_inj[k];
         gsync<T>();
@@ -380,10 +383,10 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             w.inj[g.n_gen + g.n_hidden + k] = (double)__fdiv_rn(row[2 * g.n_load + g.n_gen + k], g.unit_vn[g.n_hidden + k]);
         }
         gsync<T>();
-        if (tid == 0 && !a.rows) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1;
+        if (tid == 0 && !a.rows && a.n1_lines <= 0) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1;
     } else {
-        const double *src = a.inj + (size_t)inst * g.n_inj;
-        for (int k = tid; k < g.n_inj; k += T) w.inj[k] = src[k];
+        const double *srcp = a.inj + (size_t)src * g.n_inj;
+        for (int k = tid; k < g.n_inj; k += T) w.inj[k] = srcp[k];
     }
     const double *gen_p = w.inj;
     const double *unit_vm = w.inj + g.n_gen;
@@ -397,6 +400,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     for (int s = tid; s < g.n_slot; s += T) w.mark[s] = 0;
     gsync<T>();
     for (int l = tid; l < nl; l += T) {
+        if (l == outage) continue;
         const int bo = tv[g.line_or_pos[l]], be = tv[g.line_ex_pos[l]];
         if (bo > 0) w.mark[g.line_or_sub[l] + (bo - 1) * g.n_sub] = 1;
         if (be > 0) w.mark[g.line_ex_sub[l] + (be - 1) * g.n_sub] = 1;
@@ -489,7 +493,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         // branches -> compact end buses
         for (int l = tid; l < nl; l += T) {
             const int bo = tv[g.line_or_pos[l]], be = tv[g.line_ex_pos[l]];
-            if (bo > 0 && be > 0) {
+            if (bo > 0 && be > 0 && l != outage) {
                 w.brf[l] = w.cidx[g.line_or_sub[l] + (bo - 1) * g.n_sub];
                 w.brt[l] = w.cidx[g.line_ex_sub[l] + (be - 1) * g.n_sub];
             } else { w.brf[l] = -1; w.brt[l] = -1; }
@@ -699,7 +703,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     // ---- 7. results ----------------------------------------------------------------------------
     if (tid == 0) { a.status[inst] = status; a.iters[inst] = iters; }
     if (status != ST_OK) {
-        for (int k = tid; k < g.n_out; k += T) out[k] = qnanf();
+        if (out) for (int k = tid; k < g.n_out; k += T) out[k] = qnanf();
         if (a.busv) for (int k = tid; k < 2 * g.n_slot; k += T) a.busv[(size_t)inst * 2 * g.n_slot + k] = __longlong_as_double(0x7ff8000000000000LL);
         if (a.rho) for (int k = tid; k < nl; k += T) a.rho[(size_t)inst * nl + k] = qnanf();
         gsync<T>();
@@ -723,6 +727,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         }
         gsync<T>();
     }
+    float *const outw = out;
     float *o_p_or = out, *o_q_or = out + nl, *o_v_or = out + 2 * nl, *o_a_or = out + 3 * nl, *o_t_or = out + 4 * nl;
     float *o_p_ex = out + 5 * nl, *o_q_ex = out + 6 * nl, *o_v_ex = out + 7 * nl, *o_a_ex = out + 8 * nl, *o_t_ex = out + 9 * nl;
     for (int l = tid; l < nl; l += T) {
@@ -755,12 +760,14 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             v1 = __fmul_rn((float)vmf, g.line_or_vn[l]); v2 = __fmul_rn((float)vmt, g.line_ex_vn[l]);
             t1 = (float)(w.va[f] * RAD2DEG); t2 = (float)(w.va[t] * RAD2DEG);
         }
-        o_p_or[l] = p1; o_q_or[l] = q1; o_v_or[l] = v1; o_a_or[l] = a1; o_t_or[l] = t1;
-        o_p_ex[l] = p2; o_q_ex[l] = q2; o_v_ex[l] = v2; o_a_ex[l] = a2; o_t_ex[l] = t2;
+        if (outw) {
+            o_p_or[l] = p1; o_q_or[l] = q1; o_v_or[l] = v1; o_a_or[l] = a1; o_t_or[l] = t1;
+            o_p_ex[l] = p2; o_q_ex[l] = q2; o_v_ex[l] = v2; o_a_ex[l] = a2; o_t_ex[l] = t2;
+        }
         if (a.rho) a.rho[(size_t)inst * nl + l] = a1 / a.th_lim[l];
     }
     float *o_up = out + 10 * nl, *o_uq = o_up + g.n_unit, *o_uv = o_uq + g.n_unit, *o_ut = o_uv + g.n_unit;
-    for (int u = tid; u < g.n_unit; u += T) {
+    for (int u = tid; u < (outw ? g.n_unit : 0); u += T) {
         const int b = tv[g.unit_pos[u]];
         float p = 0.f, q = 0.f, v = 0.f, th = 0.f;
         if (b > 0) {
@@ -783,7 +790,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         o_up[u] = p; o_uq[u] = q; o_uv[u] = v; o_ut[u] = th;
     }
     float *o_lv = o_ut + g.n_unit, *o_lt = o_lv + g.n_load;
-    for (int k = tid; k < g.n_load; k += T) {
+    for (int k = tid; k < (outw ? g.n_load : 0); k += T) {
         const int b = tv[g.load_pos[k]];
         float v = 0.f, th = 0.f;
         if (b > 0) {
@@ -794,14 +801,14 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         o_lv[k] = v; o_lt[k] = th;
     }
     float *o_sv = o_lt + g.n_load;
-    for (int k = tid; k < g.n_sto; k += T) {
+    for (int k = tid; k < (outw ? g.n_sto : 0); k += T) {
         const int b = tv[g.sto_pos[k]];
         float v = 0.f;
         if (b > 0) v = __fmul_rn((float)w.vm[w.cidx[g.sto_sub[k] + (b - 1) * g.n_sub]], g.sto_vn[k]);
         o_sv[k] = v;
     }
     float *o_shp = o_sv + g.n_sto, *o_shq = o_shp + g.n_shunt, *o_shv = o_shq + g.n_shunt;
-    for (int k = tid; k < g.n_shunt; k += T) {
+    for (int k = tid; k < (outw ? g.n_shunt : 0); k += T) {
         const int b = tv[g.dim_topo + k];
         float p = 0.f, q = 0.f, v = 0.f;
         if (b > 0) {

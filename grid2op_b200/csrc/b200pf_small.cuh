@@ -99,9 +99,9 @@ __device__ __forceinline__ bool gj_small_d(const double *M, int n, int pitch, do
 }
 
 __device__ __forceinline__ void small_fail(const DevGrid &g, const RunArgs &a, int inst, int status, int iters, int lane) {
-    float *out = a.out + (size_t)inst * g.n_out;
+    float *out = a.out ? a.out + (size_t)inst * g.n_out : nullptr;
     if (lane == 0) { a.status[inst] = status; a.iters[inst] = iters; }
-    for (int k = lane; k < g.n_out; k += 32) out[k] = qnanf();
+    if (out) for (int k = lane; k < g.n_out; k += 32) out[k] = qnanf();
     if (a.busv) for (int k = lane; k < 2 * g.n_slot; k += 32) a.busv[(size_t)inst * 2 * g.n_slot + k] = __longlong_as_double(0x7ff8000000000000LL);
     if (a.rho) for (int k = lane; k < g.n_line; k += 32) a.rho[(size_t)inst * g.n_line + k] = qnanf();
     __syncwarp();
@@ -118,8 +118,10 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
     signed char *brt = brf + 32, *colth_s = brf + 64, *colv_s = brf + 96;
     float *J = reinterpret_cast<float *>(sm + L.off_mat);
     double *Md = reinterpret_cast<double *>(sm + L.off_mat);
-    const int8_t *tv = a.topo + (size_t)inst * g.n_topo_in;
-    float *out = a.out + (size_t)inst * g.n_out;
+    const int src = a.n1_lines > 0 ? inst / a.n1_lines : inst;          // record the inputs come from
+    const int outage = a.n1_lines > 0 ? inst % a.n1_lines : -1;         // line forced out of service (N-1 sweep)
+    const int8_t *tv = a.topo + (size_t)src * g.n_topo_in;
+    float *out = a.out ? a.out + (size_t)inst * g.n_out : nullptr;
     const double base = g.base_mva;
     const int nl = g.n_line, nu = g.n_unit, nh = g.n_hidden, ng = g.n_gen, nld = g.n_load, nst = g.n_sto, nsh = g.n_shunt;
     const unsigned lt = (1u << lane) - 1u;
@@ -127,8 +129,8 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
     // ---- 0. this lane's injections (lane = unit / load / storage / shunt index) ---------------------
     double u_p = 0.0, u_vm = 1.0, l_p = 0.0, l_q = 0.0, s_p = 0.0, sh_p = 0.0, sh_q = 0.0;
     if (a.series) {
-        const int sc = a.rows ? 0 : a.scen[inst], trow = a.rows ? 0 : a.t[inst];
-        const float *row = a.rows ? a.rows + (size_t)inst * (size_t)(2 * nld + 2 * ng)
+        const int sc = a.rows ? 0 : a.scen[src], trow = a.rows ? 0 : a.t[src];
+        const float *row = a.rows ? a.rows + (size_t)src * (size_t)(2 * nld + 2 * ng)
                                   : a.chron + ((size_t)sc * a.n_rows + trow) * (size_t)(2 * nld + 2 * ng);
         const double *si = a.static_inj;
         if (lane < nld) { l_p = (double)row[lane]; l_q = (double)row[nld + lane]; }
@@ -141,18 +143,18 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         if (lane < nst) s_p = si[ng + nu + 2 * nld + lane];
         if (lane < nsh) { sh_p = si[ng + nu + 2 * nld + nst + lane]; sh_q = si[ng + nu + 2 * nld + nst + nsh + lane]; }
         __syncwarp();
-        if (lane == 0 && !a.rows) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1;
+        if (lane == 0 && !a.rows && a.n1_lines <= 0) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1;
     } else {
-        const double *src = a.inj + (size_t)inst * g.n_inj;
-        if (lane < nu) { u_vm = src[ng + lane]; if (lane >= nh) u_p = src[lane - nh]; }
-        if (lane < nld) { l_p = src[ng + nu + lane]; l_q = src[ng + nu + nld + lane]; }
-        if (lane < nst) s_p = src[ng + nu + 2 * nld + lane];
-        if (lane < nsh) { sh_p = src[ng + nu + 2 * nld + nst + lane]; sh_q = src[ng + nu + 2 * nld + nst + nsh + lane]; }
+        const double *sp = a.inj + (size_t)src * g.n_inj;
+        if (lane < nu) { u_vm = sp[ng + lane]; if (lane >= nh) u_p = sp[lane - nh]; }
+        if (lane < nld) { l_p = sp[ng + nu + lane]; l_q = sp[ng + nu + nld + lane]; }
+        if (lane < nst) s_p = sp[ng + nu + 2 * nld + lane];
+        if (lane < nsh) { sh_p = sp[ng + nu + 2 * nld + nst + lane]; sh_q = sp[ng + nu + 2 * nld + nst + nsh + lane]; }
     }
 
     // ---- 1. topology: active bus slots as a bit mask ------------------------------------------------
     int slot_o = -1, slot_e = -1, slot_u = -1, slot_k = -1, slot_s = -1, slot_h = -1;
-    if (lane < nl) {
+    if (lane < nl && lane != outage) {
         const int bo = tv[g.line_or_pos[lane]], be = tv[g.line_ex_pos[lane]];
         if (bo > 0) slot_o = g.line_or_sub[lane] + (bo - 1) * g.n_sub;
         if (be > 0) slot_e = g.line_ex_sub[lane] + (be - 1) * g.n_sub;
@@ -408,8 +410,10 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
                 r[0] = (float)pf; r[1] = (float)qf; r[2] = __fmul_rn((float)vmf, vnf); r[3] = a1; r[4] = (float)(vaf * RAD2DEG);
                 r[5] = (float)pt; r[6] = (float)qt; r[7] = __fmul_rn((float)vmt, vnt); r[8] = a2; r[9] = (float)(vat * RAD2DEG);
             }
+            if (out) {
 #pragma unroll
-            for (int k = 0; k < 10; ++k) out[k * nl + lane] = r[k];
+                for (int k = 0; k < 10; ++k) out[k * nl + lane] = r[k];
+            }
             if (a.rho) a.rho[(size_t)inst * nl + lane] = r[3] / a.th_lim[lane];
         }
     }
@@ -418,7 +422,7 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         const double Pb = shfl_d(P, su), Qb = shfl_d(Q, su), pdb = shfl_d(pd, su), qdb = shfl_d(qd, su), pnr = shfl_d(pnonref, su);
         const double qmn = shfl_d(qmins, su), qmx = shfl_d(qmaxs, su), vmb = shfl_d(vm, su), vab = shfl_d(va, su);
         const int cb = __shfl_sync(FULL, cnt, su), nrb = __shfl_sync(FULL, nref, su);
-        if (lane < nu) {
+        if (lane < nu && out) {
             float p = 0.f, q = 0.f, v = 0.f, th = 0.f;
             if (bu >= 0) {
                 double pu = u_p;
@@ -436,17 +440,17 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         }
         const int sk = bk >= 0 ? bk : 0;
         const double vmk = shfl_d(vm, sk), vak = shfl_d(va, sk);
-        if (lane < nld) {
+        if (lane < nld && out) {
             float *o = out + 10 * nl + 4 * nu;
             o[lane] = bk >= 0 ? __fmul_rn((float)vmk, g.load_vn[lane]) : 0.f;
             o[nld + lane] = bk >= 0 ? (float)(vak * RAD2DEG) : 0.f;
         }
         const int ss = bs >= 0 ? bs : 0;
         const double vms = shfl_d(vm, ss);
-        if (lane < nst) out[10 * nl + 4 * nu + 2 * nld + lane] = bs >= 0 ? __fmul_rn((float)vms, g.sto_vn[lane]) : 0.f;
+        if (lane < nst && out) out[10 * nl + 4 * nu + 2 * nld + lane] = bs >= 0 ? __fmul_rn((float)vms, g.sto_vn[lane]) : 0.f;
         const int sh = bh >= 0 ? bh : 0;
         const double vmh = shfl_d(vm, sh);
-        if (lane < nsh) {
+        if (lane < nsh && out) {
             float *o = out + 10 * nl + 4 * nu + 2 * nld + nst;
             float p = 0.f, q = 0.f, v = 0.f;
             if (bh >= 0) {

@@ -30,7 +30,7 @@ ABI_SYMBOLS = (
     "b200pf_series_step", "b200pf_series_results", "b200pf_series_fetch", "b200pf_sync", "b200pf_stream",
     "b200pf_launch_count", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
     "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
-    "b200pf_run_rows_staged",
+    "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host",
 )
 
 
@@ -93,6 +93,8 @@ def load_library():
     lib.b200pf_set_static_inj.argtypes = [vp, vp]
     lib.b200pf_rows_staging.argtypes = [vp, C.POINTER(vp)]
     lib.b200pf_run_rows_staged.argtypes = [vp, i32, i32, i32, f64, i32]
+    lib.b200pf_set_thermal_limit.argtypes = [vp, vp]
+    lib.b200pf_n1_host.argtypes = [vp, i32, vp, vp, i32, f64, i32, vp, vp]
     lib.b200pf_stream.argtypes = [vp]
     lib.b200pf_stream.restype = C.c_uint64
     lib.b200pf_launch_count.argtypes = [vp]
@@ -102,7 +104,7 @@ def load_library():
                "b200pf_series_bind", "b200pf_series_set_topo", "b200pf_series_step", "b200pf_series_results",
                "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
                "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
-               "b200pf_run_rows_staged"):
+               "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host"):
         getattr(lib, nm).restype = i32
     _LIB = lib
     return lib
@@ -285,6 +287,24 @@ class PowerFlowEngine:
     def run_rows_staged(self, batch: int, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0):
         self._check(self.lib.b200pf_run_rows_staged(self.h, int(batch), int(bool(is_dc)), int(max_iter), float(tol_mva),
                                                     int(nb_cap)), "b200pf_run_rows_staged")
+
+    def n1_sweep(self, topo: np.ndarray, inj: np.ndarray, thermal_limit_a: Optional[np.ndarray] = None,
+                 max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = -1):
+        """All single-line outages of every base state in one launch.  Returns ``rho [B, n_line(outage), n_line]``
+        and ``status [B, n_line]`` (reference pattern: examples/backend_dependant_code/_obs_with_n1.py:111-125)."""
+        gm = self.gm
+        topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(-1, gm.n_topo_in)
+        inj = np.ascontiguousarray(inj, dtype=np.float64).reshape(-1, gm.n_inj)
+        B = topo.shape[0]
+        th = np.ascontiguousarray(gm.thermal_limit_a if thermal_limit_a is None else thermal_limit_a, dtype=np.float32)
+        self._check(self.lib.b200pf_set_thermal_limit(self.h, _ptr(th)), "b200pf_set_thermal_limit")
+        if nb_cap < 0:
+            nb_cap = self.max_active_buses(topo)      # an outage can only remove buses
+        rho = np.empty((B, gm.n_line, gm.n_line), dtype=np.float32)
+        status = np.empty((B, gm.n_line), dtype=np.int32)
+        self._check(self.lib.b200pf_n1_host(self.h, B, _ptr(topo), _ptr(inj), int(max_iter), float(tol_mva), int(nb_cap),
+                                            _ptr(rho), _ptr(status)), "b200pf_n1_host")
+        return rho, status
 
     def set_stream(self, stream: int):
         self._check(self.lib.b200pf_set_stream(self.h, C.c_uint64(int(stream))), "b200pf_set_stream")

@@ -144,6 +144,16 @@ int b200pf_run_staged(b200pf_handle *h, int batch, int is_dc, int max_iter, doub
  * handle's own buffer for that array */
 int b200pf_series_bind_outputs(b200pf_handle *h, float *d_out, int32_t *d_status, int32_t *d_iters,
                                float *d_rho);
+/* N-1 contingency sweep (the reference's pattern: copy_public(); _disconnect_line(i); runpf();
+ * get_relative_flow() for every line i - examples/backend_dependant_code/_obs_with_n1.py:111-125, and
+ * obs.simulate, grid2op/Observation/baseObservation.py:3365): batch base states x n_line single-line
+ * outages = batch*n_line independent AC power flows in ONE launch sharing the base records.
+ *   rho    f32   [batch][n_line outages][n_line]   a_or / thermal_limit (NaN rows where the flow diverged)
+ *   status int32 [batch][n_line]
+ * Host pointers; thermal limits from b200pf_set_thermal_limit.  batch*n_line must be <= max_batch. */
+int b200pf_set_thermal_limit(b200pf_handle *h, const float *thermal_limit_a /* [n_line] */);
+int b200pf_n1_host(b200pf_handle *h, int batch, const int8_t *topo, const double *inj, int max_iter,
+                   double tol_mva, int nb_cap, float *rho, int32_t *status);
 /* "rows" entry point: like b200pf_run_staged but the injections of this step come as the float32
  * chronics ROW of every instance (load_p, load_q, prod_p, prod_v[kV]; 2 n_load + 2 n_gen values, backend
  * element order) written by the caller into the pinned rows staging buffer (b200pf_rows_staging);
