@@ -43,6 +43,9 @@ struct b200pf_handle {
     float *d_chron = nullptr; int *d_scen = nullptr; int *d_t = nullptr; double *d_static_inj = nullptr;
     float *d_thlim = nullptr; float *d_rho = nullptr; int8_t *d_series_topo = nullptr;
     int series_batch = 0, n_scen = 0, n_rows = 0;
+    int *d_pcount = nullptr, *d_tsover = nullptr, *d_disc = nullptr, *d_done = nullptr;
+    int prot = 0, next_reset = 0, max_pc = 2; float hard_thr = 2.0f, soft_thr = 1.0f;
+    int small_ok = 0;
     int64_t launches = 0;
     int last_smem = 0, last_T = 0, last_grid = 0, last_block = 0;
 };
@@ -212,7 +215,7 @@ static int launch_small(b200pf_handle *h, RunArgs a, int cap) {
     a.nb_cap = cap;
     SmallLayout L = small_layout(cap);
     a.mat_bytes = L.total - L.off_mat;
-    auto kern = pf_kernel_small;
+    auto kern = a.prot ? pf_kernel_small<true> : pf_kernel_small<false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     int occ = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, (size_t)L.total));
@@ -242,6 +245,7 @@ static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
     if (!jd && !(nos && nos[0] == '1') && g.n_slot <= 32 && g.n_line <= 32 && g.n_unit <= 32 && g.n_load <= 32 &&
         g.n_sto <= 32 && g.n_shunt <= 32 && cap <= 17)
         return launch_small(h, a, cap);
+    if (a.prot) return fail(B200PF_E_STATE, "device-side protections need the warp-per-instance kernel (<= 32 lines / bus slots, nb_cap <= 17)");
     const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
     size_t want = ws_mat_worst(cap, jt);
     int T = 32;
@@ -340,8 +344,12 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
     int rc;
     if ((rc = dmal((void **)&h->d_chron, (size_t)n_scen * n_rows * ncol * 4)) || (rc = dmal((void **)&h->d_scen, (size_t)batch * 4)) ||
         (rc = dmal((void **)&h->d_t, (size_t)batch * 4)) ||
-        (rc = dmal((void **)&h->d_series_topo, (size_t)batch * g.n_topo_in)))
+        (rc = dmal((void **)&h->d_series_topo, (size_t)batch * g.n_topo_in)) ||
+        (rc = dmal((void **)&h->d_pcount, (size_t)batch * g.n_line * 4)) || (rc = dmal((void **)&h->d_tsover, (size_t)batch * g.n_line * 4)) ||
+        (rc = dmal((void **)&h->d_disc, (size_t)batch * g.n_line * 4)) || (rc = dmal((void **)&h->d_done, (size_t)batch * 4)))
         return rc;
+    CU(cudaMemset(h->d_pcount, 0, (size_t)batch * g.n_line * 4)); CU(cudaMemset(h->d_tsover, 0, (size_t)batch * g.n_line * 4));
+    CU(cudaMemset(h->d_disc, 0xff, (size_t)batch * g.n_line * 4)); CU(cudaMemset(h->d_done, 0, (size_t)batch * 4));
     CU(cudaMemcpy(h->d_chron, chron_host, (size_t)n_scen * n_rows * ncol * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_scen, scen, (size_t)batch * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_t, t0, (size_t)batch * 4, cudaMemcpyHostToDevice));
@@ -369,7 +377,38 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
     a.iters = h->x_iters ? h->x_iters : h->d_iters; a.busv = nullptr;
     a.series = 1; a.chron = h->d_chron; a.n_scen = h->n_scen; a.n_rows = h->n_rows; a.scen = h->d_scen; a.t = h->d_t;
     a.static_inj = h->d_static_inj; a.th_lim = h->d_thlim; a.rho = h->x_rho ? h->x_rho : h->d_rho;
+    if (h->prot) {
+        a.prot = 1; a.from_reset = h->next_reset; a.max_pc = h->max_pc; a.hard_thr = h->hard_thr; a.soft_thr = h->soft_thr;
+        a.pcount = h->d_pcount; a.ts_over = h->d_tsover; a.disc = h->d_disc; a.done = h->d_done;
+    }
+    h->next_reset = 0;
     return launch(h, a, nb_cap);
+}
+
+extern "C" int b200pf_series_protections(b200pf_handle *h, int enabled, float hard_thr, float soft_thr, int max_allowed) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
+    h->prot = enabled ? 1 : 0; h->hard_thr = hard_thr; h->soft_thr = soft_thr; h->max_pc = max_allowed;
+    return 0;
+}
+
+extern "C" int b200pf_series_next_is_reset(b200pf_handle *h) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    h->next_reset = 1;
+    return 0;
+}
+
+extern "C" int b200pf_series_fetch_state(b200pf_handle *h, int32_t *pc, int32_t *tso, int32_t *disc, int32_t *done) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t B = (size_t)h->series_batch, nl = (size_t)h->g.n_line;
+    if (pc) CU(cudaMemcpy(pc, h->d_pcount, B * nl * 4, cudaMemcpyDeviceToHost));
+    if (tso) CU(cudaMemcpy(tso, h->d_tsover, B * nl * 4, cudaMemcpyDeviceToHost));
+    if (disc) CU(cudaMemcpy(disc, h->d_disc, B * nl * 4, cudaMemcpyDeviceToHost));
+    if (done) CU(cudaMemcpy(done, h->d_done, B * 4, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 extern "C" int b200pf_series_results(b200pf_handle *h, float **d_out, int32_t **d_status, int32_t **d_iters, float **d_rho, int32_t **d_t) {

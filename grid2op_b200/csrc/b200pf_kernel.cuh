@@ -56,6 +56,13 @@ struct RunArgs {
     // time-series mode
     int series;
     const float *chron;
+    // protections / cascading failure (series mode; reference Backend.next_grid_state, backend.py:1433-1521)
+    int prot, from_reset, max_pc;
+    float hard_thr, soft_thr;
+    int *pcount;            // [B][n_line] protection counters of the environment (in/out)
+    int *ts_over;           // [B][n_line] consecutive time steps in overflow (in/out)
+    int *disc;              // [B][n_line] out: cascade iteration at which the line was disconnected, else -1
+    int *done;              // [B] in/out: 1 once an instance is game over
     int n1_lines;           // > 0: contingency mode, instance = (base state, outage line) pair, base = inst / n1_lines
     const float *rows;      // rows mode: float32 [batch][2 n_load + 2 n_gen] for this very step (overrides chron)
     int n_scen, n_rows;
@@ -66,7 +73,7 @@ struct RunArgs {
     float *rho;
 };
 
-enum { ST_OK = 0, ST_DIV = 1, ST_UNSUP = 2, ST_NOREF = 3, ST_LARGE = 4 };
+enum { ST_OK = 0, ST_DIV = 1, ST_UNSUP = 2, ST_NOREF = 3, ST_LARGE = 4, ST_DONE = 5 };
 enum { BT_PQ = 1, BT_PV = 2, BT_REF = 3 };
 
 // ---------------------------------------------------------------------------------------------

@@ -100,13 +100,15 @@ __device__ __forceinline__ bool gj_small_d(const double *M, int n, int pitch, do
 
 __device__ __forceinline__ void small_fail(const DevGrid &g, const RunArgs &a, int inst, int status, int iters, int lane) {
     float *out = a.out ? a.out + (size_t)inst * g.n_out : nullptr;
-    if (lane == 0) { a.status[inst] = status; a.iters[inst] = iters; }
+    if (lane == 0) { a.status[inst] = status; a.iters[inst] = iters; if (a.done) a.done[inst] = 1; }
+    if (a.disc && status == ST_DONE) for (int k = lane; k < g.n_line; k += 32) a.disc[(size_t)inst * g.n_line + k] = -1;
     if (out) for (int k = lane; k < g.n_out; k += 32) out[k] = qnanf();
     if (a.busv) for (int k = lane; k < 2 * g.n_slot; k += 32) a.busv[(size_t)inst * 2 * g.n_slot + k] = __longlong_as_double(0x7ff8000000000000LL);
     if (a.rho) for (int k = lane; k < g.n_line; k += 32) a.rho[(size_t)inst * g.n_line + k] = qnanf();
     __syncwarp();
 }
 
+template <bool PROT>
 __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayout &L, int inst, unsigned char *sm, int lane) {
     const unsigned FULL = 0xffffffffu;
     double2 *Vs = reinterpret_cast<double2 *>(sm + L.off_V);
@@ -152,9 +154,15 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         if (lane < nsh) { sh_p = sp[ng + nu + 2 * nld + nst + lane]; sh_q = sp[ng + nu + 2 * nld + nst + nsh + lane]; }
     }
 
+    // protections state (lane = line)
+    if (PROT && a.done[inst]) { small_fail(g, a, inst, ST_DONE, 0, lane); return; }
+    int pc_env = 0, pc = 0, disc_it = -1;
+    bool forced_off = false, inc_done = false;
+    if (PROT && lane < nl) { pc_env = a.pcount[(size_t)inst * nl + lane]; pc = pc_env; }
+    for (int casc = 0;; ++casc) {
     // ---- 1. topology: active bus slots as a bit mask ------------------------------------------------
     int slot_o = -1, slot_e = -1, slot_u = -1, slot_k = -1, slot_s = -1, slot_h = -1;
-    if (lane < nl && lane != outage) {
+    if (lane < nl && lane != outage && !(PROT && forced_off)) {
         const int bo = tv[g.line_or_pos[lane]], be = tv[g.line_ex_pos[lane]];
         if (bo > 0) slot_o = g.line_or_sub[lane] + (bo - 1) * g.n_sub;
         if (be > 0) slot_e = g.line_ex_sub[lane] + (be - 1) * g.n_sub;
@@ -388,34 +396,59 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
 
     // ---- 7. results -------------------------------------------------------------------------------------
     if (lane == 0) { a.status[inst] = ST_OK; a.iters[inst] = iters; }
+    float r[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     {   // lines (lane = line): flows from the currents of the last mismatch evaluation
         const int sf_ = bf >= 0 ? bf : 0, st_ = bt >= 0 ? bt : 0;
         const double vmf = shfl_d(vm, sf_), vmt = shfl_d(vm, st_), vaf = shfl_d(va, sf_), vat = shfl_d(va, st_);
-        if (lane < nl) {
-            float r[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (bf >= 0) {
-                double pf, qf, pt, qt, sf, st;
-                if (a.is_dc) {
-                    pf = cur[2 * lane].x * base; pt = -pf; qf = 0.0; qt = 0.0; sf = fabs(pf); st = sf;
-                } else {
-                    const double2 A = Vs[bf], B = Vs[bt], If = cur[2 * lane], It = cur[2 * lane + 1];
-                    pf = (A.x * If.x + A.y * If.y) * base; qf = (A.y * If.x - A.x * If.y) * base;
-                    pt = (B.x * It.x + B.y * It.y) * base; qt = (B.y * It.x - B.x * It.y) * base;
-                    sf = sqrt(pf * pf + qf * qf); st = sqrt(pt * pt + qt * qt);
-                }
-                const float vnf = g.line_or_vn[lane], vnt = g.line_ex_vn[lane];
-                float a1 = (float)(sf / (SQRT3 * (vmf * (double)vnf)) * 1000.0), a2 = (float)(st / (SQRT3 * (vmt * (double)vnt)) * 1000.0);
-                if (!isfinite(a1)) a1 = 0.f;
-                if (!isfinite(a2)) a2 = 0.f;
-                r[0] = (float)pf; r[1] = (float)qf; r[2] = __fmul_rn((float)vmf, vnf); r[3] = a1; r[4] = (float)(vaf * RAD2DEG);
-                r[5] = (float)pt; r[6] = (float)qt; r[7] = __fmul_rn((float)vmt, vnt); r[8] = a2; r[9] = (float)(vat * RAD2DEG);
+        if (lane < nl && bf >= 0) {
+            double pf, qf, pt, qt, sf, st;
+            if (a.is_dc) {
+                pf = cur[2 * lane].x * base; pt = -pf; qf = 0.0; qt = 0.0; sf = fabs(pf); st = sf;
+            } else {
+                const double2 A = Vs[bf], B = Vs[bt], If = cur[2 * lane], It = cur[2 * lane + 1];
+                pf = (A.x * If.x + A.y * If.y) * base; qf = (A.y * If.x - A.x * If.y) * base;
+                pt = (B.x * It.x + B.y * It.y) * base; qt = (B.y * It.x - B.x * It.y) * base;
+                sf = sqrt(pf * pf + qf * qf); st = sqrt(pt * pt + qt * qt);
             }
-            if (out) {
-#pragma unroll
-                for (int k = 0; k < 10; ++k) out[k * nl + lane] = r[k];
-            }
-            if (a.rho) a.rho[(size_t)inst * nl + lane] = r[3] / a.th_lim[lane];
+            const float vnf = g.line_or_vn[lane], vnt = g.line_ex_vn[lane];
+            float a1 = (float)(sf / (SQRT3 * (vmf * (double)vnf)) * 1000.0), a2 = (float)(st / (SQRT3 * (vmt * (double)vnt)) * 1000.0);
+            if (!isfinite(a1)) a1 = 0.f;
+            if (!isfinite(a2)) a2 = 0.f;
+            r[0] = (float)pf; r[1] = (float)qf; r[2] = __fmul_rn((float)vmf, vnf); r[3] = a1; r[4] = (float)(vaf * RAD2DEG);
+            r[5] = (float)pt; r[6] = (float)qt; r[7] = __fmul_rn((float)vmt, vnt); r[8] = a2; r[9] = (float)(vat * RAD2DEG);
         }
+    }
+    if (PROT) {
+        // cascading failure step (reference Backend.next_grid_state, backend.py:1466-1521), lane = line
+        const bool on = lane < nl && bf >= 0;
+        const float lim = lane < nl ? a.th_lim[lane] : 0.f;
+        bool to_disc = on && (r[3] > __fmul_rn(a.hard_thr, lim));
+        const bool mask_inc = !a.from_reset && on && (r[3] > __fmul_rn(a.soft_thr, lim)) && !inc_done;
+        if (mask_inc) { pc += 1; inc_done = true; }
+        if (on && pc > a.max_pc) to_disc = true;
+        if (__any_sync(FULL, to_disc)) {
+            if (to_disc) { forced_off = true; disc_it = casc; }
+            __syncwarp();
+            continue;                                   // re-solve with the lines removed
+        }
+        if (lane < nl) {
+            int *pcp = a.pcount + (size_t)inst * nl, *tsp = a.ts_over + (size_t)inst * nl;
+            // counters: baseEnv.py:3361-3370; Environment.reset() zeroes them after its step (baseEnv.py:3969-3970)
+            pcp[lane] = (!a.from_reset && r[3] > __fmul_rn(a.soft_thr, lim)) ? pc_env + 1 : 0;
+            tsp[lane] = (!a.from_reset && r[3] > lim) ? tsp[lane] + 1 : 0;
+            a.disc[(size_t)inst * nl + lane] = disc_it;
+            if (forced_off) {                           // persist the outage (_BackendAction.update_state)
+                int8_t *tw = const_cast<int8_t *>(tv);
+                tw[g.line_or_pos[lane]] = -1; tw[g.line_ex_pos[lane]] = -1;
+            }
+        }
+    }
+    if (lane < nl) {
+        if (out) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) out[k * nl + lane] = r[k];
+        }
+        if (a.rho) a.rho[(size_t)inst * nl + lane] = r[3] / a.th_lim[lane];
     }
     {   // units (lane = unit), loads, storages, shunts: read their bus through shuffles
         const int su = bu >= 0 ? bu : 0;
@@ -469,14 +502,17 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         if (isbus) { bv[myslot] = vm; bv[g.n_slot + myslot] = va; }
     }
     __syncwarp();
+    break;
+    }   // cascade loop
 #undef CIDX
 }
 
+template <bool PROT>
 __global__ void __launch_bounds__(32, B200PF_MIN_WARP_CTAS)
 pf_kernel_small(const DevGrid g, const RunArgs a, const SmallLayout L) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x;
-    for (int inst = blockIdx.x; inst < a.batch; inst += gridDim.x) solve_small(g, a, L, inst, smem, lane);
+    for (int inst = blockIdx.x; inst < a.batch; inst += gridDim.x) solve_small<PROT>(g, a, L, inst, smem, lane);
 }
 
 }  // namespace b200pf

@@ -30,7 +30,8 @@ ABI_SYMBOLS = (
     "b200pf_series_step", "b200pf_series_results", "b200pf_series_fetch", "b200pf_sync", "b200pf_stream",
     "b200pf_launch_count", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
     "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
-    "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host",
+    "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
+    "b200pf_series_next_is_reset", "b200pf_series_fetch_state",
 )
 
 
@@ -95,6 +96,9 @@ def load_library():
     lib.b200pf_run_rows_staged.argtypes = [vp, i32, i32, i32, f64, i32]
     lib.b200pf_set_thermal_limit.argtypes = [vp, vp]
     lib.b200pf_n1_host.argtypes = [vp, i32, vp, vp, i32, f64, i32, vp, vp]
+    lib.b200pf_series_protections.argtypes = [vp, i32, C.c_float, C.c_float, i32]
+    lib.b200pf_series_next_is_reset.argtypes = [vp]
+    lib.b200pf_series_fetch_state.argtypes = [vp, vp, vp, vp, vp]
     lib.b200pf_stream.argtypes = [vp]
     lib.b200pf_stream.restype = C.c_uint64
     lib.b200pf_launch_count.argtypes = [vp]
@@ -104,7 +108,8 @@ def load_library():
                "b200pf_series_bind", "b200pf_series_set_topo", "b200pf_series_step", "b200pf_series_results",
                "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
                "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
-               "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host"):
+               "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
+               "b200pf_series_next_is_reset", "b200pf_series_fetch_state"):
         getattr(lib, nm).restype = i32
     _LIB = lib
     return lib
@@ -346,6 +351,23 @@ class PowerFlowEngine:
         rho = np.empty((B, gm.n_line), dtype=np.float32) if want_rho else None
         self._check(self.lib.b200pf_series_fetch(self.h, _ptr(out), _ptr(status), _ptr(iters), _ptr(rho)), "b200pf_series_fetch")
         return out, status, iters, rho
+
+    def series_protections(self, enabled: bool = True, hard_overflow_threshold: float = 2.0,
+                           soft_overflow_threshold: float = 1.0, nb_timestep_overflow_allowed: int = 2):
+        """Defaults = grid2op.Parameters defaults (Parameters.py:255-270)."""
+        self._check(self.lib.b200pf_series_protections(self.h, int(bool(enabled)), float(hard_overflow_threshold),
+                                                       float(soft_overflow_threshold), int(nb_timestep_overflow_allowed)),
+                    "b200pf_series_protections")
+
+    def series_next_is_reset(self):
+        self._check(self.lib.b200pf_series_next_is_reset(self.h), "b200pf_series_next_is_reset")
+
+    def series_fetch_state(self):
+        gm, B = self.gm, self._series_batch
+        pc = np.empty((B, gm.n_line), dtype=np.int32); tso = np.empty((B, gm.n_line), dtype=np.int32)
+        disc = np.empty((B, gm.n_line), dtype=np.int32); done = np.empty(B, dtype=np.int32)
+        self._check(self.lib.b200pf_series_fetch_state(self.h, _ptr(pc), _ptr(tso), _ptr(disc), _ptr(done)), "b200pf_series_fetch_state")
+        return dict(protection_counter=pc, timestep_overflow=tso, disc_lines=disc, done=done)
 
     def series_device_pointers(self):
         p = [C.c_void_p() for _ in range(5)]

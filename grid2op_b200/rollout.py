@@ -32,18 +32,31 @@ def instance_schedule(n: int, n_scen: int, n_rows: int, offset: int = 0):
 
 class BatchedDoNothing:
     def __init__(self, gm: GridModel, chron: np.ndarray, batch: int, device: int = 0, offset: int = 0,
-                 max_iter: int = 10, tol_mva: float = 1e-8, is_dc: bool = False):
+                 max_iter: int = 10, tol_mva: float = 1e-8, is_dc: bool = False, scen: Optional[np.ndarray] = None,
+                 t0: Optional[np.ndarray] = None, thermal_limit_a: Optional[np.ndarray] = None,
+                 protections: bool = False, hard_overflow_threshold: float = 2.0, soft_overflow_threshold: float = 1.0,
+                 nb_timestep_overflow_allowed: int = 2):
         self.gm = gm
         self.batch = int(batch)
         self.chron = np.ascontiguousarray(chron, dtype=np.float32)
         assert self.chron.ndim == 3 and self.chron.shape[2] == 2 * gm.n_load + 2 * gm.n_gen
         self.scen, self.t0 = instance_schedule(self.batch, self.chron.shape[0], self.chron.shape[1], offset)
+        if scen is not None:
+            self.scen = np.ascontiguousarray(scen, dtype=np.int32)
+        if t0 is not None:
+            self.t0 = np.ascontiguousarray(t0, dtype=np.int32)
+        self.thermal_limit_a = np.ascontiguousarray(gm.thermal_limit_a if thermal_limit_a is None else thermal_limit_a,
+                                                    dtype=np.float32)
         self.engine = PowerFlowEngine(gm, max_batch=self.batch, device=device)
         self.max_iter, self.tol_mva, self.is_dc = int(max_iter), float(tol_mva), bool(is_dc)
         self.topo0 = np.tile(gm.default_topo(), (self.batch, 1))
         self.nb_cap = int(np.count_nonzero(np.bincount(self._slots(gm.default_topo()), minlength=gm.n_slot)))
-        self.engine.series_bind(self.chron, self.scen, self.t0, gm.default_inj(), gm.thermal_limit_a)
+        self.engine.series_bind(self.chron, self.scen, self.t0, gm.default_inj(), self.thermal_limit_a)
         self.engine.series_set_topo(self.topo0)
+        self.protections = bool(protections)
+        if self.protections:
+            # Backend.next_grid_state on the device: hard / soft overflow disconnections + cascade re-solves
+            self.engine.series_protections(True, hard_overflow_threshold, soft_overflow_threshold, nb_timestep_overflow_allowed)
         # host path state
         self._t_host = self.t0.astype(np.int64).copy()
         self._stage = None
@@ -64,8 +77,18 @@ class BatchedDoNothing:
         """Asynchronous: one fused kernel for the whole batch; results stay in HBM."""
         self.engine.series_step(is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva, nb_cap=self.nb_cap)
 
+    def reset_step(self) -> None:
+        """The step an environment performs inside ``reset()``: same solve, but no soft-overflow counting
+        (reference grid2op/Backend/backend.py:1488-1490, ``_called_from_reset``)."""
+        self.engine.series_next_is_reset()
+        self.step_device()
+
     def fetch(self):
         return self.engine.series_fetch()
+
+    def fetch_state(self):
+        """protection_counter / timestep_overflow / disc_lines [batch, n_line], done [batch]."""
+        return self.engine.series_fetch_state()
 
     # ---- host buffers in / out --------------------------------------------------------------------
     def step_host(self):

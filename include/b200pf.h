@@ -60,7 +60,8 @@ enum {
     B200PF_ST_DIVERGED = 1,   /* Newton did not reach the tolerance / singular matrix / NaN */
     B200PF_ST_UNSUPPLIED = 2, /* an in-service bus is not connected to a reference bus */
     B200PF_ST_NO_REF = 3,     /* no reference unit in service */
-    B200PF_ST_TOO_LARGE = 4   /* more active buses than the launch was sized for (nb_cap) */
+    B200PF_ST_TOO_LARGE = 4,  /* more active buses than the launch was sized for (nb_cap) */
+    B200PF_ST_DONE = 5        /* series mode with protections: the instance diverged at an earlier step */
 };
 
 /* Static grid description (host pointers, copied at create).  Element order = the reference's
@@ -127,6 +128,20 @@ int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int n_scen, in
                        const float *thermal_limit_a /* [n_line] */);
 int b200pf_series_set_topo(b200pf_handle *h, const int8_t *topo /* [batch][n_topo_in] host */);
 int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, double tol_mva, int nb_cap);
+/* Protections / cascading failure inside the series step (reference Backend.next_grid_state,
+ * grid2op/Backend/backend.py:1433-1521, and the counters of BaseEnv._aux_register_env_converged,
+ * grid2op/Environment/baseEnv.py:3361-3370): lines whose flow exceeds hard_thr * limit, or that stayed above
+ * soft_thr * limit for more than max_allowed consecutive steps, are disconnected and the flow is re-solved
+ * until no line trips; the outages persist in the device topology; an instance whose flow diverges is
+ * "done" (B200PF_ST_DONE from then on).  enabled = 0 restores NO_OVERFLOW_DISCONNECTION.
+ * Round 1: available when the warp-per-instance kernel applies (<= 32 lines / bus slots). */
+int b200pf_series_protections(b200pf_handle *h, int enabled, float hard_thr, float soft_thr, int max_allowed);
+/* the NEXT series step is an environment reset step: no soft-overflow counting (backend.py:1488-1490) */
+int b200pf_series_next_is_reset(b200pf_handle *h);
+/* host copies of the protection state after the last step (any pointer may be NULL):
+ * counters / timestep_overflow / disc_lines int32 [batch][n_line], done int32 [batch] */
+int b200pf_series_fetch_state(b200pf_handle *h, int32_t *protection_counter, int32_t *timestep_overflow,
+                              int32_t *disc_lines, int32_t *done);
 /* device pointers of the resident results of the last series step (valid until destroy) */
 int b200pf_series_results(b200pf_handle *h, float **d_out, int32_t **d_status, int32_t **d_iters,
                           float **d_rho, int32_t **d_t);

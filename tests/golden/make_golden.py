@@ -99,7 +99,18 @@ def oracle_steps(gm, chron, n=48):
                         out=out, busv=busv, iters=iters)
 
 
+def case5_chronics():
+    """all 20 scenarios of rte_case5_example through the package's own chronics reader (backend order)."""
+    from grid2op_b200.chronics import load_scenarios
+    env = "rte_case5_example"
+    gm = GridModel(os.path.join(REF, env, "grid.json"))
+    chron = load_scenarios(os.path.join(REF, env, "chronics"), gm)
+    np.savez_compressed(os.path.join(HERE, "case5_chronics.npz"), chron=chron)
+    return chron
+
+
 if __name__ == "__main__":
+    print("case5 chronics", case5_chronics().shape)
     stored_results()
     gm, chron = case14_chronics()
     print("chronics", chron.shape, chron.dtype)

@@ -1,0 +1,48 @@
+"""The package's chronics reader returns what grid2op's own GridStateFromFile serves to the backend
+(reference grid2op/Chronics/gridStateFromFile.py:749-808): same rows, columns re-ordered by NAME."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import env_grid, grid2op_root
+
+from grid2op_b200.chronics import load_scenario, load_scenarios
+from grid2op_b200.gridmodel import GridModel
+
+
+@pytest.mark.parametrize("env_name,scen", [("l2rpn_case14_sandbox", "0001"), ("rte_case5_example", "03")])
+def test_reader_matches_grid2op_loader(env_name, scen):
+    path = env_grid(env_name)
+    if path is None:
+        pytest.skip("reference data not available")
+    from grid2op_b200._bootstrap import ensure_grid2op
+    if not ensure_grid2op():
+        pytest.skip("grid2op not importable")
+    from grid2op.Chronics import GridStateFromFile
+    gm = GridModel(path)
+    folder = os.path.join(os.path.dirname(path), "chronics", scen)
+    mine = load_scenario(folder, gm)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gs = GridStateFromFile(path=folder, sep=";")
+        gs.initialize(order_backend_loads=list(gm.name_load), order_backend_prods=list(gm.name_gen),
+                      order_backend_lines=list(gm.name_line), order_backend_subs=list(gm.name_sub))
+    nl, ng = gm.n_load, gm.n_gen
+    n = min(mine.shape[0], gs.load_p.shape[0])
+    assert n >= 100
+    assert np.array_equal(mine[:n, :nl], gs.load_p[:n].astype(np.float32))
+    assert np.array_equal(mine[:n, nl:2 * nl], gs.load_q[:n].astype(np.float32))
+    assert np.array_equal(mine[:n, 2 * nl:2 * nl + ng], gs.prod_p[:n].astype(np.float32))
+    assert np.array_equal(mine[:n, 2 * nl + ng:], gs.prod_v[:n].astype(np.float32))
+
+
+def test_committed_fixture_is_what_the_reader_produces():
+    path = env_grid("l2rpn_case14_sandbox")
+    if path is None:
+        pytest.skip("reference data not available")
+    gm = GridModel(path)
+    chron = load_scenarios(os.path.join(os.path.dirname(path), "chronics"), gm)
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "case14_sandbox_chronics.npz"))["chron"]
+    assert np.array_equal(chron, fix)

@@ -1,0 +1,79 @@
+"""Device-side protections (cascading failure inside the series step) replay the reference's recorded
+DoNothing rollouts of rte_case5_example (grid2op/data/rte_case5_example/_statistics: PandaPowerBackend, AC,
+NB_TIMESTEP_OVERFLOW_ALLOWED=2, HARD_OVERFLOW_THRESHOLD=2): all 20 scenarios as ONE batch of 20 instances,
+every step one fused kernel launch, no host logic in the loop.  Lines must trip at the same step, the game
+must be over at the same step, and every observed quantity must match the recording."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import grid2op_root
+
+from grid2op_b200.gridmodel import GridModel
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_batched_rollout_with_protections_matches_recording(cuda_required):
+    root = grid2op_root()
+    stat = os.path.join(root, "data", "rte_case5_example", "_statistics") if root else None
+    if stat is None or not os.path.isdir(stat):
+        pytest.skip("reference rollouts not available")
+    from grid2op_b200.engine import OutputView
+    from grid2op_b200.rollout import BatchedDoNothing
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_rte_case5_example.npz"))
+    chron = np.load(os.path.join(GOLD, "case5_chronics.npz"))["chron"]
+    meta = json.load(open(os.path.join(stat, "metadata.json")))
+    keys = ["p_or", "q_or", "v_or", "a_or", "p_ex", "q_ex", "v_ex", "a_ex", "prod_p", "prod_q", "prod_v", "load_v", "rho",
+            "line_status", "timestep_overflow"]
+    gold = {k: np.load(os.path.join(stat, f"obs_{k}.npz"))["data"] for k in keys}
+    sid = np.load(os.path.join(stat, "scenario_ids.npz"))["data"].ravel().astype(int)
+    rows = {s: np.flatnonzero(sid == s) for s in range(20)}
+    nb_step = np.array([meta[str(s)]["nb_step"] for s in range(20)])
+    B = 20
+    env = BatchedDoNothing(gm, chron, B, scen=np.arange(B), t0=np.zeros(B), protections=True,
+                           hard_overflow_threshold=2.0, soft_overflow_threshold=1.0, nb_timestep_overflow_allowed=2)
+    assert env.engine is not None
+    worst = {k: 0.0 for k in keys}
+    first_done = np.full(B, -1)
+    n_cmp = 0
+    for k in range(int(nb_step.max())):
+        if k == 0:
+            env.reset_step()                              # the step env.reset() performs
+        else:
+            env.step_device()
+        out, status, iters, rho = env.fetch()
+        st = env.fetch_state()
+        v = OutputView(gm, out)
+        for s in range(B):
+            if st["done"][s] and first_done[s] < 0:
+                first_done[s] = k
+            if k >= nb_step[s] - 1:                       # recorded rows end one before the game-over step
+                continue
+            assert status[s] == 0, (s, k, status[s])
+            r = rows[s][k]
+            mine = dict(p_or=v.p_or[s], q_or=v.q_or[s], v_or=v.v_or[s], a_or=v.a_or[s], p_ex=v.p_ex[s], q_ex=v.q_ex[s],
+                        v_ex=v.v_ex[s], a_ex=v.a_ex[s], prod_p=v.unit_p[s], prod_q=v.unit_q[s], prod_v=v.unit_v[s],
+                        load_v=v.load_v[s], rho=rho[s])
+            for name, val in mine.items():
+                worst[name] = max(worst[name], float(np.max(np.abs(val.astype(np.float64) - gold[name][r]))))
+            assert np.array_equal(v.a_or[s] > 0, gold["line_status"][r]) or np.array_equal(
+                (np.abs(v.p_or[s]) > 0) | (v.v_or[s] > 0), gold["line_status"][r]), (s, k)
+            assert np.array_equal(st["timestep_overflow"][s], gold["timestep_overflow"][r]), (s, k)
+            n_cmp += 1
+    # game over exactly where the reference's episode ended (scenario 13 runs to the end of its chronics)
+    for s in range(B):
+        if nb_step[s] < chron.shape[1]:
+            assert first_done[s] == nb_step[s] - 1, (s, first_done[s], nb_step[s])
+    assert n_cmp > 7000
+    for name in ("p_or", "q_or", "p_ex", "q_ex", "prod_p", "prod_q"):
+        assert worst[name] <= 1e-4, (name, worst[name])          # sn_mva = 1 -> 1e-4 p.u.
+    for name in ("v_or", "v_ex", "prod_v", "load_v"):
+        assert worst[name] <= 2e-5, (name, worst[name])
+    for name in ("a_or", "a_ex"):
+        assert worst[name] <= 2e-3, (name, worst[name])
+    assert worst["rho"] <= 1e-6
+    env.close()
