@@ -110,6 +110,18 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
     UP(sto_sub, gd->storage_sub, g.n_sto) UP(sto_pos, gd->storage_pos, g.n_sto) UP(sto_vn, gd->storage_vn, g.n_sto)
     UP(sto_q, gd->storage_q, g.n_sto)
     UP(sh_sub, gd->shunt_sub, g.n_shunt) UP(sh_vn, gd->shunt_vn, g.n_shunt) UP(sh_vratio, gd->shunt_vratio, g.n_shunt)
+    {   // substation order (bandwidth reduction) and its inverse
+        std::vector<int> rank(g.n_sub), order(g.n_sub);
+        std::vector<char> seen(g.n_sub, 0);
+        bool ok = gd->sub_rank != nullptr;
+        for (int s = 0; ok && s < g.n_sub; ++s) {
+            const int r = gd->sub_rank[s];
+            if (r < 0 || r >= g.n_sub || seen[r]) ok = false; else seen[r] = 1;
+        }
+        for (int s = 0; s < g.n_sub; ++s) rank[s] = ok ? gd->sub_rank[s] : s;
+        for (int s = 0; s < g.n_sub; ++s) order[rank[s]] = s;
+        UP(sub_rank, rank.data(), rank.size()) UP(sub_order, order.data(), order.size())
+    }
     // static incidence lists: line ends per substation, in line order (deterministic summation order)
     {
         std::vector<int> ptr(g.n_sub + 1, 0), ends(2 * (size_t)g.n_line);
@@ -249,37 +261,37 @@ static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
     const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
     size_t want = ws_mat_worst(cap, jt);
     int T = 32;
-    {
+    {   // threads per instance: the big systems are latency bound -> many warps per instance
         size_t d = 2 * (size_t)cap;
-        T = d <= 64 ? 32 : (d <= 128 ? 64 : (d <= 256 ? 128 : 256));
+        T = d <= 64 ? 32 : (d <= 128 ? 128 : (d <= 256 ? 256 : 512));
     }
     int gpb = 1;
     if ((fixed + want) * gpb > (size_t)h->max_smem_optin) {
         // does not fit with 4 warps per CTA / worst case: one group per CTA, clipped matrix
-        if (T == 32) { T = 64; }
+        if (T == 32) { T = 128; }
         gpb = 1;
         if (fixed + 1024 > (size_t)h->max_smem_optin) return fail(B200PF_E_CAPACITY, "grid too large for the on-chip workspace");
         size_t avail = ((size_t)h->max_smem_optin - fixed) & ~size_t(15);
         if (want > avail) want = avail;
         size_t dmax = 1;
         while ((dmax + 1) * (dmax + 3) * jt <= want) ++dmax;
-        T = dmax <= 128 ? 64 : (dmax <= 256 ? 128 : 256);
+        T = dmax <= 128 ? 128 : (dmax <= 256 ? 256 : 512);
     }
     a.nb_cap = cap;
     a.mat_bytes = (int)want;
     if (jd) {
         switch (T) {
             case 32: return launch_t<32, double>(h, a);
-            case 64: return launch_t<64, double>(h, a);
             case 128: return launch_t<128, double>(h, a);
-            default: return launch_t<256, double>(h, a);
+            case 256: return launch_t<256, double>(h, a);
+            default: return launch_t<512, double>(h, a);
         }
     }
     switch (T) {
         case 32: return launch_t<32, float>(h, a);
-        case 64: return launch_t<64, float>(h, a);
         case 128: return launch_t<128, float>(h, a);
-        default: return launch_t<256, float>(h, a);
+        case 256: return launch_t<256, float>(h, a);
+        default: return launch_t<512, float>(h, a);
     }
 }
 

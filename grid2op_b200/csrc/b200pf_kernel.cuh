@@ -37,6 +37,8 @@ struct DevGrid {
     const int *sh_sub;
     const float *sh_vn;
     const double *sh_vratio;
+    const int *sub_rank;      // [n_sub] position of a substation in the bandwidth-reducing (RCM) order
+    const int *sub_order;     // [n_sub] inverse permutation
     const int *sub_end_ptr;   // [n_sub+1]  static incidence: line ends per substation
     const int *sub_end;       // [2 n_line] code = line*2 + side (0 = origin, 1 = extremity)
 };
@@ -99,7 +101,7 @@ __host__ __device__ inline size_t ws_fixed_bytes(int nbc, int n_slot, int n_line
     o += align16(size_t(n_inj) * 8);
     o += align16(size_t(2) * nbc * 4);
     o += align16(size_t(2) * nbc * 4);
-    o += align16(size_t(n_slot + 5 * nbc + 6 * nbc + 2 * n_line) * 2);
+    o += align16(size_t(n_slot + 7 * nbc + 6 * nbc + 2 * n_line) * 2);
     o += align16(size_t(2 * nbc + n_slot));
     o += 576;
     return o;
@@ -120,7 +122,7 @@ __host__ __device__ inline WsLayout ws_layout(int nbc, int n_slot, int n_line, i
     L.off_inj = o;   o += align16(size_t(n_inj) * 8);
     L.off_x = o;     o += align16(size_t(2) * nbc * 4);
     L.off_vf32 = o;  o += align16(size_t(2) * nbc * 4);
-    L.off_short = o; o += align16(size_t(n_slot + 5 * nbc + 6 * nbc + 2 * n_line) * 2);
+    L.off_short = o; o += align16(size_t(n_slot + 7 * nbc + 6 * nbc + 2 * n_line) * 2);
     L.off_byte = o;  o += align16(size_t(2 * nbc + n_slot));
     L.off_red = o;   o += 576;
     L.off_mat = o;
@@ -133,7 +135,7 @@ struct Ws {
     double *vm, *va, *ve, *vf, *pspec, *qspec, *gsh, *bsh, *gii, *bii, *pcalc, *qcalc, *pd, *qd, *qmins, *qmaxs, *pnonref;
     double *inj;
     float *x, *ve32, *vf32;
-    short *cidx, *colth, *colv, *bsub, *cntu, *nrefu, *rowbus, *used, *prow, *brf, *brt;
+    short *cidx, *colth, *colv, *bsub, *cntu, *nrefu, *dcol, *dbus, *rowbus, *used, *prow, *brf, *brt;
     unsigned char *btype, *reach, *mark;
     float *redf;
     int *redi;
@@ -156,6 +158,7 @@ __device__ inline Ws ws_bind(unsigned char *base, int nbc, int n_slot, int n_lin
     short *s = reinterpret_cast<short *>(base + L.off_short);
     w.cidx = s; s += n_slot;
     w.colth = s; s += nbc; w.colv = s; s += nbc; w.bsub = s; s += nbc; w.cntu = s; s += nbc; w.nrefu = s; s += nbc;
+    w.dcol = s; s += nbc; w.dbus = s; s += nbc;
     w.rowbus = s; s += 2 * nbc; w.used = s; s += 2 * nbc; w.prow = s; s += 2 * nbc;
     w.brf = s; s += n_line; w.brt = s; s += n_line;
     unsigned char *b = base + L.off_byte;
@@ -356,6 +359,125 @@ __device__ bool gauss_jordan_d(double *M, int n, int pitch, double *xs, Ws &w, i
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Band-limited LU with partial pivoting on the augmented matrix M[n][pitch] (dense storage, column n
+// = right-hand side).  The matrix has half band width bw in the (RCM bus order, interleaved unknowns)
+// numbering; rows are never moved: an explicit list of ACTIVE rows (rows that can still hold a non-zero
+// in the current column: at most bw+1) replaces the sliding window of a swap-based band LU, and the
+// fill stays within columns (k, k + 2 bw].  Work per step = (#active rows) x (2 bw + 1) instead of n x n.
+// Warps own rows, lanes own columns (conflict-free shared-memory access).  Back substitution by warp 0.
+// xv: work vector of n scalars of type S; xout: solution (may alias xv when the types match).
+// ---------------------------------------------------------------------------------------------
+template <int T, typename S, typename X>
+__device__ bool band_lu_solve(S *M, int n, int pitch, int bw, S *xv, X *xout, Ws &w, int tid) {
+    short *act = w.used;                                   // active row list (<= bw + 1 <= n entries)
+    const int lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = T / 32;
+    int *pinfo = w.redi + 20;                              // [0] pivot row, [1] its index in act, [2] status
+    if (bw < 1) bw = 1;
+    int na = min(n, bw + 1);
+    for (int r = tid; r < na; r += T) act[r] = (short)r;
+    gsync<T>();
+    for (int k = 0; k < n; ++k) {
+        // warp 0: pivot search among the active rows (one REDUX on the |a| bit patterns + ballot); the other
+        // warps wait at the barrier.  Two barriers per elimination step in total.
+        if (wid == 0) {
+            float best = -1.0f;
+            int bidx_l = 0;
+            for (int t = lane; t < na; t += 32) {
+                const float a = fabsf((float)M[(size_t)act[t] * pitch + k]);
+                if (a > best) { best = a; bidx_l = t; }          // NaN never wins
+            }
+            const unsigned bits = best > 0.0f ? __float_as_uint(best) : 0u;
+            const unsigned mx = __reduce_max_sync(0xffffffffu, bits);
+            const unsigned who = __ballot_sync(0xffffffffu, bits == mx);
+            const int src = __ffs(who) - 1;
+            const int bidx_w = __shfl_sync(0xffffffffu, bidx_l, src);
+            if (lane == 0) {
+                pinfo[2] = (mx < 0x00800000u) ? 1 : 0;        // |pivot| below the smallest normal: singular / NaN
+                pinfo[1] = bidx_w;
+                pinfo[0] = act[bidx_w];
+            }
+        }
+        gsync<T>();
+        if (pinfo[2]) return false;
+        const int bidx = pinfo[1];
+        const int p = pinfo[0];
+        const S *Mp = M + (size_t)p * pitch;
+        const S inv = S(1) / Mp[k];
+        const int c_last = min(n - 1, k + 2 * bw);          // fill never goes beyond k + 2 bw
+        const int ncols = c_last - k;                        // columns k+1 .. c_last
+        const int nchunk = (ncols + 1 + 31) >> 5;            // 32-column chunks per row (incl. the right-hand side)
+        if (nchunk <= 4) {
+            // warp = two rows per pass, lane = column within each of (up to) 4 chunks: all loads of a pass are
+            // issued before the first dependent FFMA
+            for (int t0 = wid; t0 < na; t0 += 2 * NW) {
+                const int tA = t0, tB = t0 + NW;
+                const bool vA = tA != bidx, vB = tB < na && tB != bidx;
+                S *MrA = M + (size_t)act[tA] * pitch;
+                S *MrB = M + (size_t)act[vB ? tB : tA] * pitch;
+                const S mA = vA ? MrA[k] * inv : S(0), mB = vB ? MrB[k] * inv : S(0);
+                if (mA == S(0) && mB == S(0)) continue;
+                S pa[4], ra[4], rb[4];
+                int cj[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int cc = j * 32 + lane;
+                    cj[j] = (cc < ncols) ? k + 1 + cc : ((cc == ncols) ? n : -1);
+                    if (cj[j] >= 0) { pa[j] = Mp[cj[j]]; ra[j] = MrA[cj[j]]; rb[j] = MrB[cj[j]]; }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (cj[j] >= 0) {
+                        if (mA != S(0)) MrA[cj[j]] = ra[j] - mA * pa[j];
+                        if (mB != S(0)) MrB[cj[j]] = rb[j] - mB * pa[j];
+                    }
+                }
+            }
+        } else {
+            for (int task = wid; task < na * nchunk; task += NW) {   // warp = (row, chunk), lane = column
+                const int t = task / nchunk, cc = (task - t * nchunk) * 32 + lane;
+                if (t == bidx || cc > ncols) continue;
+                S *Mr = M + (size_t)act[t] * pitch;
+                const S m = Mr[k] * inv;
+                if (m == S(0)) continue;
+                const int c = (cc == ncols) ? n : k + 1 + cc;      // last item = right-hand side
+                Mr[c] -= m * Mp[c];
+            }
+        }
+        gsync<T>();
+        // bookkeeping: the pivot row leaves the active set, the next row enters (one thread; the next
+        // reader of act is warp 0 itself in the pivot search, the others pass a barrier first)
+        if (tid == 0) {
+            w.prow[k] = (short)p;
+            act[bidx] = act[na - 1];
+            if (k + bw + 1 < n) act[na - 1] = (short)(k + bw + 1);
+        }
+        if (!(k + bw + 1 < n)) --na;
+        if (T == 32) __syncwarp();
+    }
+    gsync<T>();
+    // back substitution, reverse pivot order
+    if (wid == 0) {
+        for (int k = n - 1; k >= 0; --k) {
+            const S *Mp = M + (size_t)w.prow[k] * pitch;
+            const int c_last = min(n - 1, k + 2 * bw);
+            S s = S(0);
+            for (int c = k + 1 + lane; c <= c_last; c += 32) s += Mp[c] * xv[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) xv[k] = (Mp[n] - s) / Mp[k];
+            __syncwarp();
+        }
+    }
+    gsync<T>();
+    if ((void *)xout != (void *)xv) {
+        for (int k = tid; k < n; k += T) xout[k] = (X)xv[k];
+        gsync<T>();
+    }
+    return true;
+}
+
 __device__ __forceinline__ float qnanf() { return __int_as_float(0x7fc00000); }
 
 // ---------------------------------------------------------------------------------------------
@@ -409,24 +531,24 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     for (int l = tid; l < nl; l += T) {
         if (l == outage) continue;
         const int bo = tv[g.line_or_pos[l]], be = tv[g.line_ex_pos[l]];
-        if (bo > 0) w.mark[g.line_or_sub[l] + (bo - 1) * g.n_sub] = 1;
-        if (be > 0) w.mark[g.line_ex_sub[l] + (be - 1) * g.n_sub] = 1;
+        if (bo > 0) w.mark[g.sub_rank[g.line_or_sub[l]] * g.n_busbar + (bo - 1)] = 1;
+        if (be > 0) w.mark[g.sub_rank[g.line_ex_sub[l]] * g.n_busbar + (be - 1)] = 1;
     }
     for (int u = tid; u < g.n_unit; u += T) {
         const int b = tv[g.unit_pos[u]];
-        if (b > 0) w.mark[g.unit_sub[u] + (b - 1) * g.n_sub] = 1;
+        if (b > 0) w.mark[g.sub_rank[g.unit_sub[u]] * g.n_busbar + (b - 1)] = 1;
     }
     for (int k = tid; k < g.n_load; k += T) {
         const int b = tv[g.load_pos[k]];
-        if (b > 0) w.mark[g.load_sub[k] + (b - 1) * g.n_sub] = 1;
+        if (b > 0) w.mark[g.sub_rank[g.load_sub[k]] * g.n_busbar + (b - 1)] = 1;
     }
     for (int k = tid; k < g.n_sto; k += T) {
         const int b = tv[g.sto_pos[k]];
-        if (b > 0) w.mark[g.sto_sub[k] + (b - 1) * g.n_sub] = 1;
+        if (b > 0) w.mark[g.sub_rank[g.sto_sub[k]] * g.n_busbar + (b - 1)] = 1;
     }
     for (int k = tid; k < g.n_shunt; k += T) {
         const int b = tv[g.dim_topo + k];
-        if (b > 0) w.mark[g.sh_sub[k] + (b - 1) * g.n_sub] = 1;
+        if (b > 0) w.mark[g.sub_rank[g.sh_sub[k]] * g.n_busbar + (b - 1)] = 1;
     }
     gsync<T>();
     int nb = 0;
@@ -438,7 +560,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             if (s < g.n_slot) {
                 const int ci = nb + __popc(m & ((1u << tid) - 1u));
                 w.cidx[s] = on ? (short)ci : (short)-1;
-                if (on && ci < nbc) w.bsub[ci] = (short)(s % g.n_sub);
+                if (on && ci < nbc) w.bsub[ci] = (short)g.sub_order[s / g.n_busbar];
             }
             nb += __popc(m);
         }
@@ -449,7 +571,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     int status = ST_OK;
     if (nb > nbc) status = ST_LARGE;
 
-    int n1 = 0, npq = 0, d = 0, iters = 0;
+    int n1 = 0, npq = 0, d = 0, iters = 0, bw_dc = 0, bw_ac = 1;
     if (status == ST_OK) {
         // ---- 2. per-bus initialisation ------------------------------------------------------
         for (int i = tid; i < nb; i += T) {
@@ -465,7 +587,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             for (int u = 0; u < g.n_unit; ++u) {
                 const int b = tv[g.unit_pos[u]];
                 if (b <= 0) continue;
-                const int i = w.cidx[g.unit_sub[u] + (b - 1) * g.n_sub];
+                const int i = w.cidx[g.sub_rank[g.unit_sub[u]] * g.n_busbar + (b - 1)];
                 const double pu = (u >= g.n_hidden) ? gen_p[u - g.n_hidden] : 0.0;
                 w.vm[i] = unit_vm[u];
                 w.cntu[i] += 1;
@@ -479,20 +601,20 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             for (int k = 0; k < g.n_load; ++k) {
                 const int b = tv[g.load_pos[k]];
                 if (b <= 0) continue;
-                const int i = w.cidx[g.load_sub[k] + (b - 1) * g.n_sub];
+                const int i = w.cidx[g.sub_rank[g.load_sub[k]] * g.n_busbar + (b - 1)];
                 w.pd[i] += load_p[k]; w.qd[i] += load_q[k];
             }
             for (int k = 0; k < g.n_sto; ++k) {
                 const int b = tv[g.sto_pos[k]];
                 if (b <= 0) continue;
-                const int i = w.cidx[g.sto_sub[k] + (b - 1) * g.n_sub];
+                const int i = w.cidx[g.sub_rank[g.sto_sub[k]] * g.n_busbar + (b - 1)];
                 w.pd[i] += sto_p[k]; w.qd[i] += g.sto_q[k];
             }
         } else if (tid == 2) {
             for (int k = 0; k < g.n_shunt; ++k) {
                 const int b = tv[g.dim_topo + k];
                 if (b <= 0) continue;
-                const int i = w.cidx[g.sh_sub[k] + (b - 1) * g.n_sub];
+                const int i = w.cidx[g.sub_rank[g.sh_sub[k]] * g.n_busbar + (b - 1)];
                 w.gsh[i] += sh_p[k] * g.sh_vratio[k];
                 w.bsh[i] -= sh_q[k] * g.sh_vratio[k];
             }
@@ -501,8 +623,8 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         for (int l = tid; l < nl; l += T) {
             const int bo = tv[g.line_or_pos[l]], be = tv[g.line_ex_pos[l]];
             if (bo > 0 && be > 0 && l != outage) {
-                w.brf[l] = w.cidx[g.line_or_sub[l] + (bo - 1) * g.n_sub];
-                w.brt[l] = w.cidx[g.line_ex_sub[l] + (be - 1) * g.n_sub];
+                w.brf[l] = w.cidx[g.sub_rank[g.line_or_sub[l]] * g.n_busbar + (bo - 1)];
+                w.brt[l] = w.cidx[g.sub_rank[g.line_ex_sub[l]] * g.n_busbar + (be - 1)];
             } else { w.brf[l] = -1; w.brt[l] = -1; }
         }
         gsync<T>();
@@ -531,13 +653,18 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     }
 
     if (status == ST_OK) {
-        // ---- 4. unknown numbering: [theta of non-ref buses | |V| of PQ buses] ----------------
+        // ---- 4. unknown numbering, bus by bus in the (RCM-ordered) bus order: Newton system interleaved
+        //         [theta_i, |V|_i] so that the Jacobian is banded; the DC system numbers the non-ref buses
         if (tid == 0) {
-            int c = 0;
-            for (int i = 0; i < nb; ++i) { if (w.btype[i] != BT_REF) { w.colth[i] = (short)c; w.rowbus[c] = (short)i; ++c; } else w.colth[i] = -1; }
-            const int n1_ = c;
-            for (int i = 0; i < nb; ++i) { if (w.btype[i] == BT_PQ) { w.colv[i] = (short)c; w.rowbus[c] = (short)i; ++c; } else w.colv[i] = -1; }
-            w.redi[17] = n1_; w.redi[18] = c;
+            int c = 0, c1 = 0;
+            for (int i = 0; i < nb; ++i) {
+                if (w.btype[i] != BT_REF) {
+                    w.dcol[i] = (short)c1; w.dbus[c1] = (short)i; ++c1;
+                    w.colth[i] = (short)c; w.rowbus[c] = (short)i; ++c;
+                    if (w.btype[i] == BT_PQ) { w.colv[i] = (short)c; w.rowbus[c] = (short)i; ++c; } else w.colv[i] = -1;
+                } else { w.dcol[i] = -1; w.colth[i] = -1; w.colv[i] = -1; }
+            }
+            w.redi[17] = c1; w.redi[18] = c;
         }
         // specified injections (p.u.) and diagonal of Ybus
         for (int i = tid; i < nb; i += T) {
@@ -556,6 +683,20 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         }
         gsync<T>();
         n1 = w.redi[17]; d = w.redi[18]; npq = d - n1;
+        {   // half band widths of the DC matrix and of the Jacobian (max over in-service lines)
+            int b1 = 0, b2 = 1;
+            for (int l = tid; l < nl; l += T) {
+                const int f = w.brf[l];
+                if (f < 0) continue;
+                const int t = w.brt[l];
+                if (w.dcol[f] >= 0 && w.dcol[t] >= 0) {
+                    const int a1 = abs(w.dcol[f] - w.dcol[t]), a2 = abs(w.colth[f] - w.colth[t]) + 1;
+                    b1 = max(b1, a1); b2 = max(b2, a2);
+                }
+            }
+            bw_dc = (int)gmax<T>((double)b1, w, tid);
+            bw_ac = (int)gmax<T>((double)b2, w, tid);
+        }
         if ((size_t)n1 * ((n1 + 1) | 1) * 8 > (size_t)a.mat_bytes ||
             (!a.is_dc && (size_t)d * ((d + 1) | 1) * sizeof(JT) > (size_t)a.mat_bytes)) status = ST_LARGE;
     }
@@ -566,7 +707,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             double *M = reinterpret_cast<double *>(w.mat);
             const int pitch = (n1 + 1) | 1;
             for (int r = tid; r < n1; r += T) {
-                const int i = w.rowbus[r];
+                const int i = w.dbus[r];
                 double *Mr = M + (size_t)r * pitch;
                 for (int c = 0; c <= n1; ++c) Mr[c] = 0.0;
                 double rhs = w.pspec[i] - w.gsh[i] / base;
@@ -578,7 +719,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
                     const int j = side ? w.brf[l] : w.brt[l];
                     const double b = g.line_bdc[l];
                     Mr[r] += b;
-                    if (w.colth[j] >= 0) Mr[w.colth[j]] -= b;      // reference angle is 0 (pPB:473)
+                    if (w.dcol[j] >= 0) Mr[w.dcol[j]] -= b;        // reference angle is 0 (pPB:473)
                     rhs -= side ? -g.line_pshift[l] : g.line_pshift[l];
                 }
                 Mr[n1] = rhs;
@@ -587,10 +728,10 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             double *th = w.pcalc;   // scratch
             bool ok;
             if (T == 32 && n1 <= 16) ok = gj_warp_dispatch<double>(M, n1, pitch, th, w.pivbuf, tid);
-            else ok = gauss_jordan_d<T>(M, n1, pitch, th, w, tid);
+            else ok = band_lu_solve<T, double, double>(M, n1, pitch, bw_dc, th, th, w, tid);
             if (!ok) status = ST_DIV;
             else {
-                for (int r = tid; r < n1; r += T) w.va[w.rowbus[r]] = th[r];
+                for (int r = tid; r < n1; r += T) w.va[w.dbus[r]] = th[r];
                 gsync<T>();
                 int bad = 0;
                 for (int i = tid; i < nb; i += T) if (!isfinite(w.va[i])) bad = 1;
@@ -651,7 +792,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             // (b) Jacobian rows in the solver's precision, one thread per row
             for (int r = tid; r < d; r += T) {
                 const int i = w.rowbus[r];
-                const bool isq = r >= n1;
+                const bool isq = (r == w.colv[i]);
                 JT *Jr = J + (size_t)r * pitch;
                 for (int c = 0; c < d; ++c) Jr[c] = JT(0);
                 const JT ei = (JT)w.ve32[i], fi = (JT)w.vf32[i];
@@ -688,7 +829,10 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             bool solved;
             if (T == 32 && d <= 32 && sizeof(JT) == 4)
                 solved = gj_warp_dispatch<float>(reinterpret_cast<float *>(J), d, pitch, w.x, reinterpret_cast<float *>(w.pivbuf), tid);
-            else solved = gauss_jordan<T, JT>(J, d, pitch, w.x, w, tid);
+            else {
+                JT *xv = (sizeof(JT) == 4) ? reinterpret_cast<JT *>(w.x) : reinterpret_cast<JT *>(w.pcalc);   // work vector (2 nbc)
+                solved = band_lu_solve<T, JT, float>(J, d, pitch, bw_ac, xv, w.x, w, tid);
+            }
             if (!solved) { iters = it + 1; break; }
             // (d) fp64 state update; |V| unknown is relative (dV/V)
             for (int i = tid; i < nb; i += T) {
@@ -778,7 +922,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         const int b = tv[g.unit_pos[u]];
         float p = 0.f, q = 0.f, v = 0.f, th = 0.f;
         if (b > 0) {
-            const int i = w.cidx[g.unit_sub[u] + (b - 1) * g.n_sub];
+            const int i = w.cidx[g.sub_rank[g.unit_sub[u]] * g.n_busbar + (b - 1)];
             double pu = (u >= g.n_hidden) ? gen_p[u - g.n_hidden] : 0.0;
             if (g.unit_is_ref[u]) {
                 // slack power of the bus shared equally by its reference units (pandapower pfsoln)
@@ -801,7 +945,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         const int b = tv[g.load_pos[k]];
         float v = 0.f, th = 0.f;
         if (b > 0) {
-            const int i = w.cidx[g.load_sub[k] + (b - 1) * g.n_sub];
+            const int i = w.cidx[g.sub_rank[g.load_sub[k]] * g.n_busbar + (b - 1)];
             v = __fmul_rn((float)w.vm[i], g.load_vn[k]);
             th = (float)(w.va[i] * RAD2DEG);
         }
@@ -811,7 +955,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     for (int k = tid; k < (outw ? g.n_sto : 0); k += T) {
         const int b = tv[g.sto_pos[k]];
         float v = 0.f;
-        if (b > 0) v = __fmul_rn((float)w.vm[w.cidx[g.sto_sub[k] + (b - 1) * g.n_sub]], g.sto_vn[k]);
+        if (b > 0) v = __fmul_rn((float)w.vm[w.cidx[g.sub_rank[g.sto_sub[k]] * g.n_busbar + (b - 1)]], g.sto_vn[k]);
         o_sv[k] = v;
     }
     float *o_shp = o_sv + g.n_sto, *o_shq = o_shp + g.n_shunt, *o_shv = o_shq + g.n_shunt;
@@ -819,7 +963,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
         const int b = tv[g.dim_topo + k];
         float p = 0.f, q = 0.f, v = 0.f;
         if (b > 0) {
-            const int i = w.cidx[g.sh_sub[k] + (b - 1) * g.n_sub];
+            const int i = w.cidx[g.sub_rank[g.sh_sub[k]] * g.n_busbar + (b - 1)];
             const double v2 = a.is_dc ? 1.0 : w.vm[i] * w.vm[i];
             p = (float)(sh_p[k] * g.sh_vratio[k] * v2);
             q = a.is_dc ? 0.f : (float)(sh_q[k] * g.sh_vratio[k] * v2);
@@ -830,7 +974,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     if (a.busv) {
         double *bv = a.busv + (size_t)inst * 2 * g.n_slot;
         for (int s = tid; s < g.n_slot; s += T) {
-            const int i = w.cidx[s];
+            const int i = w.cidx[g.sub_rank[s % g.n_sub] * g.n_busbar + s / g.n_sub];      // slot = sub + (busbar-1)*n_sub
             bv[s] = (i >= 0) ? w.vm[i] : __longlong_as_double(0x7ff8000000000000LL);
             bv[g.n_slot + s] = (i >= 0) ? w.va[i] : __longlong_as_double(0x7ff8000000000000LL);
         }

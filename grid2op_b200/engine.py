@@ -53,6 +53,7 @@ class _GridDesc(C.Structure):
         ("load_sub", C.c_void_p), ("load_pos", C.c_void_p), ("load_vn", C.c_void_p),
         ("storage_sub", C.c_void_p), ("storage_pos", C.c_void_p), ("storage_vn", C.c_void_p), ("storage_q", C.c_void_p),
         ("shunt_sub", C.c_void_p), ("shunt_vn", C.c_void_p), ("shunt_vratio", C.c_void_p),
+        ("sub_rank", C.c_void_p),
     ]
 
 
@@ -147,12 +148,12 @@ class PowerFlowEngine:
     def __init__(self, gm: GridModel, max_batch: int = 1, device: int = 0):
         self.gm = gm
         self.lib = load_library()
-        if self.lib.b200pf_abi_version() != 1:
+        if self.lib.b200pf_abi_version() != 2:
             raise EngineUnavailable("libb200pf ABI version mismatch")
         self.max_batch = int(max_batch)
         self._keep = []
         d = _GridDesc()
-        d.abi_version = 1
+        d.abi_version = 2
         d.n_sub, d.n_busbar = gm.n_sub, gm.n_busbar
         d.n_line, d.n_gen, d.n_hidden, d.n_load = gm.n_line, gm.n_gen, gm.n_hidden, gm.n_load
         d.n_storage, d.n_shunt, d.dim_topo = gm.n_storage, gm.n_shunt, gm.dim_topo
@@ -176,6 +177,7 @@ class PowerFlowEngine:
         put("storage_sub", gm.storage_sub, i32); put("storage_pos", gm.storage_pos, i32)
         put("storage_vn", gm.storage_vn, f32); put("storage_q", gm.storage_q, f64)
         put("shunt_sub", gm.shunt_sub, i32); put("shunt_vn", gm.shunt_vn, f32); put("shunt_vratio", gm.shunt_vratio, f64)
+        put("sub_rank", getattr(gm, "sub_rank", np.arange(gm.n_sub)), i32)
         h = C.c_void_p()
         rc = self.lib.b200pf_create(C.byref(d), self.max_batch, int(device), C.byref(h))
         if rc != 0:
@@ -205,8 +207,6 @@ class PowerFlowEngine:
         """Largest number of active buses (bus slots with at least one connected element) over a batch
         of topology records: the tight ``nb_cap`` for a launch (0 = unknown -> size for every slot)."""
         gm = self.gm
-        if gm.n_slot > 64:
-            return 0
         if getattr(self, "_slot_tbl", None) is None:
             sub = np.zeros(gm.n_topo_in, dtype=np.int64)
             sub[gm.line_or_pos] = gm.line_or_sub; sub[gm.line_ex_pos] = gm.line_ex_sub
@@ -217,13 +217,12 @@ class PowerFlowEngine:
             sub[gm.dim_topo + gm.n_shunt:] = gm.hidden_sub
             self._slot_tbl = sub
         topo = np.asarray(topo).reshape(-1, gm.n_topo_in).astype(np.int64)
+        if topo.shape[0] == 0:
+            return 0
         slot = self._slot_tbl[None, :] + (topo - 1) * gm.n_sub
-        bits = np.where(topo > 0, np.left_shift(np.uint64(1), slot.clip(0, 63).astype(np.uint64)), np.uint64(0))
-        mask = np.bitwise_or.reduce(bits, axis=1)
-        cnt = np.zeros(mask.shape[0], dtype=np.int64)
-        for k in range(gm.n_slot):
-            cnt += ((mask >> np.uint64(k)) & np.uint64(1)).astype(np.int64)
-        return int(cnt.max()) if cnt.size else 0
+        active = np.zeros((topo.shape[0], gm.n_slot + 1), dtype=bool)
+        np.put_along_axis(active, np.where(topo > 0, slot, gm.n_slot), True, axis=1)     # column n_slot = dump
+        return int(active[:, :gm.n_slot].sum(axis=1).max())
 
     def run(self, topo: np.ndarray, inj: np.ndarray, is_dc: bool = False, max_iter: int = 10,
             tol_mva: float = 1e-8, nb_cap: int = -1, want_busv: bool = False

@@ -206,10 +206,31 @@ class GridModel:
         self.storage_pos = (off[self.storage_sub] + self.storage_to_sub_pos).astype(np.int32)
         self.unit_pos = np.concatenate([self.dim_topo + self.n_shunt + np.arange(n_hidden), self.gen_pos]).astype(np.int32)
         self.n_unit = self.n_hidden + self.n_gen
+        self.sub_rank = self._bandwidth_order()
         self.n_slot = self.n_sub * self.n_busbar
         self.n_topo_in = self.dim_topo + self.n_shunt + self.n_hidden
         self.n_inj = self.n_gen + self.n_unit + 2 * self.n_load + self.n_storage + 2 * self.n_shunt
         self.n_out = 10 * self.n_line + 4 * self.n_unit + 2 * self.n_load + self.n_storage + 3 * self.n_shunt
+
+    # ---------------------------------------------------------------------------------------------
+    def _bandwidth_order(self) -> np.ndarray:
+        """rank[sub] = position of the substation in a reverse Cuthill-McKee order of the substation graph:
+        with buses numbered in that order the admittance / Jacobian matrices are banded (the
+        CTA-per-instance kernel exploits it).  Deterministic; identity when scipy is unavailable."""
+        n = self.n_sub
+        try:
+            from scipy.sparse import coo_matrix
+            from scipy.sparse.csgraph import reverse_cuthill_mckee
+        except Exception:  # pragma: no cover
+            return np.arange(n, dtype=np.int32)
+        if self.n_line == 0:
+            return np.arange(n, dtype=np.int32)
+        a, b = self.line_or_sub.astype(np.int64), self.line_ex_sub.astype(np.int64)
+        m = coo_matrix((np.ones(2 * len(a)), (np.concatenate([a, b]), np.concatenate([b, a]))), shape=(n, n)).tocsr()
+        order = np.asarray(reverse_cuthill_mckee(m, symmetric_mode=True), dtype=np.int64)
+        rank = np.empty(n, dtype=np.int32)
+        rank[order] = np.arange(n, dtype=np.int32)
+        return rank
 
     # ---------------------------------------------------------------------------------------------
     def _branch_parameters(self, line: Table, trafo: Table, lf, th, tl):

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define B200PF_ABI_VERSION 1
+#define B200PF_ABI_VERSION 2
 
 enum {
     B200PF_OK = 0,
@@ -87,6 +87,10 @@ typedef struct b200pf_grid_desc {
     const int32_t *load_sub, *load_pos;        const float *load_vn;
     const int32_t *storage_sub, *storage_pos;  const float *storage_vn;  const double *storage_q;
     const int32_t *shunt_sub;                  const float *shunt_vn;    const double *shunt_vratio; /* (vn_bus/vn_shunt)^2*step */
+    /* [n_sub] position of every substation in a bandwidth-reducing order of the substation graph (e.g.
+     * reverse Cuthill-McKee; identity is valid): the CTA-per-instance kernel numbers buses in this order so
+     * that the Jacobian is banded and solves it with a band-limited LU.  NULL = identity. */
+    const int32_t *sub_rank;
 } b200pf_grid_desc;
 
 typedef struct b200pf_handle b200pf_handle;

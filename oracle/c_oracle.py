@@ -35,7 +35,7 @@ class COracle:
         self.nthreads = int(nthreads)
         self._keep = []
         d = _GridDesc()
-        d.abi_version = 1
+        d.abi_version = 2
         d.n_sub, d.n_busbar = gm.n_sub, gm.n_busbar
         d.n_line, d.n_gen, d.n_hidden, d.n_load = gm.n_line, gm.n_gen, gm.n_hidden, gm.n_load
         d.n_storage, d.n_shunt, d.dim_topo = gm.n_storage, gm.n_shunt, gm.dim_topo

@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in _declared_symbols():
         assert hasattr(lib, s), s
     lib.b200pf_abi_version.restype = ctypes.c_int
-    assert lib.b200pf_abi_version() == 1
+    assert lib.b200pf_abi_version() == 2
 
 
 def test_engine_fails_loudly_without_a_gpu():
