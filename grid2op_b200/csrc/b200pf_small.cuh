@@ -22,6 +22,7 @@ struct SmallLayout {
     int off_x;      // float [32] / double [16]
     int off_adj;    // unsigned [32]
     int off_b;      // bytes: brf[32] brt[32] colth[32] colv[32]
+    int off_hot;    // double [6][32]: bus-lane state parked around the Gauss-Jordan (register pressure)
     int off_mat;    // matrix region
     int pitch_j;    // floats per Jacobian row
     int pitch_d;    // doubles per DC row
@@ -36,6 +37,7 @@ __host__ __device__ inline SmallLayout small_layout(int nb_cap) {
     L.off_x = o; o += 128;
     L.off_adj = o; o += 128;
     L.off_b = o; o += 128;
+    L.off_hot = o; o += 6 * 32 * 8;
     L.off_mat = o;
     int d_cap = 2 * nb_cap - 2; if (d_cap > 32) d_cap = 32; if (d_cap < 2) d_cap = 2;
     int n1_cap = nb_cap - 1; if (n1_cap > 16) n1_cap = 16; if (n1_cap < 1) n1_cap = 1;
@@ -48,6 +50,71 @@ __host__ __device__ inline SmallLayout small_layout(int nb_cap) {
 }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ float rcp_approx(float x) {      // one MUFU.RCP (1 ulp-ish; the fp64 residual decides convergence)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+
+// N shuffles issued back to back from ONE asm statement: the consumers below cannot be interleaved with
+// them by the compiler, so the SHFL latency is paid once per batch instead of once per element.
+template <int N> struct ShflBatch;
+template <> struct ShflBatch<8> {
+    static __device__ __forceinline__ void run(float *o, const float *v, int src) {
+        asm volatile("{\n"
+                     "shfl.sync.idx.b32 %0, %8, %16, 0x1f, 0xffffffff;\n" "shfl.sync.idx.b32 %1, %9, %16, 0x1f, 0xffffffff;\n"
+                     "shfl.sync.idx.b32 %2, %10, %16, 0x1f, 0xffffffff;\n" "shfl.sync.idx.b32 %3, %11, %16, 0x1f, 0xffffffff;\n"
+                     "shfl.sync.idx.b32 %4, %12, %16, 0x1f, 0xffffffff;\n" "shfl.sync.idx.b32 %5, %13, %16, 0x1f, 0xffffffff;\n"
+                     "shfl.sync.idx.b32 %6, %14, %16, 0x1f, 0xffffffff;\n" "shfl.sync.idx.b32 %7, %15, %16, 0x1f, 0xffffffff;\n"
+                     "}"
+                     : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+                     : "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "r"(src));
+    }
+};
+template <> struct ShflBatch<4> {
+    static __device__ __forceinline__ void run(float *o, const float *v, int src) {
+        asm volatile("{\n"
+                     "shfl.sync.idx.b32 %0, %4, %8, 0x1f, 0xffffffff;\n" "shfl.sync.idx.b32 %1, %5, %8, 0x1f, 0xffffffff;\n"
+                     "shfl.sync.idx.b32 %2, %6, %8, 0x1f, 0xffffffff;\n" "shfl.sync.idx.b32 %3, %7, %8, 0x1f, 0xffffffff;\n"
+                     "}"
+                     : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(src));
+    }
+};
+template <> struct ShflBatch<2> {
+    static __device__ __forceinline__ void run(float *o, const float *v, int src) {
+        asm volatile("{\n"
+                     "shfl.sync.idx.b32 %0, %2, %4, 0x1f, 0xffffffff;\n" "shfl.sync.idx.b32 %1, %3, %4, 0x1f, 0xffffffff;\n"
+                     "}"
+                     : "=f"(o[0]), "=f"(o[1]) : "f"(v[0]), "f"(v[1]), "r"(src));
+    }
+};
+template <> struct ShflBatch<1> {
+    static __device__ __forceinline__ void run(float *o, const float *v, int src) { o[0] = __shfl_sync(0xffffffffu, v[0], src); }
+};
+
+// a[c0 .. c0+N) -= m * (row p's a[c0 .. c0+N)), N in {8,4,2,1}, then the rest of the row recursively
+template <int C0, int END>
+__device__ __forceinline__ void gj_row_update(float *a, float m, int p) {
+    if constexpr (C0 < END) {
+        constexpr int REM = END - C0;
+        constexpr int N = REM >= 8 ? 8 : (REM >= 4 ? 4 : (REM >= 2 ? 2 : 1));
+        float pr[N];
+        ShflBatch<N>::run(pr, a + C0, p);
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[C0 + j] -= m * pr[j];
+        gj_row_update<C0 + N, END>(a, m, p);
+    }
+}
+
+// compile-time dispatch on the (unrolled, hence constant) step index k
+template <int DMAX, int K = 0>
+__device__ __forceinline__ void gj_step_update(float *a, float m, int p, int k) {
+    if constexpr (K < DMAX) {
+        if (k == K) gj_row_update<K + 1, DMAX + 1>(a, m, p);
+        else gj_step_update<DMAX, K + 1>(a, m, p, k);
+    }
+}
 
 // Gauss-Jordan, rows in registers, pivot row broadcast with SHFL (see header).  M is only read.
 template <int DMAX, typename S>
@@ -72,13 +139,18 @@ __device__ __forceinline__ bool gj_warp_shfl(const S *M, int n, int pitch, S *xs
         const int p = 31 - (int)(mx & 31u);
         const S piv = __shfl_sync(0xffffffffu, a[k], p);
         S inv;
-        if (sizeof(S) == 4) inv = (S)__fdividef(1.0f, (float)piv); else inv = S(1) / piv;
+        if (sizeof(S) == 4) inv = (S)rcp_approx((float)piv); else inv = S(1) / piv;
         const bool isp = lane == p;
         const S m = isp ? S(0) : a[k] * inv;
+        // pivot row broadcast in batches (fp32: batched asm shuffles; fp64: plain)
+        if constexpr (sizeof(S) == 4) {
+            gj_step_update<DMAX>(reinterpret_cast<float *>(a), (float)m, p, k);
+        } else {
 #pragma unroll
-        for (int c = k + 1; c < DMAX + 1; ++c) {
-            const S pr = __shfl_sync(0xffffffffu, a[c], p);
-            a[c] -= m * pr;
+            for (int c = k + 1; c < DMAX + 1; ++c) {
+                const S pr = __shfl_sync(0xffffffffu, a[c], p);
+                a[c] -= m * pr;
+            }
         }
         if (isp) { used = true; mycol = k; pivval = a[k]; }
     }
@@ -118,6 +190,7 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
     unsigned *adj = reinterpret_cast<unsigned *>(sm + L.off_adj);
     signed char *brf = reinterpret_cast<signed char *>(sm + L.off_b);
     signed char *brt = brf + 32, *colth_s = brf + 64, *colv_s = brf + 96;
+    double *hot = reinterpret_cast<double *>(sm + L.off_hot);
     float *J = reinterpret_cast<float *>(sm + L.off_mat);
     double *Md = reinterpret_cast<double *>(sm + L.off_mat);
     const int src = a.n1_lines > 0 ? inst / a.n1_lines : inst;          // record the inputs come from
@@ -253,12 +326,19 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         small_fail(g, a, inst, ST_LARGE, 0, lane); return;
     }
     colth_s[lane] = (signed char)colth; colv_s[lane] = (signed char)colv;
-    const double pspec = (pg - pd) / base, qspec = -qd / base;
+    double pspec = (pg - pd) / base, qspec = -qd / base;
+    // values needed again only for the read-back are parked in thread-local memory so that they do not
+    // occupy registers during the Newton loop (the register Gauss-Jordan needs them for shuffle batching)
+    volatile double cold[8];
+    volatile int coldi[2];
+    cold[0] = pd; cold[1] = qd; cold[2] = pnonref; cold[3] = qmins; cold[4] = qmaxs; cold[5] = u_p; cold[6] = sh_p; cold[7] = sh_q;
+    coldi[0] = cnt; coldi[1] = nref;
     __syncwarp();
 
     // ---- 5. Ybus diagonal and the DC system (bus lane = matrix row) ---------------------------------
     double gii = gsh / base, bii = bsh / base, va = 0.0;
-    {
+    if (a.is_dc) {
+        // DC mode: the angles ARE the result -> fp64 system
         const int pitch = (n1 + 1) | 1;
         double *Mr = Md + (colth >= 0 ? colth : 0) * pitch;
         if (colth >= 0) for (int c = 0; c <= n1; ++c) Mr[c] = 0.0;
@@ -284,6 +364,37 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         __syncwarp();
         if (!gj_small_d(Md, n1, pitch, xd, lane)) { small_fail(g, a, inst, ST_DIV, 0, lane); return; }
         if (colth >= 0) va = xd[colth];
+    } else {
+        // AC mode: the DC angles are only the Newton start (init="dc", pPB:1086) -> fp32 system, same solver as
+        // the Jacobian (the converged state does not depend on the last bits of the start)
+        const int pitch = (n1 + 1) | 1;
+        float *Mr = J + (colth >= 0 ? colth : 0) * pitch;
+        if (colth >= 0) for (int c = 0; c <= n1; ++c) Mr[c] = 0.f;
+        float rhs = (float)(pspec - gsh / base), dsum = 0.f;
+        if (isbus) {
+            for (int e = g.sub_end_ptr[mysub]; e < g.sub_end_ptr[mysub + 1]; ++e) {
+                const int code = g.sub_end[e], l = code >> 1, side = code & 1;
+                const int f = brf[l];
+                if (f < 0) continue;
+                const int t = brt[l];
+                if ((side ? t : f) != lane) continue;
+                const int j = side ? f : t;
+                const double *y = g.line_y + l * 8 + (side ? 6 : 0);
+                gii += y[0]; bii += y[1];
+                const float b = (float)g.line_bdc[l];
+                dsum += b;
+                const int cj = colth_s[j];
+                if (colth >= 0 && cj >= 0) Mr[cj] -= b;
+                const float ps = (float)g.line_pshift[l];
+                rhs -= side ? -ps : ps;
+            }
+            if (colth >= 0) { Mr[colth] = dsum; Mr[n1] = rhs; }
+        }
+        __syncwarp();
+        if (!gj_small_f(J, n1, pitch, xs, lane)) { small_fail(g, a, inst, ST_DIV, 0, lane); return; }
+        if (colth >= 0) va = (double)xs[colth];
+    }
+    {
         const int bad = isbus && !isfinite(va);
         if (__any_sync(FULL, bad)) { small_fail(g, a, inst, ST_DIV, 0, lane); return; }
         __syncwarp();
@@ -363,7 +474,10 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
                 }
             }
             __syncwarp();
-            if (!gj_small_f(J, d, pitch, xs, lane)) { iters = it + 1; break; }
+            hot[lane] = vm; hot[32 + lane] = va; hot[64 + lane] = pspec; hot[96 + lane] = qspec; hot[128 + lane] = gii; hot[160 + lane] = bii;
+            const bool solved = gj_small_f(J, d, pitch, xs, lane);
+            vm = hot[lane]; va = hot[32 + lane]; pspec = hot[64 + lane]; qspec = hot[96 + lane]; gii = hot[128 + lane]; bii = hot[160 + lane];
+            if (!solved) { iters = it + 1; break; }
             if (isbus) {
                 if (colth >= 0) va += (double)xs[colth];
                 if (colv >= 0) vm *= 1.0 + (double)xs[colv];
@@ -452,13 +566,15 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
     }
     {   // units (lane = unit), loads, storages, shunts: read their bus through shuffles
         const int su = bu >= 0 ? bu : 0;
-        const double Pb = shfl_d(P, su), Qb = shfl_d(Q, su), pdb = shfl_d(pd, su), qdb = shfl_d(qd, su), pnr = shfl_d(pnonref, su);
-        const double qmn = shfl_d(qmins, su), qmx = shfl_d(qmaxs, su), vmb = shfl_d(vm, su), vab = shfl_d(va, su);
-        const int cb = __shfl_sync(FULL, cnt, su), nrb = __shfl_sync(FULL, nref, su);
+        const double pd_ = cold[0], qd_ = cold[1], pnonref_ = cold[2], qmins_ = cold[3], qmaxs_ = cold[4];
+        const int cnt_ = coldi[0], nref_ = coldi[1];
+        const double Pb = shfl_d(P, su), Qb = shfl_d(Q, su), pdb = shfl_d(pd_, su), qdb = shfl_d(qd_, su), pnr = shfl_d(pnonref_, su);
+        const double qmn = shfl_d(qmins_, su), qmx = shfl_d(qmaxs_, su), vmb = shfl_d(vm, su), vab = shfl_d(va, su);
+        const int cb = __shfl_sync(FULL, cnt_, su), nrb = __shfl_sync(FULL, nref_, su);
         if (lane < nu && out) {
             float p = 0.f, q = 0.f, v = 0.f, th = 0.f;
             if (bu >= 0) {
-                double pu = u_p;
+                double pu = cold[5];
                 if (g.unit_is_ref[lane]) pu = (Pb * base + pdb - pnr) / (double)nrb;     // slack share (pandapower pfsoln)
                 double qu = 0.0;
                 if (!a.is_dc) {
@@ -488,8 +604,8 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
             float p = 0.f, q = 0.f, v = 0.f;
             if (bh >= 0) {
                 const double v2 = a.is_dc ? 1.0 : vmh * vmh;
-                p = (float)(sh_p * g.sh_vratio[lane] * v2);
-                q = a.is_dc ? 0.f : (float)(sh_q * g.sh_vratio[lane] * v2);
+                p = (float)(cold[6] * g.sh_vratio[lane] * v2);
+                q = a.is_dc ? 0.f : (float)(cold[7] * g.sh_vratio[lane] * v2);
                 v = __fmul_rn((float)vmh, g.sh_vn[lane]);
             }
             o[lane] = p; o[nsh + lane] = q; o[2 * nsh + lane] = v;
