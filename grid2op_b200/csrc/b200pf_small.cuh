@@ -159,8 +159,7 @@ __device__ __forceinline__ bool gj_warp_shfl(const S *M, int n, int pitch, S *xs
     return true;
 }
 
-__device__ __forceinline__ bool gj_small_f(const float *M, int n, int pitch, float *xs, int lane) {
-    if (n <= 8) return gj_warp_shfl<8, float>(M, n, pitch, xs, lane);
+__device__ __noinline__ bool gj_small_f(const float *M, int n, int pitch, float *xs, int lane) {
     if (n <= 16) return gj_warp_shfl<16, float>(M, n, pitch, xs, lane);
     if (n <= 24) return gj_warp_shfl<24, float>(M, n, pitch, xs, lane);
     return gj_warp_shfl<32, float>(M, n, pitch, xs, lane);
