@@ -419,5 +419,32 @@ class B200Backend(Backend):
         self._engine = None
         self._gm = None
 
-    def save_file(self, full_path) -> None:
-        raise NotImplementedError("B200Backend does not write pandapower json files")
+    def save_file(self, full_path) -> None:                                     # pPB:1425-1437 (pp.to_json)
+        """Write the current grid state as a pandapower-JSON file: the source ``grid.json`` with the set points,
+        element buses (global id = sub + (busbar-1)*n_sub, like the reference's tables) and in-service flags of
+        this backend.  Buses of the extra busbars are not materialised (a file loaded back puts every element on
+        the substation of its bus id modulo n_sub), exactly one grid2op ``load_grid`` away from this state."""
+        from .ppjson import update_pp_json
+        gm = self._gm
+        nl, nf = gm.n_powerline, gm.n_gen_file
+
+        def glob(sub, bar):
+            return [int(s) + (int(b) - 1) * gm.n_sub for s, b in zip(sub, bar)]
+
+        upd = {
+            "line": {"in_service": list(self._line_on[:nl]), "from_bus": glob(gm.line_or_sub[:nl], self._lor_bus[:nl]),
+                     "to_bus": glob(gm.line_ex_sub[:nl], self._lex_bus[:nl])},
+            "load": {"p_mw": list(self._load_p), "q_mvar": list(self._load_q), "in_service": list(self._load_on),
+                     "bus": glob(gm.load_sub, self._load_bus)},
+            "gen": {"p_mw": list(self._gen_p[:nf]), "vm_pu": list(self._gen_vm[:nf]), "in_service": list(self._gen_on[:nf]),
+                    "bus": glob(gm.gen_sub[:nf], self._gen_bus[:nf])},
+        }
+        if gm.n_trafo:
+            upd["trafo"] = {"in_service": list(self._line_on[nl:]), "hv_bus": glob(gm.line_or_sub[nl:], self._lor_bus[nl:]),
+                            "lv_bus": glob(gm.line_ex_sub[nl:], self._lex_bus[nl:])}
+        if gm.n_shunt:
+            upd["shunt"] = {"p_mw": list(self._sh_p), "q_mvar": list(self._sh_q), "in_service": list(self._sh_on),
+                            "bus": glob(gm.shunt_sub, self._sh_bus)}
+        if gm.n_storage:
+            upd["storage"] = {"p_mw": list(self._sto_p), "in_service": list(self._sto_on), "bus": glob(gm.storage_sub, self._sto_bus)}
+        update_pp_json(gm.path, str(full_path), upd)

@@ -135,6 +135,7 @@ class GridModel:
                     first = False
                     n_hidden = min(n_hidden, 1)        # only the first ext_grid is kept (pPB:451)
         self.n_gen = len(g_bus)
+        self.n_gen_file = len(gen)
         self.n_hidden = n_hidden
         self.gen_sub = g_bus.astype(np.int32)
         self.gen_p0, self.gen_vm0, self.gen_on0 = g_p.astype(np.float64), g_vm.astype(np.float64), g_on

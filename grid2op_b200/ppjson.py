@@ -22,7 +22,7 @@ from typing import Any, Dict, Iterable, List, Optional
 
 import numpy as np
 
-__all__ = ["Table", "read_pp_json", "PPNet"]
+__all__ = ["Table", "read_pp_json", "PPNet", "update_pp_json"]
 
 _FLOAT_KINDS = ("float", "int", "uint", "bool")
 
@@ -166,3 +166,59 @@ def read_pp_json(path: str, tables: Iterable[str] = _ELEMENT_TABLES) -> PPNet:
         elif not isinstance(v, (dict, list)):
             fields[k] = v
     return PPNet(fields, out)
+
+
+def update_pp_json(src_path: str, dst_path: str, updates: Dict[str, Dict[str, Any]]) -> None:
+    """Write a copy of the pandapower-JSON file ``src_path`` to ``dst_path`` with some table columns replaced
+    (``updates[table][column] = sequence of new values, file row order``) - the part of ``pp.to_json`` that
+    ``Backend.save_file`` needs (reference: grid2op/Backend/pandaPowerBackend.py:1425-1437).  Everything else
+    (other tables, std_types, geodata, options) is carried over byte-for-byte; result tables are emptied of
+    nothing - they simply keep the values stored in the source file."""
+    with open(src_path, "r", encoding="utf-8") as f:
+        top = json.load(f)
+    obj = top["_object"] if isinstance(top, dict) and "_object" in top else top
+    as_string = isinstance(obj, str)
+    if as_string:
+        obj = json.loads(obj)
+    for tname, cols in updates.items():
+        spec = obj.get(tname)
+        if not (isinstance(spec, dict) and spec.get("_class") == "DataFrame"):
+            raise KeyError(f"table {tname!r} not found in {src_path}")
+        inner = spec["_object"]
+        inner_is_str = isinstance(inner, str)
+        tab = json.loads(inner) if inner_is_str else inner
+        if not ("columns" in tab and "data" in tab):
+            # orient="columns" -> convert to split so that rows can be edited uniformly
+            index = None
+            names = list(tab.keys())
+            for nm in names:
+                if index is None:
+                    index = list(tab[nm].keys())
+            data = [[tab[nm].get(k) for nm in names] for k in (index or [])]
+            tab = {"columns": names, "index": index or [], "data": data}
+            spec["orient"] = "split"
+        for cname, values in cols.items():
+            values = list(values)
+            if cname not in tab["columns"]:
+                tab["columns"].append(cname)
+                for row in tab["data"]:
+                    row.append(None)
+            j = tab["columns"].index(cname)
+            if len(values) != len(tab["data"]):
+                raise ValueError(f"{tname}.{cname}: {len(values)} values for {len(tab['data'])} rows")
+            for row, v in zip(tab["data"], values):
+                if isinstance(v, (np.bool_, bool)):
+                    row[j] = bool(v)
+                elif isinstance(v, (np.integer,)):
+                    row[j] = int(v)
+                elif isinstance(v, (np.floating, float)):
+                    row[j] = float(v)
+                else:
+                    row[j] = v
+        spec["_object"] = json.dumps(tab) if inner_is_str else tab
+    if isinstance(top, dict) and "_object" in top:
+        top["_object"] = json.dumps(obj) if as_string else obj
+    else:
+        top = obj
+    with open(dst_path, "w", encoding="utf-8") as f:
+        json.dump(top, f)
