@@ -28,6 +28,8 @@ struct b200pf_handle {
     int max_batch = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t chunk_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    int chunk_next = 0;
     float *x_out = nullptr; int *x_status = nullptr; int *x_iters = nullptr; float *x_rho = nullptr;
     DevGrid g{};
     std::vector<void *> dev_allocs;
@@ -173,6 +175,7 @@ extern "C" int b200pf_destroy(b200pf_handle *h) {
     void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv, h->h_rows};
     for (void *p : pinned) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (auto &cs : h->chunk_stream) if (cs) cudaStreamDestroy(cs);
     delete h;
     return 0;
 }
@@ -535,6 +538,38 @@ extern "C" int b200pf_run_rows_staged(b200pf_handle *h, int batch, int is_dc, in
     CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200pf_rows_chunk_launch(b200pf_handle *h, int first, int count, int is_dc, int max_iter, double tol_mva, int nb_cap) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (first < 0 || count <= 0 || first + count > h->max_batch) return fail(B200PF_E_ARG, "chunk out of range (max_batch)");
+    CU(cudaSetDevice(h->device));
+    const DevGrid &g = h->g;
+    const int ci = h->chunk_next++ & 3;
+    if (!h->chunk_stream[ci]) CU(cudaStreamCreateWithFlags(&h->chunk_stream[ci], cudaStreamNonBlocking));
+    cudaStream_t st = h->chunk_stream[ci];
+    const size_t F = (size_t)first, C = (size_t)count, ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
+    CU(cudaMemcpyAsync(h->d_topo + F * g.n_topo_in, h->h_topo + F * g.n_topo_in, C * g.n_topo_in, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_rows + F * ncol, h->h_rows + F * ncol, C * ncol * 4, cudaMemcpyHostToDevice, st));
+    RunArgs a = base_args(h, count, is_dc, max_iter, tol_mva);
+    a.topo = h->d_topo + F * g.n_topo_in; a.inj = nullptr; a.out = h->d_out + F * g.n_out; a.status = h->d_status + F;
+    a.iters = h->d_iters + F; a.busv = nullptr; a.series = 1; a.rows = h->d_rows + F * ncol; a.static_inj = h->d_static_inj;
+    cudaStream_t keep = h->stream;
+    h->stream = st;
+    int rc = launch(h, a, nb_cap);
+    h->stream = keep;
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->h_out + F * g.n_out, h->d_out + F * g.n_out, C * g.n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_status + F, h->d_status + F, C * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_iters + F, h->d_iters + F, C * 4, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+extern "C" int b200pf_rows_chunk_wait(b200pf_handle *h) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    for (auto &cs : h->chunk_stream) if (cs) CU(cudaStreamSynchronize(cs));
     return 0;
 }
 

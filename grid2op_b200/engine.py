@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "b200pf_launch_count", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
     "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
     "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
-    "b200pf_series_next_is_reset", "b200pf_series_fetch_state",
+    "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait",
 )
 
 
@@ -100,6 +100,8 @@ def load_library():
     lib.b200pf_series_protections.argtypes = [vp, i32, C.c_float, C.c_float, i32]
     lib.b200pf_series_next_is_reset.argtypes = [vp]
     lib.b200pf_series_fetch_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.b200pf_rows_chunk_launch.argtypes = [vp, i32, i32, i32, i32, f64, i32]
+    lib.b200pf_rows_chunk_wait.argtypes = [vp]
     lib.b200pf_stream.argtypes = [vp]
     lib.b200pf_stream.restype = C.c_uint64
     lib.b200pf_launch_count.argtypes = [vp]
@@ -110,7 +112,7 @@ def load_library():
                "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
                "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
                "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
-               "b200pf_series_next_is_reset", "b200pf_series_fetch_state"):
+               "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait"):
         getattr(lib, nm).restype = i32
     _LIB = lib
     return lib
@@ -309,6 +311,14 @@ class PowerFlowEngine:
         self._check(self.lib.b200pf_n1_host(self.h, B, _ptr(topo), _ptr(inj), int(max_iter), float(tol_mva), int(nb_cap),
                                             _ptr(rho), _ptr(status)), "b200pf_n1_host")
         return rho, status
+
+    def rows_chunk_launch(self, first: int, count: int, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8,
+                          nb_cap: int = 0):
+        self._check(self.lib.b200pf_rows_chunk_launch(self.h, int(first), int(count), int(bool(is_dc)), int(max_iter),
+                                                      float(tol_mva), int(nb_cap)), "b200pf_rows_chunk_launch")
+
+    def rows_chunk_wait(self):
+        self._check(self.lib.b200pf_rows_chunk_wait(self.h), "b200pf_rows_chunk_wait")
 
     def set_stream(self, stream: int):
         self._check(self.lib.b200pf_set_stream(self.h, C.c_uint64(int(stream))), "b200pf_set_stream")

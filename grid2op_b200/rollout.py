@@ -60,6 +60,7 @@ class BatchedDoNothing:
         # host path state
         self._t_host = self.t0.astype(np.int64).copy()
         self._stage = None
+        self.host_chunks = 2          # measured on B200 + PCIe Gen5: 2 chunks 222 us, 1: 271 us, 4: 227 us, 8: 296 us per 4096-step
         self._sl = gm.inj_slices()
         self._inj0 = gm.default_inj()
 
@@ -104,9 +105,17 @@ class BatchedDoNothing:
             self._chron_flat = self.chron.reshape(-1, self.chron.shape[2])
             self._row_base = self.scen.astype(np.int64) * n_rows
         st = self._stage
-        np.take(self._chron_flat, self._row_base + self._t_host, axis=0, out=self._rows[:self.batch])
+        idx = self._row_base + self._t_host
+        nch = self.host_chunks if self.batch >= 4 * self.host_chunks else 1
+        lo = 0
+        for c in range(nch):                      # gather chunk c on the host while the device works on chunk c-1
+            hi = self.batch * (c + 1) // nch
+            np.take(self._chron_flat, idx[lo:hi], axis=0, out=self._rows[lo:hi])
+            self.engine.rows_chunk_launch(lo, hi - lo, is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva,
+                                          nb_cap=self.nb_cap)
+            lo = hi
         self._t_host = (self._t_host + 1) % self.chron.shape[1]
-        self.engine.run_rows_staged(self.batch, is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva, nb_cap=self.nb_cap)
+        self.engine.rows_chunk_wait()
         return st["out"][:self.batch], st["status"][:self.batch]
 
     def bytes_per_step_host(self):

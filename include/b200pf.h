@@ -181,6 +181,12 @@ int b200pf_n1_host(b200pf_handle *h, int batch, const int8_t *topo, const double
 int b200pf_set_static_inj(b200pf_handle *h, const double *static_inj /* [n_inj] */);
 int b200pf_rows_staging(b200pf_handle *h, float **rows);
 int b200pf_run_rows_staged(b200pf_handle *h, int batch, int is_dc, int max_iter, double tol_mva, int nb_cap);
+/* Pipelined variant of b200pf_run_rows_staged: the caller fills the pinned rows / topo staging buffers chunk by
+ * chunk and launches every chunk as soon as it is ready (asynchronous: H2D, kernel, D2H of that chunk on one of
+ * a few internal streams), so host-side preparation of chunk c+1 overlaps the device work of chunk c;
+ * b200pf_rows_chunk_wait returns when every launched chunk has landed in the pinned out/status/iters buffers. */
+int b200pf_rows_chunk_launch(b200pf_handle *h, int first, int count, int is_dc, int max_iter, double tol_mva, int nb_cap);
+int b200pf_rows_chunk_wait(b200pf_handle *h);
 /* run all work of this handle on the caller's stream (cudaStream_t as integer; 0 = the handle's own) */
 int b200pf_set_stream(b200pf_handle *h, uint64_t stream);
 
