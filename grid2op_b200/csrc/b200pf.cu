@@ -541,7 +541,33 @@ extern "C" int b200pf_run_rows_staged(b200pf_handle *h, int batch, int is_dc, in
     return 0;
 }
 
+extern "C" int b200pf_pinned_alloc(size_t bytes, void **ptr) {
+    if (!ptr) return fail(B200PF_E_ARG, "null pointer");
+    CU(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return 0;
+}
+extern "C" int b200pf_pinned_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}
+
+static int rows_chunk_launch_impl(b200pf_handle *h, int first, int count, const float *src_rows, int is_dc, int max_iter,
+                                  double tol_mva, int nb_cap);
+
 extern "C" int b200pf_rows_chunk_launch(b200pf_handle *h, int first, int count, int is_dc, int max_iter, double tol_mva, int nb_cap) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    const size_t ncol = 2 * (size_t)h->g.n_load + 2 * (size_t)h->g.n_gen;
+    return rows_chunk_launch_impl(h, first, count, h->h_rows + (size_t)(first < 0 ? 0 : first) * ncol, is_dc, max_iter, tol_mva, nb_cap);
+}
+
+extern "C" int b200pf_rows_chunk_launch_from(b200pf_handle *h, int first, int count, const float *pinned_rows, int is_dc,
+                                             int max_iter, double tol_mva, int nb_cap) {
+    if (!h || !pinned_rows) return fail(B200PF_E_ARG, "null pointer");
+    return rows_chunk_launch_impl(h, first, count, pinned_rows, is_dc, max_iter, tol_mva, nb_cap);
+}
+
+static int rows_chunk_launch_impl(b200pf_handle *h, int first, int count, const float *src_rows, int is_dc, int max_iter,
+                                  double tol_mva, int nb_cap) {
     if (!h) return fail(B200PF_E_ARG, "null handle");
     if (first < 0 || count <= 0 || first + count > h->max_batch) return fail(B200PF_E_ARG, "chunk out of range (max_batch)");
     CU(cudaSetDevice(h->device));
@@ -551,7 +577,7 @@ extern "C" int b200pf_rows_chunk_launch(b200pf_handle *h, int first, int count, 
     cudaStream_t st = h->chunk_stream[ci];
     const size_t F = (size_t)first, C = (size_t)count, ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
     CU(cudaMemcpyAsync(h->d_topo + F * g.n_topo_in, h->h_topo + F * g.n_topo_in, C * g.n_topo_in, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(h->d_rows + F * ncol, h->h_rows + F * ncol, C * ncol * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_rows + F * ncol, src_rows, C * ncol * 4, cudaMemcpyHostToDevice, st));
     RunArgs a = base_args(h, count, is_dc, max_iter, tol_mva);
     a.topo = h->d_topo + F * g.n_topo_in; a.inj = nullptr; a.out = h->d_out + F * g.n_out; a.status = h->d_status + F;
     a.iters = h->d_iters + F; a.busv = nullptr; a.series = 1; a.rows = h->d_rows + F * ncol; a.static_inj = h->d_static_inj;

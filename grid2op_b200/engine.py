@@ -32,6 +32,7 @@ ABI_SYMBOLS = (
     "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
     "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
     "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait",
+    "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free",
 )
 
 
@@ -102,6 +103,9 @@ def load_library():
     lib.b200pf_series_fetch_state.argtypes = [vp, vp, vp, vp, vp]
     lib.b200pf_rows_chunk_launch.argtypes = [vp, i32, i32, i32, i32, f64, i32]
     lib.b200pf_rows_chunk_wait.argtypes = [vp]
+    lib.b200pf_rows_chunk_launch_from.argtypes = [vp, i32, i32, vp, i32, i32, f64, i32]
+    lib.b200pf_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.b200pf_pinned_free.argtypes = [vp]
     lib.b200pf_stream.argtypes = [vp]
     lib.b200pf_stream.restype = C.c_uint64
     lib.b200pf_launch_count.argtypes = [vp]
@@ -112,7 +116,8 @@ def load_library():
                "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
                "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
                "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
-               "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait"):
+               "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait",
+               "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free"):
         getattr(lib, nm).restype = i32
     _LIB = lib
     return lib
@@ -198,6 +203,9 @@ class PowerFlowEngine:
         if getattr(self, "h", None) is not None and self.h:
             self.lib.b200pf_destroy(self.h)
             self.h = None
+        for p in getattr(self, "_pinned", []):
+            self.lib.b200pf_pinned_free(p)
+        self._pinned = []
 
     def __del__(self):  # pragma: no cover
         try:
@@ -316,6 +324,21 @@ class PowerFlowEngine:
                           nb_cap: int = 0):
         self._check(self.lib.b200pf_rows_chunk_launch(self.h, int(first), int(count), int(bool(is_dc)), int(max_iter),
                                                       float(tol_mva), int(nb_cap)), "b200pf_rows_chunk_launch")
+
+    def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:
+        """numpy array backed by page-locked host memory (freed with the engine)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self.lib.b200pf_pinned_alloc(C.c_size_t(n), C.byref(p)), "b200pf_pinned_alloc")
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def rows_chunk_launch_from(self, first: int, count: int, pinned_rows: np.ndarray, is_dc: bool = False, max_iter: int = 10,
+                               tol_mva: float = 1e-8, nb_cap: int = 0):
+        self._check(self.lib.b200pf_rows_chunk_launch_from(self.h, int(first), int(count), C.c_void_p(pinned_rows.ctypes.data),
+                                                           int(bool(is_dc)), int(max_iter), float(tol_mva), int(nb_cap)),
+                    "b200pf_rows_chunk_launch_from")
 
     def rows_chunk_wait(self):
         self._check(self.lib.b200pf_rows_chunk_wait(self.h), "b200pf_rows_chunk_wait")

@@ -38,6 +38,7 @@
 #ifndef B200PF_H
 #define B200PF_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -187,6 +188,13 @@ int b200pf_run_rows_staged(b200pf_handle *h, int batch, int is_dc, int max_iter,
  * b200pf_rows_chunk_wait returns when every launched chunk has landed in the pinned out/status/iters buffers. */
 int b200pf_rows_chunk_launch(b200pf_handle *h, int first, int count, int is_dc, int max_iter, double tol_mva, int nb_cap);
 int b200pf_rows_chunk_wait(b200pf_handle *h);
+/* same, but the rows of the chunk are read from caller-provided PINNED host memory (b200pf_pinned_alloc) instead of
+ * the rows staging buffer: lets a driver pre-collate the time series once (rows of all instances for step k
+ * contiguous) and feed every step without touching the data on the host. */
+int b200pf_rows_chunk_launch_from(b200pf_handle *h, int first, int count, const float *pinned_rows, int is_dc,
+                                  int max_iter, double tol_mva, int nb_cap);
+int b200pf_pinned_alloc(size_t bytes, void **ptr);
+int b200pf_pinned_free(void *ptr);
 /* run all work of this handle on the caller's stream (cudaStream_t as integer; 0 = the handle's own) */
 int b200pf_set_stream(b200pf_handle *h, uint64_t stream);
 

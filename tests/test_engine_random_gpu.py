@@ -118,3 +118,17 @@ def test_rows_mode_matches_series_mode(cuda_required):
         assert (s1 == 0).all() and np.array_equal(s1, s2)
         assert np.array_equal(o1, o2)
     env.close()
+
+
+def test_precollated_host_path_matches_series_mode(cuda_required):
+    from grid2op_b200.rollout import BatchedDoNothing
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"]
+    env = BatchedDoNothing(gm, chron, 96)
+    assert env.precollate()
+    for _ in range(4):
+        env.step_device()
+        o1, s1, i1, _ = env.fetch()
+        o2, s2 = env.step_host()
+        assert (s1 == 0).all() and np.array_equal(s1, s2) and np.array_equal(o1, o2)
+    env.close()
