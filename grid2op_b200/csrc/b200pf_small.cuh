@@ -267,6 +267,20 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
     adj[lane] = 0u;
     __syncwarp();
     if (bf >= 0) { atomicOr(&adj[bf], 1u << bt); atomicOr(&adj[bt], 1u << bf); }
+    // per-bus list of the in-service line ends on this bus, packed 6 bits per entry (code = 2*line + side < 64):
+    // built once, used by every mismatch pass instead of re-filtering the substation's static list
+    unsigned long long adjc = 0ull;
+    int adeg = 0;
+    if (isbus) {
+        for (int e = g.sub_end_ptr[mysub]; e < g.sub_end_ptr[mysub + 1]; ++e) {
+            const int code = g.sub_end[e], l = code >> 1;
+            const int f = brf[l];
+            if (f < 0 || ((code & 1) ? brt[l] : f) != lane) continue;
+            if (adeg < 10) adjc |= (unsigned long long)code << (6 * adeg);
+            ++adeg;
+        }
+    }
+    const bool adj_packed = !__any_sync(FULL, adeg > 10);      // (a bus with more than 10 line ends: generic path)
 
     // ---- 2. per-bus aggregates, in element order (deterministic; the later unit wins the set point) -
     int btype = BT_PQ, cnt = 0, nref = 0;
@@ -335,13 +349,14 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
     __syncwarp();
 
     // ---- 5. Ybus diagonal and the DC system (bus lane = matrix row) ---------------------------------
-    double gii = gsh / base, bii = bsh / base, va = 0.0;
+    const double gs_pu = gsh / base, bs_pu = bsh / base;      // shunt admittance in p.u. (divided once)
+    double gii = gs_pu, bii = bs_pu, va = 0.0;
     if (a.is_dc) {
         // DC mode: the angles ARE the result -> fp64 system
         const int pitch = (n1 + 1) | 1;
         double *Mr = Md + (colth >= 0 ? colth : 0) * pitch;
         if (colth >= 0) for (int c = 0; c <= n1; ++c) Mr[c] = 0.0;
-        double rhs = pspec - gsh / base, dsum = 0.0;
+        double rhs = pspec - gs_pu, dsum = 0.0;
         if (isbus) {
             for (int e = g.sub_end_ptr[mysub]; e < g.sub_end_ptr[mysub + 1]; ++e) {
                 const int code = g.sub_end[e], l = code >> 1, side = code & 1;
@@ -369,7 +384,7 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         const int pitch = (n1 + 1) | 1;
         float *Mr = J + (colth >= 0 ? colth : 0) * pitch;
         if (colth >= 0) for (int c = 0; c <= n1; ++c) Mr[c] = 0.f;
-        float rhs = (float)(pspec - gsh / base), dsum = 0.f;
+        float rhs = (float)(pspec - gs_pu), dsum = 0.f;
         if (isbus) {
             for (int e = g.sub_end_ptr[mysub]; e < g.sub_end_ptr[mysub + 1]; ++e) {
                 const int code = g.sub_end[e], l = code >> 1, side = code & 1;
@@ -424,13 +439,21 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
             int viol = 0, wild = 0;
             double dP = 0.0, dQ = 0.0;
             if (isbus) {                                              // lane = bus: S = V conj(I)
-                double ir = (gsh * ve - bsh * vf) / base, ii = (gsh * vf + bsh * ve) / base;
-                for (int e = g.sub_end_ptr[mysub]; e < g.sub_end_ptr[mysub + 1]; ++e) {
-                    const int code = g.sub_end[e], l = code >> 1;
-                    const int f = brf[l];
-                    if (f < 0 || ((code & 1) ? brt[l] : f) != lane) continue;
-                    const double2 c2 = cur[code];
-                    ir += c2.x; ii += c2.y;
+                double ir = gs_pu * ve - bs_pu * vf, ii = gs_pu * vf + bs_pu * ve;
+                if (adj_packed) {
+                    unsigned long long cc = adjc;
+                    for (int j = 0; j < adeg; ++j, cc >>= 6) {
+                        const double2 c2 = cur[(int)(cc & 63ull)];
+                        ir += c2.x; ii += c2.y;
+                    }
+                } else {
+                    for (int e = g.sub_end_ptr[mysub]; e < g.sub_end_ptr[mysub + 1]; ++e) {
+                        const int code = g.sub_end[e], l = code >> 1;
+                        const int f = brf[l];
+                        if (f < 0 || ((code & 1) ? brt[l] : f) != lane) continue;
+                        const double2 c2 = cur[code];
+                        ir += c2.x; ii += c2.y;
+                    }
                 }
                 P = ve * ir + vf * ii; Q = vf * ir - ve * ii;
                 if (btype != BT_REF) { dP = P - pspec; const double m1 = fabs(dP); viol |= !(m1 < a.tol_pu); wild |= !(m1 < 1e200); }
@@ -496,7 +519,7 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
         }
         __syncwarp();
         if (isbus) {
-            double p = gsh / base;
+            double p = gs_pu;
             for (int e = g.sub_end_ptr[mysub]; e < g.sub_end_ptr[mysub + 1]; ++e) {
                 const int code = g.sub_end[e], l = code >> 1;
                 const int f = brf[l];
