@@ -41,6 +41,21 @@ def load_workload():
     return gm, chron
 
 
+def flops_view(gm, mean_iters, batch, kern_s, clocks):
+    """SURVEY.md 8(d), second view: dense-LU flops per instance-iteration (2/3 d^3 + 2 d^2, d = NR dimension with all
+    elements on busbar 1) against the fp32 CUDA-core peak at the SM clock sampled during the run (148 SMs x 128 FMA
+    lanes x 2; the solve is 22x22 per instance, not tensor-core shaped, so MEASURED_PEAKS' bf16 figure does not apply)."""
+    n_ref = 1
+    n_pv = int(len(set(int(x) for x in gm.gen_sub))) - n_ref
+    d = n_pv + 2 * (gm.n_sub - n_pv - n_ref)
+    fl = (2.0 / 3.0) * d ** 3 + 2.0 * d ** 2
+    ach = batch * fl * mean_iters / kern_s / 1e12
+    mhz = (clocks or {}).get("sm_mhz") or 1965
+    peak = 148 * 128 * 2 * mhz * 1e6 / 1e12
+    return {"nr_dimension": d, "flops_per_instance_iteration": fl, "achieved_tflops": ach, "peak_fp32_cuda_core_tflops": peak,
+            "frac": ach / peak}
+
+
 def measured_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -280,7 +295,39 @@ def run_ours(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * batch * args.steps / float(t.item())
+    e2e_sync = world * batch * args.steps / float(t.item())
+    e2e_value, e2e_mode = e2e_sync, "lockstep"
+    if args.e2e_groups >= 1:
+        # asynchronous vectorised environments: the batch is cut into G groups, each with its own stream; while the host
+        # consumes the results of one group (and issues its next step) the others are in flight.  Every instance still
+        # gets its results back on the host before its next step is launched; K steps of every instance are timed.
+        groups = env.host_groups(args.e2e_groups, direct_out=args.e2e_direct)
+        ng = len(groups)
+        for g in range(ng):
+            env.group_launch(g)
+        for _ in range(3):
+            for g in range(ng):
+                env.group_wait(g); env.group_launch(g)
+        for g in range(ng):
+            env.group_wait(g)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for g in range(ng):
+            env.group_launch(g)
+        for k in range(args.steps):
+            for g in range(ng):
+                out, st = env.group_wait(g)
+                rho_max += float((st != 0).sum())
+                if k + 1 < args.steps:
+                    env.group_launch(g)
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * batch * args.steps / float(t.item())
+        e2e_mode = f"{ng} groups in flight" + (", results stored by the kernel straight into pinned host memory" if args.e2e_direct else "")
     h2d, d2h = env.bytes_per_step_host()
 
     if rank == 0:
@@ -313,9 +360,12 @@ def run_ours(args):
                        "launch": info, "mean_newton_iterations": mean_iters, "diverged": n_bad,
                        "wall_s_incl_flush": t_wall},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "BatchedDoNothing.step_host(): per step H2D of the topology records + chronics rows (from pinned host memory, "
+                    "mode": e2e_mode, "lockstep_value": e2e_sync,
+                    "what": "BatchedDoNothing host path (group_launch/group_wait; lockstep_value = step_host()): per step H2D of the topology records + chronics rows (from pinned host memory, "
                             + ("pre-collated step-major" if collated else "gathered on the host per step")
-                            + "), kernel, D2H of the full result records, host reads the done flags; 2 pipelined chunks"},
+                            + "), kernel, D2H of the full result records, host reads the done flags of every instance before "
+                              "launching its next step; `value`: the batch is stepped as staggered groups (asynchronous "
+                              "vectorised envs), `lockstep_value`: all instances wait for each other every step (2 pipelined chunks)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -323,6 +373,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_env_step": surv, "b_iter_bytes": b_iter,
                          "compulsory_bytes_per_env_step": comp,
                          "achieved_compulsory_gbs": batch * comp / kern_s / 1e9,
+                         "flops_view": flops_view(gm, mean_iters, batch, kern_s, clocks),
                          "note": "fused whole-solve kernel: state never round-trips HBM, the kernel is issue/latency bound (see DESIGN.md)"},
         }
         if cpu is not None:
@@ -337,6 +388,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--e2e-direct", type=int, default=0, help="1: kernels store results straight into pinned host memory")
+    ap.add_argument("--e2e-groups", type=int, default=4, help="groups in flight for the end-to-end host path (<=1: lockstep only)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)

@@ -30,6 +30,12 @@ struct b200pf_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t chunk_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     int chunk_next = 0;
+    cudaStream_t group_stream[B200PF_MAX_GROUPS] = {};
+    cudaEvent_t group_event[B200PF_MAX_GROUPS] = {};
+    bool group_pending[B200PF_MAX_GROUPS] = {};
+    int small_occ[2][33] = {};
+    int group_flags = 0;                                    // bit 0: kernels store results straight into pinned host memory
+    int env_flags = -1;                                     // bit 0: B200PF_JACOBIAN_FP64, bit 1: B200PF_NO_SMALL_KERNEL
     float *x_out = nullptr; int *x_status = nullptr; int *x_iters = nullptr; float *x_rho = nullptr;
     DevGrid g{};
     std::vector<void *> dev_allocs;
@@ -176,6 +182,8 @@ extern "C" int b200pf_destroy(b200pf_handle *h) {
     for (void *p : pinned) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto &cs : h->chunk_stream) if (cs) cudaStreamDestroy(cs);
+    for (auto &cs : h->group_stream) if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+    for (auto &ev : h->group_event) if (ev) cudaEventDestroy(ev);
     delete h;
     return 0;
 }
@@ -231,10 +239,12 @@ static int launch_small(b200pf_handle *h, RunArgs a, int cap) {
     SmallLayout L = small_layout(cap);
     a.mat_bytes = L.total - L.off_mat;
     auto kern = a.prot ? pf_kernel_small<true> : pf_kernel_small<false>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, (size_t)L.total));
-    if (occ < 1) occ = 1;
+    int &occ = h->small_occ[a.prot ? 1 : 0][cap];          // launch configuration cached per (variant, capacity)
+    if (occ == 0) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, (size_t)L.total));
+        if (occ < 1) occ = 1;
+    }
     const int resident = h->sm_count * occ;
     const int rounds = (a.batch + resident - 1) / resident;
     int grid = (a.batch + rounds - 1) / rounds;
@@ -249,15 +259,17 @@ static int launch_small(b200pf_handle *h, RunArgs a, int cap) {
 
 static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
     const DevGrid &g = h->g;
-    const char *f64 = getenv("B200PF_JACOBIAN_FP64");
-    const bool jd = f64 && f64[0] == '1';
+    if (h->env_flags < 0) {
+        const char *f64 = getenv("B200PF_JACOBIAN_FP64"), *nosk = getenv("B200PF_NO_SMALL_KERNEL");
+        h->env_flags = ((f64 && f64[0] == '1') ? 1 : 0) | ((nosk && nosk[0] == '1') ? 2 : 0);
+    }
+    const bool jd = (h->env_flags & 1) != 0;
     const int jt = jd ? 8 : 4;
     int cap = nb_cap_req;
     if (cap <= 0 || cap > g.n_slot) cap = g.n_slot;
     // warp-per-instance fast path: every element class fits one warp and the caller bounds the number
     // of active buses so that the Newton system has <= 32 unknowns (see b200pf_small.cuh)
-    const char *nos = getenv("B200PF_NO_SMALL_KERNEL");
-    if (!jd && !(nos && nos[0] == '1') && g.n_slot <= 32 && g.n_line <= 32 && g.n_unit <= 32 && g.n_load <= 32 &&
+    if (!jd && !(h->env_flags & 2) && g.n_slot <= 32 && g.n_line <= 32 && g.n_unit <= 32 && g.n_load <= 32 &&
         g.n_sto <= 32 && g.n_shunt <= 32 && cap <= 17)
         return launch_small(h, a, cap);
     if (a.prot) return fail(B200PF_E_STATE, "device-side protections need the warp-per-instance kernel (<= 32 lines / bus slots, nb_cap <= 17)");
@@ -552,7 +564,7 @@ extern "C" int b200pf_pinned_free(void *ptr) {
 }
 
 static int rows_chunk_launch_impl(b200pf_handle *h, int first, int count, const float *src_rows, int is_dc, int max_iter,
-                                  double tol_mva, int nb_cap);
+                                  double tol_mva, int nb_cap, int group = -1);
 
 extern "C" int b200pf_rows_chunk_launch(b200pf_handle *h, int first, int count, int is_dc, int max_iter, double tol_mva, int nb_cap) {
     if (!h) return fail(B200PF_E_ARG, "null handle");
@@ -567,28 +579,70 @@ extern "C" int b200pf_rows_chunk_launch_from(b200pf_handle *h, int first, int co
 }
 
 static int rows_chunk_launch_impl(b200pf_handle *h, int first, int count, const float *src_rows, int is_dc, int max_iter,
-                                  double tol_mva, int nb_cap) {
+                                  double tol_mva, int nb_cap, int group) {
     if (!h) return fail(B200PF_E_ARG, "null handle");
     if (first < 0 || count <= 0 || first + count > h->max_batch) return fail(B200PF_E_ARG, "chunk out of range (max_batch)");
     CU(cudaSetDevice(h->device));
     const DevGrid &g = h->g;
-    const int ci = h->chunk_next++ & 3;
-    if (!h->chunk_stream[ci]) CU(cudaStreamCreateWithFlags(&h->chunk_stream[ci], cudaStreamNonBlocking));
-    cudaStream_t st = h->chunk_stream[ci];
+    cudaStream_t st;
+    if (group >= 0) {
+        if (!h->group_stream[group]) {
+            CU(cudaStreamCreateWithFlags(&h->group_stream[group], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->group_event[group], cudaEventDisableTiming));
+        }
+        st = h->group_stream[group];
+    } else {
+        const int ci = h->chunk_next++ & 3;
+        if (!h->chunk_stream[ci]) CU(cudaStreamCreateWithFlags(&h->chunk_stream[ci], cudaStreamNonBlocking));
+        st = h->chunk_stream[ci];
+    }
     const size_t F = (size_t)first, C = (size_t)count, ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
     CU(cudaMemcpyAsync(h->d_topo + F * g.n_topo_in, h->h_topo + F * g.n_topo_in, C * g.n_topo_in, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->d_rows + F * ncol, src_rows, C * ncol * 4, cudaMemcpyHostToDevice, st));
     RunArgs a = base_args(h, count, is_dc, max_iter, tol_mva);
     a.topo = h->d_topo + F * g.n_topo_in; a.inj = nullptr; a.out = h->d_out + F * g.n_out; a.status = h->d_status + F;
     a.iters = h->d_iters + F; a.busv = nullptr; a.series = 1; a.rows = h->d_rows + F * ncol; a.static_inj = h->d_static_inj;
+    const bool direct = group >= 0 && (h->group_flags & 1);
+    if (direct) {   // pinned host memory is device-addressable (unified addressing): result records go out as posted PCIe writes
+        a.out = h->h_out + F * g.n_out; a.status = h->h_status + F; a.iters = h->h_iters + F;
+    }
     cudaStream_t keep = h->stream;
     h->stream = st;
     int rc = launch(h, a, nb_cap);
     h->stream = keep;
     if (rc) return rc;
-    CU(cudaMemcpyAsync(h->h_out + F * g.n_out, h->d_out + F * g.n_out, C * g.n_out * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h->h_status + F, h->d_status + F, C * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h->h_iters + F, h->d_iters + F, C * 4, cudaMemcpyDeviceToHost, st));
+    if (!direct) {
+        CU(cudaMemcpyAsync(h->h_out + F * g.n_out, h->d_out + F * g.n_out, C * g.n_out * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_status + F, h->d_status + F, C * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_iters + F, h->d_iters + F, C * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (group >= 0) { CU(cudaEventRecord(h->group_event[group], st)); h->group_pending[group] = true; }
+    return 0;
+}
+
+extern "C" int b200pf_rows_group_launch(b200pf_handle *h, int group, int first, int count, const float *pinned_rows, int is_dc,
+                                        int max_iter, double tol_mva, int nb_cap) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (group < 0 || group >= B200PF_MAX_GROUPS) return fail(B200PF_E_ARG, "group out of range");
+    if (h->group_pending[group]) return fail(B200PF_E_ARG, "group still in flight: call b200pf_rows_group_wait first");
+    const size_t ncol = 2 * (size_t)h->g.n_load + 2 * (size_t)h->g.n_gen;
+    const float *src = pinned_rows ? pinned_rows : h->h_rows + (size_t)(first < 0 ? 0 : first) * ncol;
+    return rows_chunk_launch_impl(h, first, count, src, is_dc, max_iter, tol_mva, nb_cap, group);
+}
+
+extern "C" int b200pf_rows_group_config(b200pf_handle *h, int flags) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    for (bool p : h->group_pending) if (p) return fail(B200PF_E_STATE, "groups in flight");
+    h->group_flags = flags;
+    return 0;
+}
+
+extern "C" int b200pf_rows_group_wait(b200pf_handle *h, int group) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (group < 0 || group >= B200PF_MAX_GROUPS) return fail(B200PF_E_ARG, "group out of range");
+    if (!h->group_pending[group]) return 0;
+    CU(cudaEventSynchronize(h->group_event[group]));
+    h->group_pending[group] = false;
     return 0;
 }
 

@@ -32,7 +32,8 @@ ABI_SYMBOLS = (
     "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
     "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
     "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait",
-    "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free",
+    "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free", "b200pf_rows_group_launch", "b200pf_rows_group_wait",
+    "b200pf_rows_group_config",
 )
 
 
@@ -105,6 +106,9 @@ def load_library():
     lib.b200pf_rows_chunk_wait.argtypes = [vp]
     lib.b200pf_rows_chunk_launch_from.argtypes = [vp, i32, i32, vp, i32, i32, f64, i32]
     lib.b200pf_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.b200pf_rows_group_launch.argtypes = [vp, i32, i32, i32, vp, i32, i32, f64, i32]
+    lib.b200pf_rows_group_wait.argtypes = [vp, i32]
+    lib.b200pf_rows_group_config.argtypes = [vp, i32]
     lib.b200pf_pinned_free.argtypes = [vp]
     lib.b200pf_stream.argtypes = [vp]
     lib.b200pf_stream.restype = C.c_uint64
@@ -117,7 +121,8 @@ def load_library():
                "b200pf_series_bind_outputs", "b200pf_set_stream", "b200pf_set_static_inj", "b200pf_rows_staging",
                "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
                "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait",
-               "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free"):
+               "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free", "b200pf_rows_group_launch",
+               "b200pf_rows_group_wait", "b200pf_rows_group_config"):
         getattr(lib, nm).restype = i32
     _LIB = lib
     return lib
@@ -339,6 +344,20 @@ class PowerFlowEngine:
         self._check(self.lib.b200pf_rows_chunk_launch_from(self.h, int(first), int(count), C.c_void_p(pinned_rows.ctypes.data),
                                                            int(bool(is_dc)), int(max_iter), float(tol_mva), int(nb_cap)),
                     "b200pf_rows_chunk_launch_from")
+
+    def rows_group_launch(self, group: int, first: int, count: int, pinned_rows: Optional[np.ndarray] = None, is_dc: bool = False,
+                          max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0):
+        """Asynchronous: H2D -> kernel -> D2H of instances [first, first+count) on the stream of ``group``."""
+        ptr = C.c_void_p(pinned_rows.ctypes.data) if pinned_rows is not None else None
+        self._check(self.lib.b200pf_rows_group_launch(self.h, int(group), int(first), int(count), ptr, int(bool(is_dc)),
+                                                      int(max_iter), float(tol_mva), int(nb_cap)), "b200pf_rows_group_launch")
+
+    def rows_group_config(self, direct_out: bool = False):
+        """direct_out: kernels store their results straight into the pinned staging buffers (no copy-engine D2H)."""
+        self._check(self.lib.b200pf_rows_group_config(self.h, 1 if direct_out else 0), "b200pf_rows_group_config")
+
+    def rows_group_wait(self, group: int):
+        self._check(self.lib.b200pf_rows_group_wait(self.h, int(group)), "b200pf_rows_group_wait")
 
     def rows_chunk_wait(self):
         self._check(self.lib.b200pf_rows_chunk_wait(self.h), "b200pf_rows_chunk_wait")

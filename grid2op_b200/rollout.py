@@ -133,6 +133,53 @@ class BatchedDoNothing:
         self.engine.rows_chunk_wait()
         return st["out"][:self.batch], st["status"][:self.batch]
 
+    # ---- host buffers in / out, group-pipelined (asynchronous vectorised environments) -----------------------------
+    def host_groups(self, n_groups: int = 4, direct_out: bool = False):
+        """Cut the batch into ``n_groups`` contiguous groups for :meth:`group_launch` / :meth:`group_wait`: while the
+        caller consumes the results of one group the others are in flight (their PCIe copies overlap the kernels of
+        the rest).  Every instance still sees its own results before its next step is launched."""
+        if self._stage is None:
+            self.step_host()                                   # initialise staging / static inputs
+            self._t_host = self.t0.astype(np.int64).copy()
+            self._k = 0
+        n_groups = max(1, min(int(n_groups), self.batch, 16))
+        self.engine.rows_group_config(direct_out=direct_out)
+        self._groups = [(self.batch * g // n_groups, self.batch * (g + 1) // n_groups) for g in range(n_groups)]
+        self._gk = [self._k] * n_groups
+        # per-group constants of the C call (the per-step host cost bounds how many groups pay off)
+        eng = self.engine
+        self._g_fn = (eng.lib.b200pf_rows_group_launch, eng.lib.b200pf_rows_group_wait, eng.h)
+        self._g_tail = (int(self.is_dc), int(self.max_iter), float(self.tol_mva), int(self.nb_cap))
+        self._g_views = [(self._stage["out"][lo:hi], self._stage["status"][lo:hi]) for lo, hi in self._groups]
+        if self._collated is not None:
+            ncol = self.chron.shape[2]
+            self._g_base = [self._collated.ctypes.data + 4 * ncol * lo for lo, _ in self._groups]
+            self._g_stride = 4 * ncol * self.batch
+        return list(self._groups)
+
+    def group_launch(self, g: int) -> None:
+        """Asynchronous: next step of group ``g`` (H2D of its topology records + chronics rows, kernel, D2H)."""
+        lo, hi = self._groups[g]
+        launch, _, h = self._g_fn
+        if self._collated is not None:
+            k = self._gk[g]
+            self._gk[g] = k + 1
+            rows = self._g_base[g] + self._g_stride * (k % self._collated.shape[0])
+        else:
+            np.take(self._chron_flat, self._row_base[lo:hi] + self._t_host[lo:hi], axis=0, out=self._rows[lo:hi])
+            self._t_host[lo:hi] = (self._t_host[lo:hi] + 1) % self.chron.shape[1]
+            rows = None
+        rc = launch(h, g, lo, hi - lo, rows, *self._g_tail)
+        if rc:
+            self.engine._check(rc, "b200pf_rows_group_launch")
+
+    def group_wait(self, g: int):
+        """Blocks until the results of group ``g`` are in the pinned staging buffers; returns (out, status) views."""
+        rc = self._g_fn[1](self._g_fn[2], g)
+        if rc:
+            self.engine._check(rc, "b200pf_rows_group_wait")
+        return self._g_views[g]
+
     def precollate(self, max_bytes: int = 2 << 30) -> bool:
         """Data-pipeline step done once: lay the time series out step-major in pinned host memory,
         ``[n_rows, batch, ncol]`` (row k = what every instance needs at its k-th step), so that a step ships its

@@ -193,6 +193,22 @@ int b200pf_rows_chunk_wait(b200pf_handle *h);
  * contiguous) and feed every step without touching the data on the host. */
 int b200pf_rows_chunk_launch_from(b200pf_handle *h, int first, int count, const float *pinned_rows, int is_dc,
                                   int max_iter, double tol_mva, int nb_cap);
+/* Group-pipelined stepping (asynchronous vectorised environments): the batch is cut into up to B200PF_MAX_GROUPS
+ * groups of instances [first, first+count); each group owns a stream and an event.  launch enqueues H2D (topology
+ * records from the pinned staging buffer, rows from pinned_rows or, when NULL, from the pinned rows staging buffer)
+ * -> fused kernel -> D2H into the pinned out/status/iters staging buffers and returns at once; wait blocks until that
+ * group's results have landed.  While the caller consumes group g (the agent of reference
+ * grid2op/Environment/baseEnv.py:3778 `step` acting on its observations) the other groups are in flight, so PCIe
+ * transfers of one group overlap the kernels of the others.  A group must be waited for before it is launched again. */
+#define B200PF_MAX_GROUPS 16
+int b200pf_rows_group_launch(b200pf_handle *h, int group, int first, int count, const float *pinned_rows, int is_dc,
+                             int max_iter, double tol_mva, int nb_cap);
+int b200pf_rows_group_wait(b200pf_handle *h, int group);
+/* flags bit 0 (B200PF_GROUP_DIRECT_OUT): the kernel stores result records / status / iters straight into the pinned
+ * staging buffers (device-addressable host memory, posted PCIe writes that overlap the solve of the other instances)
+ * instead of a copy-engine D2H after the kernel.  Only while no group is in flight. */
+#define B200PF_GROUP_DIRECT_OUT 1
+int b200pf_rows_group_config(b200pf_handle *h, int flags);
 int b200pf_pinned_alloc(size_t bytes, void **ptr);
 int b200pf_pinned_free(void *ptr);
 /* run all work of this handle on the caller's stream (cudaStream_t as integer; 0 = the handle's own) */

@@ -132,3 +132,51 @@ def test_precollated_host_path_matches_series_mode(cuda_required):
         o2, s2 = env.step_host()
         assert (s1 == 0).all() and np.array_equal(s1, s2) and np.array_equal(o1, o2)
     env.close()
+
+
+@pytest.mark.parametrize("direct", [False, True])
+@pytest.mark.parametrize("collated", [False, True])
+def test_group_pipelined_host_path_matches_series_mode(cuda_required, collated, direct):
+    """b200pf_rows_group_launch / _wait: groups stepped out of phase give, per instance and step, exactly the
+    results of the device-resident series stepping."""
+    from grid2op_b200.rollout import BatchedDoNothing
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"]
+    B, K = 150, 4
+    ref = BatchedDoNothing(gm, chron, B)
+    want = []
+    for _ in range(K):
+        ref.step_device()
+        o, s, _, _ = ref.fetch()
+        want.append((o.copy(), s.copy()))
+    ref.close()
+    env = BatchedDoNothing(gm, chron, B)
+    if collated:
+        assert env.precollate()
+    groups = env.host_groups(3, direct_out=direct)
+    assert groups[0][0] == 0 and groups[-1][1] == B
+    # stagger the groups: group g is g steps ahead of the last one at any time
+    done = [0] * len(groups)
+    for g in range(len(groups)):
+        env.group_launch(g)
+    while min(done) < K:
+        for g, (lo, hi) in enumerate(groups):
+            if done[g] >= K:
+                continue
+            o, s = env.group_wait(g)
+            wo, ws = want[done[g]]
+            assert (s == 0).all() and np.array_equal(s, ws[lo:hi]) and np.array_equal(o, wo[lo:hi])
+            done[g] += 1
+            if done[g] < K:
+                env.group_launch(g)
+                if g == 0 and done[g] < K - 1:       # let group 0 run one extra step ahead
+                    o, s = env.group_wait(g)
+                    wo, ws = want[done[g]]
+                    assert np.array_equal(o, wo[lo:hi])
+                    done[g] += 1
+                    env.group_launch(g)
+    env.group_launch(0)
+    with pytest.raises(Exception):           # a group in flight must be waited for before its next launch
+        env.group_launch(0)
+    env.group_wait(0)
+    env.close()
