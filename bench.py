@@ -207,6 +207,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from grid2op_b200.rollout import BatchedDoNothing
+    os.environ["B200PF_PLAN_POLICY"] = str(args.policy)
     gm, chron = load_workload()
     batch = args.batch
     env = BatchedDoNothing(gm, chron, batch, device=local, offset=rank * batch)
@@ -357,7 +358,7 @@ def run_ours(args):
                        "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world} (independent instances)",
                        "l2": "flushed between timed steps (256 MiB memset, outside the event pair)",
                        "precision": "fp64 state/mismatch/flows, fp32 Jacobian+LU, tol 1e-8 MVA, max_iter 10",
-                       "launch": info, "mean_newton_iterations": mean_iters, "diverged": n_bad,
+                       "launch": info, "kernel": eng.plan_stats(), "mean_newton_iterations": mean_iters, "diverged": n_bad,
                        "wall_s_incl_flush": t_wall},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mode": e2e_mode, "lockstep_value": e2e_sync,
@@ -395,6 +396,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--policy", type=int, default=0, choices=[0, 1, 2],
+                    help="kernel policy (include/b200pf.h): 0 auto = planned sparse kernel, 1 pivoting kernels only, 2 planned always")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -3,12 +3,14 @@
 // stream per handle, and picks the thread-group size / shared-memory budget per launch.
 #include "b200pf_kernel.cuh"
 #include "b200pf_small.cuh"
+#include "b200pf_sparse.cuh"
 #include "../../include/b200pf.h"
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace b200pf;
@@ -54,6 +56,21 @@ struct b200pf_handle {
     int *d_pcount = nullptr, *d_tsover = nullptr, *d_disc = nullptr, *d_done = nullptr;
     int prot = 0, next_reset = 0, max_pc = 2; float hard_thr = 2.0f, soft_thr = 1.0f;
     int small_ok = 0;
+    // planned sparse kernel: cache of topology plans (host blobs + their device copy)
+    HostGrid hg;
+    std::unordered_map<std::string, int> plan_index;
+    std::vector<int> plan_off, plan_smem;
+    std::vector<unsigned char> plan_blobs;                  // concatenated, every plan 16-byte aligned
+    unsigned char *d_plan_blobs = nullptr; size_t d_plan_cap = 0, d_plan_used = 0;
+    int *d_plan_off = nullptr; int d_plan_off_n = 0;
+    int *d_inst_plan = nullptr, *h_inst_plan = nullptr;     // [max_batch]
+    int *d_series_plan = nullptr; int series_plan_state = 0; // 0 none, 1 per-instance plans, 2 all instances on one plan
+    int series_plan_single = 0, series_plan_smem = 0;
+    int plan_policy = 0;                                    // 0 auto, 1 never, 2 whenever a host copy of the topology exists
+    int plan_max_smem = 0;
+    int sparse_occ_smem = -1, sparse_occ = 0, sparse_occ_variant = 0, sparse_variant_override = 0;
+    int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
+    int64_t plans_built = 0;
     int64_t launches = 0;
     int last_smem = 0, last_T = 0, last_grid = 0, last_block = 0;
 };
@@ -169,6 +186,26 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
             (rc = dmal((void **)&h->d_thlim, (size_t)g.n_line * 4)) || (rc = dmal((void **)&h->d_rho, B * g.n_line * 4))) { b200pf_destroy(h); return rc; }
         if (cudaMallocHost(&h->h_rows, B * ncol * 4 + 4) != cudaSuccess) { b200pf_destroy(h); return fail(B200PF_E_CUDA, "pinned host allocation failed"); }
     }
+    {   // host copy of the grid for the plan builder; per-instance plan ids
+        HostGrid &hg = h->hg;
+        hg.n_sub = g.n_sub; hg.n_busbar = g.n_busbar; hg.n_slot = g.n_slot; hg.n_line = g.n_line; hg.n_gen = g.n_gen; hg.n_hidden = g.n_hidden;
+        hg.n_unit = g.n_unit; hg.n_load = g.n_load; hg.n_sto = g.n_sto; hg.n_shunt = g.n_shunt; hg.dim_topo = g.dim_topo;
+        hg.n_topo_in = g.n_topo_in; hg.base_mva = g.base_mva;
+#define CP(dst, src, n) hg.dst.assign(gd->src, gd->src + (size_t)(n))
+        CP(line_or_sub, line_or_sub, g.n_line); CP(line_ex_sub, line_ex_sub, g.n_line); CP(line_or_pos, line_or_pos, g.n_line);
+        CP(line_ex_pos, line_ex_pos, g.n_line); CP(line_y, line_y, 8 * g.n_line); CP(line_bdc, line_bdc, g.n_line);
+        CP(line_pshift, line_pshift, g.n_line); CP(unit_sub, unit_sub, g.n_unit); CP(unit_pos, unit_pos, g.n_unit);
+        CP(unit_is_ref, unit_is_ref, g.n_unit); CP(unit_qmin, unit_qmin, g.n_unit); CP(unit_qmax, unit_qmax, g.n_unit);
+        CP(load_sub, load_sub, g.n_load); CP(load_pos, load_pos, g.n_load); CP(sto_sub, storage_sub, g.n_sto);
+        CP(sto_pos, storage_pos, g.n_sto); CP(sh_sub, shunt_sub, g.n_shunt);
+#undef CP
+        if ((rc = dmal((void **)&h->d_inst_plan, B * 4))) { b200pf_destroy(h); return rc; }
+        if (cudaMallocHost(&h->h_inst_plan, B * 4 + 4) != cudaSuccess) { b200pf_destroy(h); return fail(B200PF_E_CUDA, "pinned host allocation failed"); }
+        const char *pol = getenv("B200PF_PLAN_POLICY");
+        if (pol && pol[0] >= '0' && pol[0] <= '2') h->plan_policy = pol[0] - '0';
+        const char *var = getenv("B200PF_SPARSE_VARIANT");     // tuning: force one (threads per instance, CTAs per SM) variant
+        if (var && var[0] >= '1' && var[0] <= '6') h->sparse_variant_override = var[0] - '0';
+    }
     *out = h;
     return 0;
 }
@@ -178,7 +215,9 @@ extern "C" int b200pf_destroy(b200pf_handle *h) {
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (void *p : h->dev_allocs) cudaFree(p);
-    void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv, h->h_rows};
+    if (h->d_plan_blobs) cudaFree(h->d_plan_blobs);
+    if (h->d_plan_off) cudaFree(h->d_plan_off);
+    void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv, h->h_rows, h->h_inst_plan};
     for (void *p : pinned) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto &cs : h->chunk_stream) if (cs) cudaStreamDestroy(cs);
@@ -225,7 +264,7 @@ static int launch_t(b200pf_handle *h, const RunArgs &a) {
     kern<<<grid, BLOCK, smem, h->stream>>>(g, a, ws_bytes);
     CU(cudaGetLastError());
     h->launches++;
-    h->last_smem = (int)smem; h->last_T = T; h->last_grid = grid; h->last_block = BLOCK;
+    h->last_smem = (int)smem; h->last_T = T; h->last_grid = grid; h->last_block = BLOCK; h->last_kernel = 2;
     return 0;
 }
 
@@ -252,12 +291,160 @@ static int launch_small(b200pf_handle *h, RunArgs a, int cap) {
     kern<<<grid, 32, L.total, h->stream>>>(g, a, L);
     CU(cudaGetLastError());
     h->launches++;
-    h->last_smem = L.total; h->last_T = 32; h->last_grid = grid; h->last_block = 32;
+    h->last_smem = L.total; h->last_T = 32; h->last_grid = grid; h->last_block = 32; h->last_kernel = 1;
     (void)g;
     return 0;
 }
 
-static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
+// ------------------------------------------------------------------------------------------------
+// topology plans of the sparse kernel (b200pf_plan.hpp): cache keyed by the topology bytes
+// ------------------------------------------------------------------------------------------------
+static const int PLAN_MAX = 32768;          // plans kept per handle
+static const int PLAN_BUILD_BUDGET = 512;   // new plans one call may build in automatic mode before it falls back
+
+struct PlanSel {
+    const int *d_inst_plan;   // device, per instance of the launch; nullptr = every instance uses plan `single`
+    int single;
+    int smem;
+};
+
+static int plan_lookup(b200pf_handle *h, const int8_t *tv, int outage, int *built) {
+    std::string key((const char *)tv, (size_t)h->g.n_topo_in);
+    if (outage >= 0) { key.push_back((char)0x7f); key.push_back((char)(outage & 0xff)); key.push_back((char)((outage >> 8) & 0xff)); }
+    auto it = h->plan_index.find(key);
+    if (it != h->plan_index.end()) return it->second;
+    if ((int)h->plan_off.size() >= PLAN_MAX) return -1;
+    PlanBuilder pb(h->hg);
+    std::vector<unsigned char> blob = pb.build(tv, outage);
+    const PlanHeader *H = reinterpret_cast<const PlanHeader *>(blob.data());
+    if (!PlanBuilder::fits(*H) || H->smem_bytes > h->max_smem_optin) return -1;
+    const int id = (int)h->plan_off.size();
+    h->plan_off.push_back((int)h->plan_blobs.size());
+    h->plan_smem.push_back(H->smem_bytes);
+    h->plan_blobs.insert(h->plan_blobs.end(), blob.begin(), blob.end());
+    while (h->plan_blobs.size() % 16) h->plan_blobs.push_back(0);
+    h->plan_index.emplace(std::move(key), id);
+    if (H->smem_bytes > h->plan_max_smem) h->plan_max_smem = H->smem_bytes;
+    ++*built; h->plans_built++;
+    return id;
+}
+
+// device copy of the plans built since the last call (synchronous copies: building a plan is a rare event, and a plan
+// must be visible to every stream of the handle)
+static int plans_sync_device(b200pf_handle *h) {
+    if (h->d_plan_used == h->plan_blobs.size() && h->d_plan_off_n == (int)h->plan_off.size()) return 0;
+    if (h->plan_blobs.size() > h->d_plan_cap) {
+        CU(cudaDeviceSynchronize());                       // launches in flight may still read the old buffer
+        if (h->d_plan_blobs) CU(cudaFree(h->d_plan_blobs));
+        h->d_plan_blobs = nullptr; h->d_plan_used = 0;
+        size_t cap = h->plan_blobs.size() * 2;
+        if (cap < (size_t(1) << 20)) cap = size_t(1) << 20;
+        CU(cudaMalloc(&h->d_plan_blobs, cap));
+        h->d_plan_cap = cap;
+    }
+    if (!h->d_plan_off) CU(cudaMalloc(&h->d_plan_off, (size_t)PLAN_MAX * 4));
+    CU(cudaMemcpy(h->d_plan_blobs + h->d_plan_used, h->plan_blobs.data() + h->d_plan_used, h->plan_blobs.size() - h->d_plan_used, cudaMemcpyHostToDevice));
+    h->d_plan_used = h->plan_blobs.size();
+    CU(cudaMemcpy(h->d_plan_off + h->d_plan_off_n, h->plan_off.data() + h->d_plan_off_n, (h->plan_off.size() - (size_t)h->d_plan_off_n) * 4, cudaMemcpyHostToDevice));
+    h->d_plan_off_n = (int)h->plan_off.size();
+    return 0;
+}
+
+// Plans of the instances [0, n_src) whose topology rows are at host_topo (times n1_lines outages each in contingency
+// mode); ids go to h_inst_plan[first ...] and, unless all are equal, to d_inst_plan[first ...] on stream st.
+// Returns 1 = use the sparse kernel with *sel, 0 = fall back to the pivoting kernels, < 0 error.
+// the warp-per-instance pivoting kernel applies (and, measured, is the faster one on these tiny systems: its whole
+// state lives in registers): every element class fits 32 lanes and the caller bounds the active buses by 17
+static bool small_kernel_applies(const b200pf_handle *h, int nb_cap) {
+    const DevGrid &g = h->g;
+    return g.n_slot <= 32 && g.n_line <= 32 && g.n_unit <= 32 && g.n_load <= 32 && g.n_sto <= 32 && g.n_shunt <= 32 &&
+           nb_cap > 0 && nb_cap <= 17;
+}
+
+static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int n1_lines, int first, cudaStream_t st, PlanSel *sel,
+                       int nb_cap) {
+    if (h->plan_policy == 1 || !host_topo) return 0;
+    if (h->plan_policy == 0 && small_kernel_applies(h, nb_cap)) return 0;
+    const DevGrid &g = h->g;
+    const size_t nt = (size_t)g.n_topo_in;
+    const int per = n1_lines > 0 ? n1_lines : 1;
+    int *ids = h->h_inst_plan + first;
+    int built = 0;
+    bool single = true;
+    for (int s = 0; s < n_src; ++s) {
+        const int8_t *tv = host_topo + (size_t)s * nt;
+        if (s > 0 && memcmp(tv, tv - nt, nt) == 0) {
+            for (int l = 0; l < per; ++l) ids[(size_t)s * per + l] = ids[(size_t)(s - 1) * per + l];
+            continue;
+        }
+        for (int l = 0; l < per; ++l) {
+            const int id = plan_lookup(h, tv, n1_lines > 0 ? l : -1, &built);
+            if (id < 0) return 0;
+            ids[(size_t)s * per + l] = id;
+            if (id != ids[0]) single = false;
+        }
+        if (h->plan_policy == 0 && built > PLAN_BUILD_BUDGET) { int rc = plans_sync_device(h); return rc ? rc : 0; }
+    }
+    int rc = plans_sync_device(h);
+    if (rc) return rc;
+    const size_t n = (size_t)n_src * per;
+    int smem = 16;
+    if (single) smem = h->plan_smem[ids[0]];
+    else smem = h->plan_max_smem;
+    sel->single = ids[0]; sel->smem = smem; sel->d_inst_plan = nullptr;
+    if (!single) {
+        CU(cudaMemcpyAsync(h->d_inst_plan + first, ids, n * 4, cudaMemcpyHostToDevice, st));
+        sel->d_inst_plan = h->d_inst_plan + first;
+    }
+    return 1;
+}
+
+template <int T, int MINB>
+static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel, int variant) {
+    const DevGrid &g = h->g;
+    auto kern = pf_kernel_sparse<T, MINB>;
+    const int smem = sel.smem;
+    if (h->sparse_occ_smem != smem || h->sparse_occ_variant != variant) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        int occ = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, (size_t)smem));
+        if (occ < 1) occ = 1;
+        h->sparse_occ = occ; h->sparse_occ_smem = smem; h->sparse_occ_variant = variant;
+    }
+    PlanArgs pa;
+    pa.blobs = h->d_plan_blobs;
+    pa.plan_off = h->d_plan_off + (sel.d_inst_plan ? 0 : sel.single);
+    pa.inst_plan = sel.d_inst_plan;
+    const int resident = h->sm_count * h->sparse_occ;
+    const int rounds = (a.batch + resident - 1) / resident;
+    int grid = (a.batch + rounds - 1) / rounds;
+    if (grid < 1) grid = 1;
+    kern<<<grid, T, (size_t)smem, h->stream>>>(g, a, pa);
+    CU(cudaGetLastError());
+    h->launches++;
+    h->last_smem = smem; h->last_T = T; h->last_grid = grid; h->last_block = T; h->last_kernel = 3;
+    return 0;
+}
+
+// Threads per instance and register budget of the planned kernel: small workspaces (5/14/36 substations) run one warp
+// per instance with as many one-warp CTAs per SM as the hardware holds (32); large ones (118 substations, ~22 KB per
+// instance) are limited to ~10 instances per SM by shared memory and get 4 warps per instance instead.
+static int launch_sparse(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
+    const int per_sm = h->max_smem_optin / (sel.smem + 1024);
+    int variant = h->sparse_variant_override;
+    if (variant <= 0) variant = per_sm >= 32 ? 1 : (per_sm >= 24 ? 2 : (per_sm >= 16 ? 3 : 4));
+    switch (variant) {
+        case 1: return launch_sparse_t<32, 32>(h, a, sel, 1);
+        case 2: return launch_sparse_t<32, 24>(h, a, sel, 2);
+        case 3: return launch_sparse_t<32, 16>(h, a, sel, 3);
+        case 4: return launch_sparse_t<128, 4>(h, a, sel, 4);
+        case 5: return launch_sparse_t<64, 8>(h, a, sel, 5);
+        default: return launch_sparse_t<32, 8>(h, a, sel, 6);
+    }
+}
+
+static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req, const PlanSel *sel = nullptr) {
+    if (sel && !a.prot) return launch_sparse(h, a, *sel);
     const DevGrid &g = h->g;
     if (h->env_flags < 0) {
         const char *f64 = getenv("B200PF_JACOBIAN_FP64"), *nosk = getenv("B200PF_NO_SMALL_KERNEL");
@@ -310,6 +497,7 @@ static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req) {
     }
 }
 
+static int series_plans(b200pf_handle *h, const int8_t *topo);
 static RunArgs base_args(const b200pf_handle *h, int batch, int is_dc, int max_iter, double tol_mva) {
     RunArgs a{};
     a.batch = batch; a.is_dc = is_dc; a.max_iter = max_iter;
@@ -328,6 +516,17 @@ extern "C" int b200pf_run_device(b200pf_handle *h, int batch, const int8_t *d_to
     return launch(h, a, nb_cap);
 }
 
+// kernel launch for the records staged in d_topo / d_inj (host copy of the topology: h_topo)
+static int run_staged_device(b200pf_handle *h, int batch, int is_dc, int max_iter, double tol_mva, int nb_cap, bool want_busv) {
+    RunArgs a = base_args(h, batch, is_dc, max_iter, tol_mva);
+    a.topo = h->d_topo; a.inj = h->d_inj; a.out = h->d_out; a.status = h->d_status; a.iters = h->d_iters;
+    a.busv = want_busv ? h->d_busv : nullptr;
+    PlanSel sel;
+    const int use = plan_select(h, h->h_topo, batch, 0, 0, h->stream, &sel, nb_cap);
+    if (use < 0) return use;
+    return launch(h, a, nb_cap, use ? &sel : nullptr);
+}
+
 extern "C" int b200pf_run_host(b200pf_handle *h, int batch, const int8_t *topo, const double *inj, int is_dc,
                                int max_iter, double tol_mva, int nb_cap, float *out, int32_t *status,
                                int32_t *iters, double *busv) {
@@ -340,8 +539,7 @@ extern "C" int b200pf_run_host(b200pf_handle *h, int batch, const int8_t *topo, 
     memcpy(h->h_inj, inj, B * g.n_inj * 8);
     CU(cudaMemcpyAsync(h->d_topo, h->h_topo, B * g.n_topo_in, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_inj, h->h_inj, B * g.n_inj * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = b200pf_run_device(h, batch, h->d_topo, h->d_inj, is_dc, max_iter, tol_mva, nb_cap, h->d_out, h->d_status,
-                               h->d_iters, busv ? h->d_busv : nullptr);
+    int rc = run_staged_device(h, batch, is_dc, max_iter, tol_mva, nb_cap, busv != nullptr);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_out, h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -384,6 +582,28 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
     CU(cudaMemcpy(h->d_thlim, thermal_limit_a, (size_t)g.n_line * 4, cudaMemcpyHostToDevice));
     CU(cudaMemset(h->d_series_topo, 1, (size_t)batch * g.n_topo_in));
     h->series_batch = batch; h->n_scen = n_scen; h->n_rows = n_rows;
+    if ((rc = dmal((void **)&h->d_series_plan, (size_t)batch * 4))) return rc;
+    {
+        std::vector<int8_t> ones((size_t)batch * g.n_topo_in, 1);
+        return series_plans(h, ones.data());
+    }
+}
+
+// plans of the device-resident series topology (it only changes through b200pf_series_set_topo, or through the
+// protections, which keep the pivoting kernels)
+static int series_plans(b200pf_handle *h, const int8_t *topo) {
+    h->series_plan_state = 0;
+    PlanSel sel;
+    CU(cudaStreamSynchronize(h->stream));
+    const int use = plan_select(h, topo, h->series_batch, 0, 0, h->stream, &sel, -1);
+    if (use < 0) return use;
+    if (!use) return 0;
+    h->series_plan_single = sel.single; h->series_plan_smem = sel.smem;
+    if (sel.d_inst_plan) {
+        CU(cudaMemcpyAsync(h->d_series_plan, h->d_inst_plan, (size_t)h->series_batch * 4, cudaMemcpyDeviceToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->series_plan_state = 1;
+    } else h->series_plan_state = 2;
     return 0;
 }
 
@@ -392,7 +612,7 @@ extern "C" int b200pf_series_set_topo(b200pf_handle *h, const int8_t *topo) {
     if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpy(h->d_series_topo, topo, (size_t)h->series_batch * h->g.n_topo_in, cudaMemcpyHostToDevice));
-    return 0;
+    return series_plans(h, topo);
 }
 
 extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, double tol_mva, int nb_cap) {
@@ -409,6 +629,12 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
         a.pcount = h->d_pcount; a.ts_over = h->d_tsover; a.disc = h->d_disc; a.done = h->d_done;
     }
     h->next_reset = 0;
+    if (h->series_plan_state && !h->prot && h->plan_policy != 1 && !(h->plan_policy == 0 && small_kernel_applies(h, nb_cap))) {
+        PlanSel sel;
+        sel.single = h->series_plan_single; sel.smem = h->series_plan_smem;
+        sel.d_inst_plan = h->series_plan_state == 1 ? h->d_series_plan : nullptr;
+        return launch(h, a, nb_cap, &sel);
+    }
     return launch(h, a, nb_cap);
 }
 
@@ -482,8 +708,7 @@ extern "C" int b200pf_run_staged(b200pf_handle *h, int batch, int is_dc, int max
     const size_t B = (size_t)batch;
     CU(cudaMemcpyAsync(h->d_topo, h->h_topo, B * g.n_topo_in, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_inj, h->h_inj, B * g.n_inj * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = b200pf_run_device(h, batch, h->d_topo, h->d_inj, is_dc, max_iter, tol_mva, nb_cap, h->d_out, h->d_status,
-                               h->d_iters, want_busv ? h->d_busv : nullptr);
+    int rc = run_staged_device(h, batch, is_dc, max_iter, tol_mva, nb_cap, want_busv != 0);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_out, h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -512,7 +737,10 @@ extern "C" int b200pf_n1_host(b200pf_handle *h, int batch, const int8_t *topo, c
     RunArgs a = base_args(h, (int)N, 0, max_iter, tol_mva);
     a.topo = h->d_topo; a.inj = h->d_inj; a.out = nullptr; a.status = h->d_status; a.iters = h->d_iters; a.busv = nullptr;
     a.n1_lines = g.n_line; a.th_lim = h->d_thlim; a.rho = h->d_rho;
-    int rc = launch(h, a, nb_cap);
+    PlanSel sel;
+    const int use = plan_select(h, topo, batch, g.n_line, 0, h->stream, &sel, nb_cap);
+    if (use < 0) return use;
+    int rc = launch(h, a, nb_cap, use ? &sel : nullptr);
     if (rc) return rc;
     CU(cudaMemcpyAsync(rho, h->d_rho, N * g.n_line * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(status, h->d_status, N * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -544,7 +772,10 @@ extern "C" int b200pf_run_rows_staged(b200pf_handle *h, int batch, int is_dc, in
     RunArgs a = base_args(h, batch, is_dc, max_iter, tol_mva);
     a.topo = h->d_topo; a.inj = nullptr; a.out = h->d_out; a.status = h->d_status; a.iters = h->d_iters; a.busv = nullptr;
     a.series = 1; a.rows = h->d_rows; a.static_inj = h->d_static_inj;
-    int rc = launch(h, a, nb_cap);
+    PlanSel sel;
+    const int use = plan_select(h, h->h_topo, batch, 0, 0, h->stream, &sel, nb_cap);
+    if (use < 0) return use;
+    int rc = launch(h, a, nb_cap, use ? &sel : nullptr);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_out, h->d_out, B * g.n_out * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -606,9 +837,12 @@ static int rows_chunk_launch_impl(b200pf_handle *h, int first, int count, const 
     if (direct) {   // pinned host memory is device-addressable (unified addressing): result records go out as posted PCIe writes
         a.out = h->h_out + F * g.n_out; a.status = h->h_status + F; a.iters = h->h_iters + F;
     }
+    PlanSel sel;
+    const int use = plan_select(h, h->h_topo + F * g.n_topo_in, count, 0, first, st, &sel, nb_cap);
+    if (use < 0) return use;
     cudaStream_t keep = h->stream;
     h->stream = st;
-    int rc = launch(h, a, nb_cap);
+    int rc = launch(h, a, nb_cap, use ? &sel : nullptr);
     h->stream = keep;
     if (rc) return rc;
     if (!direct) {
@@ -664,6 +898,21 @@ extern "C" int b200pf_set_stream(b200pf_handle *h, uint64_t stream) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     h->stream = stream ? (cudaStream_t)(uintptr_t)stream : h->own_stream;
+    return 0;
+}
+
+extern "C" int b200pf_set_kernel_policy(b200pf_handle *h, int policy) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (policy < 0 || policy > 2) return fail(B200PF_E_ARG, "policy must be 0 (auto), 1 (pivoting kernels only) or 2 (planned sparse kernel)");
+    h->plan_policy = policy;
+    return 0;
+}
+
+extern "C" int b200pf_plan_stats(const b200pf_handle *h, int64_t *n_plans, int64_t *plan_bytes, int *last_kernel) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    if (n_plans) *n_plans = (int64_t)h->plan_off.size();
+    if (plan_bytes) *plan_bytes = (int64_t)h->plan_blobs.size();
+    if (last_kernel) *last_kernel = h->last_kernel;
     return 0;
 }
 

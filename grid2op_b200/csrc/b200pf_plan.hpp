@@ -1,0 +1,457 @@
+// b200pf_plan.hpp — host-side "topology plan" of the sparse kernel (b200pf_sparse.cuh).
+//
+// Everything of a power flow that depends on the TOPOLOGY only (reference: what pandapower's pd2ppc does on
+// every runpp call, grid2op/Backend/pandaPowerBackend.py:1097-1105 — bus fusion, bus types, connectivity
+// check, Ybus / Bdc structure — plus what a sparse direct solver's symbolic phase does) is computed ONCE per
+// distinct topology vector on the host and cached:
+//   * active buses, bus types, reachability from the reference buses -> static status of the class
+//   * per-bus element lists (units, loads, storages, shunts, line ends) in element order (deterministic sums)
+//   * a minimum-degree elimination order of the non-reference buses, unknowns (theta_i, |V|_i) interleaved
+//   * the filled pattern of the Newton Jacobian in that order, positions of every entry in a packed value
+//     array, the positions each line / bus writes at assembly time
+//   * the numeric factorisation as a list of passes of independent multiply-subtract operations
+//     A[ij] -= A[ik] * A[kj] / A[kk]  (right-looking LU without pivoting, right-hand side carried along)
+//     and the level schedule of the back substitution
+//   * the DC matrix Bdc of the topology, INVERTED here in fp64 (it only depends on the topology): the DC start of
+//     every Newton solve, and the DC power flow itself, is one matrix-vector product on the device.
+// The device kernel is then a numeric interpreter of the plan: one warp (or CTA) per instance, all values in
+// shared memory.  Instances that share a topology share a plan; a launch may mix plans freely.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace b200pf {
+
+struct HostGrid {
+    int n_sub = 0, n_busbar = 0, n_slot = 0, n_line = 0, n_gen = 0, n_hidden = 0, n_unit = 0, n_load = 0, n_sto = 0,
+        n_shunt = 0, dim_topo = 0, n_topo_in = 0;
+    double base_mva = 1.0;
+    std::vector<int> line_or_sub, line_ex_sub, line_or_pos, line_ex_pos;
+    std::vector<double> line_y, line_bdc, line_pshift;
+    std::vector<int> unit_sub, unit_pos, unit_is_ref;
+    std::vector<double> unit_qmin, unit_qmax;
+    std::vector<int> load_sub, load_pos, sto_sub, sto_pos, sh_sub;
+};
+
+// Header of a plan blob.  All offsets are BYTES from the start of the blob (which is 16-byte aligned on the
+// device); u16 arrays hold 0xFFFF for "none".
+struct PlanHeader {
+    int status;            // static status of the class: ST_OK / ST_UNSUP / ST_NOREF
+    int nb, n1, d;         // active buses, non-reference buses (DC unknowns), Newton unknowns
+    int nnzF, nA;          // entries of the filled Jacobian; nA = nnzF + d (right-hand side appended) ; A[nA] = dummy
+    int n_round;           // assembly rounds of the line lanes (parallel lines write the same entries)
+    int n_pass, n_op;      // LU passes / operations
+    int n_ulev, n_urow;    // back-substitution levels / rows (= d)
+    int dc_unused0, dc_unused1;
+    int n_zero;            // entries zeroed before assembly (everything but the bus-lane entries)
+    int smem_bytes;        // per-instance workspace this plan needs
+    int total_bytes;
+    // per bus (nb entries each)
+    int o_slot, o_btype, o_colth, o_colv, o_dcidx, o_vmunit, o_cnt, o_nref, o_dpos /* [nb][4] */;
+    int o_qmins, o_qmaxs, o_ydiag /* [nb][2] */, o_dcshift;                               // doubles
+    int o_adj_ptr, o_adj, o_bu_ptr, o_bu, o_bl_ptr, o_bl, o_bs_ptr, o_bs, o_bh_ptr, o_bh;  // CSR lists (u16)
+    // per line
+    int o_brf, o_brt, o_round, o_jpos /* [n_line][8] */;
+    // per element: bus index (u16, 0xFFFF = disconnected)
+    int o_unit_bus, o_load_bus, o_sto_bus, o_sh_bus;
+    // LU
+    int o_zero, o_pass_ptr /* int32 [n_pass+1] */, o_ops /* 4 x u16 per op: ij, ik, kj, kk */;
+    int o_ulev_ptr /* u16 [n_ulev+1] */, o_urow /* u16 [d] row index */, o_urow_diag /* u16 [d] */, o_uent_ptr /* u16 [d+1] */,
+        o_uent /* 2 x u16 per entry: column, position */;
+    // DC: the inverse of Bdc (fp64, [n1][n1], stored transposed: entry (j, i) at j * n1 + i so that lanes = rows read
+    // consecutive addresses) — Bdc depends on the topology only, so its solve is a matrix-vector product at run time
+    int o_dcinv;
+    int pad2[10];
+    int pad[6];
+};
+static_assert(sizeof(PlanHeader) % 16 == 0, "plan blobs are concatenated 16-byte aligned");
+
+enum { PLAN_ST_OK = 0, PLAN_ST_UNSUP = 2, PLAN_ST_NOREF = 3 };
+enum { PLAN_BT_PQ = 1, PLAN_BT_PV = 2, PLAN_BT_REF = 3 };
+
+// per-instance shared-memory workspace of the sparse kernel for (nb buses, n_line lines, nA values)
+inline int plan_smem_bytes(int nb, int n_line, int nA) {
+    size_t o = 0;
+    o += (size_t)8 * nb * 8;                 // vm va pspec qspec P Q gs bs
+    o += (size_t)nb * 16;                    // V (e, f)
+    o += (size_t)2 * n_line * 16;            // branch currents, both ends
+    o += ((size_t)(nA + 1) * 4 + 15) & ~(size_t)15;
+    return (int)((o + 15) & ~(size_t)15);
+}
+
+class PlanBuilder {
+public:
+    explicit PlanBuilder(const HostGrid &g) : g_(g) {}
+
+    // topo: int8 [n_topo_in]; outage: line forced out of service (N-1 sweep) or -1.  Returns the blob.
+    std::vector<unsigned char> build(const int8_t *tv, int outage) const {
+        const HostGrid &g = g_;
+        const int nsub = g.n_sub, nl = g.n_line, nu = g.n_unit, nld = g.n_load, nst = g.n_sto, nsh = g.n_shunt, dt = g.dim_topo;
+        const int ns = g.n_slot;
+        // ---- active slots -> compact bus numbers (slot order) --------------------------------------
+        std::vector<int> cidx(ns, 0);
+        auto mark = [&](int sub, int b) { if (b > 0 && b <= g.n_busbar) cidx[sub + (b - 1) * nsub] = 1; };
+        auto lbus = [&](int l, int side) -> int {
+            if (l == outage) return -1;
+            return side ? tv[g.line_ex_pos[l]] : tv[g.line_or_pos[l]];
+        };
+        for (int l = 0; l < nl; ++l) { mark(g.line_or_sub[l], lbus(l, 0)); mark(g.line_ex_sub[l], lbus(l, 1)); }
+        for (int u = 0; u < nu; ++u) mark(g.unit_sub[u], tv[g.unit_pos[u]]);
+        for (int k = 0; k < nld; ++k) mark(g.load_sub[k], tv[g.load_pos[k]]);
+        for (int k = 0; k < nst; ++k) mark(g.sto_sub[k], tv[g.sto_pos[k]]);
+        for (int k = 0; k < nsh; ++k) mark(g.sh_sub[k], tv[dt + k]);
+        int nb = 0;
+        std::vector<int> slot_of;
+        for (int s = 0; s < ns; ++s) { if (cidx[s]) { cidx[s] = nb++; slot_of.push_back(s); } else cidx[s] = -1; }
+        auto bus_of = [&](int sub, int b) -> int { return (b > 0 && b <= g.n_busbar) ? cidx[sub + (b - 1) * nsub] : -1; };
+
+        std::vector<int> unit_bus(nu), load_bus(nld), sto_bus(nst), sh_bus(nsh), brf(nl), brt(nl);
+        for (int u = 0; u < nu; ++u) unit_bus[u] = bus_of(g.unit_sub[u], tv[g.unit_pos[u]]);
+        for (int k = 0; k < nld; ++k) load_bus[k] = bus_of(g.load_sub[k], tv[g.load_pos[k]]);
+        for (int k = 0; k < nst; ++k) sto_bus[k] = bus_of(g.sto_sub[k], tv[g.sto_pos[k]]);
+        for (int k = 0; k < nsh; ++k) sh_bus[k] = bus_of(g.sh_sub[k], tv[dt + k]);
+        for (int l = 0; l < nl; ++l) {
+            const int bo = lbus(l, 0), be = lbus(l, 1);
+            if (bo > 0 && be > 0) { brf[l] = bus_of(g.line_or_sub[l], bo); brt[l] = bus_of(g.line_ex_sub[l], be); }
+            else { brf[l] = -1; brt[l] = -1; }
+        }
+        // ---- bus types, static per-bus unit data --------------------------------------------------
+        std::vector<int> btype(nb, PLAN_BT_PQ), cnt(nb, 0), nref(nb, 0), vmunit(nb, -1);
+        std::vector<double> qmins(nb, 0.0), qmaxs(nb, 0.0);
+        for (int u = 0; u < nu; ++u) {
+            const int i = unit_bus[u];
+            if (i < 0) continue;
+            vmunit[i] = u; cnt[i]++; qmins[i] += g.unit_qmin[u]; qmaxs[i] += g.unit_qmax[u];
+            if (g.unit_is_ref[u]) { btype[i] = PLAN_BT_REF; nref[i]++; }
+            else if (btype[i] != PLAN_BT_REF) btype[i] = PLAN_BT_PV;
+        }
+        int status = PLAN_ST_OK;
+        {
+            std::vector<char> reach(nb, 0);
+            bool anyref = false;
+            for (int i = 0; i < nb; ++i) if (btype[i] == PLAN_BT_REF) { reach[i] = 1; anyref = true; }
+            if (!anyref) status = PLAN_ST_NOREF;
+            else {
+                for (int sweep = 0; sweep < nb + 1; ++sweep) {
+                    bool ch = false;
+                    for (int l = 0; l < nl; ++l) {
+                        const int f = brf[l], t = brt[l];
+                        if (f < 0) continue;
+                        if (reach[f] != reach[t]) { reach[f] = 1; reach[t] = 1; ch = true; }
+                    }
+                    if (!ch) break;
+                }
+                for (int i = 0; i < nb; ++i) if (!reach[i]) status = PLAN_ST_UNSUP;
+            }
+        }
+        if (status != PLAN_ST_OK) {
+            PlanHeader H;
+            memset(&H, 0, sizeof(H));
+            H.status = status; H.nb = nb; H.total_bytes = (int)sizeof(PlanHeader);
+            H.smem_bytes = 16;
+            std::vector<unsigned char> blob(sizeof(PlanHeader));
+            memcpy(blob.data(), &H, sizeof(H));
+            return blob;
+        }
+        // ---- bus graph and minimum-degree elimination order of the non-reference buses -------------
+        std::vector<char> adjm((size_t)nb * nb, 0);
+        for (int l = 0; l < nl; ++l) {
+            const int f = brf[l], t = brt[l];
+            if (f < 0 || f == t) continue;
+            adjm[(size_t)f * nb + t] = 1; adjm[(size_t)t * nb + f] = 1;
+        }
+        std::vector<int> order;         // non-reference buses in elimination order
+        {
+            std::vector<char> w(adjm);  // working copy restricted to non-ref, non-eliminated buses
+            std::vector<char> alive(nb, 0);
+            int n_alive = 0;
+            for (int i = 0; i < nb; ++i) if (btype[i] != PLAN_BT_REF) { alive[i] = 1; ++n_alive; }
+            std::vector<int> nbrs;
+            while (n_alive > 0) {
+                int best = -1, bestdeg = 1 << 30;
+                for (int i = 0; i < nb; ++i) {
+                    if (!alive[i]) continue;
+                    int deg = 0;
+                    const char *row = &w[(size_t)i * nb];
+                    for (int j = 0; j < nb; ++j) deg += (row[j] && alive[j]);
+                    if (deg < bestdeg) { bestdeg = deg; best = i; }
+                }
+                nbrs.clear();
+                for (int j = 0; j < nb; ++j) if (w[(size_t)best * nb + j] && alive[j]) nbrs.push_back(j);
+                for (size_t a = 0; a < nbrs.size(); ++a)
+                    for (size_t b = a + 1; b < nbrs.size(); ++b) {
+                        w[(size_t)nbrs[a] * nb + nbrs[b]] = 1; w[(size_t)nbrs[b] * nb + nbrs[a]] = 1;
+                    }
+                alive[best] = 0; --n_alive;
+                order.push_back(best);
+            }
+        }
+        const int n1 = (int)order.size();
+        std::vector<int> dcidx(nb, -1), colth(nb, -1), colv(nb, -1);
+        int d = 0;
+        for (int k = 0; k < n1; ++k) {
+            const int i = order[k];
+            dcidx[i] = k;
+            colth[i] = d++;
+            if (btype[i] == PLAN_BT_PQ) colv[i] = d++;
+        }
+        // ---- scalar pattern of the Jacobian, symbolic LU --------------------------------------------
+        std::vector<char> S((size_t)d * d, 0);
+        auto setblk = [&](int i, int j) {   // rows of bus i, columns of bus j
+            const int r[2] = {colth[i], colv[i]}, c[2] = {colth[j], colv[j]};
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) if (r[a] >= 0 && c[b] >= 0) S[(size_t)r[a] * d + c[b]] = 1;
+        };
+        for (int i = 0; i < nb; ++i) if (colth[i] >= 0) setblk(i, i);
+        for (int l = 0; l < nl; ++l) {
+            const int f = brf[l], t = brt[l];
+            if (f < 0) continue;
+            setblk(f, t); setblk(t, f);
+        }
+        std::vector<std::vector<int>> rowU(d), colL(d);   // columns j > k of row k ; rows i > k of column k (filled pattern)
+        {
+            std::vector<int> lst;
+            for (int k = 0; k < d; ++k) {
+                lst.clear();
+                for (int j = k + 1; j < d; ++j) if (S[(size_t)k * d + j]) lst.push_back(j);
+                rowU[k] = lst;
+                std::vector<int> &cl = colL[k];
+                for (int i = k + 1; i < d; ++i) if (S[(size_t)i * d + k]) cl.push_back(i);
+                for (int i : cl) { char *Si = &S[(size_t)i * d]; for (int j : lst) Si[j] = 1; }
+            }
+        }
+        std::vector<int> pos((size_t)d * d, -1);
+        int nnzF = 0;
+        for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) if (S[(size_t)i * d + j]) pos[(size_t)i * d + j] = nnzF++;
+        const int nA = nnzF + d;
+        const int DUMMY = nA;
+        auto P = [&](int i, int j) -> int { return (i >= 0 && j >= 0) ? pos[(size_t)i * d + j] : -1; };
+        // ---- LU + both triangular solves as ONE list of multiply-subtract operations A[ij] -= A[ik] A[kj] / A[kk]
+        //      (right-looking elimination with the right-hand side carried along, then column-oriented back
+        //      substitution on the right-hand side), list-scheduled into passes: an operation goes to the earliest
+        //      pass after the last write of everything it reads (RAW), after the previous write of its target (WAW:
+        //      two updates of one entry never share a pass, and keep their sequential order, so the rounding is that
+        //      of the sequential algorithm) and after the last read of its target (WAR).  The number of passes is
+        //      the depth of the dependency graph (about twice the height of the elimination tree), not the number
+        //      of columns.  The solution is x_k = rhs_k / A[kk] (taken by the bus lanes in the state update).
+        struct Op { uint16_t ij, ik, kj, kk; };
+        std::vector<Op> ops;
+        std::vector<int> pass_ptr(1, 0);
+        {
+            std::vector<Op> seq;
+            for (int k = 0; k < d; ++k) {
+                const int kk = P(k, k);
+                for (int i : colL[k]) {
+                    const int ik = P(i, k);
+                    for (int j : rowU[k]) seq.push_back({(uint16_t)P(i, j), (uint16_t)ik, (uint16_t)P(k, j), (uint16_t)kk});
+                    seq.push_back({(uint16_t)(nnzF + i), (uint16_t)ik, (uint16_t)(nnzF + k), (uint16_t)kk});
+                }
+            }
+            for (int k = d - 1; k >= 0; --k) {
+                const int kk = P(k, k);
+                for (int i = k - 1; i >= 0; --i)
+                    if (S[(size_t)i * d + k]) seq.push_back({(uint16_t)(nnzF + i), (uint16_t)P(i, k), (uint16_t)(nnzF + k), (uint16_t)kk});
+            }
+            std::vector<int> wlev(nA + 1, 0), rlev(nA + 1, 0), lev(seq.size(), 0);
+            int nlev = 0;
+            for (size_t q = 0; q < seq.size(); ++q) {
+                const Op &o = seq[q];
+                int lv = std::max(std::max(wlev[o.ik], wlev[o.kj]), std::max(wlev[o.kk], std::max(wlev[o.ij], rlev[o.ij]))) + 1;
+                lev[q] = lv; nlev = std::max(nlev, lv);
+                wlev[o.ij] = lv;
+                rlev[o.ik] = std::max(rlev[o.ik], lv); rlev[o.kj] = std::max(rlev[o.kj], lv); rlev[o.kk] = std::max(rlev[o.kk], lv);
+            }
+            std::vector<int> cnt_lv(nlev + 2, 0);
+            for (int lv : lev) cnt_lv[lv + 1]++;
+            for (int l = 1; l <= nlev + 1; ++l) cnt_lv[l] += cnt_lv[l - 1];
+            ops.resize(seq.size());
+            std::vector<int> fillp(cnt_lv.begin(), cnt_lv.end());
+            for (size_t q = 0; q < seq.size(); ++q) ops[fillp[lev[q]]++] = seq[q];
+            pass_ptr.clear();
+            for (int l = 1; l <= nlev + 1; ++l) pass_ptr.push_back(cnt_lv[l]);
+            if (pass_ptr.empty()) pass_ptr.push_back(0);
+        }
+        const int n_pass = (int)pass_ptr.size() - 1;
+        const int n_ulev = 0;
+        std::vector<int> ulev_ptr(1, 0), urow, urow_diag, uent_ptr(1, 0);
+        std::vector<uint16_t> uent;
+        // ---- assembly positions ------------------------------------------------------------------
+        std::vector<uint16_t> dpos((size_t)nb * 4, (uint16_t)DUMMY), jpos((size_t)nl * 8, (uint16_t)DUMMY);
+        std::vector<char> is_buslane(nA + 1, 0);
+        for (int i = 0; i < nb; ++i) {
+            const int r[2] = {colth[i], colv[i]};
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+                const int p = P(r[a], r[b]);
+                if (p >= 0) { dpos[(size_t)i * 4 + a * 2 + b] = (uint16_t)p; is_buslane[p] = 1; }
+            }
+        }
+        for (int k = 0; k < d; ++k) is_buslane[nnzF + k] = 1;      // right-hand side: written by the bus lanes
+        std::vector<int> round(nl, 0);
+        int n_round = 0;
+        {
+            std::vector<std::vector<char>> used;   // per round: position used
+            for (int l = 0; l < nl; ++l) {
+                const int f = brf[l], t = brt[l];
+                if (f < 0) continue;
+                const int rf[2] = {colth[f], colv[f]}, rt[2] = {colth[t], colv[t]};
+                uint16_t *jp = &jpos[(size_t)l * 8];
+                for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+                    int p = P(rf[a], rt[b]); if (p >= 0) jp[a * 2 + b] = (uint16_t)p;
+                    p = P(rt[a], rf[b]);     if (p >= 0) jp[4 + a * 2 + b] = (uint16_t)p;
+                }
+                int r = 0;
+                for (;; ++r) {
+                    if (r == (int)used.size()) used.emplace_back(nA + 1, 0);
+                    bool clash = false;
+                    for (int q = 0; q < 8; ++q) if (jp[q] != DUMMY && used[r][jp[q]]) clash = true;
+                    // a line whose two ends sit on the same bus writes the same entry twice: keep it alone in a round
+                    if (!clash) break;
+                }
+                for (int q = 0; q < 8; ++q) if (jp[q] != DUMMY) used[r][jp[q]] = 1;
+                round[l] = r; n_round = std::max(n_round, r + 1);
+            }
+        }
+        std::vector<uint16_t> zero;
+        for (int p = 0; p < nnzF; ++p) if (!is_buslane[p]) zero.push_back((uint16_t)p);
+        // ---- static per-bus line data ------------------------------------------------------------------
+        std::vector<double> ydiag((size_t)nb * 2, 0.0), dcshift(nb, 0.0);
+        std::vector<std::vector<int>> adj(nb), bu(nb), bl(nb), bs(nb), bh(nb);
+        for (int l = 0; l < nl; ++l) {
+            const int f = brf[l], t = brt[l];
+            if (f < 0) continue;
+            const double *y = &g.line_y[(size_t)l * 8];
+            ydiag[(size_t)f * 2] += y[0]; ydiag[(size_t)f * 2 + 1] += y[1];
+            ydiag[(size_t)t * 2] += y[6]; ydiag[(size_t)t * 2 + 1] += y[7];
+            dcshift[f] += g.line_pshift[l]; dcshift[t] -= g.line_pshift[l];
+            adj[f].push_back(2 * l); adj[t].push_back(2 * l + 1);
+        }
+        for (int i = 0; i < nb; ++i) std::sort(adj[i].begin(), adj[i].end());
+        for (int u = 0; u < nu; ++u) if (unit_bus[u] >= 0) bu[unit_bus[u]].push_back(u);
+        for (int k = 0; k < nld; ++k) if (load_bus[k] >= 0) bl[load_bus[k]].push_back(k);
+        for (int k = 0; k < nst; ++k) if (sto_bus[k] >= 0) bs[sto_bus[k]].push_back(k);
+        for (int k = 0; k < nsh; ++k) if (sh_bus[k] >= 0) bh[sh_bus[k]].push_back(k);
+        // ---- DC matrix, factorised (fp64, no pivoting: Bdc is symmetric and, for positive series reactances,
+        //      positive definite), in the elimination order of the buses --------------------------------------
+        std::vector<double> B((size_t)n1 * n1, 0.0);
+        std::vector<char> SB((size_t)n1 * n1, 0);
+        for (int l = 0; l < nl; ++l) {
+            const int f = brf[l], t = brt[l];
+            if (f < 0) continue;
+            const double b = g.line_bdc[l];
+            const int cf = dcidx[f], ct = dcidx[t];
+            if (cf >= 0) { B[(size_t)cf * n1 + cf] += b; SB[(size_t)cf * n1 + cf] = 1; if (ct >= 0) { B[(size_t)cf * n1 + ct] -= b; SB[(size_t)cf * n1 + ct] = 1; } }
+            if (ct >= 0) { B[(size_t)ct * n1 + ct] += b; SB[(size_t)ct * n1 + ct] = 1; if (cf >= 0) { B[(size_t)ct * n1 + cf] -= b; SB[(size_t)ct * n1 + cf] = 1; } }
+        }
+        {
+            std::vector<int> cj;
+            for (int k = 0; k < n1; ++k) {
+                cj.clear();
+                for (int j = k + 1; j < n1; ++j) if (SB[(size_t)k * n1 + j]) cj.push_back(j);
+                const double piv = B[(size_t)k * n1 + k];
+                for (int i = k + 1; i < n1; ++i) {
+                    if (!SB[(size_t)i * n1 + k]) continue;
+                    const double m = B[(size_t)i * n1 + k] / piv;
+                    B[(size_t)i * n1 + k] = m;                    // L (unit diagonal)
+                    for (int j : cj) { B[(size_t)i * n1 + j] -= m * B[(size_t)k * n1 + j]; SB[(size_t)i * n1 + j] = 1; }
+                }
+            }
+        }
+        std::vector<double> dcinv((size_t)n1 * n1, 0.0);
+        {
+            std::vector<double> x(n1);
+            for (int c = 0; c < n1; ++c) {
+                for (int i = 0; i < n1; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+                for (int i = c + 1; i < n1; ++i) {                 // L y = e_c (unit lower; y_i = 0 for i < c)
+                    double sacc = x[i];
+                    const double *Bi = &B[(size_t)i * n1];
+                    const char *Si = &SB[(size_t)i * n1];
+                    for (int j = c; j < i; ++j) if (Si[j]) sacc -= Bi[j] * x[j];
+                    x[i] = sacc;
+                }
+                for (int i = n1 - 1; i >= 0; --i) {                // U x = y
+                    double sacc = x[i];
+                    const double *Bi = &B[(size_t)i * n1];
+                    const char *Si = &SB[(size_t)i * n1];
+                    for (int j = i + 1; j < n1; ++j) if (Si[j]) sacc -= Bi[j] * x[j];
+                    x[i] = sacc / Bi[i];
+                }
+                for (int i = 0; i < n1; ++i) dcinv[(size_t)c * n1 + i] = x[i];   // column c of the inverse = row c of the transposed store
+            }
+        }
+        // ---- serialise ------------------------------------------------------------------------------------
+        PlanHeader H;
+        memset(&H, 0, sizeof(H));
+        H.status = PLAN_ST_OK; H.nb = nb; H.n1 = n1; H.d = d; H.nnzF = nnzF; H.nA = nA; H.n_round = n_round;
+        H.n_pass = n_pass; H.n_op = (int)ops.size(); H.n_ulev = n_ulev; H.n_urow = d;
+        H.n_zero = (int)zero.size();
+        H.smem_bytes = plan_smem_bytes(nb, nl, nA);
+        std::vector<unsigned char> blob(sizeof(PlanHeader));
+        auto align = [&](size_t a) { while (blob.size() % a) blob.push_back(0); };
+        auto put_d = [&](const std::vector<double> &v) -> int {
+            align(8);
+            const int off = (int)blob.size();
+            blob.resize(blob.size() + v.size() * 8);
+            if (!v.empty()) memcpy(&blob[off], v.data(), v.size() * 8);
+            return off;
+        };
+        auto put_u16 = [&](const std::vector<int> &v) -> int {
+            align(4);
+            const int off = (int)blob.size();
+            for (int x : v) { const uint16_t u = x < 0 ? (uint16_t)0xFFFF : (uint16_t)x; blob.push_back((unsigned char)(u & 0xff)); blob.push_back((unsigned char)(u >> 8)); }
+            return off;
+        };
+        auto put_u16v = [&](const std::vector<uint16_t> &v) -> int {
+            align(4);
+            const int off = (int)blob.size();
+            blob.resize(blob.size() + v.size() * 2);
+            if (!v.empty()) memcpy(&blob[off], v.data(), v.size() * 2);
+            return off;
+        };
+        auto put_i32 = [&](const std::vector<int> &v) -> int {
+            align(4);
+            const int off = (int)blob.size();
+            blob.resize(blob.size() + v.size() * 4);
+            if (!v.empty()) memcpy(&blob[off], v.data(), v.size() * 4);
+            return off;
+        };
+        auto put_csr = [&](const std::vector<std::vector<int>> &lists, int &o_ptr, int &o_idx) {
+            std::vector<int> ptr(1, 0), idx;
+            for (const auto &l : lists) { idx.insert(idx.end(), l.begin(), l.end()); ptr.push_back((int)idx.size()); }
+            o_ptr = put_u16(ptr); o_idx = put_u16(idx);
+        };
+        H.o_qmins = put_d(qmins); H.o_qmaxs = put_d(qmaxs); H.o_ydiag = put_d(ydiag); H.o_dcshift = put_d(dcshift);
+        H.o_dcinv = put_d(dcinv);
+        {   // ops: 8-byte records
+            align(8);
+            H.o_ops = (int)blob.size();
+            blob.resize(blob.size() + ops.size() * sizeof(Op));
+            if (!ops.empty()) memcpy(&blob[H.o_ops], ops.data(), ops.size() * sizeof(Op));
+        }
+        H.o_pass_ptr = put_i32(pass_ptr);
+        H.o_slot = put_u16(slot_of); H.o_btype = put_u16(btype); H.o_colth = put_u16(colth); H.o_colv = put_u16(colv);
+        H.o_dcidx = put_u16(dcidx); H.o_vmunit = put_u16(vmunit); H.o_cnt = put_u16(cnt); H.o_nref = put_u16(nref);
+        H.o_dpos = put_u16v(dpos);
+        put_csr(adj, H.o_adj_ptr, H.o_adj); put_csr(bu, H.o_bu_ptr, H.o_bu); put_csr(bl, H.o_bl_ptr, H.o_bl);
+        put_csr(bs, H.o_bs_ptr, H.o_bs); put_csr(bh, H.o_bh_ptr, H.o_bh);
+        H.o_brf = put_u16(brf); H.o_brt = put_u16(brt); H.o_round = put_u16(round); H.o_jpos = put_u16v(jpos);
+        H.o_unit_bus = put_u16(unit_bus); H.o_load_bus = put_u16(load_bus); H.o_sto_bus = put_u16(sto_bus); H.o_sh_bus = put_u16(sh_bus);
+        H.o_zero = put_u16v(zero);
+        H.o_ulev_ptr = put_u16(ulev_ptr); H.o_urow = put_u16(urow); H.o_urow_diag = put_u16(urow_diag); H.o_uent_ptr = put_u16(uent_ptr);
+        H.o_uent = put_u16v(uent);
+        align(16);
+        H.total_bytes = (int)blob.size();
+        memcpy(blob.data(), &H, sizeof(H));
+        return blob;
+    }
+
+    // the plan format addresses values and list entries with 16 bits
+    static bool fits(const PlanHeader &H) { return H.nA + 1 < 0xFFFF && H.n_op < (1 << 30); }
+
+private:
+    const HostGrid &g_;
+};
+
+}  // namespace b200pf

@@ -33,7 +33,7 @@ ABI_SYMBOLS = (
     "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
     "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait",
     "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free", "b200pf_rows_group_launch", "b200pf_rows_group_wait",
-    "b200pf_rows_group_config",
+    "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats",
 )
 
 
@@ -115,6 +115,8 @@ def load_library():
     lib.b200pf_launch_count.argtypes = [vp]
     lib.b200pf_launch_count.restype = C.c_int64
     lib.b200pf_last_launch_info.argtypes = [vp] + [C.POINTER(i32)] * 4
+    lib.b200pf_set_kernel_policy.argtypes = [vp, i32]
+    lib.b200pf_plan_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]
     for nm in ("b200pf_create", "b200pf_destroy", "b200pf_sizes", "b200pf_run_host", "b200pf_run_device",
                "b200pf_series_bind", "b200pf_series_set_topo", "b200pf_series_step", "b200pf_series_results",
                "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
@@ -440,6 +442,18 @@ class PowerFlowEngine:
         v = [C.c_int() for _ in range(4)]
         self.lib.b200pf_last_launch_info(self.h, *[C.byref(x) for x in v])
         return dict(smem_bytes=v[0].value, threads_per_instance=v[1].value, grid=v[2].value, block=v[3].value)
+
+    KERNEL_AUTO, KERNEL_PIVOTING, KERNEL_PLANNED = 0, 1, 2
+
+    def set_kernel_policy(self, policy: int):
+        """0: planned sparse kernel whenever it applies (default); 1: pivoting kernels only; 2: planned kernel
+        even when a call has to build many new topology plans."""
+        self._check(self.lib.b200pf_set_kernel_policy(self.h, int(policy)), "b200pf_set_kernel_policy")
+
+    def plan_stats(self):
+        n, b, k = C.c_int64(), C.c_int64(), C.c_int()
+        self._check(self.lib.b200pf_plan_stats(self.h, C.byref(n), C.byref(b), C.byref(k)), "b200pf_plan_stats")
+        return dict(n_plans=n.value, plan_bytes=b.value, last_kernel={0: "none", 1: "warp_pivoting", 2: "cta_pivoting", 3: "planned_sparse"}[k.value])
 
     def view(self, out: np.ndarray) -> OutputView:
         return OutputView(self.gm, out)

@@ -214,6 +214,19 @@ int b200pf_pinned_free(void *ptr);
 /* run all work of this handle on the caller's stream (cudaStream_t as integer; 0 = the handle's own) */
 int b200pf_set_stream(b200pf_handle *h, uint64_t stream);
 
+/* Kernel selection.  The engine owns three kernels for the same path (reference pPB:1090 / 1097-1105):
+ *   - the PLANNED SPARSE kernel (csrc/b200pf_sparse.cuh): everything that depends on the topology only (bus fusion, bus
+ *     types, connectivity check, elimination order, filled Jacobian pattern, factorisation schedule, factorised DC matrix)
+ *     is computed once per distinct topology vector on the host and cached ("plan"); the device runs the numeric part.
+ *     Needs a host copy of the topology (every entry point except b200pf_run_device has one) and no device-side
+ *     protections;
+ *   - the warp-per-instance and CTA-per-instance kernels with on-device topology discovery and partial pivoting.
+ * policy 0 (default): planned kernel whenever it applies, unless one call would have to build more than a few hundred
+ * new plans; 1: pivoting kernels only; 2: planned kernel whenever it applies.  Env B200PF_PLAN_POLICY presets it. */
+int b200pf_set_kernel_policy(b200pf_handle *h, int policy);
+/* number of cached plans, their bytes, and the kernel of the last launch (1 warp/pivoting, 2 CTA/pivoting, 3 planned sparse) */
+int b200pf_plan_stats(const b200pf_handle *h, int64_t *n_plans, int64_t *plan_bytes, int *last_kernel);
+
 int b200pf_sync(b200pf_handle *h);
 /* cudaStream_t of the handle as an integer (for event timing by the caller) */
 uint64_t b200pf_stream(b200pf_handle *h);

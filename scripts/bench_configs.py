@@ -30,6 +30,38 @@ def jitter(gm, n, seed=0):
     return inj
 
 
+def synth_chron(gm, n_rows=16, seed=0):
+    """Synthetic time series for grids without a bundled chronics fixture: the grid file's own set points, loads and
+    generations jittered row by row (float32 [1, n_rows, 2 n_load + 2 n_gen], backend element order)."""
+    sl, inj0 = gm.inj_slices(), gm.default_inj()
+    row = np.concatenate([inj0[sl["load_p"]], inj0[sl["load_q"]], inj0[sl["gen_p"]], inj0[sl["gen_vm"]] * gm.prod_pu_to_kv])
+    chron = np.tile(row, (1, n_rows, 1))
+    n = 2 * gm.n_load + gm.n_gen
+    chron[..., :n] *= np.random.default_rng(seed).uniform(0.97, 1.03, (1, n_rows, n))
+    return chron.astype(np.float32)
+
+
+def series_rate(gm, B, policy, steps=20):
+    """Device-resident DoNothing stepping (nothing crosses PCIe): seconds per step, CUDA-synchronised wall clock."""
+    os.environ["B200PF_PLAN_POLICY"] = str(policy)
+    env = BatchedDoNothing(gm, synth_chron(gm), B)
+    for _ in range(3):
+        env.step_device()
+    env.engine.sync()
+    t = time.perf_counter()
+    for _ in range(steps):
+        env.step_device()
+    env.engine.sync()
+    dt = (time.perf_counter() - t) / steps
+    _, status, iters, _ = env.fetch()
+    info = {"seconds_per_step": dt, "env_step_per_s": B / dt, "converged_fraction": float((status == 0).mean()),
+            "mean_iters": float(iters[status == 0].mean()) if (status == 0).any() else None,
+            "launch": env.engine.last_launch_info(), "kernel": env.engine.plan_stats()}
+    env.close()
+    os.environ.pop("B200PF_PLAN_POLICY", None)
+    return info
+
+
 def sub_of_pos(gm):
     m = np.zeros(gm.dim_topo, dtype=np.int64)
     m[gm.line_or_pos] = gm.line_or_sub; m[gm.line_ex_pos] = gm.line_ex_sub
@@ -41,6 +73,10 @@ def sub_of_pos(gm):
 
 def time_run(eng, topo, inj, reps=5, **kw):
     cap = eng.max_active_buses(topo)            # host-side bound, computed once (not part of the timed call)
+    t = time.perf_counter()
+    eng.run(topo, inj, nb_cap=cap, **kw)
+    eng.first_call_s = time.perf_counter() - t  # includes building the topology plans of the planned kernel
+    eng.run(topo, inj, nb_cap=cap, **kw)
     eng.run(topo, inj, nb_cap=cap, **kw)
     t = time.perf_counter()
     for _ in range(reps):
@@ -62,39 +98,56 @@ def main():
         pos = np.flatnonzero(sp == s)
         topo[i, pos] = rng.integers(1, 3, len(pos))
     inj = jitter(gm, B)
-    eng = PowerFlowEngine(gm, max_batch=B)
-    dt, status, iters = time_run(eng, topo, inj)
-    res["config3_36sub_batch1024_random_topology"] = {
-        "seconds_per_batch_host_call": dt, "env_step_per_s_e2e_host_buffers": B / dt, "converged_fraction": float((status == 0).mean()),
-        "mean_iters": float(iters[status == 0].mean()), "launch": eng.last_launch_info()}
-    eng.close()
+    for pol, tag in ((1, "pivoting"), (2, "planned")):
+        eng = PowerFlowEngine(gm, max_batch=B)
+        eng.set_kernel_policy(pol)
+        dt, status, iters = time_run(eng, topo, inj)
+        res["config3_36sub_batch1024_random_topology_" + tag] = {
+            "seconds_per_batch_host_call": dt, "env_step_per_s_e2e_host_buffers": B / dt, "converged_fraction": float((status == 0).mean()),
+            "mean_iters": float(iters[status == 0].mean()), "launch": eng.last_launch_info(), "kernel": eng.plan_stats(),
+            "first_call_seconds": eng.first_call_s}
+        eng.close()
+    for pol, tag in ((1, "pivoting"), (2, "planned")):
+        res["config3grid_36sub_batch1024_donothing_device_resident_" + tag] = series_rate(gm, 1024, pol, steps=20 if pol == 1 else 100)
     # ---- config 5: 118 substations, batch 8192 (here 2048 per call x 4), DoNothing
     gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_wcci_2022_dev.npz"))
     B = 2048
     topo = np.tile(gm.default_topo(), (B, 1))
     inj = jitter(gm, B)
-    eng = PowerFlowEngine(gm, max_batch=B)
-    dt, status, iters = time_run(eng, topo, inj, reps=2)
-    res["config5_118sub_batch2048_donothing"] = {
-        "seconds_per_batch_host_call": dt, "env_step_per_s_e2e_host_buffers": B / dt, "converged_fraction": float((status == 0).mean()),
-        "mean_iters": float(iters[status == 0].mean()), "launch": eng.last_launch_info()}
-    eng.close()
+    for pol, tag in ((1, "pivoting"), (2, "planned")):
+        eng = PowerFlowEngine(gm, max_batch=B)
+        eng.set_kernel_policy(pol)
+        dt, status, iters = time_run(eng, topo, inj, reps=2 if pol == 1 else 10)
+        res["config5_118sub_batch2048_donothing_" + tag] = {
+            "seconds_per_batch_host_call": dt, "env_step_per_s_e2e_host_buffers": B / dt, "converged_fraction": float((status == 0).mean()),
+            "mean_iters": float(iters[status == 0].mean()), "launch": eng.last_launch_info(), "kernel": eng.plan_stats(),
+            "first_call_seconds": eng.first_call_s}
+        eng.close()
+    for pol, tag in ((1, "pivoting"), (2, "planned")):
+        res["config5_118sub_batch2048_donothing_device_resident_" + tag] = series_rate(gm, 2048, pol, steps=5 if pol == 1 else 100)
+    for var, what in ((4, "T128"), (5, "T64"), (6, "T32")):
+        os.environ["B200PF_SPARSE_VARIANT"] = str(var)
+        res["config5_118sub_batch2048_device_resident_planned_" + what] = series_rate(gm, 2048, 2, steps=50)
+        res["config5_118sub_batch8192_device_resident_planned_" + what] = series_rate(gm, 8192, 2, steps=20)
+    os.environ.pop("B200PF_SPARSE_VARIANT", None)
     # ---- config 4: case14 N-1 sweep, 4096 base states x 20 outages
     gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
     B = 4096
     topo = np.tile(gm.default_topo(), (B, 1))
     inj = jitter(gm, B)
-    eng = PowerFlowEngine(gm, max_batch=B * gm.n_line)
-    eng.n1_sweep(topo, inj)
-    t = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
-        rho, status = eng.n1_sweep(topo, inj)
-    dt = (time.perf_counter() - t) / reps
-    res["config4_case14_n1_sweep_4096x20"] = {
-        "seconds_per_sweep_host_call": dt, "contingencies_per_s": B * gm.n_line / dt, "converged_fraction": float((status == 0).mean()),
-        "launch": eng.last_launch_info()}
-    eng.close()
+    for pol, tag in ((1, "pivoting"), (2, "planned")):
+        eng = PowerFlowEngine(gm, max_batch=B * gm.n_line)
+        eng.set_kernel_policy(pol)
+        eng.n1_sweep(topo, inj)
+        t = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            rho, status = eng.n1_sweep(topo, inj)
+        dt = (time.perf_counter() - t) / reps
+        res["config4_case14_n1_sweep_4096x20_" + tag] = {
+            "seconds_per_sweep_host_call": dt, "contingencies_per_s": B * gm.n_line / dt, "converged_fraction": float((status == 0).mean()),
+            "launch": eng.last_launch_info(), "kernel": eng.plan_stats()}
+        eng.close()
     # ---- config 2 with protections on (device-side cascading failure), device-resident
     chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"]
     th = np.array([541.0, 450.0, 375.0, 636.0, 175.0, 285.0, 335.0, 657.0, 496.0, 827.0, 442.0, 641.0, 840.0, 156.0, 664.0, 235.0,

@@ -1,0 +1,57 @@
+"""TEST INFRASTRUCTURE: ctypes front-end of tests/emu/sparse_emu.cpp (host build of the planned sparse kernel)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+REPO = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "libsparse_emu.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(HERE, "sparse_emu.cpp")
+    deps = [src, os.path.join(REPO, "grid2op_b200", "csrc", "b200pf_sparse.cuh"), os.path.join(REPO, "grid2op_b200", "csrc", "b200pf_plan.hpp")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(p) for p in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", LIB, src, "-lm"])
+    return LIB
+
+
+class SparseEmu:
+    """Same call signature as oracle.c_oracle.COracle.run / PowerFlowEngine.run."""
+
+    def __init__(self, gm):
+        from oracle.c_oracle import COracle
+        build()
+        self.gm = gm
+        self._co = COracle(gm)          # re-use its grid descriptor marshalling
+        self.desc = self._co.desc
+        self.lib = C.CDLL(LIB)
+        self.lib.sparse_emu_run.restype = C.c_int
+        self.stats = np.zeros(8, dtype=np.int32)
+
+    def run(self, topo, inj, is_dc=False, max_iter=10, tol_mva=1e-8, nb_cap=0, want_busv=False, n1_lines=0, th_lim=None):
+        gm = self.gm
+        topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(-1, gm.n_topo_in)
+        inj = np.ascontiguousarray(inj, dtype=np.float64).reshape(-1, gm.n_inj)
+        B = topo.shape[0]
+        N = B * n1_lines if n1_lines > 0 else B
+        out = np.empty((N, gm.n_out), dtype=np.float32)
+        status = np.empty(N, dtype=np.int32)
+        iters = np.empty(N, dtype=np.int32)
+        busv = np.empty((N, 2 * gm.n_sub * gm.n_busbar), dtype=np.float64) if want_busv else None
+        rho = np.empty((N, gm.n_line), dtype=np.float32) if th_lim is not None else None
+        thl = np.ascontiguousarray(th_lim, dtype=np.float32) if th_lim is not None else None
+        vp = C.c_void_p
+        self.lib.sparse_emu_run(C.byref(self.desc), C.c_int(B), topo.ctypes.data_as(vp), inj.ctypes.data_as(vp),
+                                C.c_int(int(bool(is_dc))), C.c_int(int(max_iter)), C.c_double(float(tol_mva)),
+                                out.ctypes.data_as(vp), status.ctypes.data_as(vp), iters.ctypes.data_as(vp),
+                                busv.ctypes.data_as(vp) if busv is not None else None, C.c_int(int(n1_lines)),
+                                thl.ctypes.data_as(vp) if thl is not None else None,
+                                rho.ctypes.data_as(vp) if rho is not None else None, self.stats.ctypes.data_as(vp))
+        if th_lim is not None:
+            return out, status, iters, busv, rho
+        return out, status, iters, busv

@@ -35,7 +35,8 @@ def _compare(gm, out, ref, ok):
 @pytest.mark.parametrize("name,n", [("rte_case5_example", 256), ("l2rpn_case14_sandbox", 512), ("educ_case14_storage", 256),
                                     ("l2rpn_2019", 128), ("l2rpn_neurips_2020_track1", 128), ("l2rpn_wcci_2022_dev", 16)])
 @pytest.mark.parametrize("dc", [False, True])
-def test_random_states(cuda_required, name, n, dc):
+@pytest.mark.parametrize("policy", [1, 2])       # 1: pivoting kernels (warp / CTA per instance), 2: planned sparse kernel
+def test_random_states(cuda_required, name, n, dc, policy):
     from grid2op_b200.engine import PowerFlowEngine
     path = env_grid(name)
     if path is None:
@@ -43,7 +44,9 @@ def test_random_states(cuda_required, name, n, dc):
     gm = GridModel(path)
     topo, inj = random_cases(gm, n, seed=11)
     eng = PowerFlowEngine(gm, max_batch=n)
+    eng.set_kernel_policy(policy)
     out, status, iters, _ = eng.run(topo, inj, is_dc=dc)
+    assert (eng.plan_stats()["last_kernel"] == "planned_sparse") == (policy == 2)
     ref, rstatus, riters, _ = COracle(gm).run(topo, inj, is_dc=dc)
     # integers: convergence / failure class must agree exactly
     assert np.array_equal(status == 0, rstatus == 0)
@@ -59,15 +62,18 @@ def test_random_states(cuda_required, name, n, dc):
     eng.close()
 
 
-def test_golden_fixture_case14(cuda_required):
+@pytest.mark.parametrize("policy", [1, 2])
+def test_golden_fixture_case14(cuda_required, policy):
     """Committed oracle fixture (tests/golden/oracle_case14_steps.npz, made by make_golden.py): runs without
     any reference file, e.g. on a GPU box that only has this repository."""
     from grid2op_b200.engine import PowerFlowEngine
     gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
     z = np.load(os.path.join(GOLD, "oracle_case14_steps.npz"))
     eng = PowerFlowEngine(gm, max_batch=len(z["topo"]))
+    eng.set_kernel_policy(policy)
     out, status, iters, busv = eng.run(z["topo"], z["inj"], want_busv=True)
     assert (status == 0).all()
+    assert (eng.plan_stats()["last_kernel"] == "planned_sparse") == (policy == 2)
     _compare(gm, out, z["out"], np.ones(len(out), dtype=bool))
     m = np.isfinite(z["busv"])
     assert np.max(np.abs(busv[m] - z["busv"][m])) <= 1e-7          # p.u. / rad, fp64 state
@@ -75,7 +81,8 @@ def test_golden_fixture_case14(cuda_required):
     eng.close()
 
 
-def test_series_mode_matches_explicit_records(cuda_required):
+@pytest.mark.parametrize("policy", [1, 2])
+def test_series_mode_matches_explicit_records(cuda_required, policy):
     """Device-resident chronics stepping == the same rows fed through the host-record entry point."""
     from grid2op_b200.engine import PowerFlowEngine
     gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
@@ -84,12 +91,14 @@ def test_series_mode_matches_explicit_records(cuda_required):
     scen = (np.arange(B) % 3).astype(np.int32)
     t0 = ((np.arange(B) * 37) % chron.shape[1]).astype(np.int32)
     eng = PowerFlowEngine(gm, max_batch=B)
+    eng.set_kernel_policy(policy)
     eng.series_bind(chron, scen, t0, gm.default_inj(), gm.thermal_limit_a)
     eng.series_set_topo(np.tile(gm.default_topo(), (B, 1)))
     sl = gm.inj_slices()
     nl, ng = gm.n_load, gm.n_gen
     for step in range(3):
         eng.series_step(nb_cap=gm.n_sub)
+        assert (eng.plan_stats()["last_kernel"] == "planned_sparse") == (policy == 2)
         out, status, iters, rho = eng.series_fetch()
         rows = chron[scen, (t0 + step) % chron.shape[1]]
         inj = np.tile(gm.default_inj(), (B, 1))

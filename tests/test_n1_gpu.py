@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,nbase", [("l2rpn_case14_sandbox", 48), ("rte_case5_example", 32), ("l2rpn_neurips_2020_track1", 6)])
-def test_n1_sweep_matches_oracle(cuda_required, name, nbase):
+@pytest.mark.parametrize("policy", [1, 2])
+def test_n1_sweep_matches_oracle(cuda_required, name, nbase, policy):
     from grid2op_b200.engine import PowerFlowEngine
     path = env_grid(name)
     if path is None:
@@ -22,7 +23,9 @@ def test_n1_sweep_matches_oracle(cuda_required, name, nbase):
     gm = GridModel(path)
     topo, inj = random_cases(gm, nbase, seed=5, p_disc=0.0)
     eng = PowerFlowEngine(gm, max_batch=nbase * gm.n_line)
+    eng.set_kernel_policy(policy)
     rho, status = eng.n1_sweep(topo, inj)
+    assert (eng.plan_stats()["last_kernel"] == "planned_sparse") == (policy == 2)
     # oracle: explicit records with line i out of service
     t2 = np.repeat(topo, gm.n_line, axis=0)
     i2 = np.repeat(inj, gm.n_line, axis=0)

@@ -26,6 +26,7 @@ def test_small_vs_generic_vs_oracle(cuda_required, name, dc):
     n = 384
     topo, inj = random_cases(gm, n, seed=23)
     eng = PowerFlowEngine(gm, max_batch=n)
+    eng.set_kernel_policy(1)                 # the two pivoting kernels first
     cap = eng.max_active_buses(topo)
     assert 0 < cap <= gm.n_slot
     if cap > 17:   # keep only the instances the small kernel is allowed to take
@@ -48,4 +49,12 @@ def test_small_vs_generic_vs_oracle(cuda_required, name, dc):
     _compare(gm, o_gen, ref, ok)
     if not dc:
         assert np.all(i_small[ok] >= ri[ok]) and np.all(i_small[ok] <= ri[ok] + 1)
+    # third implementation: the planned sparse kernel (no pivoting, static schedule per topology)
+    eng.set_kernel_policy(2)
+    o_pl, s_pl, i_pl, bv_pl = eng.run(topo, inj, is_dc=dc, want_busv=True)
+    assert eng.plan_stats()["last_kernel"] == "planned_sparse"
+    assert np.array_equal(s_pl, s_small)
+    assert np.array_equal(np.isnan(bv_pl), np.isnan(bv_gen))
+    assert np.max(np.abs(bv_pl[ok][np.isfinite(bv_gen[ok])] - bv_gen[ok][np.isfinite(bv_gen[ok])])) <= 1e-9
+    _compare(gm, o_pl, ref, ok)
     eng.close()

@@ -1,0 +1,92 @@
+"""Planned sparse kernel, HOST build (tests/emu/sparse_emu.cpp compiles grid2op_b200/csrc/b200pf_sparse.cuh with
+B200PF_EMULATE: same source as the CUDA kernel, a phase = a loop over the lanes) against the fp64 oracle: checks the
+topology plans (ordering, filled pattern, factorisation schedule, factorised DC matrix) and the kernel's arithmetic on
+a machine without a GPU.  The GPU run of the same kernel is checked in tests/test_engine_random_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import env_grid
+
+from grid2op_b200.gridmodel import GridModel
+from grid2op_b200.engine import OutputView
+from oracle.c_oracle import COracle
+from sparse_emu import SparseEmu
+from test_c_oracle import random_cases
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def compare(gm, out, ref, ok):
+    a, b = OutputView(gm, out[ok]), OutputView(gm, ref[ok])
+    tol_mw = 1e-4 * gm.sn_mva
+    for k in ("p_or", "q_or", "p_ex", "q_ex", "unit_p", "unit_q", "shunt_p", "shunt_q"):
+        x, y = getattr(a, k), getattr(b, k)
+        assert np.max(np.abs(x - y) - 4e-7 * np.abs(y), initial=0.0) <= tol_mw, k
+    for k, vn in (("v_or", gm.line_or_vn), ("v_ex", gm.line_ex_vn), ("load_v", gm.load_vn)):
+        x, y = getattr(a, k), getattr(b, k)
+        assert np.max(np.abs(x - y) / vn, initial=0.0) <= 1e-4, k
+    for k in ("theta_or", "theta_ex", "load_theta", "unit_theta"):
+        assert np.max(np.abs(getattr(a, k) - getattr(b, k)), initial=0.0) <= 1e-3, k
+    x, y = a.a_or, b.a_or
+    assert np.max(np.abs(x - y) - 1e-5 * np.abs(y), initial=0.0) <= 1e-2
+
+
+@pytest.mark.parametrize("name,n", [("rte_case5_example", 256), ("l2rpn_case14_sandbox", 384), ("educ_case14_storage", 128),
+                                    ("l2rpn_2019", 96), ("l2rpn_neurips_2020_track1", 96), ("l2rpn_wcci_2022_dev", 24)])
+@pytest.mark.parametrize("dc", [False, True])
+def test_emulated_sparse_kernel_vs_oracle(name, n, dc):
+    path = env_grid(name)
+    if path is None:
+        pytest.skip("reference grid files not available")
+    gm = GridModel(path)
+    topo, inj = random_cases(gm, n, seed=23)
+    out, status, iters, _ = SparseEmu(gm).run(topo, inj, is_dc=dc)
+    ref, rstatus, riters, _ = COracle(gm).run(topo, inj, is_dc=dc)
+    assert np.array_equal(status, rstatus)                     # convergence and failure classes agree exactly
+    bad = status != 0
+    assert np.isnan(out[bad]).all()
+    ok = ~bad
+    assert ok.sum() >= n // 4
+    compare(gm, out, ref, ok)
+    if not dc:
+        assert np.all(iters[ok] >= riters[ok]) and np.all(iters[ok] <= riters[ok] + 1)
+
+
+def test_emulated_sparse_kernel_golden_fixture():
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    z = np.load(os.path.join(GOLD, "oracle_case14_steps.npz"))
+    emu = SparseEmu(gm)
+    out, status, iters, busv = emu.run(z["topo"], z["inj"], want_busv=True)
+    assert (status == 0).all()
+    compare(gm, out, z["out"], np.ones(len(out), dtype=bool))
+    m = np.isfinite(z["busv"])
+    assert np.array_equal(np.isfinite(busv), m)
+    assert np.max(np.abs(busv[m] - z["busv"][m])) <= 1e-7
+    assert np.array_equal(iters, z["iters"])
+    nb, d, nnz, n_pass, n_op, n_ulev, smem, nbytes = emu.stats.tolist()
+    assert nb == 14 and d == 22 and nnz < d * d // 2          # the filled Jacobian stays sparse
+
+
+def test_emulated_n1_sweep_vs_oracle():
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    z = np.load(os.path.join(GOLD, "oracle_case14_steps.npz"))
+    topo, inj = z["topo"][:6], z["inj"][:6]
+    thl = gm.thermal_limit_a.astype(np.float32)
+    out, status, iters, _, rho = SparseEmu(gm).run(topo, inj, n1_lines=gm.n_line, th_lim=thl)
+    co = COracle(gm)
+    pos_or, pos_ex = np.asarray(gm.line_or_pos), np.asarray(gm.line_ex_pos)
+    for s in range(len(topo)):
+        for l in range(gm.n_line):
+            t2 = topo[s].copy()
+            t2[pos_or[l]] = -1
+            t2[pos_ex[l]] = -1
+            ref, rs, _, _ = co.run(t2[None], inj[s][None])
+            k = s * gm.n_line + l
+            assert status[k] == rs[0]
+            if rs[0] == 0:
+                a_or = OutputView(gm, ref).a_or[0]
+                assert np.allclose(rho[k], a_or / thl, rtol=2e-5, atol=1e-6)
+            else:
+                assert np.isnan(rho[k]).all()
