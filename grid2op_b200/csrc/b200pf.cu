@@ -68,7 +68,9 @@ struct b200pf_handle {
     int series_plan_single = 0, series_plan_smem = 0;
     int plan_policy = 0;                                    // 0 auto, 1 never, 2 whenever a host copy of the topology exists
     int plan_max_smem = 0;
-    int sparse_occ_smem = -1, sparse_occ = 0, sparse_occ_variant = 0, sparse_variant_override = 0;
+    int sparse_occ_smem = -1, sparse_occ = 0, sparse_occ_variant = 0;
+    int sparse_cta_cap = 0;                                 // > 0: resident CTAs per SM of the planned kernel are capped (rest of the SM's memory = L1)
+    int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0;
     int64_t launches = 0;
@@ -203,8 +205,11 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         if (cudaMallocHost(&h->h_inst_plan, B * 4 + 4) != cudaSuccess) { b200pf_destroy(h); return fail(B200PF_E_CUDA, "pinned host allocation failed"); }
         const char *pol = getenv("B200PF_PLAN_POLICY");
         if (pol && pol[0] >= '0' && pol[0] <= '2') h->plan_policy = pol[0] - '0';
-        const char *var = getenv("B200PF_SPARSE_VARIANT");     // tuning: force one (threads per instance, CTAs per SM) variant
-        if (var && var[0] >= '1' && var[0] <= '6') h->sparse_variant_override = var[0] - '0';
+        h->plan_T = g.n_line > 64 ? 64 : 32;
+        const char *capv = getenv("B200PF_SPARSE_CTAS");        // tuning: cap of resident CTAs per SM (planned kernel)
+        if (capv) h->sparse_cta_cap = atoi(capv);
+        const char *var = getenv("B200PF_SPARSE_T");            // tuning: threads per instance of the planned kernel
+        if (var) { const int t = atoi(var); if (t == 32 || t == 64 || t == 128) h->plan_T = t; }
     }
     *out = h;
     return 0;
@@ -314,7 +319,7 @@ static int plan_lookup(b200pf_handle *h, const int8_t *tv, int outage, int *buil
     auto it = h->plan_index.find(key);
     if (it != h->plan_index.end()) return it->second;
     if ((int)h->plan_off.size() >= PLAN_MAX) return -1;
-    PlanBuilder pb(h->hg);
+    PlanBuilder pb(h->hg, h->plan_T);
     std::vector<unsigned char> blob = pb.build(tv, outage);
     const PlanHeader *H = reinterpret_cast<const PlanHeader *>(blob.data());
     if (!PlanBuilder::fits(*H) || H->smem_bytes > h->max_smem_optin) return -1;
@@ -353,18 +358,10 @@ static int plans_sync_device(b200pf_handle *h) {
 // Plans of the instances [0, n_src) whose topology rows are at host_topo (times n1_lines outages each in contingency
 // mode); ids go to h_inst_plan[first ...] and, unless all are equal, to d_inst_plan[first ...] on stream st.
 // Returns 1 = use the sparse kernel with *sel, 0 = fall back to the pivoting kernels, < 0 error.
-// the warp-per-instance pivoting kernel applies (and, measured, is the faster one on these tiny systems: its whole
-// state lives in registers): every element class fits 32 lanes and the caller bounds the active buses by 17
-static bool small_kernel_applies(const b200pf_handle *h, int nb_cap) {
-    const DevGrid &g = h->g;
-    return g.n_slot <= 32 && g.n_line <= 32 && g.n_unit <= 32 && g.n_load <= 32 && g.n_sto <= 32 && g.n_shunt <= 32 &&
-           nb_cap > 0 && nb_cap <= 17;
-}
-
 static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int n1_lines, int first, cudaStream_t st, PlanSel *sel,
                        int nb_cap) {
+    (void)nb_cap;
     if (h->plan_policy == 1 || !host_topo) return 0;
-    if (h->plan_policy == 0 && small_kernel_applies(h, nb_cap)) return 0;
     const DevGrid &g = h->g;
     const size_t nt = (size_t)g.n_topo_in;
     const int per = n1_lines > 0 ? n1_lines : 1;
@@ -409,6 +406,14 @@ static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &se
         int occ = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, (size_t)smem));
         if (occ < 1) occ = 1;
+        if (h->sparse_cta_cap > 0 && occ > h->sparse_cta_cap) {
+            // fewer resident instances, more L1: the plan arrays (operation stream, positions, line data) are re-read by
+            // every instance and every Newton iteration; what shared memory does not take is L1 for them
+            occ = h->sparse_cta_cap;
+            int pct = (int)(((size_t)occ * (size_t)(smem + 1024) * 100 + (size_t)h->max_smem_optin - 1) / (size_t)h->max_smem_optin);
+            if (pct > 100) pct = 100;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
         h->sparse_occ = occ; h->sparse_occ_smem = smem; h->sparse_occ_variant = variant;
     }
     PlanArgs pa;
@@ -426,21 +431,18 @@ static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &se
     return 0;
 }
 
-// Threads per instance and register budget of the planned kernel: small workspaces (5/14/36 substations) run one warp
-// per instance with as many one-warp CTAs per SM as the hardware holds (32); large ones (118 substations, ~22 KB per
-// instance) are limited to ~10 instances per SM by shared memory and get 4 warps per instance instead.
+// Threads per instance (fixed per handle: the plans' operation streams are laid out for it) and register budget of the
+// planned kernel: one warp per instance for the 5/14/36-substation grids, with as many one-warp CTAs per SM as the
+// workspace allows (up to the hardware's 32); two warps per instance for the large grids (118 substations, ~22 KB of
+// workspace per instance limit an SM to ~10 instances: the second warp doubles the warps in flight).
 static int launch_sparse(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
     const int per_sm = h->max_smem_optin / (sel.smem + 1024);
-    int variant = h->sparse_variant_override;
-    if (variant <= 0) variant = per_sm >= 32 ? 1 : (per_sm >= 24 ? 2 : (per_sm >= 16 ? 3 : 4));
-    switch (variant) {
-        case 1: return launch_sparse_t<32, 32>(h, a, sel, 1);
-        case 2: return launch_sparse_t<32, 24>(h, a, sel, 2);
-        case 3: return launch_sparse_t<32, 16>(h, a, sel, 3);
-        case 4: return launch_sparse_t<128, 4>(h, a, sel, 4);
-        case 5: return launch_sparse_t<64, 8>(h, a, sel, 5);
-        default: return launch_sparse_t<32, 8>(h, a, sel, 6);
-    }
+    if (h->plan_T == 128) return launch_sparse_t<128, 4>(h, a, sel, 4);
+    if (h->plan_T == 64) return launch_sparse_t<64, 10>(h, a, sel, 5);
+    if (per_sm >= 32) return launch_sparse_t<32, 32>(h, a, sel, 1);
+    if (per_sm >= 24) return launch_sparse_t<32, 24>(h, a, sel, 2);
+    if (per_sm >= 16) return launch_sparse_t<32, 16>(h, a, sel, 3);
+    return launch_sparse_t<32, 8>(h, a, sel, 6);
 }
 
 static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req, const PlanSel *sel = nullptr) {
@@ -629,7 +631,7 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
         a.pcount = h->d_pcount; a.ts_over = h->d_tsover; a.disc = h->d_disc; a.done = h->d_done;
     }
     h->next_reset = 0;
-    if (h->series_plan_state && !h->prot && h->plan_policy != 1 && !(h->plan_policy == 0 && small_kernel_applies(h, nb_cap))) {
+    if (h->series_plan_state && !h->prot && h->plan_policy != 1) {
         PlanSel sel;
         sel.single = h->series_plan_single; sel.smem = h->series_plan_smem;
         sel.d_inst_plan = h->series_plan_state == 1 ? h->d_series_plan : nullptr;

@@ -44,9 +44,9 @@ struct PlanHeader {
     int nb, n1, d;         // active buses, non-reference buses (DC unknowns), Newton unknowns
     int nnzF, nA;          // entries of the filled Jacobian; nA = nnzF + d (right-hand side appended) ; A[nA] = dummy
     int n_round;           // assembly rounds of the line lanes (parallel lines write the same entries)
-    int n_pass, n_op;      // LU passes / operations
+    int n_pass, n_op;      // LU passes / operation slots (passes padded to whole rows of op_width slots)
     int n_ulev, n_urow;    // back-substitution levels / rows (= d)
-    int dc_unused0, dc_unused1;
+    int op_width, n_oprow; // threads per instance the operation stream is laid out for; rows of op_width slots
     int n_zero;            // entries zeroed before assembly (everything but the bus-lane entries)
     int smem_bytes;        // per-instance workspace this plan needs
     int total_bytes;
@@ -59,7 +59,10 @@ struct PlanHeader {
     // per element: bus index (u16, 0xFFFF = disconnected)
     int o_unit_bus, o_load_bus, o_sto_bus, o_sh_bus;
     // LU
-    int o_zero, o_pass_ptr /* int32 [n_pass+1] */, o_ops /* 4 x u16 per op: ij, ik, kj, kk */;
+    // operation stream: rows of op_width slots, thread t of the instance's group executes slot t of every row; a slot is
+    // 4 x u16 BYTE offsets into the value array (ij, ik, kj, kk | 1 on the LAST row of a pass: group barrier after it);
+    // padding slots work on A[dummy]
+    int o_zero, o_pass_ptr /* unused */, o_ops;
     int o_ulev_ptr /* u16 [n_ulev+1] */, o_urow /* u16 [d] row index */, o_urow_diag /* u16 [d] */, o_uent_ptr /* u16 [d+1] */,
         o_uent /* 2 x u16 per entry: column, position */;
     // DC: the inverse of Bdc (fp64, [n1][n1], stored transposed: entry (j, i) at j * n1 + i so that lanes = rows read
@@ -76,16 +79,16 @@ enum { PLAN_BT_PQ = 1, PLAN_BT_PV = 2, PLAN_BT_REF = 3 };
 // per-instance shared-memory workspace of the sparse kernel for (nb buses, n_line lines, nA values)
 inline int plan_smem_bytes(int nb, int n_line, int nA) {
     size_t o = 0;
+    o += ((size_t)(nA + 1) * 4 + 15) & ~(size_t)15;   // Jacobian values + right-hand side + dummy (first: shared-memory offset 0)
     o += (size_t)8 * nb * 8;                 // vm va pspec qspec P Q gs bs
     o += (size_t)nb * 16;                    // V (e, f)
     o += (size_t)2 * n_line * 16;            // branch currents, both ends
-    o += ((size_t)(nA + 1) * 4 + 15) & ~(size_t)15;
     return (int)((o + 15) & ~(size_t)15);
 }
 
 class PlanBuilder {
 public:
-    explicit PlanBuilder(const HostGrid &g) : g_(g) {}
+    explicit PlanBuilder(const HostGrid &g, int op_width = 32) : g_(g), op_width_(op_width) {}
 
     // topo: int8 [n_topo_in]; outage: line forced out of service (N-1 sweep) or -1.  Returns the blob.
     std::vector<unsigned char> build(const int8_t *tv, int outage) const {
@@ -170,22 +173,27 @@ public:
             std::vector<char> alive(nb, 0);
             int n_alive = 0;
             for (int i = 0; i < nb; ++i) if (btype[i] != PLAN_BT_REF) { alive[i] = 1; ++n_alive; }
-            std::vector<int> nbrs;
+            // minimum degree, ties broken by minimum LENGTH (MD-ML: the longest elimination path that ends in the node) —
+            // the factorisation runs as passes of independent operations, so the height of the elimination tree, not the
+            // fill alone, sets its run time
+            std::vector<int> nbrs, length(nb, 0);
             while (n_alive > 0) {
-                int best = -1, bestdeg = 1 << 30;
+                int best = -1, bestdeg = 1 << 30, bestlen = 1 << 30;
                 for (int i = 0; i < nb; ++i) {
                     if (!alive[i]) continue;
                     int deg = 0;
                     const char *row = &w[(size_t)i * nb];
                     for (int j = 0; j < nb; ++j) deg += (row[j] && alive[j]);
-                    if (deg < bestdeg) { bestdeg = deg; best = i; }
+                    if (deg < bestdeg || (deg == bestdeg && length[i] < bestlen)) { bestdeg = deg; bestlen = length[i]; best = i; }
                 }
                 nbrs.clear();
                 for (int j = 0; j < nb; ++j) if (w[(size_t)best * nb + j] && alive[j]) nbrs.push_back(j);
-                for (size_t a = 0; a < nbrs.size(); ++a)
+                for (size_t a = 0; a < nbrs.size(); ++a) {
+                    length[nbrs[a]] = std::max(length[nbrs[a]], length[best] + 1);
                     for (size_t b = a + 1; b < nbrs.size(); ++b) {
                         w[(size_t)nbrs[a] * nb + nbrs[b]] = 1; w[(size_t)nbrs[b] * nb + nbrs[a]] = 1;
                     }
+                }
                 alive[best] = 0; --n_alive;
                 order.push_back(best);
             }
@@ -264,15 +272,42 @@ public:
                 wlev[o.ij] = lv;
                 rlev[o.ik] = std::max(rlev[o.ik], lv); rlev[o.kj] = std::max(rlev[o.kj], lv); rlev[o.kk] = std::max(rlev[o.kk], lv);
             }
-            std::vector<int> cnt_lv(nlev + 2, 0);
-            for (int lv : lev) cnt_lv[lv + 1]++;
-            for (int l = 1; l <= nlev + 1; ++l) cnt_lv[l] += cnt_lv[l - 1];
-            ops.resize(seq.size());
-            std::vector<int> fillp(cnt_lv.begin(), cnt_lv.end());
-            for (size_t q = 0; q < seq.size(); ++q) ops[fillp[lev[q]]++] = seq[q];
-            pass_ptr.clear();
-            for (int l = 1; l <= nlev + 1; ++l) pass_ptr.push_back(cnt_lv[l]);
-            if (pass_ptr.empty()) pass_ptr.push_back(0);
+            {   // diagnostic: depth of the pure read-after-write graph (what multi-term operations could reach)
+                std::vector<int> w2(nA + 1, 0);
+                int dr = 0;
+                for (size_t q = 0; q < seq.size(); ++q) {
+                    const Op &o = seq[q];
+                    // an update chain of one target counts once: its value is "ready" at max(ready of its terms) + 1
+                    const int lv = std::max(std::max(w2[o.ik], w2[o.kj]), w2[o.kk]) + 1;
+                    w2[o.ij] = std::max(w2[o.ij], lv);
+                    dr = std::max(dr, lv);
+                }
+                depth_raw_ = dr;
+            }
+            // passes padded to whole rows of op_width slots; the last row of a pass carries the barrier flag
+            const int W = op_width_;
+            std::vector<std::vector<Op>> by_lv(nlev + 1);
+            for (size_t q = 0; q < seq.size(); ++q) by_lv[lev[q]].push_back(seq[q]);
+            const Op nop = {(uint16_t)DUMMY, (uint16_t)DUMMY, (uint16_t)DUMMY, (uint16_t)DUMMY};
+            pass_ptr.assign(1, 0);
+            for (int l = 1; l <= nlev; ++l) {
+                std::vector<Op> &v = by_lv[l];
+                // neighbouring slots work on neighbouring entries (fewer shared-memory bank conflicts); targets are unique
+                // within a pass, so the order inside a pass is free
+                std::sort(v.begin(), v.end(), [](const Op &a, const Op &b) { return a.ij < b.ij; });
+                while (v.size() % (size_t)W) v.push_back(nop);
+                const size_t last_row = v.size() - (size_t)W;
+                for (size_t q = last_row; q < v.size(); ++q) v[q].kk |= 0x4000u;   // becomes bit 0 of the byte offset below
+                ops.insert(ops.end(), v.begin(), v.end());
+                pass_ptr.push_back((int)ops.size());
+            }
+            while ((ops.size() / (size_t)W) % 4) ops.insert(ops.end(), (size_t)W, nop);     // whole blocks of 4 rows (prefetch unit)
+            // slots hold BYTE offsets into the value array (4 * position; the barrier flag moves to bit 0 of kk)
+            for (Op &o : ops) {
+                const unsigned flag = (o.kk & 0x4000u) ? 1u : 0u;
+                o.ij = (uint16_t)(o.ij * 4u); o.ik = (uint16_t)(o.ik * 4u); o.kj = (uint16_t)(o.kj * 4u);
+                o.kk = (uint16_t)(((o.kk & 0x3fffu) * 4u) | flag);
+            }
         }
         const int n_pass = (int)pass_ptr.size() - 1;
         const int n_ulev = 0;
@@ -386,6 +421,8 @@ public:
         memset(&H, 0, sizeof(H));
         H.status = PLAN_ST_OK; H.nb = nb; H.n1 = n1; H.d = d; H.nnzF = nnzF; H.nA = nA; H.n_round = n_round;
         H.n_pass = n_pass; H.n_op = (int)ops.size(); H.n_ulev = n_ulev; H.n_urow = d;
+        H.pad[0] = depth_raw_;
+        H.op_width = op_width_; H.n_oprow = (int)ops.size() / op_width_;
         H.n_zero = (int)zero.size();
         H.smem_bytes = plan_smem_bytes(nb, nl, nA);
         std::vector<unsigned char> blob(sizeof(PlanHeader));
@@ -448,10 +485,12 @@ public:
     }
 
     // the plan format addresses values and list entries with 16 bits
-    static bool fits(const PlanHeader &H) { return H.nA + 1 < 0xFFFF && H.n_op < (1 << 30); }
+    static bool fits(const PlanHeader &H) { return H.nA + 1 < 0x3FFF && H.n_op < (1 << 30); }
 
 private:
     const HostGrid &g_;
+    int op_width_;
+    mutable int depth_raw_ = 0;
 };
 
 }  // namespace b200pf

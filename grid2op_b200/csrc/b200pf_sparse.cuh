@@ -28,6 +28,8 @@
 namespace b200pf {
 struct double2 { double x, y; };
 struct uint2 { unsigned x, y; };
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 }
 #define PF_DEV static inline
@@ -144,11 +146,12 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
     const uint16_t *p_brf = U16(o_brf), *p_brt = U16(o_brt);
     const uint16_t *adj_ptr = U16(o_adj_ptr), *adj = U16(o_adj);
     // ---- workspace ------------------------------------------------------------------------------------
-    double *vm = reinterpret_cast<double *>(sm), *va = vm + nb, *psp = va + nb, *qsp = psp + nb, *Pc = qsp + nb, *Qc = Pc + nb,
-           *gsb = Qc + nb, *bsb = gsb + nb;
+    // A first: on the device it then sits at shared-memory offset 0 and the operation stream's byte offsets address it directly
+    float *A = reinterpret_cast<float *>(sm);
+    double *vm = reinterpret_cast<double *>(sm + (((size_t)(nA + 1) * 4 + 15) & ~(size_t)15)), *va = vm + nb, *psp = va + nb, *qsp = psp + nb,
+           *Pc = qsp + nb, *Qc = Pc + nb, *gsb = Qc + nb, *bsb = gsb + nb;
     double2 *V = reinterpret_cast<double2 *>(bsb + nb);
     double2 *cur = V + nb;
-    float *A = reinterpret_cast<float *>(cur + 2 * nl);
     // ---- injections of this instance ----------------------------------------------------------------------
     const float *row = nullptr;
     const double *rec = nullptr, *si = a.static_inj;
@@ -192,11 +195,15 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
         const int n1 = H.n1;
         PF_PHASE {
             for (int i = tid; i < n1; i += T) {
-                double s0 = 0.0, s1 = 0.0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four independent chains: the loads of the inverse overlap
+                const double *col = inv + i;
                 int j = 0;
-                for (; j + 1 < n1; j += 2) { s0 += inv[(size_t)j * n1 + i] * Pc[j]; s1 += inv[(size_t)(j + 1) * n1 + i] * Pc[j + 1]; }
-                if (j < n1) s0 += inv[(size_t)j * n1 + i] * Pc[j];
-                Qc[i] = s0 + s1;
+                for (; j + 3 < n1; j += 4) {
+                    const double a0 = col[(size_t)j * n1], a1 = col[(size_t)(j + 1) * n1], a2 = col[(size_t)(j + 2) * n1], a3 = col[(size_t)(j + 3) * n1];
+                    s0 += a0 * Pc[j]; s1 += a1 * Pc[j + 1]; s2 += a2 * Pc[j + 2]; s3 += a3 * Pc[j + 3];
+                }
+                for (; j < n1; ++j) s0 += col[(size_t)j * n1] * Pc[j];
+                Qc[i] = (s0 + s1) + (s2 + s3);
             }
         }
         PF_SYNC();
@@ -219,14 +226,15 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
     // ---- 3. Newton-Raphson ---------------------------------------------------------------------------------
     int iters = 0;
     if (!a.is_dc) {
-        const uint16_t *dpos = U16(o_dpos), *jpos = U16(o_jpos), *rnd = U16(o_round), *zero = U16(o_zero);
+        const uint16_t *dpos = U16(o_dpos), *jpos = U16(o_jpos), *rnd = U16(o_round);
         const double *ydiag = F64(o_ydiag);
-        const int *pass_ptr = reinterpret_cast<const int *>(blob + H.o_pass_ptr);
         const uint2 *ops = reinterpret_cast<const uint2 *>(blob + H.o_ops);
-        const int n_pass = H.n_pass, n_round = H.n_round, n_zero = H.n_zero;
+        const int n_oprow = H.n_oprow, n_round = H.n_round, nz4 = (nnzF + 3) >> 2;
         bool conv = false;
         for (int it = 0;; ++it) {
             PF_PHASE {                                         // lane = line: currents at both ends
+                // (the Jacobian values of the previous iteration are dead: clear them here, the assembly below adds into them)
+                for (int k = tid; k < nz4; k += T) reinterpret_cast<float4 *>(A)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int l = tid; l < nl; l += T) {
                     const int f = p_brf[l];
                     if (f == 0xFFFF) continue;
@@ -258,7 +266,6 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
             if (it >= a.max_iter || wild) { iters = it; break; }
             // Jacobian values: fill / off-diagonal entries zeroed, bus-lane entries assigned, line lanes accumulate
             PF_PHASE {
-                for (int k = tid; k < n_zero; k += T) A[zero[k]] = 0.f;
                 for (int i = tid; i < nb; i += T) {
                     const int cth = p_colth[i];
                     if (cth == 0xFFFF) continue;
@@ -301,17 +308,42 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
                 }
                 PF_SYNC();
             }
-            // numeric LU (right-hand side carried along): passes of independent operations, lane = operation
-            for (int p = 0; p < n_pass; ++p) {
-                const int o1 = pass_ptr[p + 1];
-                PF_PHASE {
-                    for (int o = pass_ptr[p] + tid; o < o1; o += T) {
-                        const uint2 op = ops[o];
-                        const float lik = A[op.x >> 16], ukj = A[op.y & 0xffffu], piv = A[op.y >> 16];
-                        A[op.x & 0xffffu] -= lik * PF_RCP(piv) * ukj;
+            // numeric LU + triangular solves: the plan's operation stream, thread = slot of every row, rows prefetched
+            // two ahead (the stream is static: its loads never wait for the arithmetic), group barrier where flagged
+            {
+#define PF_AT(off) (*reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(A) + (off)))
+#ifdef B200PF_EMULATE
+                for (int r = 0; r < n_oprow; ++r) {
+                    for (int tid = 0; tid < T; ++tid) {
+                        const uint2 op = ops[(size_t)r * T + tid];
+                        const float lik = PF_AT(op.x >> 16), ukj = PF_AT(op.y & 0xffffu), piv = PF_AT((op.y >> 16) & 0xfffcu);
+                        PF_AT(op.x & 0xffffu) -= lik * PF_RCP(piv) * ukj;
                     }
                 }
-                PF_SYNC();
+#else
+                // rows come in blocks of 4 (the plan pads the stream): the 4 loads of block b+1 are issued before block b runs.
+                // One warp per instance: a warp barrier after every row (cheaper than testing the flag).
+                const uint2 *op_t = ops + tid;
+                uint2 q0 = make_uint2(0, 0), q1 = q0, q2 = q0, q3 = q0;
+                if (n_oprow > 0) { q0 = op_t[0]; q1 = op_t[T]; q2 = op_t[2 * T]; q3 = op_t[3 * T]; }
+#define PF_EXEC(q)                                                                                                      \
+                {                                                                                                       \
+                    const float lik = PF_AT((q).x >> 16), ukj = PF_AT((q).y & 0xffffu), piv = PF_AT(((q).y >> 16) & 0xfffcu); \
+                    PF_AT((q).x & 0xffffu) -= lik * PF_RCP(piv) * ukj;                                                  \
+                    if (T == 32) __syncwarp(); else if ((q).y & 0x10000u) PF_SYNC();                                    \
+                }
+                for (int r = 0; r < n_oprow; r += 4) {
+                    uint2 n0 = make_uint2(0, 0), n1 = n0, n2 = n0, n3 = n0;
+                    if (r + 4 < n_oprow) {
+                        const uint2 *nx = op_t + (size_t)(r + 4) * T;
+                        n0 = nx[0]; n1 = nx[T]; n2 = nx[2 * T]; n3 = nx[3 * T];
+                    }
+                    PF_EXEC(q0) PF_EXEC(q1) PF_EXEC(q2) PF_EXEC(q3)
+                    q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+                }
+#undef PF_EXEC
+#endif
+#undef PF_AT
             }
             PF_PHASE {                                         // lane = bus: state update
                 for (int i = tid; i < nb; i += T) {

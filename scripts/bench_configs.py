@@ -125,11 +125,11 @@ def main():
         eng.close()
     for pol, tag in ((1, "pivoting"), (2, "planned")):
         res["config5_118sub_batch2048_donothing_device_resident_" + tag] = series_rate(gm, 2048, pol, steps=5 if pol == 1 else 100)
-    for var, what in ((4, "T128"), (5, "T64"), (6, "T32")):
-        os.environ["B200PF_SPARSE_VARIANT"] = str(var)
+    for var, what in ((128, "T128"), (64, "T64"), (32, "T32")):
+        os.environ["B200PF_SPARSE_T"] = str(var)
         res["config5_118sub_batch2048_device_resident_planned_" + what] = series_rate(gm, 2048, 2, steps=50)
         res["config5_118sub_batch8192_device_resident_planned_" + what] = series_rate(gm, 8192, 2, steps=20)
-    os.environ.pop("B200PF_SPARSE_VARIANT", None)
+    os.environ.pop("B200PF_SPARSE_T", None)
     # ---- config 4: case14 N-1 sweep, 4096 base states x 20 outages
     gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
     B = 4096

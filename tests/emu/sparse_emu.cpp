@@ -57,7 +57,7 @@ extern "C" int sparse_emu_run(const b200pf_grid_desc *gd, int batch, const int8_
         if (it == cache.end()) it = cache.emplace(key, pb.build(tv, outage)).first;
         const std::vector<unsigned char> &blob = it->second;
         const PlanHeader *H = (const PlanHeader *)blob.data();
-        if (stats) { stats[0] = H->nb; stats[1] = H->d; stats[2] = H->nnzF; stats[3] = H->n_pass; stats[4] = H->n_op; stats[5] = H->n_ulev;
+        if (stats) { stats[0] = H->nb; stats[1] = H->d; stats[2] = H->nnzF; stats[3] = H->n_pass; stats[4] = H->n_op; stats[5] = H->pad[0];
                      stats[6] = H->smem_bytes; stats[7] = H->total_bytes; }
         std::vector<double> ws((size_t)H->smem_bytes / 8 + 4);
         PlanArgs pa{};
