@@ -328,8 +328,13 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_value = world * batch * args.steps / float(t.item())
-        e2e_mode = f"{ng} groups in flight" + (", results stored by the kernel straight into pinned host memory" if args.e2e_direct else "")
+        fl = args.e2e_direct
+        e2e_mode = f"{ng} groups in flight" + (", results stored by the kernel straight into pinned host memory" if fl & 1 else "") \
+            + (", chronics rows read by the kernel straight from pinned host memory (no copy-engine H2D)" if fl & 2 else "") \
+            + (", status/iteration counts stored by the kernel into pinned host memory" if fl & 4 else "")
     h2d, d2h = env.bytes_per_step_host()
+    if eng.plan_stats()["last_kernel"] == "planned_sparse":
+        h2d -= batch * gm.n_topo_in            # the planned kernel works from the cached topology plan: no topology records cross PCIe
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -337,7 +342,7 @@ def run_ours(args):
         kern_s = dev_ms * 1e-3 / args.steps                     # one launch per step (N=1: the event pair brackets only it)
         achieved = batch * surv / kern_s / 1e9
         traffic = None
-        summ = os.path.join(REPO, "profiles", "round1_ncu_summary.json")
+        summ = os.path.join(REPO, "profiles", "round1_ncu_planned_case14_summary.json")
         if os.path.exists(summ):
             try:
                 traffic = json.load(open(summ)).get("dram_bytes_per_launch")
@@ -389,7 +394,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--e2e-direct", type=int, default=0, help="1: kernels store results straight into pinned host memory")
+    ap.add_argument("--e2e-direct", type=int, default=6,
+                    help="group flags (include/b200pf.h): 1 kernels store results straight into pinned host memory, 2 kernels read "
+                         "the chronics rows straight from pinned host memory, 4 status / iteration counts stored straight into pinned host memory")
     ap.add_argument("--e2e-groups", type=int, default=4, help="groups in flight for the end-to-end host path (<=1: lockstep only)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -69,7 +69,7 @@ struct b200pf_handle {
     int plan_policy = 0;                                    // 0 auto, 1 never, 2 whenever a host copy of the topology exists
     int plan_max_smem = 0;
     int sparse_occ_smem = -1, sparse_occ = 0, sparse_occ_variant = 0;
-    int sparse_cta_cap = 0;                                 // > 0: resident CTAs per SM of the planned kernel are capped (rest of the SM's memory = L1)
+    int sparse_cta_cap = 0;                                 // > 0: resident CTAs per SM of the planned kernel are capped (rest of the SM's memory = L1); < 0: never
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0;
@@ -406,10 +406,12 @@ static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &se
         int occ = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, (size_t)smem));
         if (occ < 1) occ = 1;
-        if (h->sparse_cta_cap > 0 && occ > h->sparse_cta_cap) {
+        int cap = h->sparse_cta_cap;
+        if (cap == 0 && smem >= 16 * 1024) cap = (164 * 1024) / (smem + 1024);   // large workspaces (118 substations): leave ~90 KB of L1 (measured +10%)
+        if (cap > 0 && occ > cap) {
             // fewer resident instances, more L1: the plan arrays (operation stream, positions, line data) are re-read by
             // every instance and every Newton iteration; what shared memory does not take is L1 for them
-            occ = h->sparse_cta_cap;
+            occ = cap;
             int pct = (int)(((size_t)occ * (size_t)(smem + 1024) * 100 + (size_t)h->max_smem_optin - 1) / (size_t)h->max_smem_optin);
             if (pct > 100) pct = 100;
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -830,25 +832,34 @@ static int rows_chunk_launch_impl(b200pf_handle *h, int first, int count, const 
         st = h->chunk_stream[ci];
     }
     const size_t F = (size_t)first, C = (size_t)count, ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
-    CU(cudaMemcpyAsync(h->d_topo + F * g.n_topo_in, h->h_topo + F * g.n_topo_in, C * g.n_topo_in, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(h->d_rows + F * ncol, src_rows, C * ncol * 4, cudaMemcpyHostToDevice, st));
-    RunArgs a = base_args(h, count, is_dc, max_iter, tol_mva);
-    a.topo = h->d_topo + F * g.n_topo_in; a.inj = nullptr; a.out = h->d_out + F * g.n_out; a.status = h->d_status + F;
-    a.iters = h->d_iters + F; a.busv = nullptr; a.series = 1; a.rows = h->d_rows + F * ncol; a.static_inj = h->d_static_inj;
-    const bool direct = group >= 0 && (h->group_flags & 1);
-    if (direct) {   // pinned host memory is device-addressable (unified addressing): result records go out as posted PCIe writes
-        a.out = h->h_out + F * g.n_out; a.status = h->h_status + F; a.iters = h->h_iters + F;
-    }
     PlanSel sel;
     const int use = plan_select(h, h->h_topo + F * g.n_topo_in, count, 0, first, st, &sel, nb_cap);
     if (use < 0) return use;
+    RunArgs a = base_args(h, count, is_dc, max_iter, tol_mva);
+    a.topo = h->d_topo + F * g.n_topo_in; a.inj = nullptr; a.out = h->d_out + F * g.n_out; a.status = h->d_status + F;
+    a.iters = h->d_iters + F; a.busv = nullptr; a.series = 1; a.rows = h->d_rows + F * ncol; a.static_inj = h->d_static_inj;
+    // group flags: bit 1 = the kernel reads its inputs straight from the pinned host buffers (a few hundred bytes per
+    // instance, read once: no H2D calls at all; the planned kernel does not read the topology records), bit 2 = status /
+    // iteration counts stored by the kernel straight into pinned host memory (8 bytes per instance), bit 0 = everything is
+    const bool zc_in = group >= 0 && (h->group_flags & 2);
+    if (zc_in) {
+        a.rows = src_rows;
+        a.topo = h->h_topo + F * g.n_topo_in;
+    } else {
+        if (!use) CU(cudaMemcpyAsync(h->d_topo + F * g.n_topo_in, h->h_topo + F * g.n_topo_in, C * g.n_topo_in, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->d_rows + F * ncol, src_rows, C * ncol * 4, cudaMemcpyHostToDevice, st));
+    }
+    const bool direct = group >= 0 && (h->group_flags & 1);
+    const bool direct_st = direct || (group >= 0 && (h->group_flags & 4));
+    if (direct) a.out = h->h_out + F * g.n_out;   // pinned host memory is device-addressable (unified addressing): posted PCIe writes
+    if (direct_st) { a.status = h->h_status + F; a.iters = h->h_iters + F; }
     cudaStream_t keep = h->stream;
     h->stream = st;
     int rc = launch(h, a, nb_cap, use ? &sel : nullptr);
     h->stream = keep;
     if (rc) return rc;
-    if (!direct) {
-        CU(cudaMemcpyAsync(h->h_out + F * g.n_out, h->d_out + F * g.n_out, C * g.n_out * 4, cudaMemcpyDeviceToHost, st));
+    if (!direct) CU(cudaMemcpyAsync(h->h_out + F * g.n_out, h->d_out + F * g.n_out, C * g.n_out * 4, cudaMemcpyDeviceToHost, st));
+    if (!direct_st) {
         CU(cudaMemcpyAsync(h->h_status + F, h->d_status + F, C * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h->h_iters + F, h->d_iters + F, C * 4, cudaMemcpyDeviceToHost, st));
     }

@@ -68,7 +68,9 @@ struct PlanHeader {
     // DC: the inverse of Bdc (fp64, [n1][n1], stored transposed: entry (j, i) at j * n1 + i so that lanes = rows read
     // consecutive addresses) — Bdc depends on the topology only, so its solve is a matrix-vector product at run time
     int o_dcinv;
-    int pad2[10];
+    int o_shidx;           // u16 [nb]: index of the bus among the buses that carry a shunt (0xFFFF: none)
+    int n_shb;
+    int pad2[8];
     int pad[6];
 };
 static_assert(sizeof(PlanHeader) % 16 == 0, "plan blobs are concatenated 16-byte aligned");
@@ -77,12 +79,14 @@ enum { PLAN_ST_OK = 0, PLAN_ST_UNSUP = 2, PLAN_ST_NOREF = 3 };
 enum { PLAN_BT_PQ = 1, PLAN_BT_PV = 2, PLAN_BT_REF = 3 };
 
 // per-instance shared-memory workspace of the sparse kernel for (nb buses, n_line lines, nA values)
-inline int plan_smem_bytes(int nb, int n_line, int nA) {
+inline int plan_smem_bytes(int nb, int n_line, int nA, int n_rowcol, int n_shunt) {
     size_t o = 0;
     o += ((size_t)(nA + 1) * 4 + 15) & ~(size_t)15;   // Jacobian values + right-hand side + dummy (first: shared-memory offset 0)
-    o += (size_t)8 * nb * 8;                 // vm va pspec qspec P Q gs bs
+    o += (size_t)6 * nb * 8;                 // vm va pspec qspec P Q
+    o += (size_t)2 * n_shunt * 8;            // shunt admittance (g, b) of the buses that carry one
     o += (size_t)nb * 16;                    // V (e, f)
     o += (size_t)2 * n_line * 16;            // branch currents, both ends
+    o += ((size_t)n_rowcol * 4 + 15) & ~(size_t)15;   // this step's chronics row (load_p, load_q, prod_p, prod_v)
     return (int)((o + 15) & ~(size_t)15);
 }
 
@@ -424,7 +428,7 @@ public:
         H.pad[0] = depth_raw_;
         H.op_width = op_width_; H.n_oprow = (int)ops.size() / op_width_;
         H.n_zero = (int)zero.size();
-        H.smem_bytes = plan_smem_bytes(nb, nl, nA);
+        H.smem_bytes = plan_smem_bytes(nb, nl, nA, 2 * nld + 2 * g.n_gen, nsh);
         std::vector<unsigned char> blob(sizeof(PlanHeader));
         auto align = [&](size_t a) { while (blob.size() % a) blob.push_back(0); };
         auto put_d = [&](const std::vector<double> &v) -> int {
@@ -475,6 +479,12 @@ public:
         put_csr(bs, H.o_bs_ptr, H.o_bs); put_csr(bh, H.o_bh_ptr, H.o_bh);
         H.o_brf = put_u16(brf); H.o_brt = put_u16(brt); H.o_round = put_u16(round); H.o_jpos = put_u16v(jpos);
         H.o_unit_bus = put_u16(unit_bus); H.o_load_bus = put_u16(load_bus); H.o_sto_bus = put_u16(sto_bus); H.o_sh_bus = put_u16(sh_bus);
+        {
+            std::vector<int> shidx(nb, -1);
+            int n_shb = 0;
+            for (int i = 0; i < nb; ++i) if (!bh[i].empty()) shidx[i] = n_shb++;
+            H.o_shidx = put_u16(shidx); H.n_shb = n_shb;
+        }
         H.o_zero = put_u16v(zero);
         H.o_ulev_ptr = put_u16(ulev_ptr); H.o_urow = put_u16(urow); H.o_urow_diag = put_u16(urow_diag); H.o_uent_ptr = put_u16(uent_ptr);
         H.o_uent = put_u16v(uent);

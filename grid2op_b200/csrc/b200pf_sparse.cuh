@@ -144,20 +144,27 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
 #define F64(off) reinterpret_cast<const double *>(blob + H.off)
     const uint16_t *p_btype = U16(o_btype), *p_colth = U16(o_colth), *p_colv = U16(o_colv), *p_dcidx = U16(o_dcidx);
     const uint16_t *p_brf = U16(o_brf), *p_brt = U16(o_brt);
-    const uint16_t *adj_ptr = U16(o_adj_ptr), *adj = U16(o_adj);
+    const uint16_t *adj_ptr = U16(o_adj_ptr), *adj = U16(o_adj), *shidx = U16(o_shidx);
     // ---- workspace ------------------------------------------------------------------------------------
     // A first: on the device it then sits at shared-memory offset 0 and the operation stream's byte offsets address it directly
     float *A = reinterpret_cast<float *>(sm);
     double *vm = reinterpret_cast<double *>(sm + (((size_t)(nA + 1) * 4 + 15) & ~(size_t)15)), *va = vm + nb, *psp = va + nb, *qsp = psp + nb,
-           *Pc = qsp + nb, *Qc = Pc + nb, *gsb = Qc + nb, *bsb = gsb + nb;
-    double2 *V = reinterpret_cast<double2 *>(bsb + nb);
+           *Pc = qsp + nb, *Qc = Pc + nb, *gsh = Qc + nb, *bsh = gsh + nsh;     // gsh / bsh: per bus WITH a shunt (plan index shidx)
+    double2 *V = reinterpret_cast<double2 *>(bsh + nsh);
     double2 *cur = V + nb;
+    float *srow = reinterpret_cast<float *>(cur + 2 * nl);
     // ---- injections of this instance ----------------------------------------------------------------------
     const float *row = nullptr;
     const double *rec = nullptr, *si = a.static_inj;
-    if (a.series) row = a.rows ? a.rows + (size_t)src * (size_t)(2 * nld + 2 * ng)
-                               : a.chron + ((size_t)sc * a.n_rows + trow) * (size_t)(2 * nld + 2 * ng);
-    else rec = a.inj + (size_t)src * g.n_inj;
+    if (a.series) {
+        // this step's row is staged in shared memory with one coalesced read (it may live in pinned HOST memory:
+        // B200PF_GROUP_ZEROCOPY_IN), every later use is a shared-memory load
+        const float *grow = a.rows ? a.rows + (size_t)src * (size_t)(2 * nld + 2 * ng)
+                                   : a.chron + ((size_t)sc * a.n_rows + trow) * (size_t)(2 * nld + 2 * ng);
+        PF_PHASE { for (int k = tid; k < 2 * nld + 2 * ng; k += T) srow[k] = grow[k]; }
+        PF_SYNC();
+        row = srow;
+    } else rec = a.inj + (size_t)src * g.n_inj;
 #define GEN_P(u) ((u) < nh ? 0.0 : (row ? (double)row[2 * nld + (u) - nh] : rec[(u) - nh]))
 #define UNIT_VM(u) (row ? ((u) >= nh ? (double)PF_FDIV(row[2 * nld + ng + (u) - nh], g.unit_vn[u]) : si[ng + (u)]) : rec[ng + (u)])
 #define LOAD_P(k) (row ? (double)row[k] : rec[ng + nu + (k)])
@@ -182,7 +189,9 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
                 const int vu = vmunit[i];
                 vm[i] = vu != 0xFFFF ? UNIT_VM(vu) : 1.0;
                 const double ps = (pg - pd) / base, gpu = gs / base;
-                psp[i] = ps; qsp[i] = -qd / base; gsb[i] = gpu; bsb[i] = bsu / base;
+                psp[i] = ps; qsp[i] = -qd / base;
+                const int sx = shidx[i];
+                if (sx != 0xFFFF) { gsh[sx] = gpu; bsh[sx] = bsu / base; }
                 const int c = p_dcidx[i];
                 if (c != 0xFFFF) Pc[c] = ps - gpu - dcshift[i];
             }
@@ -251,7 +260,9 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
             PF_PHASE {                                         // lane = bus: S = V conj(I), mismatch
                 for (int i = tid; i < nb; i += T) {
                     const double2 Vi = V[i];
-                    double ir = gsb[i] * Vi.x - bsb[i] * Vi.y, ii = gsb[i] * Vi.y + bsb[i] * Vi.x;
+                    double ir = 0.0, ii = 0.0;
+                    const int sx = shidx[i];
+                    if (sx != 0xFFFF) { const double gs = gsh[sx], bs = bsh[sx]; ir = gs * Vi.x - bs * Vi.y; ii = gs * Vi.y + bs * Vi.x; }
                     for (int e = adj_ptr[i]; e < adj_ptr[i + 1]; ++e) { const double2 c2 = cur[adj[e]]; ir += c2.x; ii += c2.y; }
                     const double P = Vi.x * ir + Vi.y * ii, Q = Vi.y * ir - Vi.x * ii;
                     Pc[i] = P; Qc[i] = Q;
@@ -271,7 +282,8 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
                     if (cth == 0xFFFF) continue;
                     const double2 Vi = V[i];
                     const float vi2 = (float)(Vi.x * Vi.x + Vi.y * Vi.y), Pf = (float)Pc[i], Qf = (float)Qc[i];
-                    const float gi = (float)(ydiag[2 * i] + gsb[i]), bi = (float)(ydiag[2 * i + 1] + bsb[i]);
+                    const int sx = shidx[i];
+                    const float gi = (float)(ydiag[2 * i] + (sx != 0xFFFF ? gsh[sx] : 0.0)), bi = (float)(ydiag[2 * i + 1] + (sx != 0xFFFF ? bsh[sx] : 0.0));
                     const uint16_t *dp = dpos + 4 * i;
                     A[dp[0]] = -Qf - bi * vi2;
                     A[nnzF + cth] = (float)(psp[i] - Pc[i]);
@@ -374,7 +386,8 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
         PF_SYNC();
         PF_PHASE {
             for (int i = tid; i < nb; i += T) {
-                double p = gsb[i];
+                const int sx = shidx[i];
+                double p = sx != 0xFFFF ? gsh[sx] : 0.0;
                 for (int e = adj_ptr[i]; e < adj_ptr[i + 1]; ++e) p += cur[adj[e]].x;
                 Pc[i] = p; Qc[i] = 0.0;
             }

@@ -354,9 +354,13 @@ class PowerFlowEngine:
         self._check(self.lib.b200pf_rows_group_launch(self.h, int(group), int(first), int(count), ptr, int(bool(is_dc)),
                                                       int(max_iter), float(tol_mva), int(nb_cap)), "b200pf_rows_group_launch")
 
-    def rows_group_config(self, direct_out: bool = False):
-        """direct_out: kernels store their results straight into the pinned staging buffers (no copy-engine D2H)."""
-        self._check(self.lib.b200pf_rows_group_config(self.h, 1 if direct_out else 0), "b200pf_rows_group_config")
+    GROUP_DIRECT_OUT, GROUP_ZEROCOPY_IN, GROUP_DIRECT_STATUS = 1, 2, 4
+
+    def rows_group_config(self, direct_out=False):
+        """Flags of include/b200pf.h (an int), or a bool: True = GROUP_DIRECT_OUT (kernels store their results straight
+        into the pinned staging buffers, no copy-engine D2H)."""
+        flags = int(direct_out) if not isinstance(direct_out, bool) else (1 if direct_out else 0)
+        self._check(self.lib.b200pf_rows_group_config(self.h, flags), "b200pf_rows_group_config")
 
     def rows_group_wait(self, group: int):
         self._check(self.lib.b200pf_rows_group_wait(self.h, int(group)), "b200pf_rows_group_wait")

@@ -134,7 +134,7 @@ class BatchedDoNothing:
         return st["out"][:self.batch], st["status"][:self.batch]
 
     # ---- host buffers in / out, group-pipelined (asynchronous vectorised environments) -----------------------------
-    def host_groups(self, n_groups: int = 4, direct_out: bool = False):
+    def host_groups(self, n_groups: int = 4, direct_out=False):
         """Cut the batch into ``n_groups`` contiguous groups for :meth:`group_launch` / :meth:`group_wait`: while the
         caller consumes the results of one group the others are in flight (their PCIe copies overlap the kernels of
         the rest).  Every instance still sees its own results before its next step is launched."""

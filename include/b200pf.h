@@ -208,6 +208,13 @@ int b200pf_rows_group_wait(b200pf_handle *h, int group);
  * staging buffers (device-addressable host memory, posted PCIe writes that overlap the solve of the other instances)
  * instead of a copy-engine D2H after the kernel.  Only while no group is in flight. */
 #define B200PF_GROUP_DIRECT_OUT 1
+/* flags bit 1 (B200PF_GROUP_ZEROCOPY_IN): the kernel reads the chronics rows (and, for the pivoting kernels, the topology
+ * records) of its instances straight from the pinned host buffers — a few hundred bytes per instance, read once — instead
+ * of two copy-engine H2D transfers per launch; bit 2 (B200PF_GROUP_DIRECT_STATUS): status / iteration counts (8 bytes per
+ * instance) are stored by the kernel straight into the pinned staging buffers, the result records still travel by the copy
+ * engine.  Both cut the number of driver calls per group launch (7 -> 3), which bounds the host-side stepping rate. */
+#define B200PF_GROUP_ZEROCOPY_IN 2
+#define B200PF_GROUP_DIRECT_STATUS 4
 int b200pf_rows_group_config(b200pf_handle *h, int flags);
 int b200pf_pinned_alloc(size_t bytes, void **ptr);
 int b200pf_pinned_free(void *ptr);
