@@ -306,6 +306,8 @@ public:
                 pass_ptr.push_back((int)ops.size());
             }
             while ((ops.size() / (size_t)W) % 4) ops.insert(ops.end(), (size_t)W, nop);     // whole blocks of 4 rows (prefetch unit)
+            n_oprow_ = (int)(ops.size() / (size_t)W);
+            ops.insert(ops.end(), (size_t)W * 4, nop);      // guard block: the prefetch of "the block after the last" reads it, nothing executes it
             // slots hold BYTE offsets into the value array (4 * position; the barrier flag moves to bit 0 of kk)
             for (Op &o : ops) {
                 const unsigned flag = (o.kk & 0x4000u) ? 1u : 0u;
@@ -426,7 +428,7 @@ public:
         H.status = PLAN_ST_OK; H.nb = nb; H.n1 = n1; H.d = d; H.nnzF = nnzF; H.nA = nA; H.n_round = n_round;
         H.n_pass = n_pass; H.n_op = (int)ops.size(); H.n_ulev = n_ulev; H.n_urow = d;
         H.pad[0] = depth_raw_;
-        H.op_width = op_width_; H.n_oprow = (int)ops.size() / op_width_;
+        H.op_width = op_width_; H.n_oprow = n_oprow_;
         H.n_zero = (int)zero.size();
         H.smem_bytes = plan_smem_bytes(nb, nl, nA, 2 * nld + 2 * g.n_gen, nsh);
         std::vector<unsigned char> blob(sizeof(PlanHeader));
@@ -500,7 +502,7 @@ public:
 private:
     const HostGrid &g_;
     int op_width_;
-    mutable int depth_raw_ = 0;
+    mutable int depth_raw_ = 0, n_oprow_ = 0;
 };
 
 }  // namespace b200pf

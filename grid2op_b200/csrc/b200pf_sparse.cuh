@@ -42,6 +42,7 @@ static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y
 #define PF_SINCOS(x, s, c) do { *(s) = sin(x); *(c) = cos(x); } while (0)
 #define PF_QNANF() (__builtin_nanf(""))
 #define PF_QNAN() (__builtin_nan(""))
+#define PF_LDCS(p) (*(p))
 #else
 #include "b200pf_kernel.cuh"
 #define PF_DEV __device__ __forceinline__
@@ -54,6 +55,7 @@ static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y
 #define PF_SINCOS(x, s, c) sincos((x), (s), (c))
 #define PF_QNANF() __int_as_float(0x7fc00000)
 #define PF_QNAN() __longlong_as_double(0x7ff8000000000000LL)
+#define PF_LDCS(p) __ldcs(p)      // streaming load: read once per instance, must not evict the re-used plan arrays from L1
 #endif
 
 namespace b200pf {
@@ -208,10 +210,11 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
                 const double *col = inv + i;
                 int j = 0;
                 for (; j + 3 < n1; j += 4) {
-                    const double a0 = col[(size_t)j * n1], a1 = col[(size_t)(j + 1) * n1], a2 = col[(size_t)(j + 2) * n1], a3 = col[(size_t)(j + 3) * n1];
+                    const double a0 = PF_LDCS(col + (size_t)j * n1), a1 = PF_LDCS(col + (size_t)(j + 1) * n1), a2 = PF_LDCS(col + (size_t)(j + 2) * n1),
+                                 a3 = PF_LDCS(col + (size_t)(j + 3) * n1);
                     s0 += a0 * Pc[j]; s1 += a1 * Pc[j + 1]; s2 += a2 * Pc[j + 2]; s3 += a3 * Pc[j + 3];
                 }
-                for (; j < n1; ++j) s0 += col[(size_t)j * n1] * Pc[j];
+                for (; j < n1; ++j) s0 += PF_LDCS(col + (size_t)j * n1) * Pc[j];
                 Qc[i] = (s0 + s1) + (s2 + s3);
             }
         }
@@ -336,20 +339,17 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
                 // rows come in blocks of 4 (the plan pads the stream): the 4 loads of block b+1 are issued before block b runs.
                 // One warp per instance: a warp barrier after every row (cheaper than testing the flag).
                 const uint2 *op_t = ops + tid;
-                uint2 q0 = make_uint2(0, 0), q1 = q0, q2 = q0, q3 = q0;
-                if (n_oprow > 0) { q0 = op_t[0]; q1 = op_t[T]; q2 = op_t[2 * T]; q3 = op_t[3 * T]; }
+                uint2 q0 = op_t[0], q1 = op_t[T], q2 = op_t[2 * T], q3 = op_t[3 * T];      // (the stream ends with a guard block)
 #define PF_EXEC(q)                                                                                                      \
                 {                                                                                                       \
                     const float lik = PF_AT((q).x >> 16), ukj = PF_AT((q).y & 0xffffu), piv = PF_AT(((q).y >> 16) & 0xfffcu); \
                     PF_AT((q).x & 0xffffu) -= lik * PF_RCP(piv) * ukj;                                                  \
                     if (T == 32) __syncwarp(); else if ((q).y & 0x10000u) PF_SYNC();                                    \
                 }
+#pragma unroll 2
                 for (int r = 0; r < n_oprow; r += 4) {
-                    uint2 n0 = make_uint2(0, 0), n1 = n0, n2 = n0, n3 = n0;
-                    if (r + 4 < n_oprow) {
-                        const uint2 *nx = op_t + (size_t)(r + 4) * T;
-                        n0 = nx[0]; n1 = nx[T]; n2 = nx[2 * T]; n3 = nx[3 * T];
-                    }
+                    op_t += 4 * T;
+                    const uint2 n0 = op_t[0], n1 = op_t[T], n2 = op_t[2 * T], n3 = op_t[3 * T];
                     PF_EXEC(q0) PF_EXEC(q1) PF_EXEC(q2) PF_EXEC(q3)
                     q0 = n0; q1 = n1; q2 = n2; q3 = n3;
                 }
@@ -362,12 +362,29 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
                     const int cth = p_colth[i], cv = p_colv[i];
                     double vmi = vm[i], vai = va[i];
                     const uint16_t *dp = dpos + 4 * i;                      // x_k = rhs_k / U_kk
-                    if (cth != 0xFFFF) vai += (double)(A[nnzF + cth] * PF_RCP(A[dp[0]]));
-                    if (cv != 0xFFFF) vmi *= 1.0 + (double)(A[nnzF + cv] * PF_RCP(A[dp[3]]));
-                    if (vmi < 0.0) { vmi = -vmi; vai += 3.14159265358979323846; }
-                    vm[i] = vmi; va[i] = vai;
-                    double s, c; PF_SINCOS(vai, &s, &c);
-                    V[i] = make_double2(vmi * c, vmi * s);
+                    const double dth = cth != 0xFFFF ? (double)(A[nnzF + cth] * PF_RCP(A[dp[0]])) : 0.0;
+                    const double dvr = cv != 0xFFFF ? (double)(A[nnzF + cv] * PF_RCP(A[dp[3]])) : 0.0;
+                    vai += dth;
+                    const double vnew = vmi * (1.0 + dvr);
+                    if (fabs(dth) < 0.25 && vnew > 0.0) {
+                        // small angle step (every step but pathological ones): rotate (e, f) by dth with the Taylor series of
+                        // sin / cos to x^13 / x^14 (remainder < 3e-18 for |x| < 0.25) instead of a full-range fp64 sincos
+                        const double x2 = dth * dth;
+                        const double sn = dth * (1.0 - x2 * (1.0 / 6.0) * (1.0 - x2 * (1.0 / 20.0) * (1.0 - x2 * (1.0 / 42.0) * (1.0 - x2 * (1.0 / 72.0) *
+                                          (1.0 - x2 * (1.0 / 110.0) * (1.0 - x2 * (1.0 / 156.0)))))));
+                        const double cs = 1.0 - x2 * 0.5 * (1.0 - x2 * (1.0 / 12.0) * (1.0 - x2 * (1.0 / 30.0) * (1.0 - x2 * (1.0 / 56.0) * (1.0 - x2 * (1.0 / 90.0) *
+                                          (1.0 - x2 * (1.0 / 132.0) * (1.0 - x2 * (1.0 / 182.0)))))));
+                        const double2 Vo = V[i];
+                        const double sc = 1.0 + dvr;
+                        V[i] = make_double2(sc * (Vo.x * cs - Vo.y * sn), sc * (Vo.x * sn + Vo.y * cs));
+                        vm[i] = vnew; va[i] = vai;
+                    } else {
+                        vmi = vnew;
+                        if (vmi < 0.0) { vmi = -vmi; vai += 3.14159265358979323846; }
+                        vm[i] = vmi; va[i] = vai;
+                        double s, c; PF_SINCOS(vai, &s, &c);
+                        V[i] = make_double2(vmi * c, vmi * s);
+                    }
                 }
             }
             PF_SYNC();
