@@ -70,7 +70,8 @@ struct PlanHeader {
     int o_dcinv;
     int o_shidx;           // u16 [nb]: index of the bus among the buses that carry a shunt (0xFFFF: none)
     int n_shb;
-    int pad2[8];
+    int o_late, n_late;    // u16 pairs (line, round) of the lines of assembly rounds >= 1 (parallel lines), sorted by round
+    int pad2[6];
     int pad[6];
 };
 static_assert(sizeof(PlanHeader) % 16 == 0, "plan blobs are concatenated 16-byte aligned");
@@ -343,9 +344,11 @@ public:
                     int p = P(rf[a], rt[b]); if (p >= 0) jp[a * 2 + b] = (uint16_t)p;
                     p = P(rt[a], rf[b]);     if (p >= 0) jp[4 + a * 2 + b] = (uint16_t)p;
                 }
-                int r = 0;
+                // round 0 is added BEFORE the bus lanes assign the diagonal blocks: a line with both ends on one bus (it
+                // writes into a diagonal block) must come later
+                int r = (f == t) ? 1 : 0;
                 for (;; ++r) {
-                    if (r == (int)used.size()) used.emplace_back(nA + 1, 0);
+                    while (r >= (int)used.size()) used.emplace_back(nA + 1, 0);
                     bool clash = false;
                     for (int q = 0; q < 8; ++q) if (jp[q] != DUMMY && used[r][jp[q]]) clash = true;
                     // a line whose two ends sit on the same bus writes the same entry twice: keep it alone in a round
@@ -486,6 +489,11 @@ public:
             int n_shb = 0;
             for (int i = 0; i < nb; ++i) if (!bh[i].empty()) shidx[i] = n_shb++;
             H.o_shidx = put_u16(shidx); H.n_shb = n_shb;
+        }
+        {
+            std::vector<int> late;
+            for (int r = 1; r < n_round; ++r) for (int l = 0; l < nl; ++l) if (brf[l] >= 0 && round[l] == r) { late.push_back(l); late.push_back(r); }
+            H.o_late = put_u16(late); H.n_late = (int)late.size() / 2;
         }
         H.o_zero = put_u16v(zero);
         H.o_ulev_ptr = put_u16(ulev_ptr); H.o_urow = put_u16(urow); H.o_urow_diag = put_u16(urow_diag); H.o_uent_ptr = put_u16(uent_ptr);

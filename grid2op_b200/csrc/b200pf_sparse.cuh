@@ -144,7 +144,7 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
     float *out = a.out ? a.out + (size_t)inst * g.n_out : nullptr;
 #define U16(off) reinterpret_cast<const uint16_t *>(blob + H.off)
 #define F64(off) reinterpret_cast<const double *>(blob + H.off)
-    const uint16_t *p_btype = U16(o_btype), *p_colth = U16(o_colth), *p_colv = U16(o_colv), *p_dcidx = U16(o_dcidx);
+    const uint16_t *p_colth = U16(o_colth), *p_colv = U16(o_colv), *p_dcidx = U16(o_dcidx);
     const uint16_t *p_brf = U16(o_brf), *p_brt = U16(o_brt);
     const uint16_t *adj_ptr = U16(o_adj_ptr), *adj = U16(o_adj), *shidx = U16(o_shidx);
     // ---- workspace ------------------------------------------------------------------------------------
@@ -236,17 +236,38 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
         if (bad) { sparse_fail<T>(g, a, inst, ST_DIV, 0, tid0); return; }
     }
     // ---- 3. Newton-Raphson ---------------------------------------------------------------------------------
+    // Four phases per iteration: [lane = line: branch currents + off-diagonal Jacobian terms] [lane = bus: S(V), mismatch,
+    // diagonal terms + right-hand side; vote] [operation stream] [lane = bus: state update; clear the dead values].
+    // The Jacobian terms are computed before the convergence vote (same operands as the currents / mismatch: V, y, P, Q
+    // are in registers) — wasted once, in the converged evaluation, instead of re-loading everything in two more phases.
     int iters = 0;
     if (!a.is_dc) {
-        const uint16_t *dpos = U16(o_dpos), *jpos = U16(o_jpos), *rnd = U16(o_round);
+        const uint16_t *dpos = U16(o_dpos), *jpos = U16(o_jpos), *rnd = U16(o_round), *zero = U16(o_zero), *late = U16(o_late);
         const double *ydiag = F64(o_ydiag);
         const uint2 *ops = reinterpret_cast<const uint2 *>(blob + H.o_ops);
-        const int n_oprow = H.n_oprow, n_round = H.n_round, nz4 = (nnzF + 3) >> 2;
+        const int n_oprow = H.n_oprow, n_round = H.n_round, n_zero = H.n_zero, n_late = H.n_late;
         bool conv = false;
+        PF_PHASE { for (int k = tid; k < n_zero; k += T) A[zero[k]] = 0.f; }      // entries the line lanes add into / pure fill
+        PF_SYNC();
+#define PF_OFFDIAG(l, Vf, Vt, y)                                                                                   \
+        {                                                                                                          \
+            const float ef = (float)(Vf).x, ff = (float)(Vf).y, et = (float)(Vt).x, ft = (float)(Vt).y;            \
+            const uint16_t *jp = jpos + 8 * (l);                                                                   \
+            {   /* rows of bus f, columns of bus t:  T = Vf conj(yft Vt) */                                        \
+                const float yr = (float)(y)[2], yi = (float)(y)[3];                                                \
+                const float ar = yr * et - yi * ft, ai = yr * ft + yi * et;                                        \
+                const float tr = ef * ar + ff * ai, ti = ff * ar - ef * ai;                                        \
+                A[jp[0]] += ti; A[jp[1]] += tr; A[jp[2]] -= tr; A[jp[3]] += ti;                                    \
+            }                                                                                                      \
+            {   /* rows of bus t, columns of bus f:  T = Vt conj(ytf Vf) */                                        \
+                const float yr = (float)(y)[4], yi = (float)(y)[5];                                                \
+                const float ar = yr * ef - yi * ff, ai = yr * ff + yi * ef;                                        \
+                const float tr = et * ar + ft * ai, ti = ft * ar - et * ai;                                        \
+                A[jp[4]] += ti; A[jp[5]] += tr; A[jp[6]] -= tr; A[jp[7]] += ti;                                    \
+            }                                                                                                      \
+        }
         for (int it = 0;; ++it) {
-            PF_PHASE {                                         // lane = line: currents at both ends
-                // (the Jacobian values of the previous iteration are dead: clear them here, the assembly below adds into them)
-                for (int k = tid; k < nz4; k += T) reinterpret_cast<float4 *>(A)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            PF_PHASE {                                         // lane = line: currents at both ends, off-diagonal terms (round 0)
                 for (int l = tid; l < nl; l += T) {
                     const int f = p_brf[l];
                     if (f == 0xFFFF) continue;
@@ -256,71 +277,51 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
                                               y[0] * Vf.y + y[1] * Vf.x + y[2] * Vt.y + y[3] * Vt.x);
                     cur[2 * l + 1] = make_double2(y[4] * Vf.x - y[5] * Vf.y + y[6] * Vt.x - y[7] * Vt.y,
                                                   y[4] * Vf.y + y[5] * Vf.x + y[6] * Vt.y + y[7] * Vt.x);
+                    if (n_round <= 1 || rnd[l] == 0) PF_OFFDIAG(l, Vf, Vt, y)
                 }
             }
             PF_SYNC();
             int viol = 0, wild = 0;
-            PF_PHASE {                                         // lane = bus: S = V conj(I), mismatch
+            PF_PHASE {                                         // lane = bus: S = V conj(I), mismatch, diagonal terms, right-hand side
                 for (int i = tid; i < nb; i += T) {
                     const double2 Vi = V[i];
-                    double ir = 0.0, ii = 0.0;
+                    double ir = 0.0, ii = 0.0, gs = 0.0, bs = 0.0;
                     const int sx = shidx[i];
-                    if (sx != 0xFFFF) { const double gs = gsh[sx], bs = bsh[sx]; ir = gs * Vi.x - bs * Vi.y; ii = gs * Vi.y + bs * Vi.x; }
+                    if (sx != 0xFFFF) { gs = gsh[sx]; bs = bsh[sx]; ir = gs * Vi.x - bs * Vi.y; ii = gs * Vi.y + bs * Vi.x; }
                     for (int e = adj_ptr[i]; e < adj_ptr[i + 1]; ++e) { const double2 c2 = cur[adj[e]]; ir += c2.x; ii += c2.y; }
                     const double P = Vi.x * ir + Vi.y * ii, Q = Vi.y * ir - Vi.x * ii;
                     Pc[i] = P; Qc[i] = Q;
-                    const int bt = p_btype[i];
-                    if (bt != BT_REF) { const double m1 = fabs(P - psp[i]); viol |= !(m1 < a.tol_pu); wild |= !(m1 < 1e200); }
-                    if (bt == BT_PQ) { const double m2 = fabs(Q - qsp[i]); viol |= !(m2 < a.tol_pu); wild |= !(m2 < 1e200); }
+                    const int cth = p_colth[i], cv = p_colv[i];          // (0xFFFF: reference bus / PV bus)
+                    if (cth == 0xFFFF) continue;
+                    const double dP = psp[i] - P;
+                    { const double m1 = fabs(dP); viol |= !(m1 < a.tol_pu); wild |= !(m1 < 1e200); }
+                    const float vi2 = (float)(Vi.x * Vi.x + Vi.y * Vi.y), Pf = (float)P, Qf = (float)Q;
+                    const float gi = (float)(ydiag[2 * i] + gs), bi = (float)(ydiag[2 * i + 1] + bs);
+                    const uint16_t *dp = dpos + 4 * i;
+                    A[dp[0]] = -Qf - bi * vi2;
+                    A[nnzF + cth] = (float)dP;
+                    if (cv != 0xFFFF) {
+                        const double dQ = qsp[i] - Q;
+                        { const double m2 = fabs(dQ); viol |= !(m2 < a.tol_pu); wild |= !(m2 < 1e200); }
+                        A[dp[1]] = Pf + gi * vi2; A[dp[2]] = Pf - gi * vi2; A[dp[3]] = Qf - bi * vi2;
+                        A[nnzF + cv] = (float)dQ;
+                    }
                 }
             }
             viol = PF_ANY(viol);
             if (!viol) { conv = true; iters = it; break; }
             wild = PF_ANY(wild);
             if (it >= a.max_iter || wild) { iters = it; break; }
-            // Jacobian values: fill / off-diagonal entries zeroed, bus-lane entries assigned, line lanes accumulate
-            PF_PHASE {
-                for (int i = tid; i < nb; i += T) {
-                    const int cth = p_colth[i];
-                    if (cth == 0xFFFF) continue;
-                    const double2 Vi = V[i];
-                    const float vi2 = (float)(Vi.x * Vi.x + Vi.y * Vi.y), Pf = (float)Pc[i], Qf = (float)Qc[i];
-                    const int sx = shidx[i];
-                    const float gi = (float)(ydiag[2 * i] + (sx != 0xFFFF ? gsh[sx] : 0.0)), bi = (float)(ydiag[2 * i + 1] + (sx != 0xFFFF ? bsh[sx] : 0.0));
-                    const uint16_t *dp = dpos + 4 * i;
-                    A[dp[0]] = -Qf - bi * vi2;
-                    A[nnzF + cth] = (float)(psp[i] - Pc[i]);
-                    const int cv = p_colv[i];
-                    if (cv != 0xFFFF) {
-                        A[dp[1]] = Pf + gi * vi2; A[dp[2]] = Pf - gi * vi2; A[dp[3]] = Qf - bi * vi2;
-                        A[nnzF + cv] = (float)(qsp[i] - Qc[i]);
-                    }
-                }
-            }
-            PF_SYNC();
-            for (int r = 0; r < n_round; ++r) {
+            for (int r = 1, q = 0; r < n_round; ++r) {         // parallel lines: later rounds, one barrier each (rare)
                 PF_PHASE {
-                    for (int l = tid; l < nl; l += T) {
-                        const int f = p_brf[l];
-                        if (f == 0xFFFF || rnd[l] != r) continue;
-                        const double2 Vf = V[f], Vt = V[p_brt[l]];
+                    for (int k = q + tid; k < n_late && late[2 * k + 1] == r; k += T) {
+                        const int l = late[2 * k];
+                        const double2 Vf = V[p_brf[l]], Vt = V[p_brt[l]];
                         const double *y = g.line_y + (size_t)l * 8;
-                        const float ef = (float)Vf.x, ff = (float)Vf.y, et = (float)Vt.x, ft = (float)Vt.y;
-                        const uint16_t *jp = jpos + 8 * l;
-                        {   // rows of bus f, columns of bus t:  T = Vf conj(yft Vt)
-                            const float yr = (float)y[2], yi = (float)y[3];
-                            const float ar = yr * et - yi * ft, ai = yr * ft + yi * et;
-                            const float tr = ef * ar + ff * ai, ti = ff * ar - ef * ai;
-                            A[jp[0]] += ti; A[jp[1]] += tr; A[jp[2]] -= tr; A[jp[3]] += ti;
-                        }
-                        {   // rows of bus t, columns of bus f:  T = Vt conj(ytf Vf)
-                            const float yr = (float)y[4], yi = (float)y[5];
-                            const float ar = yr * ef - yi * ff, ai = yr * ff + yi * ef;
-                            const float tr = et * ar + ft * ai, ti = ft * ar - et * ai;
-                            A[jp[4]] += ti; A[jp[5]] += tr; A[jp[6]] -= tr; A[jp[7]] += ti;
-                        }
+                        PF_OFFDIAG(l, Vf, Vt, y)
                     }
                 }
+                while (q < n_late && late[2 * q + 1] == r) ++q;
                 PF_SYNC();
             }
             // numeric LU + triangular solves: the plan's operation stream, thread = slot of every row, rows prefetched
@@ -357,7 +358,7 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
 #endif
 #undef PF_AT
             }
-            PF_PHASE {                                         // lane = bus: state update
+            PF_PHASE {                                         // lane = bus: state update; the assembled / filled values are dead now
                 for (int i = tid; i < nb; i += T) {
                     const int cth = p_colth[i], cv = p_colv[i];
                     double vmi = vm[i], vai = va[i];
@@ -386,9 +387,12 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
                         V[i] = make_double2(vmi * c, vmi * s);
                     }
                 }
+                // (the bus lanes above read only right-hand side and diagonal entries; the cleared set excludes them)
+                for (int k = tid; k < n_zero; k += T) A[zero[k]] = 0.f;
             }
             PF_SYNC();
         }
+#undef PF_OFFDIAG
         if (!conv) { sparse_fail<T>(g, a, inst, ST_DIV, iters, tid0); return; }
     } else {
         // DC: line lanes compute flows from the angles, bus lanes sum them for the slack share
