@@ -4,8 +4,12 @@ BACKEND element order, ready to be pinned and copied to HBM (``PowerFlowEngine.s
 Restates the part of ``grid2op.Chronics.GridStateFromFile`` the batched driver needs (reference
 grid2op/Chronics/gridStateFromFile.py:289-387 file discovery and column matching by NAME, :749-808 one row
 per step): ``load_p, load_q, prod_p, prod_v``; a missing ``prod_v`` file falls back to the set points of
-the grid file (the reference keeps the backend's values in that case).  Maintenance / hazards / forecasts
-are not read here (DoNothing driver).
+the grid file (the reference keeps the backend's values in that case).
+Also read: the ``*_forecasted`` tables of ``GridStateFromFileWithForecasts``
+(grid2op/Chronics/gridStateFromFileWithForecasts.py:110-190; what ``obs.simulate`` is fed with) and the planned /
+unplanned outage tables ``maintenance`` / ``hazards`` with the derived ``maintenance_time``,
+``maintenance_duration``, ``hazard_duration`` series (grid2op/Chronics/gridValue.py:264-470), columns matched by
+LINE name.
 """
 from __future__ import annotations
 
@@ -17,7 +21,8 @@ import numpy as np
 
 from .gridmodel import GridModel
 
-__all__ = ["read_table", "load_scenario", "load_scenarios", "list_scenarios"]
+__all__ = ["read_table", "load_scenario", "load_scenarios", "list_scenarios", "load_forecasts", "load_line_events",
+           "maintenance_time_duration", "hazard_duration"]
 
 
 def _open(path_no_ext: str):
@@ -49,14 +54,14 @@ def _ordered(tbl, names: Sequence[str], what: str, folder: str) -> np.ndarray:
     return arr[:, [pos[n] for n in names]]
 
 
-def load_scenario(folder: str, gm: GridModel, sep: str = ";") -> np.ndarray:
+def load_scenario(folder: str, gm: GridModel, sep: str = ";", suffix: str = "") -> np.ndarray:
     """float32 [n_rows, 2 n_load + 2 n_gen] = load_p | load_q | prod_p | prod_v[kV], backend order."""
-    lp = read_table(os.path.join(folder, "load_p"), sep)
-    lq = read_table(os.path.join(folder, "load_q"), sep)
-    pp = read_table(os.path.join(folder, "prod_p"), sep)
-    pv = read_table(os.path.join(folder, "prod_v"), sep)
+    lp = read_table(os.path.join(folder, "load_p" + suffix), sep)
+    lq = read_table(os.path.join(folder, "load_q" + suffix), sep)
+    pp = read_table(os.path.join(folder, "prod_p" + suffix), sep)
+    pv = read_table(os.path.join(folder, "prod_v" + suffix), sep)
     if lp is None or lq is None or pp is None:
-        raise FileNotFoundError(f"{folder}: load_p / load_q / prod_p are required")
+        raise FileNotFoundError(f"{folder}: load_p{suffix} / load_q{suffix} / prod_p{suffix} are required")
     a_lp = _ordered(lp, gm.name_load, "load_p", folder)
     a_lq = _ordered(lq, gm.name_load, "load_q", folder)
     a_pp = _ordered(pp, gm.name_gen, "prod_p", folder)
@@ -67,6 +72,60 @@ def load_scenario(folder: str, gm: GridModel, sep: str = ";") -> np.ndarray:
     else:
         a_pv = np.tile((gm.gen_vm0 * gm.prod_pu_to_kv.astype(np.float64))[None, :], (n, 1))
     return np.concatenate([a_lp[:n], a_lq[:n], a_pp[:n], a_pv[:n]], axis=1).astype(np.float32)
+
+
+def load_forecasts(folder: str, gm: GridModel, sep: str = ";") -> Optional[np.ndarray]:
+    """The ``*_forecasted`` tables in the layout of :func:`load_scenario` (row k = forecast available at step k for
+    step k + 1, one horizon like the bundled environments), or None when the folder has no forecasts.  These rows feed
+    ``PowerFlowEngine.run`` / the rows entry points exactly like real rows: a batched ``obs.simulate`` is one launch."""
+    if _open(os.path.join(folder, "load_p_forecasted")) is None:
+        return None
+    return load_scenario(folder, gm, sep, suffix="_forecasted")
+
+
+def load_line_events(folder: str, gm: GridModel, what: str = "maintenance", sep: str = ";") -> Optional[np.ndarray]:
+    """bool [n_rows, n_line] from ``maintenance`` / ``hazards`` (non-zero = the line is out), backend line order,
+    columns matched by line name; None when the file does not exist."""
+    tbl = read_table(os.path.join(folder, what), sep)
+    if tbl is None:
+        return None
+    return np.abs(_ordered(tbl, gm.name_line, what, folder)) >= 1e-7
+
+
+def _runs(col: np.ndarray):
+    """(start, end) index pairs of the runs of True in a 1-d bool array."""
+    x = np.concatenate(([0], col.astype(np.int8), [0]))
+    d = np.diff(x)
+    return np.flatnonzero(d == 1), np.flatnonzero(d == -1)
+
+
+def maintenance_time_duration(maintenance: np.ndarray):
+    """int32 [n_rows, n_line] x 2: steps until the next planned outage starts (0 while it runs, -1 when none is
+    ahead) and its (remaining) duration (0 when none is ahead) — the semantics documented at
+    grid2op/Chronics/gridValue.py:264-395."""
+    n, nl = maintenance.shape
+    t = np.full((n, nl), -1, dtype=np.int32)
+    dur = np.zeros((n, nl), dtype=np.int32)
+    for l in range(nl):
+        prev = 0
+        for b, e in zip(*_runs(maintenance[:, l])):
+            t[prev:b, l] = np.arange(b - prev, 0, -1)
+            t[b:e, l] = 0
+            dur[prev:b, l] = e - b
+            dur[b:e, l] = np.arange(e - b, 0, -1)
+            prev = e
+    return t, dur
+
+
+def hazard_duration(hazards: np.ndarray) -> np.ndarray:
+    """int32 [n_rows, n_line]: remaining duration of the running unplanned outage, 0 otherwise
+    (grid2op/Chronics/gridValue.py:403-470)."""
+    n, nl = hazards.shape
+    dur = np.zeros((n, nl), dtype=np.int32)
+    for l in range(nl):
+        for b, e in zip(*_runs(hazards[:, l])):
+            dur[b:e, l] = np.arange(e - b, 0, -1)
+    return dur
 
 
 def list_scenarios(chronics_dir: str) -> List[str]:

@@ -58,7 +58,9 @@ struct b200pf_handle {
     int small_ok = 0;
     // planned sparse kernel: cache of topology plans (host blobs + their device copy)
     HostGrid hg;
-    std::unordered_map<std::string, int> plan_index;
+    std::unordered_map<uint64_t, int> plan_index;           // hash of (topology row, outage) -> newest plan with that hash
+    std::vector<int8_t> plan_keys;                          // topology row of every plan (verification)
+    std::vector<int> plan_outage, plan_next;                // outage of every plan; next plan with the same hash
     std::vector<int> plan_off, plan_smem;
     std::vector<unsigned char> plan_blobs;                  // concatenated, every plan 16-byte aligned
     unsigned char *d_plan_blobs = nullptr; size_t d_plan_cap = 0, d_plan_used = 0;
@@ -313,11 +315,33 @@ struct PlanSel {
     int smem;
 };
 
-static int plan_lookup(b200pf_handle *h, const int8_t *tv, int outage, int *built) {
-    std::string key((const char *)tv, (size_t)h->g.n_topo_in);
-    if (outage >= 0) { key.push_back((char)0x7f); key.push_back((char)(outage & 0xff)); key.push_back((char)((outage >> 8) & 0xff)); }
+// 64-bit hash of a topology row (8 bytes at a time)
+static inline uint64_t topo_hash(const int8_t *tv, size_t n) {
+    uint64_t hsh = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, tv + i, 8);
+        hsh = (hsh ^ w) * 0xFF51AFD7ED558CCDull;
+        hsh ^= hsh >> 29;
+    }
+    uint64_t w = 0;
+    if (i < n) memcpy(&w, tv + i, n - i);
+    hsh = (hsh ^ w) * 0xC4CEB9FE1A85EC53ull;
+    hsh ^= hsh >> 32;
+    return hsh;
+}
+
+// plan of (topology row, outage): cache lookup (hash of the row computed by the caller, keys verified byte by byte),
+// built on a miss
+static int plan_lookup(b200pf_handle *h, const int8_t *tv, uint64_t row_hash, int outage, int *built) {
+    const size_t nt = (size_t)h->g.n_topo_in;
+    const uint64_t key = row_hash ^ ((uint64_t)(outage + 1) * 0x9E3779B97F4A7C15ull);
     auto it = h->plan_index.find(key);
-    if (it != h->plan_index.end()) return it->second;
+    if (it != h->plan_index.end()) {
+        for (int id = it->second; id >= 0; id = h->plan_next[id])
+            if (h->plan_outage[id] == outage && memcmp(h->plan_keys.data() + (size_t)id * nt, tv, nt) == 0) return id;
+    }
     if ((int)h->plan_off.size() >= PLAN_MAX) return -1;
     PlanBuilder pb(h->hg, h->plan_T);
     std::vector<unsigned char> blob = pb.build(tv, outage);
@@ -328,7 +352,10 @@ static int plan_lookup(b200pf_handle *h, const int8_t *tv, int outage, int *buil
     h->plan_smem.push_back(H->smem_bytes);
     h->plan_blobs.insert(h->plan_blobs.end(), blob.begin(), blob.end());
     while (h->plan_blobs.size() % 16) h->plan_blobs.push_back(0);
-    h->plan_index.emplace(std::move(key), id);
+    h->plan_keys.insert(h->plan_keys.end(), tv, tv + nt);
+    h->plan_outage.push_back(outage);
+    h->plan_next.push_back(it != h->plan_index.end() ? it->second : -1);
+    h->plan_index[key] = id;
     if (H->smem_bytes > h->plan_max_smem) h->plan_max_smem = H->smem_bytes;
     ++*built; h->plans_built++;
     return id;
@@ -374,8 +401,9 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
             for (int l = 0; l < per; ++l) ids[(size_t)s * per + l] = ids[(size_t)(s - 1) * per + l];
             continue;
         }
+        const uint64_t rh = topo_hash(tv, nt);
         for (int l = 0; l < per; ++l) {
-            const int id = plan_lookup(h, tv, n1_lines > 0 ? l : -1, &built);
+            const int id = plan_lookup(h, tv, rh, n1_lines > 0 ? l : -1, &built);
             if (id < 0) return 0;
             ids[(size_t)s * per + l] = id;
             if (id != ids[0]) single = false;
