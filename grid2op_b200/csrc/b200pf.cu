@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -332,21 +333,25 @@ static inline uint64_t topo_hash(const int8_t *tv, size_t n) {
     return hsh;
 }
 
-// plan of (topology row, outage): cache lookup (hash of the row computed by the caller, keys verified byte by byte),
-// built on a miss
-static int plan_lookup(b200pf_handle *h, const int8_t *tv, uint64_t row_hash, int outage, int *built) {
+static inline uint64_t plan_key(uint64_t row_hash, int outage) { return row_hash ^ ((uint64_t)(outage + 1) * 0x9E3779B97F4A7C15ull); }
+
+// cached plan of (topology row, outage), or -1
+static int plan_find(const b200pf_handle *h, const int8_t *tv, uint64_t row_hash, int outage) {
     const size_t nt = (size_t)h->g.n_topo_in;
-    const uint64_t key = row_hash ^ ((uint64_t)(outage + 1) * 0x9E3779B97F4A7C15ull);
-    auto it = h->plan_index.find(key);
-    if (it != h->plan_index.end()) {
-        for (int id = it->second; id >= 0; id = h->plan_next[id])
-            if (h->plan_outage[id] == outage && memcmp(h->plan_keys.data() + (size_t)id * nt, tv, nt) == 0) return id;
-    }
-    if ((int)h->plan_off.size() >= PLAN_MAX) return -1;
-    PlanBuilder pb(h->hg, h->plan_T);
-    std::vector<unsigned char> blob = pb.build(tv, outage);
+    auto it = h->plan_index.find(plan_key(row_hash, outage));
+    if (it == h->plan_index.end()) return -1;
+    for (int id = it->second; id >= 0; id = h->plan_next[id])
+        if (h->plan_outage[id] == outage && memcmp(h->plan_keys.data() + (size_t)id * nt, tv, nt) == 0) return id;
+    return -1;
+}
+
+// appends a freshly built plan to the cache; -1 when it cannot be used (does not fit the format / the shared memory)
+static int plan_insert(b200pf_handle *h, const int8_t *tv, uint64_t row_hash, int outage, const std::vector<unsigned char> &blob) {
+    const size_t nt = (size_t)h->g.n_topo_in;
     const PlanHeader *H = reinterpret_cast<const PlanHeader *>(blob.data());
-    if (!PlanBuilder::fits(*H) || H->smem_bytes > h->max_smem_optin) return -1;
+    if ((int)h->plan_off.size() >= PLAN_MAX || !PlanBuilder::fits(*H) || H->smem_bytes > h->max_smem_optin) return -1;
+    const uint64_t key = plan_key(row_hash, outage);
+    auto it = h->plan_index.find(key);
     const int id = (int)h->plan_off.size();
     h->plan_off.push_back((int)h->plan_blobs.size());
     h->plan_smem.push_back(H->smem_bytes);
@@ -357,7 +362,7 @@ static int plan_lookup(b200pf_handle *h, const int8_t *tv, uint64_t row_hash, in
     h->plan_next.push_back(it != h->plan_index.end() ? it->second : -1);
     h->plan_index[key] = id;
     if (H->smem_bytes > h->plan_max_smem) h->plan_max_smem = H->smem_bytes;
-    ++*built; h->plans_built++;
+    h->plans_built++;
     return id;
 }
 
@@ -393,8 +398,10 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     const size_t nt = (size_t)g.n_topo_in;
     const int per = n1_lines > 0 ? n1_lines : 1;
     int *ids = h->h_inst_plan + first;
-    int built = 0;
-    bool single = true;
+    // pass 1: cached plans; the misses of this call are collected (once each) ...
+    struct Miss { const int8_t *tv; uint64_t rh; int outage; int id; };
+    std::vector<Miss> miss;
+    std::unordered_map<uint64_t, std::vector<int>> miss_index;
     for (int s = 0; s < n_src; ++s) {
         const int8_t *tv = host_topo + (size_t)s * nt;
         if (s > 0 && memcmp(tv, tv - nt, nt) == 0) {
@@ -403,20 +410,48 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
         }
         const uint64_t rh = topo_hash(tv, nt);
         for (int l = 0; l < per; ++l) {
-            const int id = plan_lookup(h, tv, rh, n1_lines > 0 ? l : -1, &built);
-            if (id < 0) return 0;
+            const int outage = n1_lines > 0 ? l : -1;
+            int id = plan_find(h, tv, rh, outage);
+            if (id < 0) {
+                std::vector<int> &cand = miss_index[plan_key(rh, outage)];
+                int m = -1;
+                for (int c : cand) if (miss[c].outage == outage && memcmp(miss[c].tv, tv, nt) == 0) { m = c; break; }
+                if (m < 0) { m = (int)miss.size(); miss.push_back({tv, rh, outage, -1}); cand.push_back(m); }
+                id = -2 - m;                      // placeholder, resolved below
+            }
             ids[(size_t)s * per + l] = id;
-            if (id != ids[0]) single = false;
         }
-        if (h->plan_policy == 0 && built > PLAN_BUILD_BUDGET) { int rc = plans_sync_device(h); return rc ? rc : 0; }
+    }
+    // ... built in parallel on the host threads (the builder is pure), inserted in order
+    if (!miss.empty()) {
+        if (h->plan_policy == 0 && (int)miss.size() > PLAN_BUILD_BUDGET) return 0;
+        std::vector<std::vector<unsigned char>> blobs(miss.size());
+        const PlanBuilder pb(h->hg, h->plan_T);
+        unsigned nthr = std::thread::hardware_concurrency();
+        if (nthr > 16) nthr = 16;
+        if (nthr < 1) nthr = 1;
+        if ((size_t)nthr > miss.size() / 4 + 1) nthr = (unsigned)(miss.size() / 4 + 1);
+        if (nthr <= 1) {
+            for (size_t m = 0; m < miss.size(); ++m) blobs[m] = pb.build(miss[m].tv, miss[m].outage);
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nthr; ++t)
+                pool.emplace_back([&, t]() { for (size_t m = t; m < miss.size(); m += nthr) blobs[m] = pb.build(miss[m].tv, miss[m].outage); });
+            for (auto &th : pool) th.join();
+        }
+        for (size_t m = 0; m < miss.size(); ++m) {
+            miss[m].id = plan_insert(h, miss[m].tv, miss[m].rh, miss[m].outage, blobs[m]);
+            if (miss[m].id < 0) { int rc = plans_sync_device(h); return rc ? rc : 0; }
+        }
+        const size_t n = (size_t)n_src * per;
+        for (size_t k = 0; k < n; ++k) if (ids[k] <= -2) ids[k] = miss[(size_t)(-2 - ids[k])].id;
     }
     int rc = plans_sync_device(h);
     if (rc) return rc;
     const size_t n = (size_t)n_src * per;
-    int smem = 16;
-    if (single) smem = h->plan_smem[ids[0]];
-    else smem = h->plan_max_smem;
-    sel->single = ids[0]; sel->smem = smem; sel->d_inst_plan = nullptr;
+    bool single = true;
+    for (size_t k = 1; k < n && single; ++k) single = ids[k] == ids[0];
+    sel->single = ids[0]; sel->smem = single ? h->plan_smem[ids[0]] : h->plan_max_smem; sel->d_inst_plan = nullptr;
     if (!single) {
         CU(cudaMemcpyAsync(h->d_inst_plan + first, ids, n * 4, cudaMemcpyHostToDevice, st));
         sel->d_inst_plan = h->d_inst_plan + first;

@@ -24,6 +24,19 @@
 #include <cstring>
 #include <vector>
 
+#ifdef B200PF_PLAN_PROFILE
+#include <chrono>
+#include <map>
+#include <string>
+namespace b200pf { inline std::map<std::string, double> &plan_prof() { static std::map<std::string, double> m; return m; }
+inline std::chrono::steady_clock::time_point &plan_prof_t() { static std::chrono::steady_clock::time_point t; return t; } }
+#define PLAN_TICK(name) { auto now_ = std::chrono::steady_clock::now(); b200pf::plan_prof()[name] += std::chrono::duration<double>(now_ - b200pf::plan_prof_t()).count(); b200pf::plan_prof_t() = now_; }
+#define PLAN_TICK0() { b200pf::plan_prof_t() = std::chrono::steady_clock::now(); }
+#else
+#define PLAN_TICK(name)
+#define PLAN_TICK0()
+#endif
+
 namespace b200pf {
 
 struct HostGrid {
@@ -97,6 +110,7 @@ public:
 
     // topo: int8 [n_topo_in]; outage: line forced out of service (N-1 sweep) or -1.  Returns the blob.
     std::vector<unsigned char> build(const int8_t *tv, int outage) const {
+        PLAN_TICK0();
         const HostGrid &g = g_;
         const int nsub = g.n_sub, nl = g.n_line, nu = g.n_unit, nld = g.n_load, nst = g.n_sto, nsh = g.n_shunt, dt = g.dim_topo;
         const int ns = g.n_slot;
@@ -127,6 +141,7 @@ public:
             if (bo > 0 && be > 0) { brf[l] = bus_of(g.line_or_sub[l], bo); brt[l] = bus_of(g.line_ex_sub[l], be); }
             else { brf[l] = -1; brt[l] = -1; }
         }
+        PLAN_TICK("decode");
         // ---- bus types, static per-bus unit data --------------------------------------------------
         std::vector<int> btype(nb, PLAN_BT_PQ), cnt(nb, 0), nref(nb, 0), vmunit(nb, -1);
         std::vector<double> qmins(nb, 0.0), qmaxs(nb, 0.0);
@@ -165,6 +180,7 @@ public:
             memcpy(blob.data(), &H, sizeof(H));
             return blob;
         }
+        PLAN_TICK("types+reach");
         // ---- bus graph and minimum-degree elimination order of the non-reference buses -------------
         std::vector<char> adjm((size_t)nb * nb, 0);
         for (int l = 0; l < nl; ++l) {
@@ -174,32 +190,40 @@ public:
         }
         std::vector<int> order;         // non-reference buses in elimination order
         {
-            std::vector<char> w(adjm);  // working copy restricted to non-ref, non-eliminated buses
+            // minimum degree, ties broken by minimum LENGTH (MD-ML: the longest elimination path that ends in the node) —
+            // the factorisation runs as passes of independent operations, so the height of the elimination tree, not the
+            // fill alone, sets its run time.  Degrees are maintained incrementally (O(nb) per elimination + the clique).
+            std::vector<char> w(adjm);  // working copy; edges to reference / eliminated buses are ignored through `alive`
             std::vector<char> alive(nb, 0);
             int n_alive = 0;
             for (int i = 0; i < nb; ++i) if (btype[i] != PLAN_BT_REF) { alive[i] = 1; ++n_alive; }
-            // minimum degree, ties broken by minimum LENGTH (MD-ML: the longest elimination path that ends in the node) —
-            // the factorisation runs as passes of independent operations, so the height of the elimination tree, not the
-            // fill alone, sets its run time
-            std::vector<int> nbrs, length(nb, 0);
+            std::vector<int> nbrs, length(nb, 0), deg(nb, 0);
+            for (int i = 0; i < nb; ++i) {
+                if (!alive[i]) continue;
+                const char *row = &w[(size_t)i * nb];
+                int dg = 0;
+                for (int j = 0; j < nb; ++j) dg += (row[j] && alive[j]);
+                deg[i] = dg;
+            }
             while (n_alive > 0) {
                 int best = -1, bestdeg = 1 << 30, bestlen = 1 << 30;
                 for (int i = 0; i < nb; ++i) {
                     if (!alive[i]) continue;
-                    int deg = 0;
-                    const char *row = &w[(size_t)i * nb];
-                    for (int j = 0; j < nb; ++j) deg += (row[j] && alive[j]);
-                    if (deg < bestdeg || (deg == bestdeg && length[i] < bestlen)) { bestdeg = deg; bestlen = length[i]; best = i; }
+                    if (deg[i] < bestdeg || (deg[i] == bestdeg && length[i] < bestlen)) { bestdeg = deg[i]; bestlen = length[i]; best = i; }
                 }
                 nbrs.clear();
-                for (int j = 0; j < nb; ++j) if (w[(size_t)best * nb + j] && alive[j]) nbrs.push_back(j);
+                const char *rb = &w[(size_t)best * nb];
+                for (int j = 0; j < nb; ++j) if (rb[j] && alive[j]) nbrs.push_back(j);
+                alive[best] = 0; --n_alive;
                 for (size_t a = 0; a < nbrs.size(); ++a) {
-                    length[nbrs[a]] = std::max(length[nbrs[a]], length[best] + 1);
+                    const int u = nbrs[a];
+                    --deg[u];                                   // its edge to the eliminated bus
+                    length[u] = std::max(length[u], length[best] + 1);
                     for (size_t b = a + 1; b < nbrs.size(); ++b) {
-                        w[(size_t)nbrs[a] * nb + nbrs[b]] = 1; w[(size_t)nbrs[b] * nb + nbrs[a]] = 1;
+                        const int v = nbrs[b];
+                        if (!w[(size_t)u * nb + v]) { w[(size_t)u * nb + v] = 1; w[(size_t)v * nb + u] = 1; ++deg[u]; ++deg[v]; }
                     }
                 }
-                alive[best] = 0; --n_alive;
                 order.push_back(best);
             }
         }
@@ -212,6 +236,7 @@ public:
             colth[i] = d++;
             if (btype[i] == PLAN_BT_PQ) colv[i] = d++;
         }
+        PLAN_TICK("ordering");
         // ---- scalar pattern of the Jacobian, symbolic LU --------------------------------------------
         std::vector<char> S((size_t)d * d, 0);
         auto setblk = [&](int i, int j) {   // rows of bus i, columns of bus j
@@ -231,9 +256,8 @@ public:
                 lst.clear();
                 for (int j = k + 1; j < d; ++j) if (S[(size_t)k * d + j]) lst.push_back(j);
                 rowU[k] = lst;
-                std::vector<int> &cl = colL[k];
-                for (int i = k + 1; i < d; ++i) if (S[(size_t)i * d + k]) cl.push_back(i);
-                for (int i : cl) { char *Si = &S[(size_t)i * d]; for (int j : lst) Si[j] = 1; }
+                colL[k] = lst;              // the pattern is structurally symmetric (block pattern of the bus graph) and stays so under fill
+                for (int i : lst) { char *Si = &S[(size_t)i * d]; for (int j : lst) Si[j] = 1; }
             }
         }
         std::vector<int> pos((size_t)d * d, -1);
@@ -242,6 +266,7 @@ public:
         const int nA = nnzF + d;
         const int DUMMY = nA;
         auto P = [&](int i, int j) -> int { return (i >= 0 && j >= 0) ? pos[(size_t)i * d + j] : -1; };
+        PLAN_TICK("symbolic");
         // ---- LU + both triangular solves as ONE list of multiply-subtract operations A[ij] -= A[ik] A[kj] / A[kk]
         //      (right-looking elimination with the right-hand side carried along, then column-oriented back
         //      substitution on the right-hand side), list-scheduled into passes: an operation goes to the earliest
@@ -251,10 +276,12 @@ public:
         //      the depth of the dependency graph (about twice the height of the elimination tree), not the number
         //      of columns.  The solution is x_k = rhs_k / A[kk] (taken by the bus lanes in the state update).
         struct Op { uint16_t ij, ik, kj, kk; };
+        int depth_raw = 0, n_oprow = 0;
         std::vector<Op> ops;
         std::vector<int> pass_ptr(1, 0);
         {
             std::vector<Op> seq;
+            seq.reserve((size_t)nnzF * 4 + 64);
             for (int k = 0; k < d; ++k) {
                 const int kk = P(k, k);
                 for (int i : colL[k]) {
@@ -277,37 +304,32 @@ public:
                 wlev[o.ij] = lv;
                 rlev[o.ik] = std::max(rlev[o.ik], lv); rlev[o.kj] = std::max(rlev[o.kj], lv); rlev[o.kk] = std::max(rlev[o.kk], lv);
             }
-            {   // diagnostic: depth of the pure read-after-write graph (what multi-term operations could reach)
-                std::vector<int> w2(nA + 1, 0);
-                int dr = 0;
-                for (size_t q = 0; q < seq.size(); ++q) {
-                    const Op &o = seq[q];
-                    // an update chain of one target counts once: its value is "ready" at max(ready of its terms) + 1
-                    const int lv = std::max(std::max(w2[o.ik], w2[o.kj]), w2[o.kk]) + 1;
-                    w2[o.ij] = std::max(w2[o.ij], lv);
-                    dr = std::max(dr, lv);
-                }
-                depth_raw_ = dr;
-            }
             // passes padded to whole rows of op_width slots; the last row of a pass carries the barrier flag
             const int W = op_width_;
-            std::vector<std::vector<Op>> by_lv(nlev + 1);
-            for (size_t q = 0; q < seq.size(); ++q) by_lv[lev[q]].push_back(seq[q]);
+            std::vector<int> lv_ptr(nlev + 2, 0);
+            for (int lv : lev) lv_ptr[lv + 1]++;
+            for (int l = 1; l <= nlev + 1; ++l) lv_ptr[l] += lv_ptr[l - 1];
+            std::vector<Op> sorted_ops(seq.size());
+            {
+                std::vector<int> fillp(lv_ptr.begin(), lv_ptr.end() - 1);
+                for (size_t q = 0; q < seq.size(); ++q) sorted_ops[fillp[lev[q]]++] = seq[q];
+            }
             const Op nop = {(uint16_t)DUMMY, (uint16_t)DUMMY, (uint16_t)DUMMY, (uint16_t)DUMMY};
             pass_ptr.assign(1, 0);
+            ops.reserve(seq.size() + (size_t)(nlev + 8) * W);
             for (int l = 1; l <= nlev; ++l) {
-                std::vector<Op> &v = by_lv[l];
+                Op *b0 = sorted_ops.data() + lv_ptr[l], *b1 = sorted_ops.data() + lv_ptr[l + 1];
                 // neighbouring slots work on neighbouring entries (fewer shared-memory bank conflicts); targets are unique
                 // within a pass, so the order inside a pass is free
-                std::sort(v.begin(), v.end(), [](const Op &a, const Op &b) { return a.ij < b.ij; });
-                while (v.size() % (size_t)W) v.push_back(nop);
-                const size_t last_row = v.size() - (size_t)W;
-                for (size_t q = last_row; q < v.size(); ++q) v[q].kk |= 0x4000u;   // becomes bit 0 of the byte offset below
-                ops.insert(ops.end(), v.begin(), v.end());
+                std::sort(b0, b1, [](const Op &a, const Op &b) { return a.ij < b.ij; });
+                const size_t first = ops.size();
+                ops.insert(ops.end(), b0, b1);
+                while ((ops.size() - first) % (size_t)W) ops.push_back(nop);
+                for (size_t q = ops.size() - (size_t)W; q < ops.size(); ++q) ops[q].kk |= 0x4000u;   // becomes bit 0 of the byte offset below
                 pass_ptr.push_back((int)ops.size());
             }
             while ((ops.size() / (size_t)W) % 4) ops.insert(ops.end(), (size_t)W, nop);     // whole blocks of 4 rows (prefetch unit)
-            n_oprow_ = (int)(ops.size() / (size_t)W);
+            n_oprow = (int)(ops.size() / (size_t)W);
             ops.insert(ops.end(), (size_t)W * 4, nop);      // guard block: the prefetch of "the block after the last" reads it, nothing executes it
             // slots hold BYTE offsets into the value array (4 * position; the barrier flag moves to bit 0 of kk)
             for (Op &o : ops) {
@@ -320,6 +342,7 @@ public:
         const int n_ulev = 0;
         std::vector<int> ulev_ptr(1, 0), urow, urow_diag, uent_ptr(1, 0);
         std::vector<uint16_t> uent;
+        PLAN_TICK("ops+schedule");
         // ---- assembly positions ------------------------------------------------------------------
         std::vector<uint16_t> dpos((size_t)nb * 4, (uint16_t)DUMMY), jpos((size_t)nl * 8, (uint16_t)DUMMY);
         std::vector<char> is_buslane(nA + 1, 0);
@@ -360,6 +383,7 @@ public:
         }
         std::vector<uint16_t> zero;
         for (int p = 0; p < nnzF; ++p) if (!is_buslane[p]) zero.push_back((uint16_t)p);
+        PLAN_TICK("assembly pos");
         // ---- static per-bus line data ------------------------------------------------------------------
         std::vector<double> ydiag((size_t)nb * 2, 0.0), dcshift(nb, 0.0);
         std::vector<std::vector<int>> adj(nb), bu(nb), bl(nb), bs(nb), bh(nb);
@@ -377,6 +401,7 @@ public:
         for (int k = 0; k < nld; ++k) if (load_bus[k] >= 0) bl[load_bus[k]].push_back(k);
         for (int k = 0; k < nst; ++k) if (sto_bus[k] >= 0) bs[sto_bus[k]].push_back(k);
         for (int k = 0; k < nsh; ++k) if (sh_bus[k] >= 0) bh[sh_bus[k]].push_back(k);
+        PLAN_TICK("perbus");
         // ---- DC matrix, factorised (fp64, no pivoting: Bdc is symmetric and, for positive series reactances,
         //      positive definite), in the elimination order of the buses --------------------------------------
         std::vector<double> B((size_t)n1 * n1, 0.0);
@@ -403,38 +428,50 @@ public:
                 }
             }
         }
+        PLAN_TICK("dc factor");
         std::vector<double> dcinv((size_t)n1 * n1, 0.0);
         {
+            // row lists of the factors (non-zeros only), then one sparse forward + backward solve per unit vector
+            std::vector<int> lptr(n1 + 1, 0), uptr(n1 + 1, 0), lcol, ucol;
+            std::vector<double> lval, uval, udiag(n1, 1.0);
+            for (int i = 0; i < n1; ++i) {
+                const double *Bi = &B[(size_t)i * n1];
+                const char *Si = &SB[(size_t)i * n1];
+                for (int j = 0; j < i; ++j) if (Si[j]) { lcol.push_back(j); lval.push_back(Bi[j]); }
+                for (int j = i + 1; j < n1; ++j) if (Si[j]) { ucol.push_back(j); uval.push_back(Bi[j]); }
+                lptr[i + 1] = (int)lcol.size(); uptr[i + 1] = (int)ucol.size();
+                udiag[i] = 1.0 / Bi[i];
+            }
             std::vector<double> x(n1);
             for (int c = 0; c < n1; ++c) {
-                for (int i = 0; i < n1; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+                for (int i = 0; i < c; ++i) x[i] = 0.0;
+                x[c] = 1.0;
                 for (int i = c + 1; i < n1; ++i) {                 // L y = e_c (unit lower; y_i = 0 for i < c)
-                    double sacc = x[i];
-                    const double *Bi = &B[(size_t)i * n1];
-                    const char *Si = &SB[(size_t)i * n1];
-                    for (int j = c; j < i; ++j) if (Si[j]) sacc -= Bi[j] * x[j];
+                    double sacc = 0.0;
+                    for (int e = lptr[i]; e < lptr[i + 1]; ++e) if (lcol[e] >= c) sacc -= lval[e] * x[lcol[e]];
                     x[i] = sacc;
                 }
                 for (int i = n1 - 1; i >= 0; --i) {                // U x = y
                     double sacc = x[i];
-                    const double *Bi = &B[(size_t)i * n1];
-                    const char *Si = &SB[(size_t)i * n1];
-                    for (int j = i + 1; j < n1; ++j) if (Si[j]) sacc -= Bi[j] * x[j];
-                    x[i] = sacc / Bi[i];
+                    for (int e = uptr[i]; e < uptr[i + 1]; ++e) sacc -= uval[e] * x[ucol[e]];
+                    x[i] = sacc * udiag[i];
                 }
-                for (int i = 0; i < n1; ++i) dcinv[(size_t)c * n1 + i] = x[i];   // column c of the inverse = row c of the transposed store
+                double *dst = &dcinv[(size_t)c * n1];              // column c of the inverse = row c of the transposed store
+                for (int i = 0; i < n1; ++i) dst[i] = x[i];
             }
         }
+        PLAN_TICK("dc inverse");
         // ---- serialise ------------------------------------------------------------------------------------
         PlanHeader H;
         memset(&H, 0, sizeof(H));
         H.status = PLAN_ST_OK; H.nb = nb; H.n1 = n1; H.d = d; H.nnzF = nnzF; H.nA = nA; H.n_round = n_round;
         H.n_pass = n_pass; H.n_op = (int)ops.size(); H.n_ulev = n_ulev; H.n_urow = d;
-        H.pad[0] = depth_raw_;
-        H.op_width = op_width_; H.n_oprow = n_oprow_;
+        H.pad[0] = depth_raw;
+        H.op_width = op_width_; H.n_oprow = n_oprow;
         H.n_zero = (int)zero.size();
         H.smem_bytes = plan_smem_bytes(nb, nl, nA, 2 * nld + 2 * g.n_gen, nsh);
         std::vector<unsigned char> blob(sizeof(PlanHeader));
+        blob.reserve(sizeof(PlanHeader) + (size_t)n1 * n1 * 8 + ops.size() * 8 + (size_t)nl * 32 + (size_t)nb * 96 + 4096);
         auto align = [&](size_t a) { while (blob.size() % a) blob.push_back(0); };
         auto put_d = [&](const std::vector<double> &v) -> int {
             align(8);
@@ -446,7 +483,9 @@ public:
         auto put_u16 = [&](const std::vector<int> &v) -> int {
             align(4);
             const int off = (int)blob.size();
-            for (int x : v) { const uint16_t u = x < 0 ? (uint16_t)0xFFFF : (uint16_t)x; blob.push_back((unsigned char)(u & 0xff)); blob.push_back((unsigned char)(u >> 8)); }
+            blob.resize(blob.size() + v.size() * 2);
+            uint16_t *dst = reinterpret_cast<uint16_t *>(blob.data() + off);
+            for (size_t q = 0; q < v.size(); ++q) dst[q] = v[q] < 0 ? (uint16_t)0xFFFF : (uint16_t)v[q];
             return off;
         };
         auto put_u16v = [&](const std::vector<uint16_t> &v) -> int {
@@ -498,6 +537,7 @@ public:
         H.o_zero = put_u16v(zero);
         H.o_ulev_ptr = put_u16(ulev_ptr); H.o_urow = put_u16(urow); H.o_urow_diag = put_u16(urow_diag); H.o_uent_ptr = put_u16(uent_ptr);
         H.o_uent = put_u16v(uent);
+        PLAN_TICK("serialise");
         align(16);
         H.total_bytes = (int)blob.size();
         memcpy(blob.data(), &H, sizeof(H));
@@ -510,7 +550,6 @@ public:
 private:
     const HostGrid &g_;
     int op_width_;
-    mutable int depth_raw_ = 0, n_oprow_ = 0;
 };
 
 }  // namespace b200pf

@@ -91,3 +91,27 @@ def test_forecasts_and_outage_tables_match_grid2op_loader(env_name, scen):
         m = min(len(haz), len(gs.hazards))
         assert np.array_equal(haz[:m], gs.hazards[:m])
         assert np.array_equal(hazard_duration(haz)[:m], gs.hazard_duration[:m])
+
+
+def test_maintenance_and_hazard_series_match_gridvalue_helpers():
+    """Derived series on random outage patterns == the reference's own helpers
+    (grid2op/Chronics/gridValue.py:264-470).  Patterns start with a free step: a planned outage already running at row 0
+    is outside what the reference's diff-based helpers handle."""
+    from grid2op_b200._bootstrap import ensure_grid2op
+    if not ensure_grid2op():
+        pytest.skip("grid2op not importable")
+    from grid2op.Chronics import GridValue
+    from grid2op_b200.chronics import maintenance_time_duration, hazard_duration
+    rng = np.random.default_rng(3)
+    m = rng.random((400, 12)) < 0.08
+    for _ in range(3):                       # make runs longer than one step
+        m[1:] |= m[:-1] & (rng.random((399, 12)) < 0.6)
+    m[0] = False
+    t, d = maintenance_time_duration(m)
+    hd = hazard_duration(m)
+    for l in range(m.shape[1]):
+        col = m[:, l].astype(np.int32)
+        assert np.array_equal(t[:, l], GridValue.get_maintenance_time_1d(col))
+        assert np.array_equal(d[:, l], GridValue.get_maintenance_duration_1d(col))
+        assert np.array_equal(hd[:, l], GridValue.get_hazard_duration_1d(col))
+    assert m.any() and (t > 0).any() and (d > 1).any()

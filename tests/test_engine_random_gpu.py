@@ -143,7 +143,7 @@ def test_precollated_host_path_matches_series_mode(cuda_required):
     env.close()
 
 
-@pytest.mark.parametrize("direct", [False, True])
+@pytest.mark.parametrize("direct", [False, True, 2, 6])      # group flags of include/b200pf.h (True = 1)
 @pytest.mark.parametrize("collated", [False, True])
 def test_group_pipelined_host_path_matches_series_mode(cuda_required, collated, direct):
     """b200pf_rows_group_launch / _wait: groups stepped out of phase give, per instance and step, exactly the
