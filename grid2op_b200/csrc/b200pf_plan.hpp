@@ -58,9 +58,8 @@ struct PlanHeader {
     int nnzF, nA;          // entries of the filled Jacobian; nA = nnzF + d (right-hand side appended) ; A[nA] = dummy
     int n_round;           // assembly rounds of the line lanes (parallel lines write the same entries)
     int n_pass, n_op;      // LU passes / operation slots (passes padded to whole rows of op_width slots)
-    int n_ulev, n_urow;    // back-substitution levels / rows (= d)
     int op_width, n_oprow; // threads per instance the operation stream is laid out for; rows of op_width slots
-    int n_zero;            // entries zeroed before assembly (everything but the bus-lane entries)
+    int n_zero;            // entries the line lanes add into + pure fill (cleared after every solve; the bus lanes assign the rest)
     int smem_bytes;        // per-instance workspace this plan needs
     int total_bytes;
     // per bus (nb entries each)
@@ -75,17 +74,14 @@ struct PlanHeader {
     // operation stream: rows of op_width slots, thread t of the instance's group executes slot t of every row; a slot is
     // 4 x u16 BYTE offsets into the value array (ij, ik, kj, kk | 1 on the LAST row of a pass: group barrier after it);
     // padding slots work on A[dummy]
-    int o_zero, o_pass_ptr /* unused */, o_ops;
-    int o_ulev_ptr /* u16 [n_ulev+1] */, o_urow /* u16 [d] row index */, o_urow_diag /* u16 [d] */, o_uent_ptr /* u16 [d+1] */,
-        o_uent /* 2 x u16 per entry: column, position */;
+    int o_zero, o_pass_ptr /* int32 [n_pass + 1]: slot range of every pass (diagnostics / validation) */, o_ops;
     // DC: the inverse of Bdc (fp64, [n1][n1], stored transposed: entry (j, i) at j * n1 + i so that lanes = rows read
     // consecutive addresses) — Bdc depends on the topology only, so its solve is a matrix-vector product at run time
     int o_dcinv;
     int o_shidx;           // u16 [nb]: index of the bus among the buses that carry a shunt (0xFFFF: none)
     int n_shb;
     int o_late, n_late;    // u16 pairs (line, round) of the lines of assembly rounds >= 1 (parallel lines), sorted by round
-    int pad2[6];
-    int pad[6];
+    int pad[3];
 };
 static_assert(sizeof(PlanHeader) % 16 == 0, "plan blobs are concatenated 16-byte aligned");
 
@@ -276,7 +272,7 @@ public:
         //      the depth of the dependency graph (about twice the height of the elimination tree), not the number
         //      of columns.  The solution is x_k = rhs_k / A[kk] (taken by the bus lanes in the state update).
         struct Op { uint16_t ij, ik, kj, kk; };
-        int depth_raw = 0, n_oprow = 0;
+        int n_oprow = 0;
         std::vector<Op> ops;
         std::vector<int> pass_ptr(1, 0);
         {
@@ -339,9 +335,6 @@ public:
             }
         }
         const int n_pass = (int)pass_ptr.size() - 1;
-        const int n_ulev = 0;
-        std::vector<int> ulev_ptr(1, 0), urow, urow_diag, uent_ptr(1, 0);
-        std::vector<uint16_t> uent;
         PLAN_TICK("ops+schedule");
         // ---- assembly positions ------------------------------------------------------------------
         std::vector<uint16_t> dpos((size_t)nb * 4, (uint16_t)DUMMY), jpos((size_t)nl * 8, (uint16_t)DUMMY);
@@ -465,8 +458,7 @@ public:
         PlanHeader H;
         memset(&H, 0, sizeof(H));
         H.status = PLAN_ST_OK; H.nb = nb; H.n1 = n1; H.d = d; H.nnzF = nnzF; H.nA = nA; H.n_round = n_round;
-        H.n_pass = n_pass; H.n_op = (int)ops.size(); H.n_ulev = n_ulev; H.n_urow = d;
-        H.pad[0] = depth_raw;
+        H.n_pass = n_pass; H.n_op = (int)ops.size();
         H.op_width = op_width_; H.n_oprow = n_oprow;
         H.n_zero = (int)zero.size();
         H.smem_bytes = plan_smem_bytes(nb, nl, nA, 2 * nld + 2 * g.n_gen, nsh);
@@ -535,8 +527,6 @@ public:
             H.o_late = put_u16(late); H.n_late = (int)late.size() / 2;
         }
         H.o_zero = put_u16v(zero);
-        H.o_ulev_ptr = put_u16(ulev_ptr); H.o_urow = put_u16(urow); H.o_urow_diag = put_u16(urow_diag); H.o_uent_ptr = put_u16(uent_ptr);
-        H.o_uent = put_u16v(uent);
         PLAN_TICK("serialise");
         align(16);
         H.total_bytes = (int)blob.size();

@@ -55,3 +55,14 @@ class SparseEmu:
         if th_lim is not None:
             return out, status, iters, busv, rho
         return out, status, iters, busv
+
+
+def validate_plan(gm, topo_row, outage=-1, op_width=32):
+    """-> (return code of sparse_emu_validate_plan, residual of A x = b through the operation stream)."""
+    emu = SparseEmu(gm)
+    err = C.c_double(0.0)
+    t = np.ascontiguousarray(topo_row, dtype=np.int8)
+    emu.lib.sparse_emu_validate_plan.restype = C.c_int
+    rc = emu.lib.sparse_emu_validate_plan(C.byref(emu.desc), t.ctypes.data_as(C.c_void_p), C.c_int(int(outage)), C.c_int(int(op_width)),
+                                          C.byref(err))
+    return int(rc), float(err.value)

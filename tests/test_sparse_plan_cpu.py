@@ -90,3 +90,22 @@ def test_emulated_n1_sweep_vs_oracle():
                 assert np.allclose(rho[k], a_or / thl, rtol=2e-5, atol=1e-6)
             else:
                 assert np.isnan(rho[k]).all()
+
+
+@pytest.mark.parametrize("name,width", [("rte_case5_example", 32), ("l2rpn_case14_sandbox", 32), ("l2rpn_neurips_2020_track1", 32),
+                                        ("l2rpn_neurips_2020_track1", 64), ("l2rpn_wcci_2022_dev", 64), ("l2rpn_wcci_2022_dev", 128)])
+def test_operation_stream_is_hazard_free_and_solves_the_system(name, width):
+    """Structural check of the list-scheduled operation stream (no slot of a pass touches what another slot of the pass
+    writes, barrier flags on the last row of every pass) and a numeric one (the stream, run in fp64 on a random matrix with
+    the plan's pattern, solves A x = b), on the reference topology, random bus splits and single-line outages."""
+    from sparse_emu import validate_plan
+    gm = GridModel.from_npz(os.path.join(GOLD, f"gridmodel_{name}.npz"))
+    topo, _ = random_cases(gm, 24, seed=7)
+    rows = [gm.default_topo()] + [topo[i] for i in range(len(topo))]
+    checked = 0
+    for r in rows:
+        for outage in (-1, 0, gm.n_line - 1):
+            rc, err = validate_plan(gm, r, outage, width)
+            assert rc in (0, -1), (rc, err)          # -1: the topology has no solvable plan (islanded / no reference)
+            checked += rc == 0
+    assert checked >= 10
