@@ -67,6 +67,11 @@ struct b200pf_handle {
     unsigned char *d_plan_blobs = nullptr; size_t d_plan_cap = 0, d_plan_used = 0;
     int *d_plan_off = nullptr; int d_plan_off_n = 0;
     int *d_inst_plan = nullptr, *h_inst_plan = nullptr;     // [max_batch]
+    std::vector<int8_t> h_series_topo;                      // host mirror of the series topology (protections re-plan from it)
+    std::vector<int> h_series_plan;
+    int8_t *d_trip = nullptr, *d_incdone = nullptr; int *d_nflag = nullptr, *d_flaglist = nullptr, *d_casclist = nullptr;
+    std::vector<int8_t> h_trip; std::vector<int> h_flaglist;
+    int last_cascade_rounds = 0;
     int *d_series_plan = nullptr; int series_plan_state = 0; // 0 none, 1 per-instance plans, 2 all instances on one plan
     int series_plan_single = 0, series_plan_smem = 0;
     int plan_policy = 0;                                    // 0 auto, 1 never, 2 whenever a host copy of the topology exists
@@ -459,10 +464,10 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     return 1;
 }
 
-template <int T, int MINB>
+template <int T, int MINB, bool PROT = false>
 static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel, int variant) {
     const DevGrid &g = h->g;
-    auto kern = pf_kernel_sparse<T, MINB>;
+    auto kern = pf_kernel_sparse<T, MINB, PROT>;
     const int smem = sel.smem;
     if (h->sparse_occ_smem != smem || h->sparse_occ_variant != variant) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -502,6 +507,11 @@ static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &se
 // workspace per instance limit an SM to ~10 instances: the second warp doubles the warps in flight).
 static int launch_sparse(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
     const int per_sm = h->max_smem_optin / (sel.smem + 1024);
+    if (a.prot) {     // protections: one launch per cascade round, see series_step_planned_prot
+        if (h->plan_T == 128) return launch_sparse_t<128, 4, true>(h, a, sel, 14);
+        if (h->plan_T == 64) return launch_sparse_t<64, 10, true>(h, a, sel, 15);
+        return launch_sparse_t<32, 16, true>(h, a, sel, 13);
+    }
     if (h->plan_T == 128) return launch_sparse_t<128, 4>(h, a, sel, 4);
     if (h->plan_T == 64) return launch_sparse_t<64, 10>(h, a, sel, 5);
     if (per_sm >= 32) return launch_sparse_t<32, 32>(h, a, sel, 1);
@@ -511,7 +521,7 @@ static int launch_sparse(b200pf_handle *h, const RunArgs &a, const PlanSel &sel)
 }
 
 static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req, const PlanSel *sel = nullptr) {
-    if (sel && !a.prot) return launch_sparse(h, a, *sel);
+    if (sel) return launch_sparse(h, a, *sel);
     const DevGrid &g = h->g;
     if (h->env_flags < 0) {
         const char *f64 = getenv("B200PF_JACOBIAN_FP64"), *nosk = getenv("B200PF_NO_SMALL_KERNEL");
@@ -649,7 +659,10 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
     CU(cudaMemcpy(h->d_thlim, thermal_limit_a, (size_t)g.n_line * 4, cudaMemcpyHostToDevice));
     CU(cudaMemset(h->d_series_topo, 1, (size_t)batch * g.n_topo_in));
     h->series_batch = batch; h->n_scen = n_scen; h->n_rows = n_rows;
-    if ((rc = dmal((void **)&h->d_series_plan, (size_t)batch * 4))) return rc;
+    if ((rc = dmal((void **)&h->d_series_plan, (size_t)batch * 4)) || (rc = dmal((void **)&h->d_trip, (size_t)batch * g.n_line + 4)) ||
+        (rc = dmal((void **)&h->d_incdone, (size_t)batch * g.n_line + 4)) || (rc = dmal((void **)&h->d_nflag, 16)) ||
+        (rc = dmal((void **)&h->d_flaglist, (size_t)batch * 4)) || (rc = dmal((void **)&h->d_casclist, (size_t)batch * 4))) return rc;
+    CU(cudaMemset(h->d_trip, 0, (size_t)batch * g.n_line + 4)); CU(cudaMemset(h->d_incdone, 0, (size_t)batch * g.n_line + 4));
     {
         std::vector<int8_t> ones((size_t)batch * g.n_topo_in, 1);
         return series_plans(h, ones.data());
@@ -666,6 +679,8 @@ static int series_plans(b200pf_handle *h, const int8_t *topo) {
     if (use < 0) return use;
     if (!use) return 0;
     h->series_plan_single = sel.single; h->series_plan_smem = sel.smem;
+    h->h_series_topo.assign(topo, topo + (size_t)h->series_batch * h->g.n_topo_in);
+    h->h_series_plan.assign(h->h_inst_plan, h->h_inst_plan + h->series_batch);
     if (sel.d_inst_plan) {
         CU(cudaMemcpyAsync(h->d_series_plan, h->d_inst_plan, (size_t)h->series_batch * 4, cudaMemcpyDeviceToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -682,6 +697,62 @@ extern "C" int b200pf_series_set_topo(b200pf_handle *h, const int8_t *topo) {
     return series_plans(h, topo);
 }
 
+// One series step with protections on the planned kernel.  The kernel REPORTS the lines that must trip (a tripped line is a
+// new topology, i.e. a new plan); the host takes them out of its mirror of the topology, looks the plan up (or builds it),
+// and launches the next cascade round for the flagged instances only — the loop of Backend.next_grid_state
+// (reference backend.py:1466-1521) with the power flows of a round batched.  Synchronous: one 4-byte read-back per round.
+static int series_step_planned_prot(b200pf_handle *h, RunArgs a) {
+    const DevGrid &g = h->g;
+    const int B = h->series_batch, nl = g.n_line;
+    const size_t nt = (size_t)g.n_topo_in;
+    if (h->series_plan_state == 2) {      // make the per-instance plan array explicit
+        CU(cudaMemcpyAsync(h->d_series_plan, h->h_series_plan.data(), (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+        h->series_plan_state = 1;
+    }
+    a.trip = h->d_trip; a.incdone = h->d_incdone; a.n_flag = h->d_nflag; a.flag_list = h->d_flaglist;
+    h->h_trip.resize((size_t)B * nl); h->h_flaglist.resize(B);
+    int n = B;
+    const int *list = nullptr;
+    for (int casc = 0;; ++casc) {
+        if (casc > 2 * nl + 2) return fail(B200PF_E_STATE, "cascade did not terminate");
+        CU(cudaMemsetAsync(h->d_nflag, 0, 4, h->stream));
+        a.casc = casc; a.inst_list = list; a.batch = n;
+        PlanSel sel;
+        sel.single = 0; sel.smem = h->plan_max_smem; sel.d_inst_plan = h->d_series_plan;
+        int rc = launch_sparse(h, a, sel);
+        if (rc) return rc;
+        int nflag = 0;
+        CU(cudaMemcpyAsync(&nflag, h->d_nflag, 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->last_cascade_rounds = casc + 1;
+        if (nflag <= 0) break;
+        CU(cudaMemcpyAsync(h->h_flaglist.data(), h->d_flaglist, (size_t)nflag * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_trip.data(), h->d_trip, (size_t)B * nl, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < nflag; ++k) {
+            const int inst = h->h_flaglist[k];
+            if (inst < 0 || inst >= B) return fail(B200PF_E_STATE, "bad instance in the cascade list");
+            int8_t *row = h->h_series_topo.data() + (size_t)inst * nt;
+            apply_trips(h->hg, row, h->h_trip.data() + (size_t)inst * nl);
+            const uint64_t rh = topo_hash(row, nt);
+            int id = plan_find(h, row, rh, -1);
+            if (id < 0) {
+                PlanBuilder pb(h->hg, h->plan_T);
+                id = plan_insert(h, row, rh, -1, pb.build(row, -1));
+                if (id < 0) return fail(B200PF_E_CAPACITY, "no plan for the topology after a line trip");
+            }
+            h->h_series_plan[inst] = id;
+            CU(cudaMemcpyAsync(h->d_series_topo + (size_t)inst * nt, row, nt, cudaMemcpyHostToDevice, h->stream));
+        }
+        if ((rc = plans_sync_device(h))) return rc;
+        CU(cudaMemcpyAsync(h->d_series_plan, h->h_series_plan.data(), (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->d_trip, 0, (size_t)B * nl, h->stream));
+        CU(cudaMemcpyAsync(h->d_casclist, h->h_flaglist.data(), (size_t)nflag * 4, cudaMemcpyHostToDevice, h->stream));
+        n = nflag; list = h->d_casclist;
+    }
+    return 0;
+}
+
 extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, double tol_mva, int nb_cap) {
     if (!h) return fail(B200PF_E_ARG, "null handle");
     if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
@@ -696,6 +767,15 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
         a.pcount = h->d_pcount; a.ts_over = h->d_tsover; a.disc = h->d_disc; a.done = h->d_done;
     }
     h->next_reset = 0;
+    {
+        const DevGrid &gg = h->g;
+        const bool small_ok = gg.n_slot <= 32 && gg.n_line <= 32 && gg.n_unit <= 32 && gg.n_load <= 32 && gg.n_sto <= 32 && gg.n_shunt <= 32 &&
+                              nb_cap > 0 && nb_cap <= 17;
+        // protections: the warp kernel cascades entirely on the device (no host in the loop) and is preferred where it applies;
+        // everything else runs the planned kernel with the host re-planning the instances whose lines trip
+        if (h->prot && h->series_plan_state && h->plan_policy != 1 && (h->plan_policy == 2 || !small_ok) && !is_dc)
+            return series_step_planned_prot(h, a);
+    }
     if (h->series_plan_state && !h->prot && h->plan_policy != 1) {
         PlanSel sel;
         sel.single = h->series_plan_single; sel.smem = h->series_plan_smem;

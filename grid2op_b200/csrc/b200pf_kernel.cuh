@@ -73,6 +73,13 @@ struct RunArgs {
     const double *static_inj;
     const float *th_lim;
     float *rho;
+    // protections with the planned kernel: one launch per cascade round, the host re-plans the instances whose lines trip
+    int casc;                // cascade round of this launch (0 = the step itself)
+    const int *inst_list;    // instances of this launch (nullptr: 0 .. batch-1)
+    int8_t *trip;            // [B][n_line] out: 1 = the line trips in this round
+    int8_t *incdone;         // [B][n_line] in/out: the soft-overflow counter of the line was already incremented in this step
+    int *n_flag;             // out: number of instances with at least one tripping line
+    int *flag_list;          // out: those instances
 };
 
 enum { ST_OK = 0, ST_DIV = 1, ST_UNSUP = 2, ST_NOREF = 3, ST_LARGE = 4, ST_DONE = 5 };

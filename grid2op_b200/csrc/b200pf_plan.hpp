@@ -100,6 +100,13 @@ inline int plan_smem_bytes(int nb, int n_line, int nA, int n_rowcol, int n_shunt
     return (int)((o + 15) & ~(size_t)15);
 }
 
+// takes the tripped lines (trip[l] != 0) out of a topology row: both ends disconnected, like
+// PandaPowerBackend._disconnect_line (reference pandaPowerBackend.py:1464-1475) / _BackendAction.update_state
+inline void apply_trips(const HostGrid &g, int8_t *topo_row, const int8_t *trip) {
+    for (int l = 0; l < g.n_line; ++l)
+        if (trip[l]) { topo_row[g.line_or_pos[l]] = -1; topo_row[g.line_ex_pos[l]] = -1; }
+}
+
 class PlanBuilder {
 public:
     explicit PlanBuilder(const HostGrid &g, int op_width = 32) : g_(g), op_width_(op_width) {}

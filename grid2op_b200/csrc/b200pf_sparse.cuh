@@ -91,6 +91,13 @@ struct RunArgs {
     const double *static_inj;
     const float *th_lim;
     float *rho;
+    int prot, from_reset, max_pc;
+    float hard_thr, soft_thr;
+    int *pcount, *ts_over, *disc, *done;
+    int casc;
+    const int *inst_list;
+    int8_t *trip, *incdone;
+    int *n_flag, *flag_list;
 };
 enum { ST_OK = 0, ST_DIV = 1, ST_UNSUP = 2, ST_NOREF = 3, ST_LARGE = 4, ST_DONE = 5 };
 enum { BT_PQ = 1, BT_PV = 2, BT_REF = 3 };
@@ -113,7 +120,8 @@ PF_DEV void sparse_fail(const DevGrid &g, const RunArgs &a, int inst, int status
 #endif
     float *out = a.out ? a.out + (size_t)inst * g.n_out : nullptr;
     PF_PHASE {
-        if (tid == 0) { a.status[inst] = status; a.iters[inst] = iters; }
+        if (tid == 0) { a.status[inst] = status; a.iters[inst] = iters; if (a.prot && a.done) a.done[inst] = 1; }
+        if (a.prot && a.disc && status == ST_DONE) for (int k = tid; k < g.n_line; k += T) a.disc[(size_t)inst * g.n_line + k] = -1;
         if (out) for (int k = tid; k < g.n_out; k += T) out[k] = PF_QNANF();
         if (a.busv) for (int k = tid; k < 2 * g.n_slot; k += T) a.busv[(size_t)inst * 2 * g.n_slot + k] = PF_QNAN();
         if (a.rho) for (int k = tid; k < g.n_line; k += T) a.rho[(size_t)inst * g.n_line + k] = PF_QNANF();
@@ -122,7 +130,7 @@ PF_DEV void sparse_fail(const DevGrid &g, const RunArgs &a, int inst, int status
     (void)tid0;
 }
 
-template <int T>
+template <int T, bool PROT>
 PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, int inst, unsigned char *sm, int tid0) {
 #ifndef B200PF_EMULATE
     const int tid = tid0;
@@ -135,8 +143,10 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
     if (a.series && !a.rows) {
         sc = a.scen[src]; trow = a.t[src];
         PF_SYNC();
-        PF_PHASE { if (tid == 0 && a.n1_lines <= 0) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1; }
+        if (PROT && a.casc > 0) trow = trow == 0 ? a.n_rows - 1 : trow - 1;       // later cascade rounds re-solve the SAME row
+        PF_PHASE { if (tid == 0 && a.n1_lines <= 0 && !(PROT && a.casc > 0)) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1; }
     }
+    if (PROT && a.done[inst] && a.casc == 0) { sparse_fail<T>(g, a, inst, ST_DONE, 0, tid0); return; }
     if (H.status != PLAN_ST_OK) { sparse_fail<T>(g, a, inst, H.status, 0, tid0); return; }
     const int nb = H.nb, nl = g.n_line, nu = g.n_unit, nh = g.n_hidden, ng = g.n_gen, nld = g.n_load, nst = g.n_sto, nsh = g.n_shunt;
     const int d = H.d, nnzF = H.nnzF, nA = H.nA;
@@ -505,6 +515,51 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
             PF_SYNC();
         }
     }
+    if (PROT) {
+        // Cascading-failure round (reference Backend.next_grid_state, backend.py:1466-1521; counters baseEnv.py:3361-3370),
+        // lane = line, same rules as pf_kernel_small: a line trips when its flow exceeds hard_thr * limit or stayed above
+        // soft_thr * limit for more than max_pc steps.  A tripping line changes the topology, i.e. the plan: this launch
+        // only REPORTS it (trip / flag_list); the host takes the lines out, re-plans the instance and launches the next
+        // round for the flagged instances.  Without a trip the step is final: counters, disc, the next step's state.
+        const size_t base_l = (size_t)inst * nl;
+        int any_trip = 0;
+        PF_PHASE {
+            for (int l = tid; l < nl; l += T) {
+                const bool on = p_brf[l] != 0xFFFF;
+                const float aor = out[3 * nl + l], lim = a.th_lim[l];
+                int inc = a.casc > 0 ? (int)a.incdone[base_l + l] : 0;
+                int pc = a.pcount[base_l + l] + inc;
+                bool to_disc = on && (aor > PF_FMUL(a.hard_thr, lim));
+                if (!a.from_reset && on && (aor > PF_FMUL(a.soft_thr, lim)) && !inc) { pc += 1; inc = 1; }
+                if (on && pc > a.max_pc) to_disc = true;
+                a.incdone[base_l + l] = (int8_t)inc;
+                if (a.casc == 0) a.disc[base_l + l] = -1;
+                if (to_disc) { a.trip[base_l + l] = 1; a.disc[base_l + l] = a.casc; any_trip = 1; }
+            }
+        }
+        any_trip = PF_ANY(any_trip);
+        PF_PHASE {
+            if (any_trip) {
+                if (tid == 0) {
+#ifdef B200PF_EMULATE
+                    const int slot = (*a.n_flag)++;
+#else
+                    const int slot = atomicAdd(a.n_flag, 1);
+#endif
+                    a.flag_list[slot] = inst;
+                }
+            } else {
+                for (int l = tid; l < nl; l += T) {
+                    const float aor = out[3 * nl + l], lim = a.th_lim[l];
+                    int *pcp = a.pcount + base_l, *tsp = a.ts_over + base_l;
+                    pcp[l] = (!a.from_reset && aor > PF_FMUL(a.soft_thr, lim)) ? pcp[l] + 1 : 0;
+                    tsp[l] = (!a.from_reset && aor > lim) ? tsp[l] + 1 : 0;
+                    a.incdone[base_l + l] = 0;
+                }
+            }
+        }
+        PF_SYNC();
+    }
     (void)d; (void)nA;
 #undef U16
 #undef F64
@@ -518,12 +573,13 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
 }
 
 #ifndef B200PF_EMULATE
-template <int T, int MINB>
+template <int T, int MINB, bool PROT>
 __global__ void __launch_bounds__(T, MINB)
 pf_kernel_sparse(const DevGrid g, const RunArgs a, const PlanArgs pa) {
     extern __shared__ __align__(16) unsigned char smem[];
-    for (int inst = blockIdx.x; inst < a.batch; inst += gridDim.x) {
-        solve_sparse<T>(g, a, pa, inst, smem, threadIdx.x);
+    for (int k = blockIdx.x; k < a.batch; k += gridDim.x) {
+        const int inst = (PROT && a.inst_list) ? a.inst_list[k] : k;
+        solve_sparse<T, PROT>(g, a, pa, inst, smem, threadIdx.x);
         sp_sync<T>();
     }
 }

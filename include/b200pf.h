@@ -139,7 +139,11 @@ int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, double tol_mva
  * soft_thr * limit for more than max_allowed consecutive steps, are disconnected and the flow is re-solved
  * until no line trips; the outages persist in the device topology; an instance whose flow diverges is
  * "done" (B200PF_ST_DONE from then on).  enabled = 0 restores NO_OVERFLOW_DISCONNECTION.
- * Round 1: available when the warp-per-instance kernel applies (<= 32 lines / bus slots). */
+ * Two implementations: grids that fit the warp-per-instance kernel (<= 32 lines / bus slots) cascade entirely on the
+ * device, inside one launch; all other grids (and every grid under kernel policy 2) run the planned kernel, which reports
+ * the lines that trip — a tripped line is a new topology, i.e. a new plan — and the library re-plans those instances on
+ * the host and launches the next cascade round for them (b200pf_series_step is then synchronous: one 4-byte read-back
+ * per round). */
 int b200pf_series_protections(b200pf_handle *h, int enabled, float hard_thr, float soft_thr, int max_allowed);
 /* the NEXT series step is an environment reset step: no soft-overflow counting (backend.py:1488-1490) */
 int b200pf_series_next_is_reset(b200pf_handle *h);

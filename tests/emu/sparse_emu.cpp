@@ -63,7 +63,7 @@ extern "C" int sparse_emu_run(const b200pf_grid_desc *gd, int batch, const int8_
         PlanArgs pa{};
         int off0 = 0;
         pa.blobs = blob.data(); pa.plan_off = &off0; pa.inst_plan = nullptr;
-        solve_sparse<32>(g, a, pa, inst, (unsigned char *)ws.data(), 0);
+        solve_sparse<32, false>(g, a, pa, inst, (unsigned char *)ws.data(), 0);
     }
     return 0;
 }
@@ -144,4 +144,69 @@ extern "C" int sparse_emu_validate_plan(const b200pf_grid_desc *gd, const int8_t
     }
     if (max_err) *max_err = err;
     return err < 1e-9 ? 0 : 8;
+}
+
+// One batched DoNothing step in series mode WITH protections, the way b200pf_series_step drives the planned kernel: launch
+// for all instances, then cascade rounds for the instances whose lines tripped (the host takes the lines out of the
+// topology and re-plans them).  State arrays are caller owned (in/out), like the device-resident state of the library.
+extern "C" int sparse_emu_series_prot_step(const b200pf_grid_desc *gd, int batch, int8_t *topo /* [B][n_topo_in] in/out */,
+                                           const float *chron, int n_scen, int n_rows, const int32_t *scen, int32_t *t,
+                                           const double *static_inj, const float *th_lim, int from_reset, float hard_thr,
+                                           float soft_thr, int max_pc, int max_iter, double tol_mva, float *out, int32_t *status,
+                                           int32_t *iters, float *rho, int32_t *pcount, int32_t *ts_over, int32_t *disc,
+                                           int32_t *done, int32_t *n_rounds) {
+    HostGrid hg = host_grid(gd);
+    PlanBuilder pb(hg);
+    DevGrid g{};
+    g.n_sub = hg.n_sub; g.n_busbar = hg.n_busbar; g.n_slot = hg.n_slot; g.n_line = hg.n_line; g.n_gen = hg.n_gen; g.n_hidden = hg.n_hidden;
+    g.n_unit = hg.n_unit; g.n_load = hg.n_load; g.n_sto = hg.n_sto; g.n_shunt = hg.n_shunt; g.dim_topo = hg.dim_topo;
+    g.n_topo_in = hg.n_topo_in;
+    g.n_inj = g.n_gen + g.n_unit + 2 * g.n_load + g.n_sto + 2 * g.n_shunt;
+    g.n_out = 10 * g.n_line + 4 * g.n_unit + 2 * g.n_load + g.n_sto + 3 * g.n_shunt;
+    g.base_mva = hg.base_mva;
+    g.line_y = gd->line_y; g.line_bdc = gd->line_bdc; g.line_pshift = gd->line_pshift; g.line_or_vn = gd->line_or_vn; g.line_ex_vn = gd->line_ex_vn;
+    g.unit_is_ref = gd->unit_is_ref; g.unit_qmin = gd->unit_qmin; g.unit_qmax = gd->unit_qmax; g.unit_vn = gd->unit_vn;
+    g.load_vn = gd->load_vn; g.sto_vn = gd->storage_vn; g.sh_vn = gd->shunt_vn; g.sto_q = gd->storage_q; g.sh_vratio = gd->shunt_vratio;
+    const int nl = hg.n_line;
+    std::vector<int8_t> trip((size_t)batch * nl, 0), incdone((size_t)batch * nl, 0);
+    std::vector<int> flag_list(batch), list;
+    int n_flag = 0;
+    RunArgs a{};
+    a.is_dc = 0; a.max_iter = max_iter; a.tol_pu = tol_mva / hg.base_mva; a.out = out; a.status = status; a.iters = iters;
+    a.series = 1; a.chron = chron; a.n_scen = n_scen; a.n_rows = n_rows; a.scen = scen; a.t = t; a.static_inj = static_inj;
+    a.th_lim = th_lim; a.rho = rho; a.prot = 1; a.from_reset = from_reset; a.max_pc = max_pc; a.hard_thr = hard_thr; a.soft_thr = soft_thr;
+    a.pcount = pcount; a.ts_over = ts_over; a.disc = disc; a.done = done;
+    a.trip = trip.data(); a.incdone = incdone.data(); a.n_flag = &n_flag; a.flag_list = flag_list.data();
+    std::map<std::string, std::vector<unsigned char>> cache;
+    int rounds = 0;
+    for (int casc = 0;; ++casc) {
+        a.casc = casc;
+        n_flag = 0;
+        const int n = casc == 0 ? batch : (int)list.size();
+        for (int k = 0; k < n; ++k) {
+            const int inst = casc == 0 ? k : list[k];
+            const int8_t *tv = topo + (size_t)inst * hg.n_topo_in;
+            std::string key((const char *)tv, hg.n_topo_in);
+            auto it = cache.find(key);
+            if (it == cache.end()) it = cache.emplace(key, pb.build(tv, -1)).first;
+            const std::vector<unsigned char> &blob = it->second;
+            const PlanHeader *H = (const PlanHeader *)blob.data();
+            std::vector<double> ws((size_t)H->smem_bytes / 8 + 4);
+            PlanArgs pa{};
+            int off0 = 0;
+            pa.blobs = blob.data(); pa.plan_off = &off0; pa.inst_plan = nullptr;
+            solve_sparse<32, true>(g, a, pa, inst, (unsigned char *)ws.data(), 0);
+        }
+        ++rounds;
+        if (n_flag == 0) break;
+        list.assign(flag_list.begin(), flag_list.begin() + n_flag);
+        for (int inst : list) {
+            int8_t *tv = topo + (size_t)inst * hg.n_topo_in;
+            apply_trips(hg, tv, trip.data() + (size_t)inst * nl);
+            for (int l = 0; l < nl; ++l) trip[(size_t)inst * nl + l] = 0;
+        }
+        if (casc > 2 * nl + 2) return 1;
+    }
+    if (n_rounds) *n_rounds = rounds;
+    return 0;
 }

@@ -66,3 +66,42 @@ def validate_plan(gm, topo_row, outage=-1, op_width=32):
     rc = emu.lib.sparse_emu_validate_plan(C.byref(emu.desc), t.ctypes.data_as(C.c_void_p), C.c_int(int(outage)), C.c_int(int(op_width)),
                                           C.byref(err))
     return int(rc), float(err.value)
+
+
+class EmuProtRollout:
+    """Batched DoNothing rollout with protections through the emulated planned kernel + the host cascade loop
+    (tests/emu/sparse_emu.cpp: sparse_emu_series_prot_step), state held in numpy arrays."""
+
+    def __init__(self, gm, chron, scen, t0, thermal_limit_a, hard=2.0, soft=1.0, max_allowed=2):
+        self.emu = SparseEmu(gm)
+        self.gm = gm
+        self.chron = np.ascontiguousarray(chron, dtype=np.float32)
+        self.B = len(scen)
+        self.scen = np.ascontiguousarray(scen, dtype=np.int32)
+        self.t = np.ascontiguousarray(t0, dtype=np.int32).copy()
+        self.topo = np.ascontiguousarray(np.tile(gm.default_topo(), (self.B, 1)), dtype=np.int8)
+        self.static_inj = np.ascontiguousarray(gm.default_inj(), dtype=np.float64)
+        self.th = np.ascontiguousarray(thermal_limit_a, dtype=np.float32)
+        self.hard, self.soft, self.max_allowed = float(hard), float(soft), int(max_allowed)
+        nl = gm.n_line
+        self.out = np.zeros((self.B, gm.n_out), dtype=np.float32)
+        self.status = np.zeros(self.B, dtype=np.int32)
+        self.iters = np.zeros(self.B, dtype=np.int32)
+        self.rho = np.zeros((self.B, nl), dtype=np.float32)
+        self.pcount = np.zeros((self.B, nl), dtype=np.int32)
+        self.ts_over = np.zeros((self.B, nl), dtype=np.int32)
+        self.disc = np.full((self.B, nl), -1, dtype=np.int32)
+        self.done = np.zeros(self.B, dtype=np.int32)
+        self.rounds = np.zeros(1, dtype=np.int32)
+        self.emu.lib.sparse_emu_series_prot_step.restype = C.c_int
+
+    def step(self, from_reset=False):
+        vp = C.c_void_p
+        p = lambda a: a.ctypes.data_as(vp)     # noqa: E731
+        rc = self.emu.lib.sparse_emu_series_prot_step(
+            C.byref(self.emu.desc), C.c_int(self.B), p(self.topo), p(self.chron), C.c_int(self.chron.shape[0]), C.c_int(self.chron.shape[1]),
+            p(self.scen), p(self.t), p(self.static_inj), p(self.th), C.c_int(int(from_reset)), C.c_float(self.hard), C.c_float(self.soft),
+            C.c_int(self.max_allowed), C.c_int(10), C.c_double(1e-8), p(self.out), p(self.status), p(self.iters), p(self.rho),
+            p(self.pcount), p(self.ts_over), p(self.disc), p(self.done), p(self.rounds))
+        assert rc == 0, rc
+        return int(self.rounds[0])

@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def test_batched_rollout_with_protections_matches_recording(cuda_required):
+@pytest.mark.parametrize("policy", [0, 2])      # 0: warp kernel, cascade entirely on the device; 2: planned kernel + host re-planning
+def test_batched_rollout_with_protections_matches_recording(cuda_required, policy):
     root = grid2op_root()
     stat = os.path.join(root, "data", "rte_case5_example", "_statistics") if root else None
     if stat is None or not os.path.isdir(stat):
@@ -36,7 +37,7 @@ def test_batched_rollout_with_protections_matches_recording(cuda_required):
     B = 20
     env = BatchedDoNothing(gm, chron, B, scen=np.arange(B), t0=np.zeros(B), protections=True,
                            hard_overflow_threshold=2.0, soft_overflow_threshold=1.0, nb_timestep_overflow_allowed=2)
-    assert env.engine is not None
+    env.engine.set_kernel_policy(policy)
     worst = {k: 0.0 for k in keys}
     first_done = np.full(B, -1)
     n_cmp = 0
@@ -46,6 +47,7 @@ def test_batched_rollout_with_protections_matches_recording(cuda_required):
         else:
             env.step_device()
         out, status, iters, rho = env.fetch()
+        assert (env.engine.plan_stats()["last_kernel"] == "planned_sparse") == (policy == 2)
         st = env.fetch_state()
         v = OutputView(gm, out)
         for s in range(B):
@@ -76,4 +78,57 @@ def test_batched_rollout_with_protections_matches_recording(cuda_required):
     for name in ("a_or", "a_ex"):
         assert worst[name] <= 2e-3, (name, worst[name])
     assert worst["rho"] <= 1e-6
+    env.close()
+
+
+def test_planned_protections_on_a_large_grid_match_the_emulated_kernel(cuda_required):
+    """36 substations (beyond the warp kernel): device run of the planned kernel with protections == the host build of the
+    same kernel + cascade loop (tests/emu), thermal limits lowered so that lines trip and cascades happen."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from bench_configs import synth_chron
+    from grid2op_b200.rollout import BatchedDoNothing
+    from sparse_emu import EmuProtRollout
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_neurips_2020_track1.npz"))
+    chron = synth_chron(gm, n_rows=12, seed=4)
+    B = 24
+    scen = np.zeros(B, dtype=np.int32)
+    t0 = (np.arange(B) % chron.shape[1]).astype(np.int32)
+    # limits: a base solve's flows scaled so that a few lines sit above 100 % and one or two above 200 %
+    probe = BatchedDoNothing(gm, chron, B, scen=scen, t0=t0)
+    probe.step_device()
+    out, status, _, _ = probe.fetch()
+    probe.close()
+    assert (status == 0).all()
+    from grid2op_b200.engine import OutputView
+    a0 = OutputView(gm, out).a_or.max(axis=0)
+    th = np.maximum(a0 * 1.3, 1.0).astype(np.float32)
+    order = np.argsort(-a0)
+    th[order[0]] = a0[order[0]] * 0.45          # hard overflow at once
+    th[order[3]] = a0[order[3]] * 0.9           # soft overflow -> trips after the allowed steps
+    th[order[5]] = a0[order[5]] * 0.95
+    env = BatchedDoNothing(gm, chron, B, scen=scen, t0=t0, protections=True, thermal_limit_a=th,
+                           hard_overflow_threshold=2.0, soft_overflow_threshold=1.0, nb_timestep_overflow_allowed=2)
+    ref = EmuProtRollout(gm, chron, scen, t0, th, hard=2.0, soft=1.0, max_allowed=2)
+    n_trip = 0
+    for k in range(10):
+        if k == 0:
+            env.reset_step()
+        else:
+            env.step_device()
+        ref.step(from_reset=(k == 0))
+        assert env.engine.plan_stats()["last_kernel"] == "planned_sparse"
+        out, status, iters, rho = env.fetch()
+        st = env.fetch_state()
+        assert np.array_equal(st["done"], ref.done), k
+        assert np.array_equal(status, ref.status), k
+        live = ref.done == 0
+        assert np.array_equal(st["disc_lines"][live], ref.disc[live]), k
+        assert np.array_equal(st["timestep_overflow"][live], ref.ts_over[live]), k
+        assert np.array_equal(st["protection_counter"][live], ref.pcount[live]), k
+        ok = live & (status == 0)
+        assert np.allclose(rho[ok], ref.rho[ok], rtol=2e-5, atol=1e-6), k
+        assert np.allclose(out[ok], ref.out[ok], rtol=2e-5, atol=2e-4), k
+        n_trip += int((ref.disc[live] >= 0).sum())
+    assert n_trip > 0
     env.close()

@@ -109,3 +109,54 @@ def test_operation_stream_is_hazard_free_and_solves_the_system(name, width):
             assert rc in (0, -1), (rc, err)          # -1: the topology has no solvable plan (islanded / no reference)
             checked += rc == 0
     assert checked >= 10
+
+
+def test_emulated_protections_replay_the_recorded_rollouts():
+    """Planned kernel + host cascade loop (a tripped line = a new topology = a new plan; one launch per cascade round)
+    against the reference's recorded DoNothing rollouts of rte_case5_example (PandaPowerBackend with protections, 7930
+    steps): same trips, same game-over step, same observed values.  CPU counterpart of tests/test_protections_gpu.py."""
+    import json
+    from conftest import grid2op_root
+    from sparse_emu import EmuProtRollout
+    root = grid2op_root()
+    stat = os.path.join(root, "data", "rte_case5_example", "_statistics") if root else None
+    if stat is None or not os.path.isdir(stat):
+        pytest.skip("reference rollouts not available")
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_rte_case5_example.npz"))
+    chron = np.load(os.path.join(GOLD, "case5_chronics.npz"))["chron"]
+    meta = json.load(open(os.path.join(stat, "metadata.json")))
+    keys = ["p_or", "q_or", "v_or", "a_or", "p_ex", "q_ex", "prod_p", "prod_q", "rho", "line_status", "timestep_overflow"]
+    gold = {k: np.load(os.path.join(stat, f"obs_{k}.npz"))["data"] for k in keys}
+    sid = np.load(os.path.join(stat, "scenario_ids.npz"))["data"].ravel().astype(int)
+    rows = {s: np.flatnonzero(sid == s) for s in range(20)}
+    nb_step = np.array([meta[str(s)]["nb_step"] for s in range(20)])
+    B = 20
+    env = EmuProtRollout(gm, chron, np.arange(B), np.zeros(B), gm.thermal_limit_a, hard=2.0, soft=1.0, max_allowed=2)
+    worst = {k: 0.0 for k in keys}
+    first_done = np.full(B, -1)
+    n_cmp = n_casc = 0
+    for k in range(int(nb_step.max())):
+        n_casc += env.step(from_reset=(k == 0)) - 1
+        v = OutputView(gm, env.out)
+        for s in range(B):
+            if env.done[s] and first_done[s] < 0:
+                first_done[s] = k
+            if k >= nb_step[s] - 1:
+                continue
+            assert env.status[s] == 0, (s, k, env.status[s])
+            r = rows[s][k]
+            mine = dict(p_or=v.p_or[s], q_or=v.q_or[s], v_or=v.v_or[s], a_or=v.a_or[s], p_ex=v.p_ex[s], q_ex=v.q_ex[s],
+                        prod_p=v.unit_p[s], prod_q=v.unit_q[s], rho=env.rho[s])
+            for name, val in mine.items():
+                worst[name] = max(worst[name], float(np.max(np.abs(val.astype(np.float64) - gold[name][r]))))
+            assert np.array_equal(v.a_or[s] > 0, gold["line_status"][r]) or np.array_equal(
+                (np.abs(v.p_or[s]) > 0) | (v.v_or[s] > 0), gold["line_status"][r]), (s, k)
+            assert np.array_equal(env.ts_over[s], gold["timestep_overflow"][r]), (s, k)
+            n_cmp += 1
+    for s in range(B):
+        if nb_step[s] < chron.shape[1]:
+            assert first_done[s] == nb_step[s] - 1, (s, first_done[s], nb_step[s])
+    assert n_cmp > 7000 and n_casc > 0
+    for name in ("p_or", "q_or", "p_ex", "q_ex", "prod_p", "prod_q"):
+        assert worst[name] <= 1e-4, (name, worst[name])
+    assert worst["v_or"] <= 2e-5 and worst["a_or"] <= 2e-3 and worst["rho"] <= 1e-6
