@@ -56,7 +56,6 @@ struct b200pf_handle {
     int series_batch = 0, n_scen = 0, n_rows = 0;
     int *d_pcount = nullptr, *d_tsover = nullptr, *d_disc = nullptr, *d_done = nullptr;
     int prot = 0, next_reset = 0, max_pc = 2; float hard_thr = 2.0f, soft_thr = 1.0f;
-    int small_ok = 0;
     // planned sparse kernel: cache of topology plans (host blobs + their device copy)
     HostGrid hg;
     std::unordered_map<uint64_t, int> plan_index;           // hash of (topology row, outage) -> newest plan with that hash
@@ -313,6 +312,7 @@ static int launch_small(b200pf_handle *h, RunArgs a, int cap) {
 // topology plans of the sparse kernel (b200pf_plan.hpp): cache keyed by the topology bytes
 // ------------------------------------------------------------------------------------------------
 static const int PLAN_MAX = 32768;          // plans kept per handle
+static const size_t PLAN_MAX_BYTES = size_t(1) << 30;   // ... and their total size (host copy + device copy each)
 static const int PLAN_BUILD_BUDGET = 512;   // new plans one call may build in automatic mode before it falls back
 
 struct PlanSel {
@@ -354,7 +354,9 @@ static int plan_find(const b200pf_handle *h, const int8_t *tv, uint64_t row_hash
 static int plan_insert(b200pf_handle *h, const int8_t *tv, uint64_t row_hash, int outage, const std::vector<unsigned char> &blob) {
     const size_t nt = (size_t)h->g.n_topo_in;
     const PlanHeader *H = reinterpret_cast<const PlanHeader *>(blob.data());
-    if ((int)h->plan_off.size() >= PLAN_MAX || !PlanBuilder::fits(*H) || H->smem_bytes > h->max_smem_optin) return -1;
+    if ((int)h->plan_off.size() >= PLAN_MAX || h->plan_blobs.size() + blob.size() > PLAN_MAX_BYTES || !PlanBuilder::fits(*H) ||
+        H->smem_bytes > h->max_smem_optin)
+        return -1;      // the caller falls back to the pivoting kernels
     const uint64_t key = plan_key(row_hash, outage);
     auto it = h->plan_index.find(key);
     const int id = (int)h->plan_off.size();
