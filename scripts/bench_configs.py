@@ -109,6 +109,20 @@ def main():
         eng.close()
     for pol, tag in ((1, "pivoting"), (2, "planned")):
         res["config3grid_36sub_batch1024_donothing_device_resident_" + tag] = series_rate(gm, 1024, pol, steps=20 if pol == 1 else 100)
+    if True:   # protections on a grid beyond the warp kernel: planned kernel + host re-planning of tripped instances
+        env = BatchedDoNothing(gm, synth_chron(gm), 1024, protections=True)
+        env.reset_step()
+        env.engine.sync()
+        t = time.perf_counter()
+        for _ in range(50):
+            env.step_device()
+        env.engine.sync()
+        dt = (time.perf_counter() - t) / 50
+        st = env.fetch_state()
+        res["config3grid_36sub_batch1024_protections_on_device_resident_planned"] = {
+            "seconds_per_step": dt, "env_step_per_s": 1024 / dt, "done_fraction_after_50_steps": float(st["done"].mean()),
+            "tripped_lines": int((st["disc_lines"] >= 0).sum()), "kernel": env.engine.plan_stats()}
+        env.close()
     # ---- config 5: 118 substations, batch 8192 (here 2048 per call x 4), DoNothing
     gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_wcci_2022_dev.npz"))
     B = 2048
