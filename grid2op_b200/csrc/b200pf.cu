@@ -608,6 +608,20 @@ static int run_staged_device(b200pf_handle *h, int batch, int is_dc, int max_ite
     return launch(h, a, nb_cap, use ? &sel : nullptr);
 }
 
+extern "C" int b200pf_run_device_topo(b200pf_handle *h, int batch, const int8_t *host_topo, const int8_t *d_topo, const double *d_inj,
+                                      int is_dc, int max_iter, double tol_mva, int nb_cap, float *d_out, int32_t *d_status,
+                                      int32_t *d_iters, double *d_busv) {
+    if (!h || !host_topo || !d_topo || !d_inj || !d_out || !d_status || !d_iters) return fail(B200PF_E_ARG, "null pointer");
+    if (batch <= 0 || batch > h->max_batch) return fail(B200PF_E_ARG, "batch out of range (max_batch)");
+    CU(cudaSetDevice(h->device));
+    RunArgs a = base_args(h, batch, is_dc, max_iter, tol_mva);
+    a.topo = d_topo; a.inj = d_inj; a.out = d_out; a.status = d_status; a.iters = d_iters; a.busv = d_busv;
+    PlanSel sel;
+    const int use = plan_select(h, host_topo, batch, 0, 0, h->stream, &sel, nb_cap);
+    if (use < 0) return use;
+    return launch(h, a, nb_cap, use ? &sel : nullptr);
+}
+
 extern "C" int b200pf_run_host(b200pf_handle *h, int batch, const int8_t *topo, const double *inj, int is_dc,
                                int max_iter, double tol_mva, int nb_cap, float *out, int32_t *status,
                                int32_t *iters, double *busv) {

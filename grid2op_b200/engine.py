@@ -33,7 +33,7 @@ ABI_SYMBOLS = (
     "b200pf_run_rows_staged", "b200pf_set_thermal_limit", "b200pf_n1_host", "b200pf_series_protections",
     "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait",
     "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free", "b200pf_rows_group_launch", "b200pf_rows_group_wait",
-    "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats",
+    "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats", "b200pf_run_device_topo",
 )
 
 
@@ -84,6 +84,7 @@ def load_library():
     lib.b200pf_sizes.argtypes = [vp] + [C.POINTER(i32)] * 4
     lib.b200pf_run_host.argtypes = [vp, i32, vp, vp, i32, i32, f64, i32, vp, vp, vp, vp]
     lib.b200pf_run_device.argtypes = [vp, i32, vp, vp, i32, i32, f64, i32, vp, vp, vp, vp]
+    lib.b200pf_run_device_topo.argtypes = [vp, i32, vp, vp, vp, i32, i32, f64, i32, vp, vp, vp, vp]
     lib.b200pf_series_bind.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, vp]
     lib.b200pf_series_set_topo.argtypes = [vp, vp]
     lib.b200pf_series_step.argtypes = [vp, i32, i32, f64, i32]
@@ -264,8 +265,17 @@ class PowerFlowEngine:
         return out, status, iters, busv
 
     def run_device(self, batch: int, d_topo: int, d_inj: int, d_out: int, d_status: int, d_iters: int,
-                   d_busv: int = 0, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0):
-        """Device-pointer entry point (asynchronous on the handle's stream)."""
+                   d_busv: int = 0, is_dc: bool = False, max_iter: int = 10, tol_mva: float = 1e-8, nb_cap: int = 0,
+                   host_topo: Optional[np.ndarray] = None):
+        """Device-pointer entry point (asynchronous on the handle's stream).  ``host_topo`` (the same records as
+        ``d_topo``, as a host array) lets the engine use the planned sparse kernel."""
+        if host_topo is not None:
+            ht = np.ascontiguousarray(host_topo, dtype=np.int8)
+            rc = self.lib.b200pf_run_device_topo(self.h, int(batch), _ptr(ht), C.c_void_p(d_topo), C.c_void_p(d_inj), int(bool(is_dc)),
+                                                 int(max_iter), float(tol_mva), int(nb_cap), C.c_void_p(d_out),
+                                                 C.c_void_p(d_status), C.c_void_p(d_iters), C.c_void_p(d_busv) if d_busv else None)
+            self._check(rc, "b200pf_run_device_topo")
+            return
         rc = self.lib.b200pf_run_device(self.h, int(batch), C.c_void_p(d_topo), C.c_void_p(d_inj), int(bool(is_dc)),
                                         int(max_iter), float(tol_mva), int(nb_cap), C.c_void_p(d_out),
                                         C.c_void_p(d_status), C.c_void_p(d_iters), C.c_void_p(d_busv) if d_busv else None)

@@ -120,6 +120,13 @@ int b200pf_run_device(b200pf_handle *h, int batch, const int8_t *d_topo, const d
                       int is_dc, int max_iter, double tol_mva, int nb_cap, float *d_out,
                       int32_t *d_status, int32_t *d_iters, double *d_busv);
 
+/* b200pf_run_device plus a HOST copy of the same topology records: with it the engine can use the planned sparse kernel
+ * (its topology plans are looked up / built on the host) for inputs that already live in device memory, e.g. injections
+ * written by another kernel or a torch model.  The per-instance plan ids travel on the handle's stream before the launch. */
+int b200pf_run_device_topo(b200pf_handle *h, int batch, const int8_t *host_topo, const int8_t *d_topo, const double *d_inj,
+                           int is_dc, int max_iter, double tol_mva, int nb_cap, float *d_out, int32_t *d_status,
+                           int32_t *d_iters, double *d_busv);
+
 /* Batched time-series stepping (the DoNothing subset of BaseEnv.step, reference
  * grid2op/Environment/baseEnv.py:3778-3872 with NO_OVERFLOW_DISCONNECTION): the chronics
  * (grid2op/Chronics/gridStateFromFile.py:749-808 rows: load_p, load_q, prod_p, prod_v[kV] in

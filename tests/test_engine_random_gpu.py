@@ -189,3 +189,30 @@ def test_group_pipelined_host_path_matches_series_mode(cuda_required, collated, 
         env.group_launch(0)
     env.group_wait(0)
     env.close()
+
+
+@pytest.mark.parametrize("with_host_topo", [False, True])
+def test_device_pointer_entry_points(cuda_required, with_host_topo):
+    """b200pf_run_device (pivoting kernels: no host copy of the topology) and b200pf_run_device_topo (planned kernel) on
+    torch tensors == the host-buffer entry point."""
+    import torch
+    from grid2op_b200.engine import PowerFlowEngine
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    z = np.load(os.path.join(GOLD, "oracle_case14_steps.npz"))
+    topo, inj = np.ascontiguousarray(z["topo"], dtype=np.int8), np.ascontiguousarray(z["inj"], dtype=np.float64)
+    B = len(topo)
+    eng = PowerFlowEngine(gm, max_batch=B)
+    want, ws, wi, _ = eng.run(topo, inj)
+    dev = torch.device("cuda", 0)
+    t_topo, t_inj = torch.from_numpy(topo).to(dev), torch.from_numpy(inj).to(dev)
+    t_out = torch.empty((B, gm.n_out), dtype=torch.float32, device=dev)
+    t_st = torch.empty(B, dtype=torch.int32, device=dev)
+    t_it = torch.empty(B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    eng.run_device(B, t_topo.data_ptr(), t_inj.data_ptr(), t_out.data_ptr(), t_st.data_ptr(), t_it.data_ptr(),
+                   host_topo=topo if with_host_topo else None)
+    eng.sync()
+    assert (eng.plan_stats()["last_kernel"] == "planned_sparse") == with_host_topo
+    assert np.array_equal(t_st.cpu().numpy(), ws) and np.array_equal(t_it.cpu().numpy(), wi)
+    _compare(gm, t_out.cpu().numpy(), want, ws == 0)
+    eng.close()
