@@ -77,6 +77,7 @@ struct b200pf_handle {
     int plan_max_smem = 0;
     int sparse_occ_smem = -1, sparse_occ = 0, sparse_occ_variant = 0;
     int sparse_cta_cap = 0;                                 // > 0: resident CTAs per SM of the planned kernel are capped (rest of the SM's memory = L1); < 0: never
+    int sparse_minb = 32;                                   // tuning: one-warp CTAs per SM the small-workspace variant is compiled for (32 or 28)
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0;
@@ -215,6 +216,8 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         // one warp per instance, two for the large grids — and for the mid-size ones when the batch cannot fill the SMs anyway
         // (36 substations: batch 1024 21.4 vs 19.9 M env.step/s with 64 threads, batch 8192 26 vs 35 M/s)
         h->plan_T = g.n_line > 64 ? 64 : ((g.n_line > 32 && max_batch <= 2048) ? 64 : 32);
+        const char *mb = getenv("B200PF_SPARSE_MINB");
+        if (mb && atoi(mb) == 28) h->sparse_minb = 28;
         const char *capv = getenv("B200PF_SPARSE_CTAS");        // tuning: cap of resident CTAs per SM (planned kernel)
         if (capv) h->sparse_cta_cap = atoi(capv);
         const char *var = getenv("B200PF_SPARSE_T");            // tuning: threads per instance of the planned kernel
@@ -518,6 +521,7 @@ static int launch_sparse(b200pf_handle *h, const RunArgs &a, const PlanSel &sel)
     }
     if (h->plan_T == 128) return launch_sparse_t<128, 4>(h, a, sel, 4);
     if (h->plan_T == 64) return launch_sparse_t<64, 10>(h, a, sel, 5);
+    if (per_sm >= 32 && h->sparse_minb == 28) return launch_sparse_t<32, 28>(h, a, sel, 7);   // 73 registers, 4144 resident warps
     if (per_sm >= 32) return launch_sparse_t<32, 32>(h, a, sel, 1);
     if (per_sm >= 24) return launch_sparse_t<32, 24>(h, a, sel, 2);
     if (per_sm >= 16) return launch_sparse_t<32, 16>(h, a, sel, 3);
