@@ -438,7 +438,9 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     if (!miss.empty()) {
         if (h->plan_policy == 0 && (int)miss.size() > PLAN_BUILD_BUDGET) return 0;
         std::vector<std::vector<unsigned char>> blobs(miss.size());
-        const PlanBuilder pb(h->hg, h->plan_T);
+        // a handful of new plans: they will be re-used by many solves (rollouts, N-1 sweeps) -> bank-conflict-optimised layout
+        // (not for single environments: there the build time of a new topology is part of the step latency)
+        const PlanBuilder pb(h->hg, h->plan_T, miss.size() <= 32 && (size_t)n_src * per >= 256);
         unsigned nthr = std::thread::hardware_concurrency();
         if (nthr > 16) nthr = 16;
         if (nthr < 1) nthr = 1;

@@ -109,7 +109,10 @@ inline void apply_trips(const HostGrid &g, int8_t *topo_row, const int8_t *trip)
 
 class PlanBuilder {
 public:
-    explicit PlanBuilder(const HostGrid &g, int op_width = 32) : g_(g), op_width_(op_width) {}
+    // optimize_layout: spend ~1 ms per plan on a bank-conflict-reducing layout of the value array (plans that are re-used by
+    // many solves: device-resident rollouts; not worth it when hundreds of plans are built for one call)
+    explicit PlanBuilder(const HostGrid &g, int op_width = 32, bool optimize_layout = false)
+        : g_(g), op_width_(op_width), optimize_layout_(optimize_layout) {}
 
     // topo: int8 [n_topo_in]; outage: line forced out of service (N-1 sweep) or -1.  Returns the blob.
     std::vector<unsigned char> build(const int8_t *tv, int outage) const {
@@ -334,12 +337,6 @@ public:
             while ((ops.size() / (size_t)W) % 4) ops.insert(ops.end(), (size_t)W, nop);     // whole blocks of 4 rows (prefetch unit)
             n_oprow = (int)(ops.size() / (size_t)W);
             ops.insert(ops.end(), (size_t)W * 4, nop);      // guard block: the prefetch of "the block after the last" reads it, nothing executes it
-            // slots hold BYTE offsets into the value array (4 * position; the barrier flag moves to bit 0 of kk)
-            for (Op &o : ops) {
-                const unsigned flag = (o.kk & 0x4000u) ? 1u : 0u;
-                o.ij = (uint16_t)(o.ij * 4u); o.ik = (uint16_t)(o.ik * 4u); o.kj = (uint16_t)(o.kj * 4u);
-                o.kk = (uint16_t)(((o.kk & 0x3fffu) * 4u) | flag);
-            }
         }
         const int n_pass = (int)pass_ptr.size() - 1;
         PLAN_TICK("ops+schedule");
@@ -461,6 +458,89 @@ public:
             }
         }
         PLAN_TICK("dc inverse");
+        // ---- physical layout of the matrix entries: a permutation of the slots [0, nnzF) that spreads the entries one warp-row
+        //      of the operation stream touches together over the 32 shared-memory banks (right-hand side and dummy keep their
+        //      slots: the kernel addresses them implicitly).  Local search over swaps, cost = wavefronts of the stream.
+        if (optimize_layout_ && nnzF > 32) {
+            const int W = op_width_;
+            const int n_wrow = n_oprow * (W / 32);
+            // groups: (warp-row, stream) -> distinct movable positions + fixed per-bank counts of the rest
+            struct Group { std::vector<int> pos; int fixed[32]; int cnt[32]; int weight; };
+            std::vector<Group> groups((size_t)n_wrow * 4);
+            std::vector<std::vector<int>> memb(nnzF);
+            std::vector<int> mark(nA + 1, -1);
+            for (int wr = 0; wr < n_wrow; ++wr)
+                for (int st = 0; st < 4; ++st) {
+                    Group &G = groups[(size_t)wr * 4 + st];
+                    for (int b = 0; b < 32; ++b) G.fixed[b] = 0;
+                    G.weight = st == 0 ? 2 : 1;
+                    const int gid = wr * 4 + st;
+                    for (int l = 0; l < 32; ++l) {
+                        const Op &o = ops[(size_t)wr * 32 + l];
+                        const int p = st == 0 ? o.ij : (st == 1 ? o.ik : (st == 2 ? o.kj : (o.kk & 0x3fff)));
+                        if (mark[p] == gid) continue;
+                        mark[p] = gid;
+                        if (p < nnzF) { G.pos.push_back(p); memb[p].push_back(gid); } else G.fixed[p % 32]++;
+                    }
+                }
+            std::vector<int> slot(nnzF), owner(nnzF);
+            for (int p = 0; p < nnzF; ++p) { slot[p] = p; owner[p] = p; }
+            auto gcost = [](const Group &G) { int m = 1; for (int b = 0; b < 32; ++b) m = std::max(m, G.cnt[b]); return m * G.weight; };
+            for (Group &G : groups) { for (int b = 0; b < 32; ++b) G.cnt[b] = G.fixed[b]; for (int p : G.pos) G.cnt[slot[p] % 32]++; }
+            uint32_t rng = 0x9E3779B9u ^ (uint32_t)nnzF;
+            auto rnd = [&]() { rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5; return rng; };
+            std::vector<int> touched;
+            for (int sweep = 0; sweep < 6; ++sweep) {
+                int improved = 0;
+                for (size_t gi = 0; gi < groups.size(); ++gi) {
+                    Group &G = groups[gi];
+                    int bmax = 0;
+                    for (int b = 1; b < 32; ++b) if (G.cnt[b] > G.cnt[bmax]) bmax = b;
+                    if (G.cnt[bmax] <= 1) continue;
+                    for (int p : G.pos) {
+                        if (slot[p] % 32 != bmax) continue;
+                        bool done = false;
+                        for (int trial = 0; trial < 12 && !done; ++trial) {
+                            const int s2 = (int)(rnd() % (uint32_t)nnzF);
+                            const int q = owner[s2], bp = slot[p] % 32, bq = s2 % 32;
+                            if (q == p || bq == bp || G.cnt[bq] >= G.cnt[bmax] - 1) continue;
+                            // cost change over the groups of p and q
+                            touched.clear();
+                            for (int g2 : memb[p]) touched.push_back(g2);
+                            for (int g2 : memb[q]) touched.push_back(g2);
+                            std::sort(touched.begin(), touched.end());
+                            touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+                            int before = 0, after = 0;
+                            for (int g2 : touched) before += gcost(groups[g2]);
+                            for (int g2 : memb[p]) { groups[g2].cnt[bp]--; groups[g2].cnt[bq]++; }
+                            for (int g2 : memb[q]) { groups[g2].cnt[bq]--; groups[g2].cnt[bp]++; }
+                            for (int g2 : touched) after += gcost(groups[g2]);
+                            if (after < before) {
+                                std::swap(slot[p], slot[q]); owner[slot[p]] = p; owner[slot[q]] = q;
+                                ++improved; done = true;
+                            } else {
+                                for (int g2 : memb[p]) { groups[g2].cnt[bp]++; groups[g2].cnt[bq]--; }
+                                for (int g2 : memb[q]) { groups[g2].cnt[bq]++; groups[g2].cnt[bp]--; }
+                            }
+                        }
+                        if (done) break;
+                    }
+                }
+                if (!improved) break;
+            }
+            auto mp = [&](uint16_t v) -> uint16_t { return v < nnzF ? (uint16_t)slot[v] : v; };
+            for (Op &o : ops) { o.ij = mp(o.ij); o.ik = mp(o.ik); o.kj = mp(o.kj); o.kk = (uint16_t)((o.kk & 0x4000u) | mp((uint16_t)(o.kk & 0x3fffu))); }
+            for (uint16_t &v : dpos) v = mp(v);
+            for (uint16_t &v : jpos) v = mp(v);
+            for (uint16_t &v : zero) v = mp(v);
+        }
+        // slots hold BYTE offsets into the value array (4 * position; the barrier flag moves to bit 0 of kk)
+        for (Op &o : ops) {
+            const unsigned flag = (o.kk & 0x4000u) ? 1u : 0u;
+            o.ij = (uint16_t)(o.ij * 4u); o.ik = (uint16_t)(o.ik * 4u); o.kj = (uint16_t)(o.kj * 4u);
+            o.kk = (uint16_t)(((o.kk & 0x3fffu) * 4u) | flag);
+        }
+        PLAN_TICK("layout");
         // ---- serialise ------------------------------------------------------------------------------------
         PlanHeader H;
         memset(&H, 0, sizeof(H));
@@ -547,6 +627,7 @@ public:
 private:
     const HostGrid &g_;
     int op_width_;
+    bool optimize_layout_;
 };
 
 }  // namespace b200pf

@@ -5,6 +5,7 @@
 #include "../../grid2op_b200/csrc/b200pf_sparse.cuh"
 #include "../../include/b200pf.h"
 
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -32,7 +33,8 @@ extern "C" int sparse_emu_run(const b200pf_grid_desc *gd, int batch, const int8_
                               double tol_mva, float *out, int32_t *status, int32_t *iters, double *busv, int n1_lines,
                               const float *th_lim, float *rho, int32_t *stats /* [8] of the last plan, may be NULL */) {
     HostGrid hg = host_grid(gd);
-    PlanBuilder pb(hg);
+    const char *optl = getenv("SPARSE_EMU_OPTIMIZE_LAYOUT");
+    PlanBuilder pb(hg, 32, optl && optl[0] == '1');
     DevGrid g{};
     g.n_sub = hg.n_sub; g.n_busbar = hg.n_busbar; g.n_slot = hg.n_slot; g.n_line = hg.n_line; g.n_gen = hg.n_gen; g.n_hidden = hg.n_hidden;
     g.n_unit = hg.n_unit; g.n_load = hg.n_load; g.n_sto = hg.n_sto; g.n_shunt = hg.n_shunt; g.dim_topo = hg.dim_topo;
@@ -74,7 +76,7 @@ extern "C" int sparse_emu_run(const b200pf_grid_desc *gd, int batch, const int8_
 // pattern solves A x = b (checked against dense Gaussian elimination).  Returns 0 when everything holds.
 extern "C" int sparse_emu_validate_plan(const b200pf_grid_desc *gd, const int8_t *topo, int outage, int op_width, double *max_err) {
     HostGrid hg = host_grid(gd);
-    PlanBuilder pb(hg, op_width);
+    PlanBuilder pb(hg, op_width < 0 ? -op_width : op_width, op_width < 0);      // negative width: with the optimised layout
     std::vector<unsigned char> blob = pb.build(topo, outage);
     const PlanHeader *H = (const PlanHeader *)blob.data();
     if (H->status != PLAN_ST_OK) return -1;
@@ -209,4 +211,38 @@ extern "C" int sparse_emu_series_prot_step(const b200pf_grid_desc *gd, int batch
     }
     if (n_rounds) *n_rounds = rounds;
     return 0;
+}
+
+// shared-memory wavefronts of the operation stream (32 banks x 4 bytes): for every row of `width` slots processed by warps of
+// 32 lanes, each of the 5 access streams (loads ik, kj, kk, ij; store ij) costs max over banks of the number of DISTINCT
+// addresses in that bank.  Returns total wavefronts / (5 * number of warp-rows): 1.0 = conflict free.
+extern "C" double sparse_emu_bank_conflicts(const b200pf_grid_desc *gd, const int8_t *topo, int outage, int op_width, int optimize) {
+    HostGrid hg = host_grid(gd);
+    PlanBuilder pb(hg, op_width, optimize != 0);
+    std::vector<unsigned char> blob = pb.build(topo, outage);
+    const PlanHeader *H = (const PlanHeader *)blob.data();
+    if (H->status != PLAN_ST_OK) return -1.0;
+    const uint16_t *ops = (const uint16_t *)(blob.data() + H->o_ops);
+    const int W = H->op_width;
+    long wf = 0, rows = 0;
+    for (int r = 0; r < H->n_oprow; ++r)
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            for (int stream = 0; stream < 4; ++stream) {
+                std::vector<std::vector<int>> bank(32);
+                for (int l = 0; l < 32; ++l) {
+                    const int o = r * W + w0 + l;
+                    int off = ops[4 * o + stream];
+                    if (stream == 3) off &= 0xfffc;
+                    const int word = off / 4, b = word % 32;
+                    bool seen = false;
+                    for (int a : bank[b]) if (a == word) seen = true;
+                    if (!seen) bank[b].push_back(word);
+                }
+                size_t mx = 1;
+                for (auto &v : bank) mx = std::max(mx, v.size());
+                wf += (long)mx * (stream == 0 ? 2 : 1);      // the target is loaded and stored
+            }
+            ++rows;
+        }
+    return rows ? (double)wf / (5.0 * rows) : 0.0;
 }

@@ -108,6 +108,8 @@ def test_operation_stream_is_hazard_free_and_solves_the_system(name, width):
             rc, err = validate_plan(gm, r, outage, width)
             assert rc in (0, -1), (rc, err)          # -1: the topology has no solvable plan (islanded / no reference)
             checked += rc == 0
+            rc2, err2 = validate_plan(gm, r, outage, -width)      # same with the bank-conflict-optimised layout
+            assert rc2 == rc, (rc2, err2)
     assert checked >= 10
 
 
@@ -160,3 +162,24 @@ def test_emulated_protections_replay_the_recorded_rollouts():
     for name in ("p_or", "q_or", "p_ex", "q_ex", "prod_p", "prod_q"):
         assert worst[name] <= 1e-4, (name, worst[name])
     assert worst["v_or"] <= 2e-5 and worst["a_or"] <= 2e-3 and worst["rho"] <= 1e-6
+
+
+def test_optimised_layout_gives_the_same_results_with_fewer_bank_conflicts(monkeypatch):
+    """The layout optimisation only permutes where the Jacobian entries live in shared memory: results are unchanged, the
+    operation stream needs fewer shared-memory wavefronts."""
+    import ctypes as C
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_neurips_2020_track1.npz"))
+    topo, inj = random_cases(gm, 48, seed=5)
+    base = SparseEmu(gm).run(topo, inj)
+    monkeypatch.setenv("SPARSE_EMU_OPTIMIZE_LAYOUT", "1")
+    emu = SparseEmu(gm)
+    opt = emu.run(topo, inj)
+    assert np.array_equal(base[1], opt[1]) and np.array_equal(base[2], opt[2])
+    ok = base[1] == 0
+    assert np.allclose(base[0][ok], opt[0][ok], rtol=1e-6, atol=1e-5)
+    emu.lib.sparse_emu_bank_conflicts.restype = C.c_double
+    t = np.ascontiguousarray(gm.default_topo(), dtype=np.int8)
+    args = (C.byref(emu.desc), t.ctypes.data_as(C.c_void_p), C.c_int(-1), C.c_int(32))
+    before = emu.lib.sparse_emu_bank_conflicts(*args, C.c_int(0))
+    after = emu.lib.sparse_emu_bank_conflicts(*args, C.c_int(1))
+    assert 1.0 <= after < before
