@@ -246,3 +246,20 @@ extern "C" double sparse_emu_bank_conflicts(const b200pf_grid_desc *gd, const in
         }
     return rows ? (double)wf / (5.0 * rows) : 0.0;
 }
+
+// diagnostics: number of real (non-padding) operations of every pass of the plan of one topology; returns the pass count
+extern "C" int sparse_emu_pass_sizes(const b200pf_grid_desc *gd, const int8_t *topo, int outage, int op_width, int32_t *sizes, int cap) {
+    HostGrid hg = host_grid(gd);
+    PlanBuilder pb(hg, op_width);
+    std::vector<unsigned char> blob = pb.build(topo, outage);
+    const PlanHeader *H = (const PlanHeader *)blob.data();
+    if (H->status != PLAN_ST_OK) return -1;
+    const uint16_t *ops = (const uint16_t *)(blob.data() + H->o_ops);
+    const int *pass_ptr = (const int *)(blob.data() + H->o_pass_ptr);
+    for (int p = 0; p < H->n_pass && p < cap; ++p) {
+        int n = 0;
+        for (int o = pass_ptr[p]; o < pass_ptr[p + 1]; ++o) n += ops[4 * o] / 4 != H->nA;
+        sizes[p] = n;
+    }
+    return H->n_pass;
+}
