@@ -302,6 +302,9 @@ public:
                     if (S[(size_t)i * d + k]) seq.push_back({(uint16_t)(nnzF + i), (uint16_t)P(i, k), (uint16_t)(nnzF + k), (uint16_t)kk});
             }
             std::vector<int> wlev(nA + 1, 0), rlev(nA + 1, 0), lev(seq.size(), 0);
+            // successor edges of the dependency graph (RAW, WAW, WAR), for the row balancing below
+            std::vector<std::vector<int>> succ(seq.size()), readers(nA + 1);
+            std::vector<int> lastw(nA + 1, -1);
             int nlev = 0;
             for (size_t q = 0; q < seq.size(); ++q) {
                 const Op &o = seq[q];
@@ -309,9 +312,40 @@ public:
                 lev[q] = lv; nlev = std::max(nlev, lv);
                 wlev[o.ij] = lv;
                 rlev[o.ik] = std::max(rlev[o.ik], lv); rlev[o.kj] = std::max(rlev[o.kj], lv); rlev[o.kk] = std::max(rlev[o.kk], lv);
+                const int rd[3] = {o.ik, o.kj, o.kk};
+                for (int r : rd) if (lastw[r] >= 0) succ[lastw[r]].push_back((int)q);
+                if (lastw[o.ij] >= 0) succ[lastw[o.ij]].push_back((int)q);
+                for (int r : readers[o.ij]) succ[r].push_back((int)q);
+                readers[o.ij].clear();
+                for (int r : rd) readers[r].push_back((int)q);
+                lastw[o.ij] = (int)q;
+            }
+            const int W = op_width_;
+            {   // Row balancing: a pass costs ceil(n / W) rows.  Going down the passes, the operations of the last, partly
+                // filled row move to the next pass when they have slack (every successor at least two passes later; those with
+                // the most slack first): that saves a row here and costs at most one there, where the remainder rolls on.
+                // Dependencies are untouched by construction (tests/ validate every stream).
+                std::vector<std::vector<int>> at(nlev + 2);
+                for (size_t q = 0; q < seq.size(); ++q) at[lev[q]].push_back((int)q);
+                std::vector<std::pair<int, int>> cand;
+                for (int l = 1; l < nlev; ++l) {
+                    const int r = (int)at[l].size() % W;
+                    if (r == 0) continue;
+                    cand.clear();
+                    for (int q : at[l]) {
+                        int ms = 1 << 30;
+                        for (int sq : succ[q]) ms = std::min(ms, lev[sq]);
+                        if (ms >= l + 2) cand.push_back({-ms, q});
+                    }
+                    if ((int)cand.size() < r) continue;
+                    std::sort(cand.begin(), cand.end());
+                    for (int c = 0; c < r; ++c) { const int q = cand[c].second; lev[q] = l + 1; at[l + 1].push_back(q); }
+                    std::vector<int> keep;
+                    for (int q : at[l]) if (lev[q] == l) keep.push_back(q);
+                    at[l].swap(keep);
+                }
             }
             // passes padded to whole rows of op_width slots; the last row of a pass carries the barrier flag
-            const int W = op_width_;
             std::vector<int> lv_ptr(nlev + 2, 0);
             for (int lv : lev) lv_ptr[lv + 1]++;
             for (int l = 1; l <= nlev + 1; ++l) lv_ptr[l] += lv_ptr[l - 1];
