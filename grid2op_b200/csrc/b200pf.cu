@@ -438,19 +438,25 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     if (!miss.empty()) {
         if (h->plan_policy == 0 && (int)miss.size() > PLAN_BUILD_BUDGET) return 0;
         std::vector<std::vector<unsigned char>> blobs(miss.size());
-        // a handful of new plans: they will be re-used by many solves (rollouts, N-1 sweeps) -> bank-conflict-optimised layout
-        // (not for single environments: there the build time of a new topology is part of the step latency)
-        const PlanBuilder pb(h->hg, h->plan_T, miss.size() <= 32 && (size_t)n_src * per >= 256);
+        // a handful of new plans of a batched launch: they will be re-used by many solves (rollouts, N-1 sweeps) -> searched
+        // elimination order + bank-conflict-optimised layout (not for single environments: there the build time of a new
+        // topology is part of the step latency; not for bulk builds)
+        const bool searched = miss.size() <= 32 && (size_t)n_src * per >= 256;
+        const int n_seeds = h->g.n_slot <= 128 ? 12 : 4;
+        const PlanBuilder pb(h->hg, h->plan_T);
+        auto build_one = [&](size_t m) {
+            blobs[m] = searched ? build_plan_searched(h->hg, h->plan_T, miss[m].tv, miss[m].outage, n_seeds) : pb.build(miss[m].tv, miss[m].outage);
+        };
         unsigned nthr = std::thread::hardware_concurrency();
         if (nthr > 16) nthr = 16;
         if (nthr < 1) nthr = 1;
         if ((size_t)nthr > miss.size() / 4 + 1) nthr = (unsigned)(miss.size() / 4 + 1);
         if (nthr <= 1) {
-            for (size_t m = 0; m < miss.size(); ++m) blobs[m] = pb.build(miss[m].tv, miss[m].outage);
+            for (size_t m = 0; m < miss.size(); ++m) build_one(m);
         } else {
             std::vector<std::thread> pool;
             for (unsigned t = 0; t < nthr; ++t)
-                pool.emplace_back([&, t]() { for (size_t m = t; m < miss.size(); m += nthr) blobs[m] = pb.build(miss[m].tv, miss[m].outage); });
+                pool.emplace_back([&, t]() { for (size_t m = t; m < miss.size(); m += nthr) build_one(m); });
             for (auto &th : pool) th.join();
         }
         for (size_t m = 0; m < miss.size(); ++m) {

@@ -56,7 +56,8 @@ extern "C" int sparse_emu_run(const b200pf_grid_desc *gd, int batch, const int8_
         std::string key((const char *)tv, hg.n_topo_in);
         key.push_back((char)(outage & 0xff)); key.push_back((char)((outage >> 8) & 0xff));
         auto it = cache.find(key);
-        if (it == cache.end()) it = cache.emplace(key, pb.build(tv, outage)).first;
+        if (it == cache.end())
+            it = cache.emplace(key, (optl && optl[0] == '2') ? build_plan_searched(hg, 32, tv, outage, 12) : pb.build(tv, outage)).first;
         const std::vector<unsigned char> &blob = it->second;
         const PlanHeader *H = (const PlanHeader *)blob.data();
         if (stats) { stats[0] = H->nb; stats[1] = H->d; stats[2] = H->nnzF; stats[3] = H->n_pass; stats[4] = H->n_op; stats[5] = H->n_oprow;
@@ -76,8 +77,8 @@ extern "C" int sparse_emu_run(const b200pf_grid_desc *gd, int batch, const int8_
 // pattern solves A x = b (checked against dense Gaussian elimination).  Returns 0 when everything holds.
 extern "C" int sparse_emu_validate_plan(const b200pf_grid_desc *gd, const int8_t *topo, int outage, int op_width, double *max_err) {
     HostGrid hg = host_grid(gd);
-    PlanBuilder pb(hg, op_width < 0 ? -op_width : op_width, op_width < 0);      // negative width: with the optimised layout
-    std::vector<unsigned char> blob = pb.build(topo, outage);
+    // negative width: the searched plan (best of several elimination orders) with the optimised layout
+    std::vector<unsigned char> blob = op_width < 0 ? build_plan_searched(hg, -op_width, topo, outage, 12) : PlanBuilder(hg, op_width).build(topo, outage);
     const PlanHeader *H = (const PlanHeader *)blob.data();
     if (H->status != PLAN_ST_OK) return -1;
     const int W = H->op_width, nA = H->nA, nnzF = H->nnzF, d = H->d;
@@ -250,7 +251,8 @@ extern "C" double sparse_emu_bank_conflicts(const b200pf_grid_desc *gd, const in
 // diagnostics: number of real (non-padding) operations of every pass of the plan of one topology; returns the pass count
 extern "C" int sparse_emu_pass_sizes(const b200pf_grid_desc *gd, const int8_t *topo, int outage, int op_width, int32_t *sizes, int cap) {
     HostGrid hg = host_grid(gd);
-    PlanBuilder pb(hg, op_width);
+    const char *sd = getenv("SPARSE_EMU_ORDER_SEED");
+    PlanBuilder pb(hg, op_width, false, sd ? atoi(sd) : 0);
     std::vector<unsigned char> blob = pb.build(topo, outage);
     const PlanHeader *H = (const PlanHeader *)blob.data();
     if (H->status != PLAN_ST_OK) return -1;
