@@ -265,3 +265,15 @@ extern "C" int sparse_emu_pass_sizes(const b200pf_grid_desc *gd, const int8_t *t
     }
     return H->n_pass;
 }
+
+// rows of the operation stream and a checksum of the whole plan blob (default vs searched plan): for the tests that the plan
+// search is deterministic and never worse than the default order
+extern "C" int sparse_emu_plan_rows(const b200pf_grid_desc *gd, const int8_t *topo, int outage, int op_width, int searched, uint64_t *checksum) {
+    HostGrid hg = host_grid(gd);
+    std::vector<unsigned char> blob = searched ? build_plan_searched(hg, op_width, topo, outage, 12) : PlanBuilder(hg, op_width).build(topo, outage);
+    const PlanHeader *H = (const PlanHeader *)blob.data();
+    uint64_t c = 1469598103934665603ull;
+    for (unsigned char b : blob) { c ^= b; c *= 1099511628211ull; }
+    if (checksum) *checksum = c;
+    return H->status == PLAN_ST_OK ? H->n_oprow : -1;
+}

@@ -183,3 +183,20 @@ def test_optimised_layout_gives_the_same_results_with_fewer_bank_conflicts(monke
     before = emu.lib.sparse_emu_bank_conflicts(*args, C.c_int(0))
     after = emu.lib.sparse_emu_bank_conflicts(*args, C.c_int(1))
     assert 1.0 <= after < before
+
+
+@pytest.mark.parametrize("name,width", [("l2rpn_case14_sandbox", 32), ("l2rpn_neurips_2020_track1", 32), ("l2rpn_wcci_2022_dev", 64)])
+def test_plan_search_is_deterministic_and_never_worse(name, width):
+    import ctypes as C
+    gm = GridModel.from_npz(os.path.join(GOLD, f"gridmodel_{name}.npz"))
+    emu = SparseEmu(gm)
+    topo, _ = random_cases(gm, 6, seed=2)
+    for r in [gm.default_topo()] + [topo[i] for i in range(len(topo))]:
+        t = np.ascontiguousarray(r, dtype=np.int8)
+        c1, c2 = C.c_uint64(0), C.c_uint64(0)
+        args = (C.byref(emu.desc), t.ctypes.data_as(C.c_void_p), C.c_int(-1), C.c_int(width))
+        base = emu.lib.sparse_emu_plan_rows(*args, C.c_int(0), None)
+        a = emu.lib.sparse_emu_plan_rows(*args, C.c_int(1), C.byref(c1))
+        b = emu.lib.sparse_emu_plan_rows(*args, C.c_int(1), C.byref(c2))
+        assert a == b and c1.value == c2.value          # same plan, byte for byte
+        assert (base < 0 and a < 0) or (0 < a <= base)  # rows of the operation stream
