@@ -4,6 +4,7 @@
 #include "b200pf_kernel.cuh"
 #include "b200pf_small.cuh"
 #include "b200pf_sparse.cuh"
+#include "b200pf_redo.cuh"
 #include "../../include/b200pf.h"
 
 #include <cstdio>
@@ -82,6 +83,10 @@ struct b200pf_handle {
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0;
     int64_t launches = 0;
+    int redo_enabled = 1;                                   // pivoting re-solve of what the planned kernel leaves as ST_DIV (B200PF_NO_REDO=1 turns it off)
+    int dbg_div_mod = 0;                                    // test knob, see b200pf_set_debug
+    int64_t redo_launches = 0;
+    cudaEvent_t inst_plan_ev = nullptr; bool inst_plan_pending = false;   // last H2D copy out of h_inst_plan
     int last_smem = 0, last_T = 0, last_grid = 0, last_block = 0;
 };
 
@@ -220,6 +225,8 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         if (mb && atoi(mb) == 28) h->sparse_minb = 28;
         const char *capv = getenv("B200PF_SPARSE_CTAS");        // tuning: cap of resident CTAs per SM (planned kernel)
         if (capv) h->sparse_cta_cap = atoi(capv);
+        const char *nr = getenv("B200PF_NO_REDO");              // measurement only: planned kernel without its safety net
+        if (nr && nr[0] == '1') h->redo_enabled = 0;
         const char *var = getenv("B200PF_SPARSE_T");            // tuning: threads per instance of the planned kernel
         if (var) { const int t = atoi(var); if (t == 32 || t == 64 || t == 128) h->plan_T = t; }
     }
@@ -240,6 +247,7 @@ extern "C" int b200pf_destroy(b200pf_handle *h) {
     for (auto &cs : h->chunk_stream) if (cs) cudaStreamDestroy(cs);
     for (auto &cs : h->group_stream) if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
     for (auto &ev : h->group_event) if (ev) cudaEventDestroy(ev);
+    if (h->inst_plan_ev) cudaEventDestroy(h->inst_plan_ev);
     delete h;
     return 0;
 }
@@ -378,9 +386,11 @@ static int plan_insert(b200pf_handle *h, const int8_t *tv, uint64_t row_hash, in
     return id;
 }
 
-// device copy of the plans built since the last call (synchronous copies: building a plan is a rare event, and a plan
-// must be visible to every stream of the handle)
-static int plans_sync_device(b200pf_handle *h) {
+// device copy of the plans built since the last call.  The copies are issued on the launching stream and the stream is
+// drained before returning: the sources are pageable host vectors (a plain cudaMemcpy may return before its DMA has
+// finished, and the handle's non-blocking streams are not ordered against the legacy stream), and a plan must be visible
+// to every stream of the handle.  Building a plan is a rare event (a new topology), the wait is noise next to it.
+static int plans_sync_device(b200pf_handle *h, cudaStream_t st) {
     if (h->d_plan_used == h->plan_blobs.size() && h->d_plan_off_n == (int)h->plan_off.size()) return 0;
     if (h->plan_blobs.size() > h->d_plan_cap) {
         CU(cudaDeviceSynchronize());                       // launches in flight may still read the old buffer
@@ -392,10 +402,13 @@ static int plans_sync_device(b200pf_handle *h) {
         h->d_plan_cap = cap;
     }
     if (!h->d_plan_off) CU(cudaMalloc(&h->d_plan_off, (size_t)PLAN_MAX * 4));
-    CU(cudaMemcpy(h->d_plan_blobs + h->d_plan_used, h->plan_blobs.data() + h->d_plan_used, h->plan_blobs.size() - h->d_plan_used, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(h->d_plan_blobs + h->d_plan_used, h->plan_blobs.data() + h->d_plan_used, h->plan_blobs.size() - h->d_plan_used,
+                       cudaMemcpyHostToDevice, st));
     h->d_plan_used = h->plan_blobs.size();
-    CU(cudaMemcpy(h->d_plan_off + h->d_plan_off_n, h->plan_off.data() + h->d_plan_off_n, (h->plan_off.size() - (size_t)h->d_plan_off_n) * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(h->d_plan_off + h->d_plan_off_n, h->plan_off.data() + h->d_plan_off_n,
+                       (h->plan_off.size() - (size_t)h->d_plan_off_n) * 4, cudaMemcpyHostToDevice, st));
     h->d_plan_off_n = (int)h->plan_off.size();
+    CU(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -409,6 +422,7 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     const DevGrid &g = h->g;
     const size_t nt = (size_t)g.n_topo_in;
     const int per = n1_lines > 0 ? n1_lines : 1;
+    if (h->inst_plan_pending) { CU(cudaEventSynchronize(h->inst_plan_ev)); h->inst_plan_pending = false; }
     int *ids = h->h_inst_plan + first;
     // pass 1: cached plans; the misses of this call are collected (once each) ...
     struct Miss { const int8_t *tv; uint64_t rh; int outage; int id; };
@@ -461,12 +475,12 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
         }
         for (size_t m = 0; m < miss.size(); ++m) {
             miss[m].id = plan_insert(h, miss[m].tv, miss[m].rh, miss[m].outage, blobs[m]);
-            if (miss[m].id < 0) { int rc = plans_sync_device(h); return rc ? rc : 0; }
+            if (miss[m].id < 0) { int rc = plans_sync_device(h, st); return rc ? rc : 0; }
         }
         const size_t n = (size_t)n_src * per;
         for (size_t k = 0; k < n; ++k) if (ids[k] <= -2) ids[k] = miss[(size_t)(-2 - ids[k])].id;
     }
-    int rc = plans_sync_device(h);
+    int rc = plans_sync_device(h, st);
     if (rc) return rc;
     const size_t n = (size_t)n_src * per;
     bool single = true;
@@ -474,6 +488,9 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     sel->single = ids[0]; sel->smem = single ? h->plan_smem[ids[0]] : h->plan_max_smem; sel->d_inst_plan = nullptr;
     if (!single) {
         CU(cudaMemcpyAsync(h->d_inst_plan + first, ids, n * 4, cudaMemcpyHostToDevice, st));
+        if (!h->inst_plan_ev) CU(cudaEventCreateWithFlags(&h->inst_plan_ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(h->inst_plan_ev, st));          // the next call waits for this copy before it reuses h_inst_plan
+        h->inst_plan_pending = true;
         sel->d_inst_plan = h->d_inst_plan + first;
     }
     return 1;
@@ -536,8 +553,90 @@ static int launch_sparse(b200pf_handle *h, const RunArgs &a, const PlanSel &sel)
     return launch_sparse_t<32, 8>(h, a, sel, 6);
 }
 
+// Sizing of the generic pivoting kernel for nb_cap active buses: threads per instance, matrix bytes (see the policy above
+// launch_small).  jt = bytes of a Jacobian entry.  Returns 0, or an error when not even a clipped matrix fits.
+static int generic_config(b200pf_handle *h, int cap, int jt, int *T_out, size_t *want_out) {
+    const DevGrid &g = h->g;
+    const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
+    size_t want = ws_mat_worst(cap, jt);
+    int T = 32;
+    {   // threads per instance: the big systems are latency bound -> many warps per instance
+        size_t d = 2 * (size_t)cap;
+        T = d <= 64 ? 32 : (d <= 128 ? 128 : (d <= 256 ? 256 : 512));
+    }
+    if (fixed + want > (size_t)h->max_smem_optin) {
+        // does not fit with the worst case: clipped matrix (the kernel checks the ACTUAL system of every instance against it)
+        if (T == 32) { T = 128; }
+        if (fixed + 1024 > (size_t)h->max_smem_optin) return fail(B200PF_E_CAPACITY, "grid too large for the on-chip workspace");
+        size_t avail = ((size_t)h->max_smem_optin - fixed) & ~size_t(15);
+        if (want > avail) want = avail;
+        size_t dmax = 1;
+        while ((dmax + 1) * (dmax + 3) * jt <= want) ++dmax;
+        T = dmax <= 128 ? 128 : (dmax <= 256 ? 256 : 512);
+    }
+    *T_out = T; *want_out = want;
+    return 0;
+}
+
+// Safety net behind a planned launch (b200pf_redo.cuh): re-solves, with partial pivoting, the instances of the launch whose
+// status reads ST_DIV.  Same stream, no host round trip.  fp64 Jacobian whenever the actual systems fit the workspace with
+// it (5 / 14 / 36 substations), fp32 band LU otherwise (118 substations).
+template <int T, typename JT>
+static int launch_redo_t(b200pf_handle *h, const RunArgs &a) {
+    const DevGrid &g = h->g;
+    WsLayout L = ws_layout(a.nb_cap, g.n_slot, g.n_line, g.n_inj, (size_t)a.mat_bytes);
+    const size_t smem = L.total;
+    if (smem > (size_t)h->max_smem_optin) return fail(B200PF_E_CAPACITY, "workspace does not fit in shared memory");
+    auto kern = pf_kernel_redo<T, JT>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (a.batch + 31) / 32;
+    const int cap = h->sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<grid, T, smem, h->stream>>>(g, a, (int)smem);
+    CU(cudaGetLastError());
+    h->redo_launches++;
+    return 0;
+}
+
+static int launch_redo(b200pf_handle *h, RunArgs a, int nb_cap_req) {
+    if (!h->redo_enabled || a.is_dc || !a.topo) return 0;     // (the DC solve is a product with the plan's inverse: nothing to pivot)
+    const DevGrid &g = h->g;
+    int cap = nb_cap_req;
+    if (cap <= 0 || cap > g.n_slot) cap = g.n_slot;
+    // fp64 Jacobian when the system of the plain topology plus a margin of 8 split buses fits; fp32 otherwise
+    int jt = 8, T = 32;
+    size_t want = 0;
+    {
+        const size_t d_typ = 2 * (size_t)g.n_sub + 16;
+        const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
+        if (fixed + d_typ * (d_typ + 2) * 8 > (size_t)h->max_smem_optin) jt = 4;
+    }
+    int rc = generic_config(h, cap, jt, &T, &want);
+    if (rc) return rc;
+    a.redo = 1; a.nb_cap = cap; a.mat_bytes = (int)want;
+    if (jt == 8) {
+        switch (T) {
+            case 32: return launch_redo_t<32, double>(h, a);
+            case 128: return launch_redo_t<128, double>(h, a);
+            case 256: return launch_redo_t<256, double>(h, a);
+            default: return launch_redo_t<512, double>(h, a);
+        }
+    }
+    switch (T) {
+        case 32: return launch_redo_t<32, float>(h, a);
+        case 128: return launch_redo_t<128, float>(h, a);
+        case 256: return launch_redo_t<256, float>(h, a);
+        default: return launch_redo_t<512, float>(h, a);
+    }
+}
+
 static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req, const PlanSel *sel = nullptr) {
-    if (sel) return launch_sparse(h, a, *sel);
+    if (sel) {
+        int rc = launch_sparse(h, a, *sel);
+        if (rc || a.prot) return rc;           // (protections: series_step_planned_prot launches the safety net itself)
+        return launch_redo(h, a, nb_cap_req);
+    }
     const DevGrid &g = h->g;
     if (h->env_flags < 0) {
         const char *f64 = getenv("B200PF_JACOBIAN_FP64"), *nosk = getenv("B200PF_NO_SMALL_KERNEL");
@@ -553,25 +652,10 @@ static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req, const PlanSel *se
         g.n_sto <= 32 && g.n_shunt <= 32 && cap <= 17)
         return launch_small(h, a, cap);
     if (a.prot) return fail(B200PF_E_STATE, "device-side protections need the warp-per-instance kernel (<= 32 lines / bus slots, nb_cap <= 17)");
-    const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
-    size_t want = ws_mat_worst(cap, jt);
     int T = 32;
-    {   // threads per instance: the big systems are latency bound -> many warps per instance
-        size_t d = 2 * (size_t)cap;
-        T = d <= 64 ? 32 : (d <= 128 ? 128 : (d <= 256 ? 256 : 512));
-    }
-    int gpb = 1;
-    if ((fixed + want) * gpb > (size_t)h->max_smem_optin) {
-        // does not fit with 4 warps per CTA / worst case: one group per CTA, clipped matrix
-        if (T == 32) { T = 128; }
-        gpb = 1;
-        if (fixed + 1024 > (size_t)h->max_smem_optin) return fail(B200PF_E_CAPACITY, "grid too large for the on-chip workspace");
-        size_t avail = ((size_t)h->max_smem_optin - fixed) & ~size_t(15);
-        if (want > avail) want = avail;
-        size_t dmax = 1;
-        while ((dmax + 1) * (dmax + 3) * jt <= want) ++dmax;
-        T = dmax <= 128 ? 128 : (dmax <= 256 ? 256 : 512);
-    }
+    size_t want = 0;
+    int rc = generic_config(h, cap, jt, &T, &want);
+    if (rc) return rc;
     a.nb_cap = cap;
     a.mat_bytes = (int)want;
     if (jd) {
@@ -595,6 +679,7 @@ static RunArgs base_args(const b200pf_handle *h, int batch, int is_dc, int max_i
     RunArgs a{};
     a.batch = batch; a.is_dc = is_dc; a.max_iter = max_iter;
     a.tol_pu = tol_mva / h->g.base_mva;
+    a.dbg_div_mod = h->dbg_div_mod;
     return a;
 }
 
@@ -751,6 +836,7 @@ static int series_step_planned_prot(b200pf_handle *h, RunArgs a) {
         sel.single = 0; sel.smem = h->plan_max_smem; sel.d_inst_plan = h->d_series_plan;
         int rc = launch_sparse(h, a, sel);
         if (rc) return rc;
+        if ((rc = launch_redo(h, a, 0))) return rc;       // pivoting re-solve (+ the protection rules) of what ended as ST_DIV
         int nflag = 0;
         CU(cudaMemcpyAsync(&nflag, h->d_nflag, 4, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -774,7 +860,7 @@ static int series_step_planned_prot(b200pf_handle *h, RunArgs a) {
             h->h_series_plan[inst] = id;
             CU(cudaMemcpyAsync(h->d_series_topo + (size_t)inst * nt, row, nt, cudaMemcpyHostToDevice, h->stream));
         }
-        if ((rc = plans_sync_device(h))) return rc;
+        if ((rc = plans_sync_device(h, h->stream))) return rc;
         CU(cudaMemcpyAsync(h->d_series_plan, h->h_series_plan.data(), (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemsetAsync(h->d_trip, 0, (size_t)B * nl, h->stream));
         CU(cudaMemcpyAsync(h->d_casclist, h->h_flaglist.data(), (size_t)nflag * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1019,6 +1105,8 @@ static int rows_chunk_launch_impl(b200pf_handle *h, int first, int count, const 
         a.rows = src_rows;
         a.topo = h->h_topo + F * g.n_topo_in;
     } else {
+        // planned kernel: no topology record crosses PCIe; the (rare) pivoting re-solve reads it from the pinned staging buffer
+        if (use) a.topo = h->h_topo + F * g.n_topo_in;
         if (!use) CU(cudaMemcpyAsync(h->d_topo + F * g.n_topo_in, h->h_topo + F * g.n_topo_in, C * g.n_topo_in, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(h->d_rows + F * ncol, src_rows, C * ncol * 4, cudaMemcpyHostToDevice, st));
     }
@@ -1101,6 +1189,15 @@ extern "C" int b200pf_plan_stats(const b200pf_handle *h, int64_t *n_plans, int64
     if (last_kernel) *last_kernel = h->last_kernel;
     return 0;
 }
+
+extern "C" int b200pf_set_debug(b200pf_handle *h, int planned_div_mod, int redo_enabled) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    h->dbg_div_mod = planned_div_mod > 0 ? planned_div_mod : 0;
+    h->redo_enabled = redo_enabled ? 1 : 0;
+    return 0;
+}
+
+extern "C" int64_t b200pf_redo_launch_count(const b200pf_handle *h) { return h ? h->redo_launches : 0; }
 
 extern "C" int b200pf_sync(b200pf_handle *h) {
     if (!h) return fail(B200PF_E_ARG, "null handle");

@@ -80,6 +80,10 @@ struct RunArgs {
     int8_t *incdone;         // [B][n_line] in/out: the soft-overflow counter of the line was already incremented in this step
     int *n_flag;             // out: number of instances with at least one tripping line
     int *flag_list;          // out: those instances
+    // safety net of the non-pivoting planned kernel (b200pf_redo.cuh): 1 = this launch re-solves, with partial pivoting,
+    // the instances the planned kernel left as ST_DIV; the series row of such an instance was already advanced
+    int redo;
+    int dbg_div_mod;         // test knob: > 0 makes the planned kernel give up (ST_DIV) on every instance with inst % mod == 0
 };
 
 enum { ST_OK = 0, ST_DIV = 1, ST_UNSUP = 2, ST_NOREF = 3, ST_LARGE = 4, ST_DONE = 5 };
@@ -504,7 +508,8 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     // ---- 0. stage the injection record -----------------------------------------------------
     if (a.series) {
         const int sc = a.rows ? 0 : a.scen[src];
-        const int trow = a.rows ? 0 : a.t[src];
+        int trow = a.rows ? 0 : a.t[src];
+        if (a.redo && !a.rows) trow = trow == 0 ? a.n_rows - 1 : trow - 1;     // the planned kernel advanced the row already
         const float *row = a.rows ? a.rows + (size_t)src * (size_t)(2 * g.n_load + 2 * g.n_gen)
                                   : a.chron + ((size_t)sc * a.n_rows + trow) * (size_t)(2 * g.n_load + 2 * g.n_gen);
         for (int k = tid; k < g.n_inj; k += T) w.inj[k] = a.static_inj[k];
@@ -519,7 +524,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
             w.inj[g.n_gen + g.n_hidden + k] = (double)__fdiv_rn(row[2 * g.n_load + g.n_gen + k], g.unit_vn[g.n_hidden + k]);
         }
         gsync<T>();
-        if (tid == 0 && !a.rows && a.n1_lines <= 0) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1;
+        if (tid == 0 && !a.rows && a.n1_lines <= 0 && !a.redo) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1;
     } else {
         const double *srcp = a.inj + (size_t)src * g.n_inj;
         for (int k = tid; k < g.n_inj; k += T) w.inj[k] = srcp[k];
@@ -859,6 +864,7 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     }
 
     // ---- 7. results ----------------------------------------------------------------------------
+    if (a.redo && status == ST_LARGE) status = ST_DIV;      // the safety net could not hold the system: the first verdict stands
     if (tid == 0) { a.status[inst] = status; a.iters[inst] = iters; }
     if (status != ST_OK) {
         if (out) for (int k = tid; k < g.n_out; k += T) out[k] = qnanf();

@@ -12,7 +12,8 @@
 // Same arithmetic plan as the other kernels (fp64 state / mismatch / flows, fp32 Jacobian and solve, the fp64
 // residual decides convergence with pandapower's criterion), same result record, same status classes.
 // Elimination is WITHOUT pivoting on the (theta_i, |V|_i)-interleaved minimum-degree order: a breakdown shows
-// up as a non-finite update and ends as ST_DIV; the host re-runs such instances with the pivoting kernels.
+// up as a non-finite update and ends as ST_DIV.  ST_DIV is never final here: the library launches pf_kernel_redo
+// (b200pf_redo.cuh) right behind this kernel, which re-solves every such instance with partial pivoting.
 //
 // The body is written as a sequence of PHASES separated by group barriers, every piece of state that crosses a
 // phase lives in the (shared-memory) workspace.  With B200PF_EMULATE the same source compiles as plain host
@@ -98,6 +99,7 @@ struct RunArgs {
     const int *inst_list;
     int8_t *trip, *incdone;
     int *n_flag, *flag_list;
+    int redo, dbg_div_mod;
 };
 enum { ST_OK = 0, ST_DIV = 1, ST_UNSUP = 2, ST_NOREF = 3, ST_LARGE = 4, ST_DONE = 5 };
 enum { BT_PQ = 1, BT_PV = 2, BT_REF = 3 };
@@ -148,6 +150,7 @@ PF_DEV void solve_sparse(const DevGrid &g, const RunArgs &a, const PlanArgs &pa,
     }
     if (PROT && a.done[inst] && a.casc == 0) { sparse_fail<T>(g, a, inst, ST_DONE, 0, tid0); return; }
     if (H.status != PLAN_ST_OK) { sparse_fail<T>(g, a, inst, H.status, 0, tid0); return; }
+    if (a.dbg_div_mod > 0 && inst % a.dbg_div_mod == 0) { sparse_fail<T>(g, a, inst, ST_DIV, 0, tid0); return; }   // test knob (b200pf_set_debug)
     const int nb = H.nb, nl = g.n_line, nu = g.n_unit, nh = g.n_hidden, ng = g.n_gen, nld = g.n_load, nst = g.n_sto, nsh = g.n_shunt;
     const int d = H.d, nnzF = H.nnzF, nA = H.nA;
     const double base = g.base_mva;

@@ -34,6 +34,7 @@ ABI_SYMBOLS = (
     "b200pf_series_next_is_reset", "b200pf_series_fetch_state", "b200pf_rows_chunk_launch", "b200pf_rows_chunk_wait",
     "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free", "b200pf_rows_group_launch", "b200pf_rows_group_wait",
     "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats", "b200pf_run_device_topo",
+    "b200pf_set_debug", "b200pf_redo_launch_count",
 )
 
 
@@ -118,6 +119,9 @@ def load_library():
     lib.b200pf_last_launch_info.argtypes = [vp] + [C.POINTER(i32)] * 4
     lib.b200pf_set_kernel_policy.argtypes = [vp, i32]
     lib.b200pf_plan_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]
+    lib.b200pf_set_debug.argtypes = [vp, i32, i32]
+    lib.b200pf_redo_launch_count.argtypes = [vp]
+    lib.b200pf_redo_launch_count.restype = C.c_int64
     for nm in ("b200pf_create", "b200pf_destroy", "b200pf_sizes", "b200pf_run_host", "b200pf_run_device",
                "b200pf_series_bind", "b200pf_series_set_topo", "b200pf_series_step", "b200pf_series_results",
                "b200pf_series_fetch", "b200pf_sync", "b200pf_last_launch_info", "b200pf_staging", "b200pf_run_staged",
@@ -463,6 +467,15 @@ class PowerFlowEngine:
         """0: planned sparse kernel whenever it applies (default); 1: pivoting kernels only; 2: planned kernel
         even when a call has to build many new topology plans."""
         self._check(self.lib.b200pf_set_kernel_policy(self.h, int(policy)), "b200pf_set_kernel_policy")
+
+    def set_debug(self, planned_div_mod: int = 0, redo_enabled: bool = True):
+        """TEST knob (include/b200pf.h): make the planned kernel give up on every ``planned_div_mod``-th instance, and / or
+        switch the pivoting re-solve off."""
+        self._check(self.lib.b200pf_set_debug(self.h, int(planned_div_mod), int(bool(redo_enabled))), "b200pf_set_debug")
+
+    @property
+    def redo_launch_count(self) -> int:
+        return int(self.lib.b200pf_redo_launch_count(self.h))
 
     def plan_stats(self):
         n, b, k = C.c_int64(), C.c_int64(), C.c_int()

@@ -245,6 +245,17 @@ int b200pf_set_kernel_policy(b200pf_handle *h, int policy);
 /* number of cached plans, their bytes, and the kernel of the last launch (1 warp/pivoting, 2 CTA/pivoting, 3 planned sparse) */
 int b200pf_plan_stats(const b200pf_handle *h, int64_t *n_plans, int64_t *plan_bytes, int *last_kernel);
 
+/* Safety net of the planned kernel.  The planned kernel eliminates without pivoting on an fp32 Jacobian; the reference's
+ * solver (pp.runpp, pPB:1097-1105) pivots in fp64, and a failed power flow is a game over (pPB:1241-1255,
+ * grid2op/Environment/baseEnv.py:3523-3524).  Every planned launch is therefore followed, on the same stream and inside the
+ * same C-ABI call, by a launch that re-solves with partial pivoting (fp64 Jacobian where the workspace allows) the instances
+ * the planned kernel left as DIVERGED; a status only leaves the library after that.  b200pf_set_debug is a TEST knob:
+ * planned_div_mod > 0 makes the planned kernel give up on every instance with (index % planned_div_mod == 0), which
+ * exercises the re-solve path; redo_enabled = 0 switches the safety net off (measurements).  Env B200PF_NO_REDO=1 presets
+ * the latter.  b200pf_redo_launch_count: safety-net launches so far (they are not part of b200pf_launch_count). */
+int b200pf_set_debug(b200pf_handle *h, int planned_div_mod, int redo_enabled);
+int64_t b200pf_redo_launch_count(const b200pf_handle *h);
+
 int b200pf_sync(b200pf_handle *h);
 /* cudaStream_t of the handle as an integer (for event timing by the caller) */
 uint64_t b200pf_stream(b200pf_handle *h);

@@ -14,7 +14,7 @@ import warnings
 
 import pytest
 
-from conftest import data_test_dir, have_cuda
+from conftest import have_cuda  # noqa: F401
 
 from grid2op_b200._bootstrap import ensure_grid2op
 
@@ -47,7 +47,35 @@ if _have_suites:
     def _mk_gpu(self, detailed_infos_for_cascading_failures=False):
         return B200Backend(detailed_infos_for_cascading_failures=detailed_infos_for_cascading_failures)
 
-    _extended = data_test_dir() is not None and os.path.isdir(os.path.join(os.path.dirname(grid2op.__file__), "data_test"))
+    def _data_test_fixture_dir():
+        """The located grid2op has no ``data_test`` next to it (pip-installed reference, e.g. on the GPU box): unpack the
+        committed fixtures (tests/golden/data_test.tar.gz, the files the extended suites open, made by make_golden.py)
+        and point the reference's ``helper_path_test`` constants at them BEFORE the suites import them."""
+        import tarfile
+        import tempfile
+        gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_test.tar.gz")
+        if not os.path.exists(gold):
+            return None
+        dst = os.path.join(tempfile.gettempdir(), f"grid2op_b200_data_test_{os.getuid()}")
+        if not os.path.exists(os.path.join(dst, "data_test", "test_PandaPower", "test_case14.json")):
+            with tarfile.open(gold) as tar:
+                tar.extractall(dst, filter="data")
+        return os.path.join(dst, "data_test")
+
+    _extended = os.path.isdir(os.path.join(os.path.dirname(grid2op.__file__), "data_test"))
+    if not _extended:
+        _fix = _data_test_fixture_dir()
+        if _fix is not None:
+            # `import grid2op` has already imported grid2op.tests.* (grid2op/__init__.py pulls in _create_test_suite), so the
+            # path constants are re-pointed in every module that holds a copy
+            _old = os.path.join(os.path.dirname(os.path.abspath(grid2op.__file__)), "data_test")
+            for _name, _mod in list(sys.modules.items()):
+                if not _name.startswith("grid2op.tests") or _mod is None:
+                    continue
+                for _k, _v in list(vars(_mod).items()):
+                    if isinstance(_v, str) and _v.startswith(_old):
+                        setattr(_mod, _k, _fix + _v[len(_old):])
+            _extended = True
     _skip_cls = ("TestLoadingBackendPandaPower",)   # hard-codes PandaPowerBackend() in its setUp
 
     def _build(make, tag, marks):
@@ -69,6 +97,13 @@ if _have_suites:
                 cls = m(cls)
             globals()[cls.__name__] = cls
 
+    def _mk_ref(self, detailed_infos_for_cascading_failures=False):
+        # the oracle's restatement of PandaPowerBackend itself (oracle/ppbackend_ref.py): pins the ORACLE to the reference's
+        # golden vectors, independent of B200Backend's host logic
+        from oracle.ppbackend_ref import PandaPowerBackendRef
+        return PandaPowerBackendRef(detailed_infos_for_cascading_failures=detailed_infos_for_cascading_failures)
+
+    _build(_mk_ref, "oracleref", [pytest.mark.filterwarnings("ignore")])
     _build(_mk_cpu, "hostlogic", [pytest.mark.filterwarnings("ignore")])
     _build(_mk_gpu, "b200", [pytest.mark.gpu, pytest.mark.filterwarnings("ignore")])
 else:

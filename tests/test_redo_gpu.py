@@ -1,0 +1,213 @@
+"""Safety net of the non-pivoting planned kernel (csrc/b200pf_redo.cuh) and the large random stress that backs the
+planned kernel as the default path.
+
+The reference solves with partial pivoting in fp64 (pp.runpp, grid2op/Backend/pandaPowerBackend.py:1097-1105) and a failed
+power flow ends the episode (pPB:1241-1255), so a status may only say DIVERGED when the pivoting solver says so too.
+* `b200pf_set_debug(planned_div_mod)` makes the planned kernel give up on chosen instances: the pivoting re-solve inside the
+  same C-ABI call must hand back the oracle's result for them (every entry point: host records, series, rows, N-1,
+  protections).
+* stress: >= 20 000 random states per grid (bus splits, outages, +-20 % injections, islanded and diverging cases) on six
+  grids, planned kernel vs the fp64 pivoting oracle: status classes identical, iteration counts within +1.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import env_grid
+
+from grid2op_b200.gridmodel import GridModel
+from oracle.c_oracle import COracle
+from test_c_oracle import random_cases
+from test_engine_random_gpu import _compare
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def fast_random_cases(gm, n, seed, p_sub=0.6, p_disc=0.02, jitter=0.2, stress_share=0.1):
+    """Vectorised random states: up to two substations per instance get a random busbar assignment, a few lines are out,
+    injections move by +-jitter; a share of the instances is additionally loaded x1.5 .. x4 (near / beyond collapse)."""
+    rng = np.random.default_rng(seed)
+    topo = np.tile(gm.default_topo(), (n, 1))
+    inj = np.tile(gm.default_inj(), (n, 1))
+    sub_of = np.zeros(gm.dim_topo, dtype=np.int64)
+    sub_of[gm.line_or_pos] = gm.line_or_sub; sub_of[gm.line_ex_pos] = gm.line_ex_sub
+    sub_of[gm.gen_pos] = gm.gen_sub; sub_of[gm.load_pos] = gm.load_sub
+    if gm.n_storage:
+        sub_of[gm.storage_pos] = gm.storage_sub
+    for _ in range(2):
+        s = rng.integers(0, gm.n_sub, n)
+        act = rng.random(n) < p_sub
+        bits = rng.random((n, gm.dim_topo)) < 0.5
+        m = (sub_of[None, :] == s[:, None]) & act[:, None] & bits & (topo[:, :gm.dim_topo] > 0)
+        topo[:, :gm.dim_topo][m] = 2
+    out = rng.random((n, gm.n_line)) < p_disc
+    ii, ll = np.nonzero(out)
+    topo[ii, np.asarray(gm.line_or_pos)[ll]] = -1
+    topo[ii, np.asarray(gm.line_ex_pos)[ll]] = -1
+    sl = gm.inj_slices()
+    for k, m in (("load_p", gm.n_load), ("load_q", gm.n_load), ("gen_p", gm.n_gen)):
+        inj[:, sl[k]] *= rng.uniform(1.0 - jitter, 1.0 + jitter, (n, m))
+    heavy = rng.random(n) < stress_share
+    f = rng.uniform(1.5, 4.0, n)
+    for k in ("load_p", "load_q", "gen_p"):
+        inj[heavy, sl[k]] *= f[heavy, None]
+    topo[0] = gm.default_topo(); inj[0] = gm.default_inj()
+    return topo, inj
+
+
+GRIDS6 = ["rte_case5_example", "l2rpn_case14_sandbox", "educ_case14_storage", "l2rpn_2019", "l2rpn_neurips_2020_track1",
+          "l2rpn_wcci_2022_dev"]
+
+
+@pytest.mark.parametrize("name", GRIDS6)
+def test_stress_planned_kernel_vs_pivoting_oracle(cuda_required, name):
+    from grid2op_b200.engine import PowerFlowEngine
+    path = env_grid(name)
+    if path is None:
+        pytest.skip("reference grid files not available")
+    gm = GridModel(path)
+    n_total, chunk = 20480, 4096
+    eng = PowerFlowEngine(gm, max_batch=chunk)
+    eng.set_kernel_policy(2)
+    orc = COracle(gm)
+    n_conv = n_div = n_isl = 0
+    worst_it = 0
+    for c in range(n_total // chunk):
+        topo, inj = fast_random_cases(gm, chunk, seed=1000 + c)
+        out, status, iters, _ = eng.run(topo, inj)
+        assert eng.plan_stats()["last_kernel"] == "planned_sparse"
+        ref, rstatus, riters, _ = orc.run(topo, inj)
+        assert np.array_equal(status, rstatus), np.flatnonzero(status != rstatus)[:10]
+        ok = status == 0
+        assert np.isnan(out[~ok]).all()
+        _compare(gm, out, ref, ok)
+        d = iters[ok] - riters[ok]
+        assert d.min() >= 0 and d.max() <= 1, (d.min(), d.max())
+        worst_it = max(worst_it, int(d.max()))
+        n_conv += int(ok.sum()); n_div += int((status == 1).sum()); n_isl += int((status >= 2).sum())
+    assert n_conv >= n_total // 4 and n_div > 0 and n_isl > 0, (n_conv, n_div, n_isl)
+    assert eng.redo_launch_count > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name,n", [("rte_case5_example", 128), ("l2rpn_case14_sandbox", 384), ("l2rpn_neurips_2020_track1", 128),
+                                    ("l2rpn_wcci_2022_dev", 64)])
+def test_forced_breakdowns_are_resolved_by_the_pivoting_kernel(cuda_required, name, n):
+    from grid2op_b200.engine import PowerFlowEngine
+    path = env_grid(name)
+    if path is None:
+        pytest.skip("reference grid files not available")
+    gm = GridModel(path)
+    topo, inj = random_cases(gm, n, seed=5)
+    ref, rstatus, riters, _ = COracle(gm).run(topo, inj)
+    eng = PowerFlowEngine(gm, max_batch=n)
+    eng.set_kernel_policy(2)
+    # the knob works: without the safety net every third solvable instance ends as DIVERGED
+    eng.set_debug(3, redo_enabled=False)
+    out0, st0, _, _ = eng.run(topo, inj)
+    forced = (np.arange(n) % 3 == 0) & (rstatus < 2)
+    assert (st0[forced] == 1).all() and np.array_equal(st0[~forced], rstatus[~forced])
+    # with it, statuses and results are the oracle's; the re-solved instances take exactly the oracle's iterations (fp64 Jacobian
+    # with pivoting where the workspace holds it), the others at most one more
+    eng.set_debug(3, redo_enabled=True)
+    out, status, iters, busv = eng.run(topo, inj, want_busv=True)
+    assert np.array_equal(status, rstatus)
+    ok = status == 0
+    _compare(gm, out, ref, ok)
+    d = iters[ok] - riters[ok]
+    assert d.min() >= 0 and d.max() <= 1
+    assert np.isfinite(busv[ok]).any(axis=1).all()
+    # and the plain run (no forced failures) agrees with it to solver tolerance
+    eng.set_debug(0, redo_enabled=True)
+    out2, status2, _, _ = eng.run(topo, inj)
+    assert np.array_equal(status2, status)
+    _compare(gm, out, out2, ok)
+    eng.close()
+
+
+def test_forced_breakdowns_in_series_rows_and_n1_modes(cuda_required):
+    from grid2op_b200.engine import PowerFlowEngine
+    from grid2op_b200.rollout import BatchedDoNothing
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"]
+    B = 200
+    ref = BatchedDoNothing(gm, chron, B)
+    env = BatchedDoNothing(gm, chron, B)
+    env.engine.set_debug(2, True)
+    for k in range(4):
+        ref.step_device(); env.step_device()
+        o1, s1, i1, r1 = ref.fetch()
+        o2, s2, i2, r2 = env.fetch()
+        assert (s1 == 0).all() and (s2 == 0).all()            # the row of a re-solved instance is NOT advanced twice
+        _compare(gm, o2, o1, s1 == 0)
+        assert np.allclose(r1, r2, rtol=1e-5, atol=1e-6)
+        assert np.array_equal(o1[1::2], o2[1::2])              # untouched instances: same kernel, bit-equal
+    assert env.engine.redo_launch_count >= 4
+    # host rows path (pipelined chunks) and the group path with zero-copy inputs
+    for _ in range(2):
+        ref.step_device()
+        o1, s1, _, _ = ref.fetch()
+        o2, s2 = env.step_host()
+        assert (s2 == 0).all()
+        _compare(gm, o2.copy(), o1, s1 == 0)
+    ref.close(); env.close()
+    # N-1 sweep
+    z = np.load(os.path.join(GOLD, "oracle_case14_steps.npz"))
+    topo, inj = z["topo"][:8], z["inj"][:8]
+    eng = PowerFlowEngine(gm, max_batch=8 * gm.n_line)
+    eng.set_kernel_policy(2)
+    rho0, st0 = eng.n1_sweep(topo, inj)
+    eng.set_debug(3, True)
+    rho1, st1 = eng.n1_sweep(topo, inj)
+    assert np.array_equal(st0, st1)
+    ok = st0 == 0
+    assert np.allclose(rho0[ok], rho1[ok], rtol=2e-5, atol=1e-6)
+    eng.close()
+
+
+def test_forced_breakdowns_with_protections_replay_the_recording(cuda_required):
+    """Planned kernel + host re-planning of tripped lines + forced failures on every second instance: the recorded
+    rte_case5_example rollouts (PandaPowerBackend, protections on) must still be reproduced step by step."""
+    import json
+    from conftest import grid2op_root
+    root = grid2op_root()
+    stat = os.path.join(root, "data", "rte_case5_example", "_statistics") if root else None
+    if stat is None or not os.path.isdir(stat):
+        pytest.skip("reference rollouts not available")
+    from grid2op_b200.engine import OutputView
+    from grid2op_b200.rollout import BatchedDoNothing
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_rte_case5_example.npz"))
+    chron = np.load(os.path.join(GOLD, "case5_chronics.npz"))["chron"]
+    meta = json.load(open(os.path.join(stat, "metadata.json")))
+    gold = {k: np.load(os.path.join(stat, f"obs_{k}.npz"))["data"] for k in ("a_or", "p_or", "timestep_overflow", "line_status")}
+    sid = np.load(os.path.join(stat, "scenario_ids.npz"))["data"].ravel().astype(int)
+    rows = {s: np.flatnonzero(sid == s) for s in range(20)}
+    nb_step = np.array([meta[str(s)]["nb_step"] for s in range(20)])
+    B = 20
+    env = BatchedDoNothing(gm, chron, B, scen=np.arange(B), t0=np.zeros(B), protections=True)
+    env.engine.set_kernel_policy(2)
+    env.engine.set_debug(2, True)
+    first_done = np.full(B, -1)
+    K = 400
+    for k in range(K):
+        env.reset_step() if k == 0 else env.step_device()
+        out, status, iters, rho = env.fetch()
+        st = env.fetch_state()
+        v = OutputView(gm, out)
+        for s in range(B):
+            if st["done"][s] and first_done[s] < 0:
+                first_done[s] = k
+            if k >= nb_step[s] - 1:
+                continue
+            assert status[s] == 0, (s, k, status[s])
+            r = rows[s][k]
+            assert np.max(np.abs(v.a_or[s].astype(np.float64) - gold["a_or"][r])) <= 2e-3, (s, k)
+            assert np.max(np.abs(v.p_or[s].astype(np.float64) - gold["p_or"][r])) <= 1e-4, (s, k)
+            assert np.array_equal(st["timestep_overflow"][s], gold["timestep_overflow"][r]), (s, k)
+    for s in range(B):
+        if nb_step[s] <= K:
+            assert first_done[s] == nb_step[s] - 1, (s, first_done[s], nb_step[s])
+    assert env.engine.redo_launch_count > 0
+    env.close()
