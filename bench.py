@@ -3,13 +3,20 @@
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle's C restatement on the host cores
+    python bench.py --workload wcci --gpus N ...             # BASELINE.json configs[4]: 118 substations, batch 8192 in total
 
-Workload at N=1 (BASELINE.json configs[1]): l2rpn_case14_sandbox, AC Newton-Raphson, batch 4096 per
-GPU, DoNothing rollout over the bundled chronics (instance i -> scenario i mod 3, start row (i*37) mod
-576), NO_OVERFLOW_DISCONNECTION like the reference's own profiling script.  A "step" is
-one pass of the hot path over the whole batch = batch env.step() calls.  N>1: weak scaling (4096 per
-GPU), no data-path collective inside the solve, one NCCL gather of rho per step to rank 0
-(asynchronous, overlapped with the next step's solve).
+Workload `case14` (default; BASELINE.json configs[1], the configuration the metric is quoted on): l2rpn_case14_sandbox, AC
+Newton-Raphson, batch 4096 per GPU (weak scaling), DoNothing rollout over the bundled chronics (instance i -> scenario i mod 3,
+start row (i*37) mod 576), NO_OVERFLOW_DISCONNECTION like the reference's own profiling script.
+Workload `wcci` (configs[4]): l2rpn_wcci_2022 (= grid2op/data/l2rpn_wcci_2022_dev, 118 substations), AC, batch 8192 IN TOTAL
+sharded over the N GPUs (strong scaling), DoNothing over the bundled 289-row scenario.
+A "step" is one pass of the hot path over the whole batch = batch env.step() calls.
+
+N > 1: independent instances, no collective inside the solve.  The step results every rank owes the agent's rank (rho, 4 bytes
+per line and instance) are stored BY THE KERNEL ITSELF into rank 0's HBM through a peer mapping over NVLink (CUDA IPC,
+include/b200pf.h "Multi-GPU result collection"): no collective launch per 60-microsecond step.  NCCL carries the set-up, the
+arrival signal every --gather-every steps (one 4-byte all-reduce) and the timing reduction; `--collect nccl` selects the plain
+alternative (device ring + one NCCL gather every --gather-every steps), also the fallback when peer mapping is unavailable.
 
 One JSON line on stdout (rank 0).  Keys documented in DESIGN.md section "Measurement".
 """
@@ -30,24 +37,37 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 GOLD = os.path.join(REPO, "tests", "golden")
 
-METRIC = "env.step()/sec at batch on l2rpn_case14 AC"
 UNIT = "env.step()/s"
+WORKLOADS = {
+    "case14": dict(metric="env.step()/sec at batch on l2rpn_case14 AC", env="l2rpn_case14_sandbox",
+                   grid="gridmodel_l2rpn_case14_sandbox.npz", chron="case14_sandbox_chronics.npz", batch_per_gpu=4096,
+                   total_batch=None, scaling="weak"),
+    "wcci": dict(metric="env.step()/sec at batch on l2rpn_wcci_2022 AC", env="l2rpn_wcci_2022 (l2rpn_wcci_2022_dev, 118 substations)",
+                 grid="gridmodel_l2rpn_wcci_2022_dev.npz", chron="wcci_2022_dev_chronics.npz", batch_per_gpu=None,
+                 total_batch=8192, scaling="strong"),
+}
 
 
-def load_workload():
+def load_workload(name="case14"):
     from grid2op_b200.gridmodel import GridModel
-    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
-    chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"]
+    w = WORKLOADS[name]
+    gm = GridModel.from_npz(os.path.join(GOLD, w["grid"]))
+    chron = np.load(os.path.join(GOLD, w["chron"]))["chron"]
     return gm, chron
+
+
+def nr_dimension(gm):
+    n_ref = 1
+    n_pv = int(len(set(int(x) for x in gm.gen_sub))) - n_ref
+    return n_pv + 2 * (gm.n_sub - n_pv - n_ref)
 
 
 def flops_view(gm, mean_iters, batch, kern_s, clocks):
     """SURVEY.md 8(d), second view: dense-LU flops per instance-iteration (2/3 d^3 + 2 d^2, d = NR dimension with all
     elements on busbar 1) against the fp32 CUDA-core peak at the SM clock sampled during the run (148 SMs x 128 FMA
-    lanes x 2; the solve is 22x22 per instance, not tensor-core shaped, so MEASURED_PEAKS' bf16 figure does not apply)."""
-    n_ref = 1
-    n_pv = int(len(set(int(x) for x in gm.gen_sub))) - n_ref
-    d = n_pv + 2 * (gm.n_sub - n_pv - n_ref)
+    lanes x 2; the per-instance systems are far too small and sparse for tensor cores, so MEASURED_PEAKS' bf16 figure
+    does not apply).  The planned kernels do the SPARSE factorisation, i.e. far fewer flops than this view credits."""
+    d = nr_dimension(gm)
     fl = (2.0 / 3.0) * d ** 3 + 2.0 * d ** 2
     ach = batch * fl * mean_iters / kern_s / 1e12
     mhz = (clocks or {}).get("sm_mhz") or 1965
@@ -77,6 +97,26 @@ def algorithmic_bytes(gm, mean_iters):
     survey = b_iter * mean_iters + result
     compulsory = 4 * (2 * gm.n_load + 2 * gm.n_gen) + gm.n_topo_in + 8 + 4 * gm.n_out + 4 * gm.n_line + 8
     return float(survey), float(compulsory), int(b_iter)
+
+
+def profiled_traffic(kernel_tag):
+    """dram bytes per launch of the dominant kernel from the newest committed `ncu --set full` summary whose kernel tag equals
+    the kernel this run launched; None when no such profile exists (a stale number is worse than none)."""
+    pdir = os.path.join(REPO, "profiles")
+    best = None
+    try:
+        for fn in sorted(os.listdir(pdir)):
+            if not (fn.endswith("_summary.json") and "ncu" in fn):
+                continue
+            try:
+                d = json.load(open(os.path.join(pdir, fn)))
+            except Exception:
+                continue
+            if d.get("kernel_tag") == kernel_tag and d.get("dram_bytes_per_launch") is not None:
+                best = (d["dram_bytes_per_launch"], fn)
+    except OSError:
+        pass
+    return best
 
 
 class ClockSampler(threading.Thread):
@@ -115,29 +155,115 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rate(gm, chron, n_inst, seconds_budget=12.0, nthreads=0):
-    """Times oracle/pf_oracle.c (OpenMP over instances) on chronics rows of the same workload."""
-    from oracle.c_oracle import COracle
-    from grid2op_b200.rollout import instance_schedule
-    orc = COracle(gm, nthreads=nthreads)
-    scen, t0 = instance_schedule(n_inst, chron.shape[0], chron.shape[1])
-    sl = gm.inj_slices()
-    nl, ng = gm.n_load, gm.n_gen
-    topo = np.tile(gm.default_topo(), (n_inst, 1))
-    inj = np.tile(gm.default_inj(), (n_inst, 1))
-    done, t_used, k = 0, 0.0, 0
-    orc.run(topo[:256], inj[:256])   # warm-up (thread pool, page faults)
-    while t_used < seconds_budget:
-        rows = chron[scen, (t0 + k) % chron.shape[1]]
-        inj[:, sl["load_p"]] = rows[:, :nl]; inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
-        inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
-        inj[:, sl["gen_vm"]] = rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def host_cpu_info():
+    """logical CPUs this process may run on, physical cores among them, and the cgroup CPU quota (None = unlimited)"""
+    try:
+        aff = sorted(os.sched_getaffinity(0))
+    except Exception:
+        aff = list(range(os.cpu_count() or 1))
+    cores = set()
+    try:
+        phys, core, proc = None, None, None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("processor"):
+                proc = int(line.split(":")[1])
+            elif line.startswith("physical id"):
+                phys = int(line.split(":")[1])
+            elif line.startswith("core id"):
+                core = int(line.split(":")[1])
+            elif not line.strip():
+                if proc in aff and core is not None:
+                    cores.add((phys, core))
+                phys = core = proc = None
+    except Exception:
+        pass
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    return {"logical": len(aff), "physical": len(cores) or len(aff), "cgroup_quota_cpus": quota}
+
+
+def _pin_openmp():
+    # must happen before libgomp is loaded (the first COracle): threads stay on their cores, spin instead of sleeping
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    os.environ.pop("OMP_NUM_THREADS", None)           # torchrun exports OMP_NUM_THREADS=1; the arm sets its count explicitly
+
+
+class CpuArm:
+    """oracle/pf_oracle.c (fp64 dense Newton, OpenMP over instances) stepping the same DoNothing workload."""
+
+    def __init__(self, gm, chron, n_inst):
+        from oracle.c_oracle import COracle
+        from grid2op_b200.rollout import instance_schedule
+        self.COracle = COracle
+        self.gm, self.chron, self.n = gm, chron, n_inst
+        self.scen, self.t0 = instance_schedule(n_inst, chron.shape[0], chron.shape[1])
+        self.sl = gm.inj_slices()
+        self.topo = np.tile(gm.default_topo(), (n_inst, 1))
+        self.inj = np.tile(gm.default_inj(), (n_inst, 1))
+        self.info = host_cpu_info()
+        self.orc = None
+        self.nthreads = 0
+
+    def _fill(self, k):
+        gm, sl, nl, ng = self.gm, self.sl, self.gm.n_load, self.gm.n_gen
+        rows = self.chron[self.scen, (self.t0 + k) % self.chron.shape[1]]
+        self.inj[:, sl["load_p"]] = rows[:, :nl]; self.inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
+        self.inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
+        self.inj[:, sl["gen_vm"]] = rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]
+
+    def calibrate(self):
+        """thread count: logical CPUs, physical cores, the cgroup quota - whichever steps the batch fastest (>= 0.3 s each)"""
+        info = self.info
+        cands = {info["logical"], info["physical"]}
+        if info["cgroup_quota_cpus"]:
+            cands.add(max(1, int(round(info["cgroup_quota_cpus"]))))
+        best = None
+        self._fill(0)
+        for nt in sorted(c for c in cands if c >= 1):
+            o = self.COracle(self.gm, nthreads=nt)
+            o.run(self.topo, self.inj)
+            t, reps = time.perf_counter(), 0
+            while time.perf_counter() - t < 0.3:
+                o.run(self.topo, self.inj); reps += 1
+            rate = reps * self.n / (time.perf_counter() - t)
+            if best is None or rate > best[0]:
+                best = (rate, nt, o)
+        self.orc, self.nthreads = best[2], best[1]
+
+    def step(self, k):
+        self._fill(k)
         t = time.perf_counter()
-        out, status, iters, _ = orc.run(topo, inj)
-        t_used += time.perf_counter() - t
+        out, status, iters, _ = self.orc.run(self.topo, self.inj)
+        dt = time.perf_counter() - t
         assert (status == 0).all()
-        done += n_inst; k += 1
-    return done / t_used, orc.max_threads if nthreads <= 0 else nthreads, done, t_used
+        return dt
+
+    def sample(self, min_steps, min_seconds, warmup=2):
+        """-> per-step solver times (the host-side row gather is not counted, like the GPU arm's resident inputs)"""
+        if self.orc is None:
+            self.calibrate()
+        for k in range(warmup):
+            self.step(k)
+        ts, k = [], warmup
+        while len(ts) < min_steps or sum(ts) < min_seconds:
+            ts.append(self.step(k)); k += 1
+        return np.array(ts)
+
+    def describe(self, ts):
+        info = self.info
+        return (f"{len(ts)} steps x {self.n} instances in {ts.sum():.1f} s, oracle/pf_oracle.c (fp64 dense Newton), OpenMP x{self.nthreads} "
+                f"pinned (host: {info['logical']} logical / {info['physical']} physical CPUs"
+                + (f", cgroup quota {info['cgroup_quota_cpus']:.1f}" if info["cgroup_quota_cpus"] else "") + ")")
 
 
 def run_reference(args):
@@ -147,52 +273,56 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    gm, chron = load_workload()
-    batch = args.batch
-    from oracle.c_oracle import COracle
-    from grid2op_b200.rollout import instance_schedule
-    scen, t0 = instance_schedule(batch, chron.shape[0], chron.shape[1])
-    sl = gm.inj_slices(); nl, ng = gm.n_load, gm.n_gen
-    topo = np.tile(gm.default_topo(), (batch, 1)); inj = np.tile(gm.default_inj(), (batch, 1))
-    # "all the host threads it can use": try the logical and the physical core count, keep the faster
-    ncpu = os.cpu_count() or 1
-    best = None
-    for nt in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
-        o = COracle(gm, nthreads=nt)
-        o.run(topo, inj)
-        t = time.perf_counter(); o.run(topo, inj); dt_ = time.perf_counter() - t
-        if best is None or dt_ < best[0]:
-            best = (dt_, nt, o)
-    orc = best[2]
-    n_threads = best[1]
-
-    def step(k):
-        rows = chron[scen, (t0 + k) % chron.shape[1]]
-        inj[:, sl["load_p"]] = rows[:, :nl]; inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
-        inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
-        inj[:, sl["gen_vm"]] = rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]
-        out, status, iters, _ = orc.run(topo, inj)
-        return status
-
-    for k in range(args.warmup):
-        step(k)
-    t = time.perf_counter()
-    for k in range(args.steps):
-        st = step(args.warmup + k)
-    dt = time.perf_counter() - t
-    value = batch * args.steps / dt
+    _pin_openmp()
+    w = WORKLOADS[args.workload]
+    gm, chron = load_workload(args.workload)
+    batch = args.batch or (w["batch_per_gpu"] or w["total_batch"])
+    arm = CpuArm(gm, chron, batch)
+    ts = arm.sample(args.steps, max(2.0, args.cpu_min_seconds), warmup=max(args.warmup, 1))
+    rates = batch / ts
+    value = float(np.median(rates))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic (bundled l2rpn_case14_sandbox chronics rows replayed, DoNothing)",
-        "config": {"workload": f"l2rpn_case14_sandbox AC Newton-Raphson, batch {batch}, DoNothing rollout, host CPU",
-                   "batch_per_step": batch},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {batch} instances (whole batch per step), oracle/pf_oracle.c, OpenMP x{n_threads}"},
+        "impl": "reference", "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": int(len(ts)),
+        "warmup": max(args.warmup, 1), "ms_per_step": float(1e3 * np.median(ts)), "higher_is_better": True, "scaling": w["scaling"],
+        "vs_baseline": None, "dtype": "f64", "data": f"synthetic (bundled {w['env']} chronics rows replayed, DoNothing)",
+        "config": {"workload": f"{w['env']} AC Newton-Raphson, batch {batch}, DoNothing rollout, host CPU", "batch_per_step": batch,
+                   "requested_steps": args.steps,
+                   "note": "value = median over the steps of batch / step time; the arm runs at least 2 s whatever --steps says"},
+        "spread": {"min": float(rates.min()), "median": value, "max": float(rates.max()), "unit": UNIT, "n": int(len(ts))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.nthreads, "kind": "port", "sample": arm.describe(ts),
+                         "host": arm.info},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def parity_sample(gm, chron, env, out, status, n_series_steps, n_sample=256):
+    """Self-check of the timed path: the result records of the LAST timed step, for a sample of instances, against the
+    fp64 oracle (C restatement) on the same chronics rows.  -> dict; max_err_pu in p.u. (flows / sn_mva, voltages / vn)."""
+    from oracle.c_oracle import COracle
+    from grid2op_b200.engine import OutputView
+    B = env.batch
+    idx = np.unique(np.linspace(0, B - 1, min(n_sample, B)).astype(np.int64))
+    rows = chron[env.scen[idx], (env.t0[idx].astype(np.int64) + n_series_steps - 1) % chron.shape[1]]
+    sl, nl, ng = gm.inj_slices(), gm.n_load, gm.n_gen
+    inj = np.tile(gm.default_inj(), (len(idx), 1))
+    inj[:, sl["load_p"]] = rows[:, :nl]; inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
+    inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
+    inj[:, sl["gen_vm"]] = (rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]).astype(np.float32)
+    ref, rstatus, _, _ = COracle(gm).run(np.tile(gm.default_topo(), (len(idx), 1)), inj)
+    a, b = OutputView(gm, out[idx]), OutputView(gm, ref)
+    err = 0.0
+    for k in ("p_or", "q_or", "p_ex", "q_ex", "unit_p", "unit_q"):
+        err = max(err, float(np.max(np.abs(getattr(a, k).astype(np.float64) - getattr(b, k)))) / gm.sn_mva)
+    for k, vn in (("v_or", gm.line_or_vn), ("v_ex", gm.line_ex_vn), ("load_v", gm.load_vn)):
+        err = max(err, float(np.max(np.abs(getattr(a, k).astype(np.float64) - getattr(b, k)) / vn)))
+    same_status = bool(np.array_equal(status[idx], rstatus))
+    return {"instances": int(len(idx)), "max_err_pu": err, "tolerance_pu": 1e-4, "status_equal": same_status,
+            "ok": bool(err < 1e-4 and same_status), "against": "oracle/pf_oracle.c (fp64, partial pivoting) on the same chronics rows"}
 
 
 def run_ours(args):
@@ -206,52 +336,104 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from grid2op_b200.engine import PeerBuffer
     from grid2op_b200.rollout import BatchedDoNothing
     os.environ["B200PF_PLAN_POLICY"] = str(args.policy)
-    gm, chron = load_workload()
-    batch = args.batch
+    if args.no_redo:
+        os.environ["B200PF_NO_REDO"] = "1"
+    w = WORKLOADS[args.workload]
+    gm, chron = load_workload(args.workload)
+    if args.batch:
+        batch = args.batch
+    elif w["batch_per_gpu"]:
+        batch = w["batch_per_gpu"]
+    else:
+        batch = w["total_batch"] // world
     env = BatchedDoNothing(gm, chron, batch, device=local, offset=rank * batch)
     eng = env.engine
     stream = torch.cuda.Stream()            # a real (non-default) stream shared by torch events and the engine
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
-    # results land in torch tensors (so NCCL can gather them); rho is double-buffered so that the gather of
-    # step k (NCCL stream) overlaps the solve of step k+1 (compute stream)
-    rho_bufs = [torch.empty((batch, gm.n_line), dtype=torch.float32, device="cuda") for _ in range(2)]
     status = torch.empty((batch,), dtype=torch.int32, device="cuda")
     iters = torch.empty((batch,), dtype=torch.int32, device="cuda")
-    gather_lists = [[torch.empty_like(rho_bufs[0]) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    nl = gm.n_line
+    K = max(1, args.gather_every)
+    slot_elems = batch * nl
+    # ---- where rho goes: a ring of 2K step slots per rank inside ONE buffer in rank 0's HBM ------------------------------
+    # (two halves of K slots: while the kernels fill one half the agent owns the other)
+    collect = args.collect if world > 1 else "local"
+    peer, ring_local, gather_lists = None, None, None
+    ring_bytes = world * 2 * K * slot_elems * 4
+    if collect == "p2p":
+        ok = 1
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        try:
+            if rank == 0:
+                peer = PeerBuffer(ring_bytes)
+                handle.copy_(torch.frombuffer(bytearray(peer.handle), dtype=torch.uint8))
+        except Exception as exc:      # noqa: BLE001
+            ok = 0
+            print(f"bench.py: peer buffer export failed on rank 0: {exc}", file=sys.stderr)
+        dist.broadcast(handle, src=0)
+        if rank != 0 and ok:
+            try:
+                peer = PeerBuffer(handle=bytes(handle.cpu().numpy().tobytes()))
+            except Exception as exc:  # noqa: BLE001
+                ok = 0
+                print(f"bench.py: rank {rank} could not map rank 0's buffer: {exc}", file=sys.stderr)
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if peer is not None:
+                peer.close(); peer = None
+            collect = "nccl"
+    if collect in ("nccl", "local"):
+        ring_local = torch.zeros((2 * K, batch, nl), dtype=torch.float32, device="cuda")
+        if collect == "nccl" and rank == 0:
+            gather_lists = [[torch.empty((K, batch, nl), dtype=torch.float32, device="cuda") for _ in range(world)] for _ in range(2)]
+    signal = torch.zeros(1, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-    state = {"k": 0, "pending": None}
+    state = {"k": 0, "works": []}
+
+    def rho_ptr(slot):
+        if peer is not None:
+            return peer.ptr + 4 * ((rank * 2 * K + slot) * slot_elems)
+        return ring_local[slot].data_ptr()
 
     def one_step():
         k = state["k"]
-        buf = rho_bufs[k % 2]
-        eng.series_bind_outputs(0, status.data_ptr(), iters.data_ptr(), buf.data_ptr())
+        slot = k % (2 * K)
+        eng.series_bind_outputs(0, status.data_ptr(), iters.data_ptr(), rho_ptr(slot))
         env.step_device()
-        if world > 1:
-            if state["pending"] is not None:
-                state["pending"].wait()                 # gather of step k-1 overlapped this step's kernel
-            state["pending"] = dist.gather(buf, gather_lists[k % 2], dst=0, async_op=True)
+        if world > 1 and (k + 1) % K == 0:
+            half = slot // K
+            if collect == "p2p":
+                # arrival signal: once it completes on rank 0, every rank's kernels of this half have finished, i.e. their
+                # stores sit in rank 0's HBM
+                state["works"].append(dist.all_reduce(signal, async_op=True))
+            else:
+                state["works"].append(dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None,
+                                                  dst=0, async_op=True))
+            while len(state["works"]) > 1:          # keep one in flight: the other half of the ring is being filled meanwhile
+                state["works"].pop(0).wait()
         state["k"] = k + 1
 
     def drain():
-        if state["pending"] is not None:
-            state["pending"].wait()
-            state["pending"] = None
+        while state["works"]:
+            state["works"].pop(0).wait()
 
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
         one_step()
     drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches0 = eng.launch_count
+    launches0 = eng.launch_count + eng.redo_launch_count
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    iter_sum = 0.0
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for a, b in evs:
@@ -261,15 +443,17 @@ def run_ours(args):
         b.record()
     tail_a, tail_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tail_a.record()
-    drain()                                 # the last gather is timed too
+    drain()                                 # outstanding arrival signals / gathers are timed too
     tail_b.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
-    launches = eng.launch_count - launches0
-    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs)) + float(tail_a.elapsed_time(tail_b))
+    launches = eng.launch_count + eng.redo_launch_count - launches0
+    step_ms = np.array([a.elapsed_time(b) for a, b in evs], dtype=np.float64)
+    tail_ms = float(tail_a.elapsed_time(tail_b))
+    dev_ms = float(step_ms.sum()) + tail_ms
     n_bad = int((status != 0).sum().item())
     mean_iters = float(iters.float().mean().item())
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -277,6 +461,33 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
     value = world * batch * args.steps / (dev_ms_max * 1e-3)
+    n_series_steps = n_warm + args.steps
+
+    # ---- self-checks of what was just timed -----------------------------------------------------------------------------
+    out_h, status_h, iters_h, rho_h = eng.series_fetch()      # rho_h is read back from wherever the kernel stored it (rank 0's HBM)
+    from grid2op_b200.engine import OutputView
+    a_or = OutputView(gm, out_h).a_or
+    collected_ok = bool(np.allclose(rho_h, a_or / gm.thermal_limit_a[None, :].astype(np.float32), rtol=1e-6, atol=0, equal_nan=True))
+    parity = parity_sample(gm, chron, env, out_h, status_h, n_series_steps) if rank == 0 else None
+    if world > 1:
+        flag = torch.tensor([1 if collected_ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        collected_ok = bool(int(flag.item()))
+    if world > 1:
+        # rank 0 compares what sits in ITS memory (slices written by the other ranks' kernels, or gathered by NCCL) with the
+        # checksum every rank computes from its own result records
+        mine = torch.tensor([float(np.nansum(rho_h.astype(np.float64)))], dtype=torch.float64, device="cuda")
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            last = (state["k"] - 1) % (2 * K)
+            for r in range(world):
+                if peer is not None:
+                    got = peer.read(4 * ((r * 2 * K + last) * slot_elems), slot_elems)
+                else:
+                    got = gather_lists[last // K][r][last % K].cpu().numpy().ravel()
+                if not np.isclose(float(np.nansum(got.astype(np.float64))), float(sums[r].item()), rtol=1e-9):
+                    collected_ok = False
 
     # ---- end to end through host buffers (C-ABI staged call), every rank, max over ranks ----------
     eng.set_stream(0)
@@ -333,49 +544,56 @@ def run_ours(args):
             + (", chronics rows read by the kernel straight from pinned host memory (no copy-engine H2D)" if fl & 2 else "") \
             + (", status/iteration counts stored by the kernel into pinned host memory" if fl & 4 else "")
     h2d, d2h = env.bytes_per_step_host()
-    if eng.plan_stats()["last_kernel"] == "planned_sparse":
-        h2d -= batch * gm.n_topo_in            # the planned kernel works from the cached topology plan: no topology records cross PCIe
+    kstats = eng.plan_stats()
+    if kstats["last_kernel"].startswith("planned"):
+        h2d -= batch * gm.n_topo_in            # the planned kernels work from the cached topology plan: no topology records cross PCIe
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         surv, comp, b_iter = algorithmic_bytes(gm, mean_iters)
-        kern_s = dev_ms * 1e-3 / args.steps                     # one launch per step (N=1: the event pair brackets only it)
+        kern_s = float(np.mean(step_ms)) * 1e-3                  # the event pair of a step brackets its launch(es) only
         achieved = batch * surv / kern_s / 1e9
-        traffic = None
-        summ = os.path.join(REPO, "profiles", "round1_ncu_planned_case14_summary.json")
-        if os.path.exists(summ):
-            try:
-                traffic = json.load(open(summ)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        cpu_rate, cores, cpu_n, cpu_t = (None, None, 0, 0.0)
+        info = eng.last_launch_info()
+        kernel_tag = f"{kstats['last_kernel']}:{args.workload}:T{info['threads_per_instance']}"
+        prof = profiled_traffic(kernel_tag)
         cpu = None
         if world == 1 and not args.no_cpu:
-            cpu_rate, cores, cpu_n, cpu_t = cpu_port_rate(gm, chron, 8192, seconds_budget=args.cpu_seconds)
-            cpu = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cpu_n} instance-steps of the same workload in {cpu_t:.1f} s, oracle/pf_oracle.c (fp64 dense Newton), OpenMP"}
-        info = eng.last_launch_info()
+            arm = CpuArm(gm, chron, 8192)
+            ts = arm.sample(3, args.cpu_seconds)
+            cpu = {"value": float(np.median(8192 / ts)), "unit": UNIT, "cores": arm.nthreads, "kind": "port", "sample": arm.describe(ts),
+                   "spread": {"min": float((8192 / ts).min()), "max": float((8192 / ts).max())}}
+        rate = world * batch / (step_ms * 1e-3)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic (bundled l2rpn_case14_sandbox chronics rows replayed, DoNothing)",
-            "config": {"workload": f"l2rpn_case14_sandbox AC Newton-Raphson, batch {batch} envs per GPU, DoNothing rollout",
+            "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": f"synthetic (bundled {w['env']} chronics rows replayed, DoNothing)",
+            "config": {"workload": f"{w['env']} AC Newton-Raphson, batch {batch} envs per GPU, DoNothing rollout",
                        "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world} (independent instances)",
                        "l2": "flushed between timed steps (256 MiB memset, outside the event pair)",
-                       "precision": "fp64 state/mismatch/flows, fp32 Jacobian+LU, tol 1e-8 MVA, max_iter 10",
-                       "launch": info, "kernel": eng.plan_stats(), "mean_newton_iterations": mean_iters, "diverged": n_bad,
+                       "precision": "fp64 state/mismatch/flows, fp32 Jacobian+LU, tol 1e-8 MVA, max_iter 10; pivoting fp64 re-solve of "
+                                    "whatever the planned kernel leaves unsolved" + (" (OFF in this run)" if args.no_redo else ""),
+                       "launch": info, "kernel": kstats, "kernel_tag": kernel_tag, "mean_newton_iterations": mean_iters, "diverged": n_bad,
+                       "result_collection": {"local": "single GPU: rho stays in this GPU's HBM",
+                                             "p2p": f"kernels store rho straight into rank 0's HBM (CUDA IPC peer mapping over NVLink), "
+                                                    f"one 4-byte NCCL all-reduce as arrival signal every {K} steps",
+                                             "nccl": f"device ring, one NCCL gather to rank 0 every {K} steps"}[collect],
+                       "collected_equals_results": collected_ok,
                        "wall_s_incl_flush": t_wall},
+            "spread": {"unit": UNIT, "min": float(rate.min()), "median": float(np.median(rate)), "max": float(rate.max()),
+                       "tail_ms": tail_ms, "what": "per-step CUDA-event times of rank 0, as whole-job rates"},
+            "parity_check": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mode": e2e_mode, "lockstep_value": e2e_sync,
-                    "what": "BatchedDoNothing host path (group_launch/group_wait; lockstep_value = step_host()): per step H2D of the topology records + chronics rows (from pinned host memory, "
+                    "what": "BatchedDoNothing host path (group_launch/group_wait; lockstep_value = step_host()): per step H2D of the chronics rows (from pinned host memory, "
                             + ("pre-collated step-major" if collated else "gathered on the host per step")
                             + "), kernel, D2H of the full result records, host reads the done flags of every instance before "
                               "launching its next step; `value`: the batch is stepped as staggered groups (asynchronous "
-                              "vectorised envs), `lockstep_value`: all instances wait for each other every step (2 pipelined chunks)"},
+                              "vectorised envs), `lockstep_value`: all instances wait for each other every step (2 pipelined chunks).  "
+                              "DoNothing only: no action crosses the boundary in the timed region (topology plans are cached)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": prof[0] if prof else None, "traffic_source": prof[1] if prof else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": surv, "b_iter_bytes": b_iter,
                          "compulsory_bytes_per_env_step": comp,
                          "achieved_compulsory_gbs": batch * comp / kern_s / 1e9,
@@ -385,7 +603,16 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["ok"]:
+            print(f"bench.py: PARITY CHECK FAILED: {parity}", file=sys.stderr)
+            env.close()
+            raise SystemExit(3)
+        if not collected_ok:
+            print("bench.py: collected rho differs from the result records", file=sys.stderr)
+            raise SystemExit(4)
     env.close()
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -394,17 +621,22 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--workload", default="case14", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-direct", type=int, default=6,
                     help="group flags (include/b200pf.h): 1 kernels store results straight into pinned host memory, 2 kernels read "
                          "the chronics rows straight from pinned host memory, 4 status / iteration counts stored straight into pinned host memory")
     ap.add_argument("--e2e-groups", type=int, default=4, help="groups in flight for the end-to-end host path (<=1: lockstep only)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="length of the in-run cpu_baseline sample (N=1)")
+    ap.add_argument("--cpu-min-seconds", type=float, default=4.0, help="--impl reference: run at least this long whatever --steps")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-redo", action="store_true", help="measurement only: planned kernel without its pivoting safety net")
+    ap.add_argument("--gather-every", type=int, default=16, help="N>1: steps per arrival signal / gather")
+    ap.add_argument("--collect", default="p2p", choices=["p2p", "nccl"], help="N>1: how rho reaches rank 0")
     ap.add_argument("--policy", type=int, default=0, choices=[0, 1, 2],
-                    help="kernel policy (include/b200pf.h): 0 auto = planned sparse kernel, 1 pivoting kernels only, 2 planned always")
+                    help="kernel policy (include/b200pf.h): 0 auto = planned kernel, 1 pivoting kernels only, 2 planned always")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1190,6 +1190,45 @@ extern "C" int b200pf_plan_stats(const b200pf_handle *h, int64_t *n_plans, int64
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// multi-GPU result collection without a collective launch: peer-mapped device memory (CUDA IPC over NVLink)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200pf_device_alloc(size_t bytes, void **d_ptr) {
+    if (!d_ptr) return fail(B200PF_E_ARG, "null pointer");
+    CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    CU(cudaMemset(*d_ptr, 0, bytes ? bytes : 1));
+    return 0;
+}
+extern "C" int b200pf_device_free(void *d_ptr) {
+    if (d_ptr) CU(cudaFree(d_ptr));
+    return 0;
+}
+extern "C" int b200pf_device_read(const void *d_src, void *host_dst, size_t bytes) {
+    if (!d_src || !host_dst) return fail(B200PF_E_ARG, "null pointer");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int b200pf_ipc_export(const void *d_ptr, unsigned char *handle64) {
+    if (!d_ptr || !handle64) return fail(B200PF_E_ARG, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, const_cast<void *>(d_ptr)));
+    memcpy(handle64, &hd, 64);
+    return 0;
+}
+extern "C" int b200pf_ipc_open(const unsigned char *handle64, void **d_ptr) {
+    if (!d_ptr || !handle64) return fail(B200PF_E_ARG, "null pointer");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int b200pf_ipc_close(void *d_ptr) {
+    if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
 extern "C" int b200pf_set_debug(b200pf_handle *h, int planned_div_mod, int redo_enabled) {
     if (!h) return fail(B200PF_E_ARG, "null handle");
     h->dbg_div_mod = planned_div_mod > 0 ? planned_div_mod : 0;

@@ -13,7 +13,7 @@ import numpy as np
 
 from .gridmodel import GridModel
 
-__all__ = ["PowerFlowEngine", "EngineUnavailable", "lib_path", "load_library",
+__all__ = ["PowerFlowEngine", "PeerBuffer", "EngineUnavailable", "lib_path", "load_library",
            "ST_CONVERGED", "ST_DIVERGED", "ST_UNSUPPLIED", "ST_NO_REF", "ST_TOO_LARGE", "ABI_SYMBOLS"]
 
 ST_CONVERGED, ST_DIVERGED, ST_UNSUPPLIED, ST_NO_REF, ST_TOO_LARGE = 0, 1, 2, 3, 4
@@ -35,6 +35,7 @@ ABI_SYMBOLS = (
     "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free", "b200pf_rows_group_launch", "b200pf_rows_group_wait",
     "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats", "b200pf_run_device_topo",
     "b200pf_set_debug", "b200pf_redo_launch_count",
+    "b200pf_device_alloc", "b200pf_device_free", "b200pf_ipc_export", "b200pf_ipc_open", "b200pf_ipc_close", "b200pf_device_read",
 )
 
 
@@ -120,6 +121,15 @@ def load_library():
     lib.b200pf_set_kernel_policy.argtypes = [vp, i32]
     lib.b200pf_plan_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]
     lib.b200pf_set_debug.argtypes = [vp, i32, i32]
+    lib.b200pf_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.b200pf_device_free.argtypes = [vp]
+    lib.b200pf_ipc_export.argtypes = [vp, vp]
+    lib.b200pf_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    lib.b200pf_ipc_close.argtypes = [vp]
+    lib.b200pf_device_read.argtypes = [vp, vp, C.c_size_t]
+    lib.b200pf_device_read.restype = i32
+    for nm in ("b200pf_set_debug", "b200pf_device_alloc", "b200pf_device_free", "b200pf_ipc_export", "b200pf_ipc_open", "b200pf_ipc_close"):
+        getattr(lib, nm).restype = i32
     lib.b200pf_redo_launch_count.argtypes = [vp]
     lib.b200pf_redo_launch_count.restype = C.c_int64
     for nm in ("b200pf_create", "b200pf_destroy", "b200pf_sizes", "b200pf_run_host", "b200pf_run_device",
@@ -133,6 +143,44 @@ def load_library():
         getattr(lib, nm).restype = i32
     _LIB = lib
     return lib
+
+
+class PeerBuffer:
+    """Device buffer of the agent's rank that the other ranks (one process per GPU) map over NVLink (CUDA IPC) and let their
+    kernels store results into directly (include/b200pf.h, "Multi-GPU result collection")."""
+
+    def __init__(self, nbytes: int = 0, handle: Optional[bytes] = None):
+        self.lib = load_library()
+        self.owner = handle is None
+        p = C.c_void_p()
+        if self.owner:
+            rc = self.lib.b200pf_device_alloc(C.c_size_t(int(nbytes)), C.byref(p))
+            if rc:
+                raise RuntimeError(f"b200pf_device_alloc failed: {self.lib.b200pf_last_error().decode()}")
+            buf = (C.c_ubyte * 64)()
+            rc = self.lib.b200pf_ipc_export(p, C.cast(buf, C.c_void_p))
+            if rc:
+                raise RuntimeError(f"b200pf_ipc_export failed: {self.lib.b200pf_last_error().decode()}")
+            self.handle = bytes(buf)
+        else:
+            buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+            rc = self.lib.b200pf_ipc_open(C.cast(buf, C.c_void_p), C.byref(p))
+            if rc:
+                raise RuntimeError(f"b200pf_ipc_open failed: {self.lib.b200pf_last_error().decode()}")
+            self.handle = bytes(handle)
+        self.ptr = int(p.value)
+
+    def read(self, offset_bytes: int, n_float32: int) -> np.ndarray:
+        out = np.empty(int(n_float32), dtype=np.float32)
+        rc = self.lib.b200pf_device_read(C.c_void_p(self.ptr + int(offset_bytes)), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes))
+        if rc:
+            raise RuntimeError(f"b200pf_device_read failed: {self.lib.b200pf_last_error().decode()}")
+        return out
+
+    def close(self):
+        if getattr(self, "ptr", 0):
+            (self.lib.b200pf_device_free if self.owner else self.lib.b200pf_ipc_close)(C.c_void_p(self.ptr))
+            self.ptr = 0
 
 
 def _ptr(a: Optional[np.ndarray]):

@@ -245,6 +245,19 @@ int b200pf_set_kernel_policy(b200pf_handle *h, int policy);
 /* number of cached plans, their bytes, and the kernel of the last launch (1 warp/pivoting, 2 CTA/pivoting, 3 planned sparse) */
 int b200pf_plan_stats(const b200pf_handle *h, int64_t *n_plans, int64_t *plan_bytes, int *last_kernel);
 
+/* Multi-GPU result collection (instances shard across GPUs, the step results go to the agent's rank).  Instead
+ * of one collective launch per 60-microsecond step, the agent's rank allocates the result buffer with b200pf_device_alloc
+ * and exports it (CUDA IPC); every other rank (one process per GPU) opens the handle — the buffer is then peer-mapped over
+ * NVLink — and binds a slice of it as its `rho` output (b200pf_series_bind_outputs): the kernel's own result stores land in
+ * the agent's HBM, fused with the solve, no extra launch.  Completion is signalled by whatever orders the streams (a tiny
+ * NCCL all-reduce every K steps in bench.py).  handle64: 64 bytes (cudaIpcMemHandle_t). */
+int b200pf_device_alloc(size_t bytes, void **d_ptr);
+int b200pf_device_free(void *d_ptr);
+int b200pf_device_read(const void *d_src, void *host_dst, size_t bytes);   /* synchronous D2H copy (checks) */
+int b200pf_ipc_export(const void *d_ptr, unsigned char *handle64);
+int b200pf_ipc_open(const unsigned char *handle64, void **d_ptr);
+int b200pf_ipc_close(void *d_ptr);
+
 /* Safety net of the planned kernel.  The planned kernel eliminates without pivoting on an fp32 Jacobian; the reference's
  * solver (pp.runpp, pPB:1097-1105) pivots in fp64, and a failed power flow is a game over (pPB:1241-1255,
  * grid2op/Environment/baseEnv.py:3523-3524).  Every planned launch is therefore followed, on the same stream and inside the
