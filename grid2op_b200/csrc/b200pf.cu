@@ -4,6 +4,7 @@
 #include "b200pf_kernel.cuh"
 #include "b200pf_small.cuh"
 #include "b200pf_sparse.cuh"
+#include "b200pf_block.cuh"
 #include "b200pf_redo.cuh"
 #include "../../include/b200pf.h"
 
@@ -80,6 +81,8 @@ struct b200pf_handle {
     int sparse_cta_cap = 0;                                 // > 0: resident CTAs per SM of the planned kernel are capped (rest of the SM's memory = L1); < 0: never
     int sparse_minb = 32;                                   // tuning: one-warp CTAs per SM the small-workspace variant is compiled for (32 or 28)
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
+    int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
+    int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0;
     int64_t launches = 0;
@@ -100,6 +103,8 @@ static int upload(b200pf_handle *h, const Tp *src, size_t n, const Tp **dst) {
     *dst = d;
     return 0;
 }
+
+static bool block_variant_exists(int T, int U);
 
 extern "C" const char *b200pf_last_error(void) { return g_err.c_str(); }
 extern "C" int b200pf_abi_version(void) { return B200PF_ABI_VERSION; }
@@ -225,6 +230,12 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         if (mb && atoi(mb) == 28) h->sparse_minb = 28;
         const char *capv = getenv("B200PF_SPARSE_CTAS");        // tuning: cap of resident CTAs per SM (planned kernel)
         if (capv) h->sparse_cta_cap = atoi(capv);
+        // block kernel: lanes per instance x operations per lane and row (B200PF_BLOCK=0: scalar planned kernel)
+        h->blk_T = g.n_line <= 32 ? 4 : (g.n_line <= 64 ? 8 : 32);
+        h->blk_U = g.n_line <= 64 ? 2 : 1;
+        const char *bk = getenv("B200PF_BLOCK"), *bt = getenv("B200PF_BLOCK_T"), *bu = getenv("B200PF_BLOCK_U");
+        if (bk && bk[0] == '0') h->blk = 0;
+        if (bt && bu && block_variant_exists(atoi(bt), atoi(bu))) { h->blk_T = atoi(bt); h->blk_U = atoi(bu); }
         const char *nr = getenv("B200PF_NO_REDO");              // measurement only: planned kernel without its safety net
         if (nr && nr[0] == '1') h->redo_enabled = 0;
         const char *var = getenv("B200PF_SPARSE_T");            // tuning: threads per instance of the planned kernel
@@ -334,6 +345,14 @@ struct PlanSel {
     int smem;
 };
 
+// plan builder of the handle's kernel family (scalar stream laid out for plan_T threads, or block stream for blk_T x blk_U)
+static PlanBuilder make_builder(const b200pf_handle *h, bool optimize_layout = false, int seed = 0) {
+    PlanBuilder pb(h->hg, h->plan_T, optimize_layout && !h->blk, seed);
+    if (h->blk) pb.block_mode(h->blk_T, h->blk_U);
+    return pb;
+}
+static inline int blk_G(const b200pf_handle *h) { return (h->blk && h->blk_T < 32) ? 32 / h->blk_T : 1; }
+
 // 64-bit hash of a topology row (8 bytes at a time)
 static inline uint64_t topo_hash(const int8_t *tv, size_t n) {
     uint64_t hsh = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
@@ -368,7 +387,7 @@ static int plan_insert(b200pf_handle *h, const int8_t *tv, uint64_t row_hash, in
     const size_t nt = (size_t)h->g.n_topo_in;
     const PlanHeader *H = reinterpret_cast<const PlanHeader *>(blob.data());
     if ((int)h->plan_off.size() >= PLAN_MAX || h->plan_blobs.size() + blob.size() > PLAN_MAX_BYTES || !PlanBuilder::fits(*H) ||
-        H->smem_bytes > h->max_smem_optin)
+        (long)H->smem_bytes * blk_G(h) > (long)h->max_smem_optin)
         return -1;      // the caller falls back to the pivoting kernels
     const uint64_t key = plan_key(row_hash, outage);
     auto it = h->plan_index.find(key);
@@ -457,9 +476,10 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
         // topology is part of the step latency; not for bulk builds)
         const bool searched = miss.size() <= 32 && (size_t)n_src * per >= 256;
         const int n_seeds = h->g.n_slot <= 128 ? 12 : 4;
-        const PlanBuilder pb(h->hg, h->plan_T);
+        const PlanBuilder pb = make_builder(h);
         auto build_one = [&](size_t m) {
-            blobs[m] = searched ? build_plan_searched(h->hg, h->plan_T, miss[m].tv, miss[m].outage, n_seeds) : pb.build(miss[m].tv, miss[m].outage);
+            blobs[m] = searched ? build_plan_searched(h->hg, h->plan_T, miss[m].tv, miss[m].outage, n_seeds, h->blk ? h->blk_T : 0, h->blk_U)
+                                : pb.build(miss[m].tv, miss[m].outage);
         };
         unsigned nthr = std::thread::hardware_concurrency();
         if (nthr > 16) nthr = 16;
@@ -537,7 +557,9 @@ static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &se
 // planned kernel: one warp per instance for the 5/14/36-substation grids, with as many one-warp CTAs per SM as the
 // workspace allows (up to the hardware's 32); two warps per instance for the large grids (118 substations, ~22 KB of
 // workspace per instance limit an SM to ~10 instances: the second warp doubles the warps in flight).
+static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel);
 static int launch_sparse(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
+    if (h->blk) return launch_block(h, a, sel);
     const int per_sm = h->max_smem_optin / (sel.smem + 1024);
     if (a.prot) {     // protections: one launch per cascade round, see series_step_planned_prot
         if (h->plan_T == 128) return launch_sparse_t<128, 4, true>(h, a, sel, 14);
@@ -629,6 +651,70 @@ static int launch_redo(b200pf_handle *h, RunArgs a, int nb_cap_req) {
         case 256: return launch_redo_t<256, float>(h, a);
         default: return launch_redo_t<512, float>(h, a);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-planned kernel (b200pf_block.cuh)
+// ------------------------------------------------------------------------------------------------
+template <int T, int U, int MINB, bool PROT>
+static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
+    const DevGrid &g = h->g;
+    constexpr int G = T < 32 ? 32 / T : 1;
+    constexpr int BLOCK = T < 32 ? 32 : T;
+    auto kern = pf_kernel_block<T, U, MINB, PROT>;
+    const int smem = sel.smem * G;                       // workspace of one warp / CTA
+    const int variant = 1000 + T * 16 + U * 2 + (PROT ? 1 : 0);
+    if (h->sparse_occ_smem != smem || h->sparse_occ_variant != variant) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        int occ = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, (size_t)smem));
+        if (occ < 1) occ = 1;
+        int cap = h->sparse_cta_cap;
+        if (cap == 0 && G == 1 && smem >= 16 * 1024) cap = (164 * 1024) / (smem + 1024);   // large workspaces: leave ~90 KB of L1 for the plan arrays
+        if (cap > 0 && occ > cap) {
+            occ = cap;
+            int pct = (int)(((size_t)occ * (size_t)(smem + 1024) * 100 + (size_t)h->max_smem_optin - 1) / (size_t)h->max_smem_optin);
+            if (pct > 100) pct = 100;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
+        h->sparse_occ = occ; h->sparse_occ_smem = smem; h->sparse_occ_variant = variant;
+    }
+    PlanArgs pa;
+    pa.blobs = h->d_plan_blobs;
+    pa.plan_off = h->d_plan_off + (sel.d_inst_plan ? 0 : sel.single);
+    pa.inst_plan = sel.d_inst_plan;
+    const int n_grp = (a.batch + G - 1) / G;
+    const int resident = h->sm_count * h->sparse_occ;
+    const int rounds = (n_grp + resident - 1) / resident;
+    int grid = (n_grp + rounds - 1) / rounds;
+    if (grid < 1) grid = 1;
+    kern<<<grid, BLOCK, (size_t)smem, h->stream>>>(g, a, pa);
+    CU(cudaGetLastError());
+    h->launches++;
+    h->last_smem = smem; h->last_T = T; h->last_grid = grid; h->last_block = BLOCK; h->last_kernel = 4;
+    return 0;
+}
+
+#define B200PF_BLOCK_VARIANTS(X) X(2, 4) X(4, 1) X(4, 2) X(4, 4) X(8, 1) X(8, 2) X(16, 1) X(16, 2) X(32, 1) X(32, 2) X(64, 1)
+static bool block_variant_exists(int T, int U) {
+#define X(t, u) if (T == t && U == u) return true;
+    B200PF_BLOCK_VARIANTS(X)
+#undef X
+    return false;
+}
+
+static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
+    const int T = h->blk_T, U = h->blk_U;
+    if (a.prot) {
+#define X(t, u) if (T == t && U == u) return launch_block_t<t, u, (t <= 32 ? 8 : 4), true>(h, a, sel);
+        B200PF_BLOCK_VARIANTS(X)
+#undef X
+    } else {
+#define X(t, u) if (T == t && U == u) return launch_block_t<t, u, (t <= 32 ? 8 : 4), false>(h, a, sel);
+        B200PF_BLOCK_VARIANTS(X)
+#undef X
+    }
+    return fail(B200PF_E_ARG, "no block kernel variant for this (lanes, operations per lane) pair");
 }
 
 static int launch(b200pf_handle *h, RunArgs a, int nb_cap_req, const PlanSel *sel = nullptr) {
@@ -853,8 +939,7 @@ static int series_step_planned_prot(b200pf_handle *h, RunArgs a) {
             const uint64_t rh = topo_hash(row, nt);
             int id = plan_find(h, row, rh, -1);
             if (id < 0) {
-                PlanBuilder pb(h->hg, h->plan_T);
-                id = plan_insert(h, row, rh, -1, pb.build(row, -1));
+                id = plan_insert(h, row, rh, -1, make_builder(h).build(row, -1));
                 if (id < 0) return fail(B200PF_E_CAPACITY, "no plan for the topology after a line trip");
             }
             h->h_series_plan[inst] = id;

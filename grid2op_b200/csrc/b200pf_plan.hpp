@@ -81,7 +81,18 @@ struct PlanHeader {
     int o_shidx;           // u16 [nb]: index of the bus among the buses that carry a shunt (0xFFFF: none)
     int n_shb;
     int o_late, n_late;    // u16 pairs (line, round) of the lines of assembly rounds >= 1 (parallel lines), sorted by round
-    int pad[3];
+    // ---- BLOCK plans (b200pf_block.cuh): the Jacobian as 2x2 blocks per bus pair, values = float4 per block -------------
+    int blk;               // 0: scalar plan (b200pf_sparse.cuh), 1: block plan
+    int blk_T, blk_U, blk_G;   // lanes per instance, operations per lane and row, instances per warp the streams are laid out for
+    int nblk, nblkA;       // blocks of the filled pattern; nblkA = nblk + n1 (right-hand-side blocks); block nblkA = dummy
+    int n_brow, n_bpass;   // rows of blk_T * blk_U slots; passes
+    int o_bops;            // 8-byte slots {u16 d, a, b, flags}: BYTE offsets (16 * blk_G * block index) into the value array;
+                           // flags bit 0: barrier after this row, bit 1: row type (0: D -= A B, 1: D = inv(A) D)
+    int o_bdpos;           // u16 [nb]: block index of the diagonal block of the bus (0xFFFF: reference bus)
+    int o_bjpos;           // u16 [n_line][2]: block (from,to) and (to,from) of the line (dummy when an end is a reference bus)
+    int o_bzero, n_bzero;  // u16 block indices cleared before every assembly (all off-diagonal blocks incl. fill)
+    int o_bpass_ptr;       // int32 [n_bpass + 1] slot range of every pass (validation)
+    int pad2[1];
 };
 static_assert(sizeof(PlanHeader) % 16 == 0, "plan blobs are concatenated 16-byte aligned");
 
@@ -100,6 +111,18 @@ inline int plan_smem_bytes(int nb, int n_line, int nA, int n_rowcol, int n_shunt
     return (int)((o + 15) & ~(size_t)15);
 }
 
+// per-INSTANCE workspace of the block kernel (a warp holds blk_G of them, element-interleaved)
+inline int plan_block_smem_bytes(int nb, int n_line, int nblkA, int n_rowcol, int n_shunt) {
+    size_t o = 0;
+    o += (size_t)(nblkA + 1) * 16;           // blocks + right-hand-side blocks + dummy
+    o += (size_t)6 * nb * 8;                 // vm va pspec qspec P Q
+    o += (size_t)2 * n_shunt * 8;            // shunt admittance (g, b) of the buses that carry one
+    o += (size_t)nb * 16;                    // V (e, f)
+    o += (size_t)2 * n_line * 16;            // branch currents, both ends
+    o += ((size_t)n_rowcol * 4 + 15) & ~(size_t)15;
+    return (int)((o + 15) & ~(size_t)15);
+}
+
 // takes the tripped lines (trip[l] != 0) out of a topology row: both ends disconnected, like
 // PandaPowerBackend._disconnect_line (reference pandaPowerBackend.py:1464-1475) / _BackendAction.update_state
 inline void apply_trips(const HostGrid &g, int8_t *topo_row, const int8_t *trip) {
@@ -113,6 +136,8 @@ public:
     // many solves: device-resident rollouts; not worth it when hundreds of plans are built for one call)
     explicit PlanBuilder(const HostGrid &g, int op_width = 32, bool optimize_layout = false, int order_seed = 0)
         : g_(g), op_width_(op_width), optimize_layout_(optimize_layout), order_seed_(order_seed) {}
+    // block plans: T lanes per instance, U operations per lane and row, G instances per warp (G = 32 / T for T < 32, else 1)
+    PlanBuilder &block_mode(int T, int U) { blk_ = 1; blk_T_ = T; blk_U_ = U < 1 ? 1 : U; blk_G_ = T < 32 ? 32 / T : 1; return *this; }
 
     // topo: int8 [n_topo_in]; outage: line forced out of service (N-1 sweep) or -1.  Returns the blob.
     std::vector<unsigned char> build(const int8_t *tv, int outage) const {
@@ -246,6 +271,16 @@ public:
             if (btype[i] == PLAN_BT_PQ) colv[i] = d++;
         }
         PLAN_TICK("ordering");
+        struct Op { uint16_t ij, ik, kj, kk; };
+        struct BOp { uint16_t d, a, b, fl; };
+        int n_oprow = 0, nnzF = 0, nA = 0, n_pass = 0, n_round = 0;
+        std::vector<Op> ops;
+        std::vector<int> pass_ptr(1, 0), round(nl, 0);
+        std::vector<uint16_t> dpos, jpos, zero;
+        int nblk = 0, nblkA = 0, n_brow = 0, n_bpass = 0;            // block plans
+        std::vector<BOp> bops;
+        std::vector<int> bdpos(nb, -1), bjpos((size_t)nl * 2, -1), bzero, bpass_ptr(1, 0);
+        if (!blk_) {
         // ---- scalar pattern of the Jacobian, symbolic LU --------------------------------------------
         std::vector<char> S((size_t)d * d, 0);
         auto setblk = [&](int i, int j) {   // rows of bus i, columns of bus j
@@ -270,9 +305,9 @@ public:
             }
         }
         std::vector<int> pos((size_t)d * d, -1);
-        int nnzF = 0;
+        nnzF = 0;
         for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) if (S[(size_t)i * d + j]) pos[(size_t)i * d + j] = nnzF++;
-        const int nA = nnzF + d;
+        nA = nnzF + d;
         const int DUMMY = nA;
         auto P = [&](int i, int j) -> int { return (i >= 0 && j >= 0) ? pos[(size_t)i * d + j] : -1; };
         PLAN_TICK("symbolic");
@@ -284,10 +319,6 @@ public:
         //      of the sequential algorithm) and after the last read of its target (WAR).  The number of passes is
         //      the depth of the dependency graph (about twice the height of the elimination tree), not the number
         //      of columns.  The solution is x_k = rhs_k / A[kk] (taken by the bus lanes in the state update).
-        struct Op { uint16_t ij, ik, kj, kk; };
-        int n_oprow = 0;
-        std::vector<Op> ops;
-        std::vector<int> pass_ptr(1, 0);
         {
             std::vector<Op> seq;
             seq.reserve((size_t)nnzF * 4 + 64);
@@ -375,10 +406,10 @@ public:
             n_oprow = (int)(ops.size() / (size_t)W);
             ops.insert(ops.end(), (size_t)W * 4, nop);      // guard block: the prefetch of "the block after the last" reads it, nothing executes it
         }
-        const int n_pass = (int)pass_ptr.size() - 1;
+        n_pass = (int)pass_ptr.size() - 1;
         PLAN_TICK("ops+schedule");
         // ---- assembly positions ------------------------------------------------------------------
-        std::vector<uint16_t> dpos((size_t)nb * 4, (uint16_t)DUMMY), jpos((size_t)nl * 8, (uint16_t)DUMMY);
+        dpos.assign((size_t)nb * 4, (uint16_t)DUMMY); jpos.assign((size_t)nl * 8, (uint16_t)DUMMY);
         std::vector<char> is_buslane(nA + 1, 0);
         for (int i = 0; i < nb; ++i) {
             const int r[2] = {colth[i], colv[i]};
@@ -388,8 +419,6 @@ public:
             }
         }
         for (int k = 0; k < d; ++k) is_buslane[nnzF + k] = 1;      // right-hand side: written by the bus lanes
-        std::vector<int> round(nl, 0);
-        int n_round = 0;
         {
             std::vector<std::vector<char>> used;   // per round: position used
             for (int l = 0; l < nl; ++l) {
@@ -415,9 +444,124 @@ public:
                 round[l] = r; n_round = std::max(n_round, r + 1);
             }
         }
-        std::vector<uint16_t> zero;
         for (int p = 0; p < nnzF; ++p) if (!is_buslane[p]) zero.push_back((uint16_t)p);
         PLAN_TICK("assembly pos");
+        } else {
+            // ---- BLOCK plan: the Jacobian as 2x2 blocks (rows P_i, Q_i x columns theta_j, |V|_j) per bus pair in elimination
+            //      order; a PV bus keeps its block shape with an identity Q row / a zero |V| column (b200pf_block.cuh), so every
+            //      block is a float4 and every operation of the factorisation a 2x2 product:
+            //        row k normalised     U'_kj = inv(A_kk) A_kj ,  r'_k = inv(A_kk) r_k                       (type 1)
+            //        rows below updated   A_ij -= A_ik U'_kj     ,  r_i -= A_ik r'_k                            (type 0)
+            //        back substitution    r'_i -= U'_ik x_k  (x_k = r'_k once all its updates are done)         (type 0)
+            //      list-scheduled into passes exactly like the scalar stream (RAW / WAW / WAR levels).  One block operation
+            //      replaces ~8 scalar ones at 3 vector loads + 1 vector store instead of 8 x (4 loads + 1 store).
+            std::vector<char> SBk((size_t)n1 * n1, 0);
+            for (int k = 0; k < n1; ++k) SBk[(size_t)k * n1 + k] = 1;
+            for (int l = 0; l < nl; ++l) {
+                const int f = brf[l], t = brt[l];
+                if (f < 0) continue;
+                const int cf = dcidx[f], ct = dcidx[t];
+                if (cf >= 0 && ct >= 0 && cf != ct) { SBk[(size_t)cf * n1 + ct] = 1; SBk[(size_t)ct * n1 + cf] = 1; }
+            }
+            std::vector<std::vector<int>> rowUb(n1);
+            {
+                std::vector<int> lst;
+                for (int k = 0; k < n1; ++k) {
+                    lst.clear();
+                    for (int j = k + 1; j < n1; ++j) if (SBk[(size_t)k * n1 + j]) lst.push_back(j);
+                    rowUb[k] = lst;
+                    for (int i : lst) { char *Si = &SBk[(size_t)i * n1]; for (int j : lst) Si[j] = 1; }
+                }
+            }
+            std::vector<int> bpos((size_t)n1 * n1, -1);
+            for (int i = 0; i < n1; ++i) for (int j = 0; j < n1; ++j) if (SBk[(size_t)i * n1 + j]) bpos[(size_t)i * n1 + j] = nblk++;
+            nblkA = nblk + n1;
+            const int BD = nblkA;
+            auto BP = [&](int r, int c) -> int { return bpos[(size_t)r * n1 + c]; };
+            struct SOp { int d, a, b, type; };
+            std::vector<SOp> seq;
+            seq.reserve((size_t)nblk * 6 + 64);
+            for (int k = 0; k < n1; ++k) {
+                const int kk = BP(k, k);
+                for (int j : rowUb[k]) seq.push_back({BP(k, j), kk, BD, 1});
+                seq.push_back({nblk + k, kk, BD, 1});
+                for (int i : rowUb[k]) {
+                    const int ik = BP(i, k);
+                    for (int j : rowUb[k]) seq.push_back({BP(i, j), ik, BP(k, j), 0});
+                    seq.push_back({nblk + i, ik, nblk + k, 0});
+                }
+            }
+            for (int k = n1 - 1; k >= 0; --k)
+                for (int i = k - 1; i >= 0; --i)
+                    if (SBk[(size_t)i * n1 + k]) seq.push_back({nblk + i, BP(i, k), nblk + k, 0});
+            std::vector<int> wlev(nblkA + 1, 0), rlev(nblkA + 1, 0), lev(seq.size(), 0);
+            int nlev = 0;
+            for (size_t q = 0; q < seq.size(); ++q) {
+                const SOp &o = seq[q];
+                int lv = std::max(std::max(wlev[o.a], wlev[o.d]), rlev[o.d]);
+                if (o.type == 0) lv = std::max(lv, wlev[o.b]);
+                lv += 1;
+                lev[q] = lv; nlev = std::max(nlev, lv);
+                wlev[o.d] = lv;
+                rlev[o.a] = std::max(rlev[o.a], lv);
+                if (o.type == 0) rlev[o.b] = std::max(rlev[o.b], lv);
+            }
+            const int W = blk_T_ * blk_U_;
+            const size_t osc = (size_t)16 * blk_G_;
+            auto emit = [&](int dd, int aa, int bb, int type) {
+                BOp r;
+                r.d = (uint16_t)((size_t)dd * osc); r.a = (uint16_t)((size_t)aa * osc); r.b = (uint16_t)((size_t)bb * osc);
+                r.fl = (uint16_t)(type ? 2 : 0);
+                bops.push_back(r);
+            };
+            {
+                std::vector<std::vector<int>> at(nlev + 1);
+                for (size_t q = 0; q < seq.size(); ++q) at[lev[q]].push_back((int)q);
+                for (int l = 1; l <= nlev; ++l) {
+                    for (int type = 1; type >= 0; --type) {
+                        std::vector<int> grp;
+                        for (int q : at[l]) if (seq[q].type == type) grp.push_back(q);
+                        if (grp.empty()) continue;
+                        std::sort(grp.begin(), grp.end(), [&](int x, int y) { return seq[x].d < seq[y].d; });
+                        for (int q : grp) emit(seq[q].d, seq[q].a, seq[q].b, type);
+                        while (bops.size() % (size_t)W) emit(BD, BD, BD, type);
+                    }
+                    for (size_t q = bops.size() - (size_t)W; q < bops.size(); ++q) bops[q].fl |= 1;     // barrier after the last row of the pass
+                    bpass_ptr.push_back((int)bops.size());
+                }
+            }
+            n_brow = (int)(bops.size() / (size_t)W);
+            n_bpass = (int)bpass_ptr.size() - 1;
+            for (int q = 0; q < W; ++q) emit(BD, BD, BD, 0);          // guard row: the prefetch of "the row after the last" reads it
+            // ---- assembly positions ------------------------------------------------------------------------
+            for (int i = 0; i < nb; ++i) if (dcidx[i] >= 0) bdpos[i] = BP(dcidx[i], dcidx[i]);
+            {
+                std::vector<std::vector<char>> used;
+                for (int l = 0; l < nl; ++l) {
+                    const int f = brf[l], t = brt[l];
+                    bjpos[(size_t)2 * l] = BD; bjpos[(size_t)2 * l + 1] = BD;
+                    if (f < 0) continue;
+                    const int cf = dcidx[f], ct = dcidx[t];
+                    if (cf >= 0 && ct >= 0) { bjpos[(size_t)2 * l] = BP(cf, ct); bjpos[(size_t)2 * l + 1] = BP(ct, cf); }
+                    // round 0 is added BEFORE the bus lanes assign the diagonal blocks: a line with both ends on one bus (it
+                    // adds into a diagonal block) must come later
+                    int r = (f == t) ? 1 : 0;
+                    for (;; ++r) {
+                        while (r >= (int)used.size()) used.emplace_back(nblkA + 1, 0);
+                        bool clash = false;
+                        for (int q = 0; q < 2; ++q) { const int p = bjpos[(size_t)2 * l + q]; if (p != BD && used[r][p]) clash = true; }
+                        if (!clash) break;
+                    }
+                    for (int q = 0; q < 2; ++q) { const int p = bjpos[(size_t)2 * l + q]; if (p != BD) used[r][p] = 1; }
+                    round[l] = r; n_round = std::max(n_round, r + 1);
+                }
+            }
+            {
+                std::vector<char> isdiag(nblk, 0);
+                for (int k = 0; k < n1; ++k) isdiag[BP(k, k)] = 1;
+                for (int p = 0; p < nblk; ++p) if (!isdiag[p]) bzero.push_back(p);
+            }
+        }
         // ---- static per-bus line data ------------------------------------------------------------------
         std::vector<double> ydiag((size_t)nb * 2, 0.0), dcshift(nb, 0.0);
         std::vector<std::vector<int>> adj(nb), bu(nb), bl(nb), bs(nb), bh(nb);
@@ -586,6 +730,11 @@ public:
         H.op_width = op_width_; H.n_oprow = n_oprow;
         H.n_zero = (int)zero.size();
         H.smem_bytes = plan_smem_bytes(nb, nl, nA, 2 * nld + 2 * g.n_gen, nsh);
+        if (blk_) {
+            H.blk = 1; H.blk_T = blk_T_; H.blk_U = blk_U_; H.blk_G = blk_G_; H.nblk = nblk; H.nblkA = nblkA; H.n_brow = n_brow;
+            H.n_bpass = n_bpass; H.n_bzero = (int)bzero.size();
+            H.smem_bytes = plan_block_smem_bytes(nb, nl, nblkA, 2 * nld + 2 * g.n_gen, nsh);
+        }
         std::vector<unsigned char> blob(sizeof(PlanHeader));
         blob.reserve(sizeof(PlanHeader) + (size_t)n1 * n1 * 8 + ops.size() * 8 + (size_t)nl * 32 + (size_t)nb * 96 + 4096);
         auto align = [&](size_t a) { while (blob.size() % a) blob.push_back(0); };
@@ -651,6 +800,13 @@ public:
             H.o_late = put_u16(late); H.n_late = (int)late.size() / 2;
         }
         H.o_zero = put_u16v(zero);
+        if (blk_) {
+            align(8);
+            H.o_bops = (int)blob.size();
+            blob.resize(blob.size() + bops.size() * sizeof(BOp));
+            if (!bops.empty()) memcpy(&blob[H.o_bops], bops.data(), bops.size() * sizeof(BOp));
+            H.o_bdpos = put_u16(bdpos); H.o_bjpos = put_u16(bjpos); H.o_bzero = put_u16(bzero); H.o_bpass_ptr = put_i32(bpass_ptr);
+        }
         PLAN_TICK("serialise");
         align(16);
         H.total_bytes = (int)blob.size();
@@ -659,29 +815,38 @@ public:
     }
 
     // the plan format addresses values and list entries with 16 bits
-    static bool fits(const PlanHeader &H) { return H.nA + 1 < 0x3FFF && H.n_op < (1 << 30); }
+    static bool fits(const PlanHeader &H) {
+        if (H.blk) return (size_t)(H.nblkA + 1) * 16 * (size_t)H.blk_G <= 0xFFFF && H.nb < 0xFFFF;
+        return H.nA + 1 < 0x3FFF && H.n_op < (1 << 30);
+    }
 
 private:
     const HostGrid &g_;
     int op_width_;
     bool optimize_layout_;
     int order_seed_;      // 0: deterministic tie-breaking of the elimination order; > 0: randomised ties (plan search)
+    int blk_ = 0, blk_T_ = 32, blk_U_ = 1, blk_G_ = 1;
 };
 
 // Plan for a topology that many solves will re-use (batched launches): the elimination order's ties are broken in
 // `n_seeds` different ways, the variant whose operation stream needs the fewest rows (then the fewest operations) wins —
 // case14: 29 -> 25 rows, 36 substations: 48 -> 43 — and gets the bank-conflict-aware layout.  Deterministic (fixed seeds).
-inline std::vector<unsigned char> build_plan_searched(const HostGrid &g, int op_width, const int8_t *tv, int outage, int n_seeds) {
+inline std::vector<unsigned char> build_plan_searched(const HostGrid &g, int op_width, const int8_t *tv, int outage, int n_seeds,
+                                                      int blk_T = 0, int blk_U = 1) {
     int best_seed = 0;
     long best_cost = -1;
     for (int seed = 0; seed < n_seeds; ++seed) {
-        const std::vector<unsigned char> blob = PlanBuilder(g, op_width, false, seed).build(tv, outage);
+        PlanBuilder pb(g, op_width, false, seed);
+        if (blk_T > 0) pb.block_mode(blk_T, blk_U);
+        const std::vector<unsigned char> blob = pb.build(tv, outage);
         const PlanHeader *H = reinterpret_cast<const PlanHeader *>(blob.data());
         if (H->status != PLAN_ST_OK) return blob;                       // nothing to optimise
-        const long cost = (long)H->n_oprow * 100000L + H->nnzF;
+        const long cost = blk_T > 0 ? (long)H->n_brow * 100000L + H->nblk : (long)H->n_oprow * 100000L + H->nnzF;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_seed = seed; }
     }
-    return PlanBuilder(g, op_width, true, best_seed).build(tv, outage);
+    PlanBuilder pb(g, op_width, blk_T <= 0, best_seed);
+    if (blk_T > 0) pb.block_mode(blk_T, blk_U);
+    return pb.build(tv, outage);
 }
 
 }  // namespace b200pf

@@ -528,7 +528,7 @@ class PowerFlowEngine:
     def plan_stats(self):
         n, b, k = C.c_int64(), C.c_int64(), C.c_int()
         self._check(self.lib.b200pf_plan_stats(self.h, C.byref(n), C.byref(b), C.byref(k)), "b200pf_plan_stats")
-        return dict(n_plans=n.value, plan_bytes=b.value, last_kernel={0: "none", 1: "warp_pivoting", 2: "cta_pivoting", 3: "planned_sparse"}[k.value])
+        return dict(n_plans=n.value, plan_bytes=b.value, last_kernel={0: "none", 1: "warp_pivoting", 2: "cta_pivoting", 3: "planned_sparse", 4: "planned_block"}[k.value])
 
     def view(self, out: np.ndarray) -> OutputView:
         return OutputView(self.gm, out)

@@ -3,6 +3,7 @@
 // plan builder and the kernel's numerics can be checked against the oracle on a machine without a GPU.
 #define B200PF_EMULATE 1
 #include "../../grid2op_b200/csrc/b200pf_sparse.cuh"
+#include "../../grid2op_b200/csrc/b200pf_block.cuh"
 #include "../../include/b200pf.h"
 
 #include <cstdlib>
@@ -276,4 +277,183 @@ extern "C" int sparse_emu_plan_rows(const b200pf_grid_desc *gd, const int8_t *to
     for (unsigned char b : blob) { c ^= b; c *= 1099511628211ull; }
     if (checksum) *checksum = c;
     return H->status == PLAN_ST_OK ? H->n_oprow : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// BLOCK-planned kernel (b200pf_block.cuh): host build, T lanes per instance, U operations per lane and row; the G = 32 / T
+// instances of a warp run one after the other on the same element-interleaved workspace (exactly the device layout).
+// ------------------------------------------------------------------------------------------------------------------
+static DevGrid dev_grid(const HostGrid &hg, const b200pf_grid_desc *gd) {
+    DevGrid g{};
+    g.n_sub = hg.n_sub; g.n_busbar = hg.n_busbar; g.n_slot = hg.n_slot; g.n_line = hg.n_line; g.n_gen = hg.n_gen; g.n_hidden = hg.n_hidden;
+    g.n_unit = hg.n_unit; g.n_load = hg.n_load; g.n_sto = hg.n_sto; g.n_shunt = hg.n_shunt; g.dim_topo = hg.dim_topo;
+    g.n_topo_in = hg.n_topo_in;
+    g.n_inj = g.n_gen + g.n_unit + 2 * g.n_load + g.n_sto + 2 * g.n_shunt;
+    g.n_out = 10 * g.n_line + 4 * g.n_unit + 2 * g.n_load + g.n_sto + 3 * g.n_shunt;
+    g.base_mva = hg.base_mva;
+    g.line_y = gd->line_y; g.line_bdc = gd->line_bdc; g.line_pshift = gd->line_pshift; g.line_or_vn = gd->line_or_vn; g.line_ex_vn = gd->line_ex_vn;
+    g.unit_is_ref = gd->unit_is_ref; g.unit_qmin = gd->unit_qmin; g.unit_qmax = gd->unit_qmax; g.unit_vn = gd->unit_vn;
+    g.load_vn = gd->load_vn; g.sto_vn = gd->storage_vn; g.sh_vn = gd->shunt_vn; g.sto_q = gd->storage_q; g.sh_vratio = gd->shunt_vratio;
+    return g;
+}
+
+template <int T, int U, bool PROT>
+static void block_group(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, const int *insts, int n, unsigned char *ws) {
+    constexpr int G = T < 32 ? 32 / T : 1;
+    for (int gi = 0; gi < n && gi < G; ++gi) solve_block<T, U, G, PROT>(g, a, pa, insts[gi], ws, gi, 0, 0u);
+}
+
+#define BLOCK_DISPATCH(PROT, ...)                                                              \
+    do {                                                                                       \
+        const int key = T * 16 + U;                                                            \
+        switch (key) {                                                                         \
+            case 1 * 16 + 1: block_group<1, 1, PROT>(__VA_ARGS__); break;                      \
+            case 1 * 16 + 4: block_group<1, 4, PROT>(__VA_ARGS__); break;                      \
+            case 2 * 16 + 2: block_group<2, 2, PROT>(__VA_ARGS__); break;                      \
+            case 2 * 16 + 4: block_group<2, 4, PROT>(__VA_ARGS__); break;                      \
+            case 4 * 16 + 1: block_group<4, 1, PROT>(__VA_ARGS__); break;                      \
+            case 4 * 16 + 2: block_group<4, 2, PROT>(__VA_ARGS__); break;                      \
+            case 8 * 16 + 1: block_group<8, 1, PROT>(__VA_ARGS__); break;                      \
+            case 8 * 16 + 2: block_group<8, 2, PROT>(__VA_ARGS__); break;                      \
+            case 16 * 16 + 1: block_group<16, 1, PROT>(__VA_ARGS__); break;                    \
+            case 32 * 16 + 1: block_group<32, 1, PROT>(__VA_ARGS__); break;                    \
+            case 32 * 16 + 2: block_group<32, 2, PROT>(__VA_ARGS__); break;                    \
+            case 64 * 16 + 1: block_group<64, 1, PROT>(__VA_ARGS__); break;                    \
+            default: return -2;                                                                \
+        }                                                                                      \
+    } while (0)
+
+extern "C" int block_emu_run(const b200pf_grid_desc *gd, int T, int U, int batch, const int8_t *topo, const double *inj, int is_dc, int max_iter,
+                             double tol_mva, float *out, int32_t *status, int32_t *iters, double *busv, int n1_lines,
+                             const float *th_lim, float *rho, int32_t *stats /* [8] of the last plan, may be NULL */) {
+    HostGrid hg = host_grid(gd);
+    PlanBuilder pb(hg, 32);
+    pb.block_mode(T, U);
+    const int G = T < 32 ? 32 / T : 1;
+    DevGrid g = dev_grid(hg, gd);
+    RunArgs a{};
+    a.batch = n1_lines > 0 ? batch * n1_lines : batch;
+    a.inj = inj; a.is_dc = is_dc; a.max_iter = max_iter; a.tol_pu = tol_mva / hg.base_mva; a.out = out; a.status = status; a.iters = iters;
+    a.busv = busv; a.n1_lines = n1_lines; a.th_lim = th_lim; a.rho = rho;
+    // plans of all instances (cache by topology + outage), then instance groups of G that share... nothing: every instance
+    // brings its own plan, as on the device (inst_plan)
+    std::map<std::string, int> index;
+    std::vector<unsigned char> blobs;
+    std::vector<int> plan_off, inst_plan(a.batch);
+    int max_smem = 16;
+    for (int inst = 0; inst < a.batch; ++inst) {
+        const int src = n1_lines > 0 ? inst / n1_lines : inst, outage = n1_lines > 0 ? inst % n1_lines : -1;
+        const int8_t *tv = topo + (size_t)src * hg.n_topo_in;
+        std::string key((const char *)tv, hg.n_topo_in);
+        key.push_back((char)(outage & 0xff)); key.push_back((char)((outage >> 8) & 0xff));
+        auto it = index.find(key);
+        if (it == index.end()) {
+            std::vector<unsigned char> blob = pb.build(tv, outage);
+            const PlanHeader *H = (const PlanHeader *)blob.data();
+            if (H->status == PLAN_ST_OK && !PlanBuilder::fits(*H)) return -3;
+            if (H->smem_bytes > max_smem) max_smem = H->smem_bytes;
+            if (stats) { stats[0] = H->nb; stats[1] = H->d; stats[2] = H->nblk; stats[3] = H->n_bpass; stats[4] = H->n_brow; stats[5] = H->blk_T * H->blk_U;
+                         stats[6] = H->smem_bytes; stats[7] = H->total_bytes; }
+            it = index.emplace(key, (int)plan_off.size()).first;
+            plan_off.push_back((int)blobs.size());
+            blobs.insert(blobs.end(), blob.begin(), blob.end());
+            while (blobs.size() % 16) blobs.push_back(0);
+        }
+        inst_plan[inst] = it->second;
+    }
+    PlanArgs pa{};
+    pa.blobs = blobs.data(); pa.plan_off = plan_off.data(); pa.inst_plan = inst_plan.data();
+    std::vector<double> ws((size_t)max_smem * G / 8 + 8);
+    std::vector<int> grp(G);
+    for (int first = 0; first < a.batch; first += G) {
+        const int n = std::min(G, a.batch - first);
+        for (int k = 0; k < n; ++k) grp[k] = first + k;
+        // poison the workspace: nothing may depend on what a previous group left behind
+        for (double &v : ws) v = __builtin_nan("");
+        BLOCK_DISPATCH(false, g, a, pa, grp.data(), n, (unsigned char *)ws.data());
+    }
+    return 0;
+}
+
+// Block plan checks: (1) inside a pass no slot writes a block another slot of the pass reads or writes, rows are
+// type-homogeneous, the barrier flag sits exactly on the last row of every pass; (2) executing the stream in fp64 on a random
+// block-diagonally-dominant matrix with the plan's pattern solves A x = b (against dense Gaussian elimination with pivoting).
+extern "C" int block_emu_validate_plan(const b200pf_grid_desc *gd, const int8_t *topo, int outage, int T, int U, double *max_err, int32_t *info) {
+    HostGrid hg = host_grid(gd);
+    PlanBuilder pb(hg, 32);
+    pb.block_mode(T, U);
+    std::vector<unsigned char> blob = pb.build(topo, outage);
+    const PlanHeader *H = (const PlanHeader *)blob.data();
+    if (H->status != PLAN_ST_OK) return -1;
+    const int W = H->blk_T * H->blk_U, nblk = H->nblk, nblkA = H->nblkA, n1 = H->n1, Gs = H->blk_G;
+    const uint16_t *ops = (const uint16_t *)(blob.data() + H->o_bops);
+    const int *pass_ptr = (const int *)(blob.data() + H->o_bpass_ptr);
+    if (info) { info[0] = nblk; info[1] = H->n_bpass; info[2] = H->n_brow; info[3] = H->smem_bytes; }
+    if (pass_ptr[H->n_bpass] != H->n_brow * W) return 1;
+    const int scale = 16 * Gs;
+    std::vector<int> wr(nblkA + 1), rd(nblkA + 1);
+    int n_real = 0;
+    for (int p = 0; p < H->n_bpass; ++p) {
+        std::fill(wr.begin(), wr.end(), 0); std::fill(rd.begin(), rd.end(), 0);
+        if ((pass_ptr[p + 1] - pass_ptr[p]) % W) return 2;
+        for (int o = pass_ptr[p]; o < pass_ptr[p + 1]; ++o) {
+            if (ops[4 * o] % scale || ops[4 * o + 1] % scale || ops[4 * o + 2] % scale) return 9;
+            const int dd = ops[4 * o] / scale, aa = ops[4 * o + 1] / scale, bb = ops[4 * o + 2] / scale, fl = ops[4 * o + 3];
+            const bool last_row = o >= pass_ptr[p + 1] - W;
+            if (((fl & 1) != 0) != last_row) return 3;
+            if ((fl & 2) != (ops[4 * (o - o % W) + 3] & 2)) return 10;      // row of one type
+            if (dd == nblkA) continue;                                      // padding slot
+            if (dd > nblkA || aa > nblkA || bb > nblkA) return 4;
+            ++n_real;
+            wr[dd]++; rd[aa]++; if (!(fl & 2)) rd[bb]++;
+        }
+        for (int q = 0; q < nblkA; ++q) { if (wr[q] > 1) return 5; if (wr[q] && rd[q]) return 6; }
+    }
+    if (info) info[4] = n_real;
+    // numeric check through the assembly positions
+    const uint16_t *bdpos = (const uint16_t *)(blob.data() + H->o_bdpos), *bjpos = (const uint16_t *)(blob.data() + H->o_bjpos);
+    const uint16_t *dcidx = (const uint16_t *)(blob.data() + H->o_dcidx), *brf = (const uint16_t *)(blob.data() + H->o_brf), *brt = (const uint16_t *)(blob.data() + H->o_brt);
+    std::vector<int> prow(nblk, -1), pcol(nblk, -1);
+    for (int i = 0; i < H->nb; ++i) if (bdpos[i] != 0xFFFF) { prow[bdpos[i]] = dcidx[i]; pcol[bdpos[i]] = dcidx[i]; }
+    for (int l = 0; l < hg.n_line; ++l) {
+        if (brf[l] == 0xFFFF) continue;
+        const int b0 = bjpos[2 * l], b1 = bjpos[2 * l + 1];
+        if (b0 != nblkA) { prow[b0] = dcidx[brf[l]]; pcol[b0] = dcidx[brt[l]]; }
+        if (b1 != nblkA) { prow[b1] = dcidx[brt[l]]; pcol[b1] = dcidx[brf[l]]; }
+    }
+    const int d = 2 * n1;
+    std::vector<double> A((size_t)(nblkA + 1) * 4, 0.0), M((size_t)d * d, 0.0), b(d), x(d);
+    unsigned seed = 4321u;
+    auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return (double)(seed >> 8) / (double)(1u << 24) - 0.5; };
+    for (int p = 0; p < nblk; ++p) {
+        if (prow[p] < 0) continue;                     // pure fill: starts at zero
+        for (int q = 0; q < 4; ++q) A[(size_t)p * 4 + q] = rnd();
+        if (prow[p] == pcol[p]) { A[(size_t)p * 4] += 8.0; A[(size_t)p * 4 + 3] += 8.0; }
+        for (int q = 0; q < 4; ++q) M[(size_t)(2 * prow[p] + q / 2) * d + 2 * pcol[p] + q % 2] = A[(size_t)p * 4 + q];
+    }
+    for (int k = 0; k < n1; ++k) { b[2 * k] = rnd(); b[2 * k + 1] = rnd(); A[(size_t)(nblk + k) * 4] = b[2 * k]; A[(size_t)(nblk + k) * 4 + 2] = b[2 * k + 1]; }
+    for (int o = 0; o < H->n_brow * W; ++o) {
+        const int dd = ops[4 * o] / scale, aa = ops[4 * o + 1] / scale, bb = ops[4 * o + 2] / scale, fl = ops[4 * o + 3];
+        if (dd == nblkA) continue;
+        double *D = &A[(size_t)dd * 4];
+        const double *P = &A[(size_t)aa * 4], *Q = &A[(size_t)bb * 4];
+        if (fl & 2) {
+            const double det = P[0] * P[3] - P[1] * P[2];
+            const double nx = (P[3] * D[0] - P[1] * D[2]) / det, ny = (P[3] * D[1] - P[1] * D[3]) / det;
+            const double nz = (P[0] * D[2] - P[2] * D[0]) / det, nw = (P[0] * D[3] - P[2] * D[1]) / det;
+            D[0] = nx; D[1] = ny; D[2] = nz; D[3] = nw;
+        } else {
+            const double d0 = P[0] * Q[0] + P[1] * Q[2], d1 = P[0] * Q[1] + P[1] * Q[3], d2 = P[2] * Q[0] + P[3] * Q[2], d3 = P[2] * Q[1] + P[3] * Q[3];
+            D[0] -= d0; D[1] -= d1; D[2] -= d2; D[3] -= d3;
+        }
+    }
+    double err = 0.0;
+    for (int k = 0; k < n1; ++k) { x[2 * k] = A[(size_t)(nblk + k) * 4]; x[2 * k + 1] = A[(size_t)(nblk + k) * 4 + 2]; }
+    for (int i = 0; i < d; ++i) {
+        double r = -b[i];
+        for (int j = 0; j < d; ++j) r += M[(size_t)i * d + j] * x[j];
+        if (fabs(r) > err) err = fabs(r);
+    }
+    if (max_err) *max_err = err;
+    return err < 1e-9 ? 0 : 8;
 }

@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libsparse_emu.so")
 
 def build(force: bool = False) -> str:
     src = os.path.join(HERE, "sparse_emu.cpp")
-    deps = [src, os.path.join(REPO, "grid2op_b200", "csrc", "b200pf_sparse.cuh"), os.path.join(REPO, "grid2op_b200", "csrc", "b200pf_plan.hpp")]
+    deps = [src] + [os.path.join(REPO, "grid2op_b200", "csrc", f) for f in ("b200pf_sparse.cuh", "b200pf_plan.hpp", "b200pf_block.cuh")]
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(p) for p in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", LIB, src, "-lm"])
     return LIB
@@ -55,6 +55,51 @@ class SparseEmu:
         if th_lim is not None:
             return out, status, iters, busv, rho
         return out, status, iters, busv
+
+
+class BlockEmu(SparseEmu):
+    """Host build of the BLOCK-planned kernel (csrc/b200pf_block.cuh) with T lanes per instance, U operations per lane and row."""
+
+    def __init__(self, gm, T=4, U=2):
+        super().__init__(gm)
+        self.T, self.U = int(T), int(U)
+        self.lib.block_emu_run.restype = C.c_int
+
+    def run(self, topo, inj, is_dc=False, max_iter=10, tol_mva=1e-8, nb_cap=0, want_busv=False, n1_lines=0, th_lim=None):
+        gm = self.gm
+        topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(-1, gm.n_topo_in)
+        inj = np.ascontiguousarray(inj, dtype=np.float64).reshape(-1, gm.n_inj)
+        B = topo.shape[0]
+        N = B * n1_lines if n1_lines > 0 else B
+        out = np.empty((N, gm.n_out), dtype=np.float32)
+        status = np.empty(N, dtype=np.int32)
+        iters = np.empty(N, dtype=np.int32)
+        busv = np.empty((N, 2 * gm.n_sub * gm.n_busbar), dtype=np.float64) if want_busv else None
+        rho = np.empty((N, gm.n_line), dtype=np.float32) if th_lim is not None else None
+        thl = np.ascontiguousarray(th_lim, dtype=np.float32) if th_lim is not None else None
+        vp = C.c_void_p
+        rc = self.lib.block_emu_run(C.byref(self.desc), C.c_int(self.T), C.c_int(self.U), C.c_int(B), topo.ctypes.data_as(vp),
+                                    inj.ctypes.data_as(vp), C.c_int(int(bool(is_dc))), C.c_int(int(max_iter)), C.c_double(float(tol_mva)),
+                                    out.ctypes.data_as(vp), status.ctypes.data_as(vp), iters.ctypes.data_as(vp),
+                                    busv.ctypes.data_as(vp) if busv is not None else None, C.c_int(int(n1_lines)),
+                                    thl.ctypes.data_as(vp) if thl is not None else None,
+                                    rho.ctypes.data_as(vp) if rho is not None else None, self.stats.ctypes.data_as(vp))
+        assert rc == 0, rc
+        if th_lim is not None:
+            return out, status, iters, busv, rho
+        return out, status, iters, busv
+
+
+def validate_block_plan(gm, topo_row, outage=-1, T=4, U=2):
+    """-> (return code of block_emu_validate_plan, residual, [nblk, passes, rows, smem bytes per instance, real operations])"""
+    emu = SparseEmu(gm)
+    err = C.c_double(0.0)
+    info = np.zeros(8, dtype=np.int32)
+    t = np.ascontiguousarray(topo_row, dtype=np.int8)
+    emu.lib.block_emu_validate_plan.restype = C.c_int
+    rc = emu.lib.block_emu_validate_plan(C.byref(emu.desc), t.ctypes.data_as(C.c_void_p), C.c_int(int(outage)), C.c_int(int(T)), C.c_int(int(U)),
+                                         C.byref(err), info.ctypes.data_as(C.c_void_p))
+    return int(rc), float(err.value), info[:5].tolist()
 
 
 def validate_plan(gm, topo_row, outage=-1, op_width=32):

@@ -25,7 +25,7 @@ def test_n1_sweep_matches_oracle(cuda_required, name, nbase, policy):
     eng = PowerFlowEngine(gm, max_batch=nbase * gm.n_line)
     eng.set_kernel_policy(policy)
     rho, status = eng.n1_sweep(topo, inj)
-    assert (eng.plan_stats()["last_kernel"] == "planned_sparse") == (policy == 2)
+    assert (eng.plan_stats()["last_kernel"].startswith("planned")) == (policy == 2)
     # oracle: explicit records with line i out of service
     t2 = np.repeat(topo, gm.n_line, axis=0)
     i2 = np.repeat(inj, gm.n_line, axis=0)

@@ -77,7 +77,7 @@ def test_stress_planned_kernel_vs_pivoting_oracle(cuda_required, name):
     for c in range(n_total // chunk):
         topo, inj = fast_random_cases(gm, chunk, seed=1000 + c)
         out, status, iters, _ = eng.run(topo, inj)
-        assert eng.plan_stats()["last_kernel"] == "planned_sparse"
+        assert eng.plan_stats()["last_kernel"].startswith("planned")
         ref, rstatus, riters, _ = orc.run(topo, inj)
         assert np.array_equal(status, rstatus), np.flatnonzero(status != rstatus)[:10]
         ok = status == 0
