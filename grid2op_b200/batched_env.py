@@ -1,0 +1,226 @@
+"""Batched ``env.step`` WITH actions: the driver next to :class:`grid2op_b200.rollout.BatchedDoNothing` for agents that
+act on the topology (BASELINE.json configs[2]: "random topology actions"), with the environment-side bookkeeping a
+topology agent depends on.
+
+What one :meth:`BatchedEnv.step` restates for a whole batch of independent environments (reference, per env —
+``BaseEnv.step`` grid2op/Environment/baseEnv.py:3778-3872 and what it calls), for the action subset
+{do nothing, set the busbars of ONE substation, set the status of ONE line} (``MAX_SUB_CHANGED = MAX_LINE_STATUS_CHANGED
+= 1``, grid2op/Parameters.py:279):
+
+1. legality — ``DefaultRules``: an action that touches a line whose ``times_before_line_status_actionable`` is > 0 or a
+   substation whose ``times_before_topology_actionable`` is > 0 is illegal and replaced by "do nothing"
+   (grid2op/Rules/PreventReconnection.py:33-60, baseEnv.py:3798-3820);
+2. ``_backend_action += action`` (baseEnv.py:3822-3846): busbars of the substation's elements, line disconnection
+   (both ends -1) / reconnection (each end back on its last busbar, grid2op/Action/_backendAction.py ``last_topo_registered``);
+3. the environment's own modifications of this step: next chronics row (gridStateFromFile.py:766-776), lines in
+   ``maintenance`` / ``hazards`` forced out (gridStateFromFile.py:780-797, baseAction ``maintenance`` / ``hazards`` keys);
+4. ``backend.next_grid_state`` — one batched power flow with the protections of backend.py:1433-1521 on the device;
+5. the cooldown bookkeeping of baseEnv.py:3352-3393: line cooldowns decrease, lines tripped by the protections get
+   ``NB_TIMESTEP_RECONNECTION``, maintenance / hazard durations are folded in (baseEnv.py:2566-2597), lines / substations
+   the (legal) action named get ``NB_TIMESTEP_COOLDOWN_LINE`` / ``NB_TIMESTEP_COOLDOWN_SUB``;
+6. game over when the power flow fails (baseEnv.py:3523-3524); a finished instance stays finished.
+
+The topology lives on the HOST (int8 [batch, n_topo_in]); a step that changed it hands the rows to
+``PowerFlowEngine.series_set_topo`` — cached plans are looked up by hash, new topologies are planned on the host threads
+(see DESIGN.md "config 3").  Everything numeric stays on the device as in :class:`BatchedDoNothing`.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from .gridmodel import GridModel
+from .rollout import BatchedDoNothing
+
+__all__ = ["BatchedEnv", "random_substation_actions"]
+
+
+class BatchedEnv(BatchedDoNothing):
+    def __init__(self, gm: GridModel, chron: np.ndarray, batch: int, *, maintenance: Optional[np.ndarray] = None,
+                 hazards: Optional[np.ndarray] = None, nb_timestep_cooldown_line: int = 0, nb_timestep_cooldown_sub: int = 0,
+                 nb_timestep_reconnection: int = 10, engine=None, **kw):
+        """``maintenance`` / ``hazards``: bool [n_scen, n_rows, n_line] (:func:`grid2op_b200.chronics.load_line_events` per
+        scenario), row-aligned with ``chron``.  Cooldown parameters: grid2op.Parameters NB_TIMESTEP_COOLDOWN_LINE /
+        NB_TIMESTEP_COOLDOWN_SUB / NB_TIMESTEP_RECONNECTION (Parameters.py:255-300)."""
+        super().__init__(gm, chron, batch, engine=engine, **kw)
+        B, nl = self.batch, gm.n_line
+        self.topo = self.topo0.copy()                                      # int8 [B, n_topo_in], -1 = disconnected
+        self.last_bus = np.where(self.topo[:, :gm.dim_topo] > 0, self.topo[:, :gm.dim_topo], 1).astype(np.int8)
+        self.line_cooldown = np.zeros((B, nl), dtype=np.int32)             # times_before_line_status_actionable
+        self.sub_cooldown = np.zeros((B, gm.n_sub), dtype=np.int32)        # times_before_topology_actionable
+        self.done = np.zeros(B, dtype=bool)
+        self.row = self.t0.astype(np.int64).copy()                         # chronics row the NEXT solve uses
+        self.cd_line, self.cd_sub, self.cd_reco = int(nb_timestep_cooldown_line), int(nb_timestep_cooldown_sub), int(nb_timestep_reconnection)
+        self._maint = self._maint_time = self._maint_dur = self._haz = self._haz_dur = None
+        if maintenance is not None:
+            from .chronics import maintenance_time_duration
+            self._maint = np.asarray(maintenance, dtype=bool)
+            td = [maintenance_time_duration(m) for m in self._maint]
+            self._maint_time = np.stack([x[0] for x in td]); self._maint_dur = np.stack([x[1] for x in td])
+        if hazards is not None:
+            from .chronics import hazard_duration
+            self._haz = np.asarray(hazards, dtype=bool)
+            self._haz_dur = np.stack([hazard_duration(h) for h in self._haz])
+        # element positions of every substation in the topology vector (grid2op order), padded
+        sub_of = np.full(gm.dim_topo, -1, dtype=np.int64)
+        sub_of[gm.line_or_pos] = gm.line_or_sub; sub_of[gm.line_ex_pos] = gm.line_ex_sub
+        sub_of[gm.gen_pos] = gm.gen_sub; sub_of[gm.load_pos] = gm.load_sub
+        if gm.n_storage:
+            sub_of[gm.storage_pos] = gm.storage_sub
+        self.sub_of_pos = sub_of
+        self.sub_size = np.bincount(sub_of, minlength=gm.n_sub)
+        self.max_sub_size = int(self.sub_size.max())
+        self.sub_pos = np.full((gm.n_sub, self.max_sub_size), -1, dtype=np.int64)
+        for s in range(gm.n_sub):
+            p = np.flatnonzero(sub_of == s)
+            self.sub_pos[s, :len(p)] = p
+        self.line_or_pos, self.line_ex_pos = np.asarray(gm.line_or_pos, dtype=np.int64), np.asarray(gm.line_ex_pos, dtype=np.int64)
+        self._topo_dirty = False
+        self.n_illegal = 0
+        self.n_steps = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def line_status(self) -> np.ndarray:
+        return (self.topo[:, self.line_or_pos] > 0) & (self.topo[:, self.line_ex_pos] > 0)
+
+    def _apply_agent(self, sub_id, sub_bus, line_id, line_status):
+        """-> (aff_lines bool [B, n_line], aff_subs bool [B, n_sub]) of the LEGAL actions, applied to self.topo"""
+        gm, B = self.gm, self.batch
+        aff_l = np.zeros((B, gm.n_line), dtype=bool)
+        aff_s = np.zeros((B, gm.n_sub), dtype=bool)
+        idx = np.arange(B)
+        has_sub = np.zeros(B, dtype=bool)
+        has_line = np.zeros(B, dtype=bool)
+        if sub_id is not None:
+            sub_id = np.asarray(sub_id, dtype=np.int64)
+            sub_bus = np.asarray(sub_bus, dtype=np.int8)
+            has_sub = (sub_id >= 0) & (np.abs(sub_bus) > 0).any(axis=1)
+        if line_id is not None:
+            line_id = np.asarray(line_id, dtype=np.int64)
+            line_status = np.asarray(line_status, dtype=np.int64)
+            has_line = (line_id >= 0) & (line_status != 0)
+        # legality (PreventReconnection on what the action names), finished instances ignore their action
+        illegal = np.zeros(B, dtype=bool)
+        if has_sub.any():
+            illegal |= has_sub & (self.sub_cooldown[idx, np.where(has_sub, sub_id, 0)] > 0)
+        if has_line.any():
+            illegal |= has_line & (self.line_cooldown[idx, np.where(has_line, line_id, 0)] > 0)
+        self.n_illegal += int((illegal & ~self.done).sum())
+        ok = ~illegal & ~self.done
+        if has_sub.any():
+            who = np.flatnonzero(has_sub & ok)
+            if len(who):
+                pos = self.sub_pos[sub_id[who]]                                  # [n, max_sub_size]
+                val = sub_bus[who][:, :self.max_sub_size]
+                m = (pos >= 0) & (val > 0)
+                ii = np.broadcast_to(who[:, None], pos.shape)[m]
+                pp = pos[m]
+                cur = self.topo[ii, pp]
+                live = cur > 0                                                    # (the driver does not reconnect through set_bus)
+                self.topo[ii[live], pp[live]] = val[m][live]
+                self.last_bus[ii[live], pp[live]] = val[m][live]
+                aff_s[who, sub_id[who]] = True
+                self._topo_dirty = True
+        if has_line.any():
+            who = np.flatnonzero(has_line & ok)
+            if len(who):
+                l = line_id[who]
+                po, pe = self.line_or_pos[l], self.line_ex_pos[l]
+                off = line_status[who] < 0
+                self.topo[who[off], po[off]] = -1; self.topo[who[off], pe[off]] = -1
+                on = ~off
+                self.topo[who[on], po[on]] = self.last_bus[who[on], po[on]]
+                self.topo[who[on], pe[on]] = self.last_bus[who[on], pe[on]]
+                aff_l[who, l] = True
+                self._topo_dirty = True
+        return aff_l, aff_s
+
+    def _apply_environment(self):
+        """maintenance / hazards of the row every instance is about to solve: those lines are out"""
+        gm = self.gm
+        forced = None
+        r = self.row % self.chron.shape[1]
+        if self._maint is not None:
+            forced = self._maint[self.scen, r]
+        if self._haz is not None:
+            h = self._haz[self.scen, r]
+            forced = h if forced is None else (forced | h)
+        if forced is None:
+            return
+        forced = forced & ~self.done[:, None]
+        ii, ll = np.nonzero(forced)
+        if len(ii):
+            was_on = (self.topo[ii, self.line_or_pos[ll]] > 0) | (self.topo[ii, self.line_ex_pos[ll]] > 0)
+            self.topo[ii, self.line_or_pos[ll]] = -1
+            self.topo[ii, self.line_ex_pos[ll]] = -1
+            if was_on.any():
+                self._topo_dirty = True
+
+    def step(self, sub_id=None, sub_bus=None, line_id=None, line_status=None, from_reset: bool = False):
+        """One env.step of every instance.  ``sub_id`` int [B] (-1: none) with ``sub_bus`` int8 [B, >= max_sub_size] (busbar per
+        element of that substation in topology-vector order, 0 = leave); ``line_id`` int [B] (-1: none) with ``line_status``
+        int [B] (+1 reconnect / -1 disconnect).  Returns ``(rho [B, n_line], done [B], info)``; the full records stay on the
+        device (:meth:`fetch`)."""
+        gm = self.gm
+        aff_l, aff_s = self._apply_agent(sub_id, sub_bus, line_id, line_status) if not from_reset else (
+            np.zeros((self.batch, gm.n_line), dtype=bool), np.zeros((self.batch, gm.n_sub), dtype=bool))
+        self._apply_environment()
+        if self._topo_dirty:
+            self.engine.series_set_topo(self.topo)
+            self._topo_dirty = False
+        if from_reset:
+            self.engine.series_next_is_reset()
+        self.step_device()
+        out, status, iters, rho = self.engine.series_fetch(want_out=False)
+        disc = None
+        if self.protections:
+            st = self.engine.series_fetch_state()
+            disc = st["disc_lines"]
+            tripped = (disc >= 0) & ~self.done[:, None]
+            ii, ll = np.nonzero(tripped)
+            if len(ii):                       # _backend_action.update_state(disc_lines): the tripped lines stay out
+                self.topo[ii, self.line_or_pos[ll]] = -1
+                self.topo[ii, self.line_ex_pos[ll]] = -1
+                # (the engine's own mirror of the series topology already holds them: no re-upload needed)
+        r = self.row % self.chron.shape[1]
+        # ---- cooldowns (baseEnv.py:3352-3393, :2566-2597), in the reference's order --------------------------------------
+        live = ~self.done
+        lc = self.line_cooldown
+        lc[(lc > 0) & live[:, None]] -= 1
+        if disc is not None:
+            lc[(disc >= 0) & live[:, None]] = self.cd_reco
+        if self._maint is not None:
+            mt, md = self._maint_time[self.scen, r], self._maint_dur[self.scen, r]
+            first = (mt == 0) & live[:, None]
+            lc[first] = np.maximum(lc[first], md[first])
+        if self._haz_dur is not None:
+            hd = self._haz_dur[self.scen, r]
+            lc[live] = np.maximum(lc[live], hd[live])
+        if not from_reset:
+            if self.cd_line > 0:
+                cond = aff_l & (lc < self.cd_line)
+                lc[cond] = self.cd_line
+            if self.cd_sub > 0:
+                sc = self.sub_cooldown
+                sc[(sc > 0) & live[:, None]] -= 1
+                sc[aff_s] = self.cd_sub
+        newly_done = live & (status != 0)
+        self.done |= newly_done
+        self.row = self.row + 1
+        self.n_steps += 1
+        return rho, self.done.copy(), {"status": status, "iters": iters, "disc_lines": disc, "newly_done": newly_done}
+
+    def reset_step(self):
+        """the solve ``env.reset()`` performs on the first row (no soft-overflow counting, no cooldown from actions)"""
+        return self.step(from_reset=True)
+
+
+def random_substation_actions(env: BatchedEnv, rng: np.random.Generator):
+    """BASELINE.json configs[2] / SURVEY.md 8(d) config 3: every instance draws one substation and a uniformly random busbar
+    in {1, 2} for each of its elements (``MAX_SUB_CHANGED = 1``).  -> (sub_id [B], sub_bus [B, max_sub_size])"""
+    B = env.batch
+    sub = rng.integers(0, env.gm.n_sub, B)
+    bus = rng.integers(1, 3, (B, env.max_sub_size)).astype(np.int8)
+    bus[np.arange(env.max_sub_size)[None, :] >= env.sub_size[sub][:, None]] = 0
+    return sub, bus

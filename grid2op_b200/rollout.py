@@ -35,7 +35,7 @@ class BatchedDoNothing:
                  max_iter: int = 10, tol_mva: float = 1e-8, is_dc: bool = False, scen: Optional[np.ndarray] = None,
                  t0: Optional[np.ndarray] = None, thermal_limit_a: Optional[np.ndarray] = None,
                  protections: bool = False, hard_overflow_threshold: float = 2.0, soft_overflow_threshold: float = 1.0,
-                 nb_timestep_overflow_allowed: int = 2):
+                 nb_timestep_overflow_allowed: int = 2, engine=None):
         self.gm = gm
         self.batch = int(batch)
         self.chron = np.ascontiguousarray(chron, dtype=np.float32)
@@ -47,7 +47,8 @@ class BatchedDoNothing:
             self.t0 = np.ascontiguousarray(t0, dtype=np.int32)
         self.thermal_limit_a = np.ascontiguousarray(gm.thermal_limit_a if thermal_limit_a is None else thermal_limit_a,
                                                     dtype=np.float32)
-        self.engine = PowerFlowEngine(gm, max_batch=self.batch, device=device)
+        # (engine: an object with the series API of PowerFlowEngine — tests inject the oracle adapter to check host logic on CPU)
+        self.engine = engine if engine is not None else PowerFlowEngine(gm, max_batch=self.batch, device=device)
         self.max_iter, self.tol_mva, self.is_dc = int(max_iter), float(tol_mva), bool(is_dc)
         self.topo0 = np.tile(gm.default_topo(), (self.batch, 1))
         self.nb_cap = int(np.count_nonzero(np.bincount(self._slots(gm.default_topo()), minlength=gm.n_slot)))

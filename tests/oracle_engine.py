@@ -202,3 +202,60 @@ class OracleEngine:
             out[b], status[b], iters[b], busv[b] = self._one(topo[b], inj[b], is_dc, max_iter, tol_mva)
         self.launch_count += 1
         return out, status, iters, (busv if want_busv else None)
+
+
+class COracleSeriesEngine:
+    """TEST INFRASTRUCTURE: the series API of ``PowerFlowEngine`` (bind / set_topo / step / fetch) on top of the oracle's C
+    restatement, WITHOUT protections — lets ``BatchedEnv`` / ``BatchedDoNothing`` host logic be checked on a machine without
+    a GPU (``engine=`` injection).  Never importable from the product package."""
+
+    def __init__(self, gm: GridModel):
+        from oracle.c_oracle import COracle
+        self.gm = gm
+        self.orc = COracle(gm)
+        self.prot = False
+        self.launch_count = 0
+
+    def series_bind(self, chron, scen, t0, static_inj, thermal_limit_a):
+        self.chron = np.asarray(chron, dtype=np.float32)
+        self.scen = np.asarray(scen, dtype=np.int64)
+        self.t = np.asarray(t0, dtype=np.int64).copy()
+        self.static_inj = np.asarray(static_inj, dtype=np.float64)
+        self.th = np.asarray(thermal_limit_a, dtype=np.float32)
+        self.B = len(self.scen)
+        self.topo = np.tile(self.gm.default_topo(), (self.B, 1))
+
+    def series_set_topo(self, topo):
+        self.topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(self.B, self.gm.n_topo_in).copy()
+
+    def series_protections(self, enabled=True, *a, **k):
+        if enabled:
+            raise NotImplementedError("the CPU stand-in has no protections")
+
+    def series_next_is_reset(self):
+        pass
+
+    def series_step(self, is_dc=False, max_iter=10, tol_mva=1e-8, nb_cap=0):
+        gm = self.gm
+        rows = self.chron[self.scen, self.t % self.chron.shape[1]]
+        sl, nl, ng = gm.inj_slices(), gm.n_load, gm.n_gen
+        inj = np.tile(self.static_inj, (self.B, 1))
+        inj[:, sl["load_p"]] = rows[:, :nl]; inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
+        inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
+        inj[:, sl["gen_vm"]] = (rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]).astype(np.float32)
+        self.out, self.status, self.iters, _ = self.orc.run(self.topo, inj, is_dc=is_dc, max_iter=max_iter, tol_mva=tol_mva)
+        self.t = (self.t + 1) % self.chron.shape[1]
+        self.launch_count += 1
+
+    def series_fetch(self, want_out=True, want_rho=True):
+        rho = OutputView(self.gm, self.out).a_or / self.th[None, :] if want_rho else None
+        return (self.out if want_out else None), self.status, self.iters, rho
+
+    def series_fetch_state(self):
+        raise NotImplementedError
+
+    def plan_stats(self):
+        return {"last_kernel": "oracle"}
+
+    def close(self):
+        pass

@@ -1,0 +1,161 @@
+"""``BatchedEnv`` (grid2op_b200/batched_env.py: batched env.step WITH actions, cooldowns, maintenance) against unmodified
+grid2op environments stepped one by one with the same scripted agent, on l2rpn_neurips_2020_track1 (36 substations; its
+chronics carry a maintenance table): topology vectors, line status and both cooldown vectors must be EQUAL after every step,
+rho within tolerance, illegal actions counted the same.
+
+* CPU (``not gpu``): host logic only — the reference environments run B200Backend with the oracle adapter as engine, the
+  batched driver runs on the oracle's C restatement (tests/oracle_engine.py: test infrastructure), protections off;
+* GPU (``-m gpu``): the real CUDA engine on both sides, protections ON (Backend.next_grid_state on the device vs the
+  reference's host loop), a longer run that crosses the end of the maintenance.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import env_grid, have_cuda
+
+ENV = "l2rpn_neurips_2020_track1"
+
+
+def _scripted(k, rng, obs_topo, line_status, line_cd, sub_cd, sub_pos, sub_size, n_line, is_line_pos):
+    """-> dict(sub=-1|s, bus=[...], line=-1|l, status=0|+-1): what the agent does at step k (may be illegal on purpose).
+    Substation actions put two of the connected line ends on busbar 2 (a pass-through node: nothing gets isolated) or
+    everything back on busbar 1."""
+    act = dict(sub=-1, bus=None, line=-1, status=0)
+    if k % 3 == 0:
+        s = int(rng.integers(0, len(sub_size)))
+        pos = sub_pos[s, :sub_size[s]]
+        live = obs_topo[pos] > 0
+        bus = np.where(live, 1, 0)
+        ends = np.flatnonzero(live & is_line_pos[pos])
+        if len(ends) >= 4 and rng.random() < 0.7:
+            bus[rng.choice(ends, 2, replace=False)] = 2
+        if (bus > 0).any():
+            act.update(sub=s, bus=bus)
+    elif k % 5 == 1:
+        l = int(rng.integers(0, n_line))
+        act.update(line=l, status=-1 if line_status[l] else +1)
+    return act
+
+
+def _run(n_steps, start_row, backend_factory, engine_factory, protections, seeds=(0, 1, 2), scen_name="Scenario_august_dummy"):
+    import grid2op
+    from grid2op.Parameters import Parameters
+    from grid2op_b200.batched_env import BatchedEnv
+    from grid2op_b200.chronics import load_line_events, load_scenarios
+    from grid2op_b200.gridmodel import GridModel
+    grid = env_grid(ENV)
+    gm = GridModel(grid)
+    cdir = os.path.join(os.path.dirname(grid), "chronics")
+    folder = os.path.join(cdir, scen_name)
+    chron = load_scenarios(cdir, gm, scenarios=[folder])
+    maint = load_line_events(folder, gm, "maintenance")[None]
+    B = len(seeds)
+    p = Parameters()
+    p.NO_OVERFLOW_DISCONNECTION = not protections
+    p.NB_TIMESTEP_COOLDOWN_LINE = 3
+    p.NB_TIMESTEP_COOLDOWN_SUB = 2
+    envs = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(B):
+            e = grid2op.make(ENV, test=True, backend=backend_factory(), param=p, opponent_init_budget=0., opponent_budget_per_ts=0.,
+                             _add_to_name=f"benv{i}_{int(protections)}")
+            sid = [j for j, f in enumerate(sorted(os.listdir(cdir))) if f == scen_name][0]
+            e.set_id(sid)
+            e.reset()
+            e.fast_forward_chronics(start_row)
+            envs.append(e)
+    obs = [e.get_obs() for e in envs]
+    th = np.asarray(envs[0].get_thermal_limit(), dtype=np.float32)
+    benv = BatchedEnv(gm, chron, B, maintenance=maint, scen=np.zeros(B, dtype=np.int32), t0=np.full(B, start_row + 1, dtype=np.int32),
+                      thermal_limit_a=th, nb_timestep_cooldown_line=3, nb_timestep_cooldown_sub=2,
+                      nb_timestep_reconnection=p.NB_TIMESTEP_RECONNECTION, protections=protections,
+                      hard_overflow_threshold=p.HARD_OVERFLOW_THRESHOLD, soft_overflow_threshold=p.SOFT_OVERFLOW_THRESHOLD,
+                      nb_timestep_overflow_allowed=p.NB_TIMESTEP_OVERFLOW_ALLOWED, engine=engine_factory(gm))
+    # bring the batched state to the reference's state after fast_forward (same topology: everything on busbar 1)
+    for i in range(B):
+        assert np.array_equal(obs[i].topo_vect, benv.topo[i, :gm.dim_topo])
+        benv.line_cooldown[i] = obs[i].time_before_cooldown_line
+        benv.sub_cooldown[i] = obs[i].time_before_cooldown_sub
+    rngs = [np.random.default_rng(100 + s) for s in seeds]
+    is_line_pos = np.zeros(gm.dim_topo, dtype=bool)
+    is_line_pos[gm.line_or_pos] = True; is_line_pos[gm.line_ex_pos] = True
+    n_illegal_ref = 0
+    saw = dict(maint=False, illegal=False, sub=False, line=False)
+    alive = np.ones(B, dtype=bool)
+    for k in range(n_steps):
+        sub_id = np.full(B, -1, dtype=np.int64); sub_bus = np.zeros((B, benv.max_sub_size), dtype=np.int8)
+        line_id = np.full(B, -1, dtype=np.int64); line_st = np.zeros(B, dtype=np.int64)
+        infos = []
+        for i, e in enumerate(envs):
+            if not alive[i]:
+                infos.append(None)
+                continue
+            o = obs[i]
+            a = _scripted(k, rngs[i], o.topo_vect, o.line_status, o.time_before_cooldown_line, o.time_before_cooldown_sub,
+                          benv.sub_pos, benv.sub_size, gm.n_line, is_line_pos)
+            spec = {}
+            if a["sub"] >= 0:
+                spec["set_bus"] = {"substations_id": [(a["sub"], a["bus"].astype(int).tolist())]}
+                sub_id[i] = a["sub"]; sub_bus[i, :len(a["bus"])] = a["bus"]
+                saw["sub"] = True
+            if a["line"] >= 0:
+                spec["set_line_status"] = [(a["line"], int(a["status"]))]
+                line_id[i] = a["line"]; line_st[i] = a["status"]
+                saw["line"] = True
+            o2, r, d, info = e.step(e.action_space(spec))
+            obs[i] = o2
+            infos.append((d, info))
+            if info["is_illegal"]:
+                n_illegal_ref += 1; saw["illegal"] = True
+        rho, done, binfo = benv.step(sub_id, sub_bus, line_id, line_st)
+        for i in range(B):
+            if not alive[i]:
+                continue
+            d, info = infos[i]
+            assert bool(done[i]) == bool(d), (k, i, info["exception"], binfo["status"][i])
+            if d:
+                alive[i] = False
+                continue
+            o = obs[i]
+            assert np.array_equal(o.topo_vect, benv.topo[i, :gm.dim_topo]), (k, i, np.flatnonzero(o.topo_vect != benv.topo[i, :gm.dim_topo]))
+            assert np.array_equal(o.line_status, benv.line_status()[i]), (k, i)
+            assert np.array_equal(o.time_before_cooldown_line, benv.line_cooldown[i]), (k, i, o.time_before_cooldown_line, benv.line_cooldown[i])
+            assert np.array_equal(o.time_before_cooldown_sub, benv.sub_cooldown[i]), (k, i)
+            assert np.allclose(o.rho, rho[i], rtol=2e-4, atol=2e-5), (k, i, float(np.max(np.abs(o.rho - rho[i]))))
+            if (o.time_next_maintenance == 0).any():
+                saw["maint"] = True
+    assert benv.n_illegal == n_illegal_ref
+    saw["steps_alive"] = int(benv.n_steps)
+    saw["n_alive"] = int(alive.sum())
+    for e in envs:
+        e.close()
+    benv.close()
+    return saw
+
+
+def test_batched_env_host_logic_vs_reference_env():
+    if env_grid(ENV) is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    from oracle_engine import COracleSeriesEngine, OracleEngine
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    saw = _run(24, 96, HostLogicBackend, COracleSeriesEngine, protections=False, seeds=(0, 1))
+    assert saw["maint"] and saw["sub"] and saw["line"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("protections", [False, True])
+def test_batched_env_vs_reference_env_gpu(cuda_required, protections):
+    if env_grid(ENV) is None:
+        pytest.skip("reference data not available")
+    from grid2op_b200.backend import B200Backend
+    saw = _run(130, 96, B200Backend, lambda gm: None, protections=protections, seeds=(0, 1, 2, 3))
+    assert saw["maint"] and saw["sub"] and saw["line"] and saw["illegal"]
