@@ -84,7 +84,8 @@ struct b200pf_handle {
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
-    int64_t plans_built = 0;
+    int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
+    bool series_plans_stale = false;                        // the cache was reset under the series' plan ids: re-resolve before the next step
     int64_t launches = 0;
     int redo_enabled = 1;                                   // pivoting re-solve of what the planned kernel leaves as ST_DIV (B200PF_NO_REDO=1 turns it off)
     int dbg_div_mod = 0;                                    // test knob, see b200pf_set_debug
@@ -431,6 +432,18 @@ static int plans_sync_device(b200pf_handle *h, cudaStream_t st) {
     return 0;
 }
 
+// Drops every cached plan (host + device copy).  Plan ids handed out before are void afterwards: the series mode re-resolves
+// its ids before its next step (series_plans_stale).  Launches in flight may still read the device copy -> device-wide sync.
+static int plan_cache_clear(b200pf_handle *h) {
+    CU(cudaDeviceSynchronize());
+    h->plan_index.clear(); h->plan_keys.clear(); h->plan_outage.clear(); h->plan_next.clear();
+    h->plan_off.clear(); h->plan_smem.clear(); h->plan_blobs.clear();
+    h->d_plan_used = 0; h->d_plan_off_n = 0; h->plan_max_smem = 0;
+    h->plan_cache_resets++;
+    if (h->series_plan_state) h->series_plans_stale = true;
+    return 0;
+}
+
 // Plans of the instances [0, n_src) whose topology rows are at host_topo (times n1_lines outages each in contingency
 // mode); ids go to h_inst_plan[first ...] and, unless all are equal, to d_inst_plan[first ...] on stream st.
 // Returns 1 = use the sparse kernel with *sel, 0 = fall back to the pivoting kernels, < 0 error.
@@ -447,25 +460,36 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     struct Miss { const int8_t *tv; uint64_t rh; int outage; int id; };
     std::vector<Miss> miss;
     std::unordered_map<uint64_t, std::vector<int>> miss_index;
-    for (int s = 0; s < n_src; ++s) {
-        const int8_t *tv = host_topo + (size_t)s * nt;
-        if (s > 0 && memcmp(tv, tv - nt, nt) == 0) {
-            for (int l = 0; l < per; ++l) ids[(size_t)s * per + l] = ids[(size_t)(s - 1) * per + l];
-            continue;
-        }
-        const uint64_t rh = topo_hash(tv, nt);
-        for (int l = 0; l < per; ++l) {
-            const int outage = n1_lines > 0 ? l : -1;
-            int id = plan_find(h, tv, rh, outage);
-            if (id < 0) {
-                std::vector<int> &cand = miss_index[plan_key(rh, outage)];
-                int m = -1;
-                for (int c : cand) if (miss[c].outage == outage && memcmp(miss[c].tv, tv, nt) == 0) { m = c; break; }
-                if (m < 0) { m = (int)miss.size(); miss.push_back({tv, rh, outage, -1}); cand.push_back(m); }
-                id = -2 - m;                      // placeholder, resolved below
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        miss.clear(); miss_index.clear();
+        for (int s = 0; s < n_src; ++s) {
+            const int8_t *tv = host_topo + (size_t)s * nt;
+            if (s > 0 && memcmp(tv, tv - nt, nt) == 0) {
+                for (int l = 0; l < per; ++l) ids[(size_t)s * per + l] = ids[(size_t)(s - 1) * per + l];
+                continue;
             }
-            ids[(size_t)s * per + l] = id;
+            const uint64_t rh = topo_hash(tv, nt);
+            for (int l = 0; l < per; ++l) {
+                const int outage = n1_lines > 0 ? l : -1;
+                int id = plan_find(h, tv, rh, outage);
+                if (attempt == 0) { h->plan_lookups++; if (id >= 0) h->plan_hits++; }
+                if (id < 0) {
+                    std::vector<int> &cand = miss_index[plan_key(rh, outage)];
+                    int m = -1;
+                    for (int c : cand) if (miss[c].outage == outage && memcmp(miss[c].tv, tv, nt) == 0) { m = c; break; }
+                    if (m < 0) { m = (int)miss.size(); miss.push_back({tv, rh, outage, -1}); cand.push_back(m); }
+                    id = -2 - m;                      // placeholder, resolved below
+                }
+                ids[(size_t)s * per + l] = id;
+            }
         }
+        // the cache is a plain append-only store: when this call's new plans would overflow it, start over with an empty one
+        // (agents that walk through ever new topologies — BASELINE configs[2] — fill any cache)
+        const size_t avg = h->plan_off.empty() ? (size_t)64 * 1024 : h->plan_blobs.size() / h->plan_off.size() + 1;
+        const bool overflow = h->plan_off.size() + miss.size() > (size_t)PLAN_MAX || h->plan_blobs.size() + miss.size() * avg > PLAN_MAX_BYTES;
+        if (!overflow || attempt == 1 || h->plan_off.empty()) break;
+        int rc = plan_cache_clear(h);
+        if (rc) return rc;
     }
     // ... built in parallel on the host threads (the builder is pure), inserted in order
     if (!miss.empty()) {
@@ -482,7 +506,11 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
                                 : pb.build(miss[m].tv, miss[m].outage);
         };
         unsigned nthr = std::thread::hardware_concurrency();
-        if (nthr > 16) nthr = 16;
+        if (nthr > 64) nthr = 64;
+        {   // (a cgroup CPU quota smaller than the visible CPUs: B200PF_PLAN_THREADS caps the builder threads)
+            const char *pt = getenv("B200PF_PLAN_THREADS");
+            if (pt && atoi(pt) > 0 && (unsigned)atoi(pt) < nthr) nthr = (unsigned)atoi(pt);
+        }
         if (nthr < 1) nthr = 1;
         if ((size_t)nthr > miss.size() / 4 + 1) nthr = (unsigned)(miss.size() / 4 + 1);
         if (nthr <= 1) {
@@ -874,6 +902,7 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
 // protections, which keep the pivoting kernels)
 static int series_plans(b200pf_handle *h, const int8_t *topo) {
     h->series_plan_state = 0;
+    h->series_plans_stale = false;
     PlanSel sel;
     CU(cudaStreamSynchronize(h->stream));
     const int use = plan_select(h, topo, h->series_batch, 0, 0, h->stream, &sel, -1);
@@ -968,6 +997,12 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
         a.pcount = h->d_pcount; a.ts_over = h->d_tsover; a.disc = h->d_disc; a.done = h->d_done;
     }
     h->next_reset = 0;
+    if (h->series_plans_stale) {
+        h->series_plans_stale = false;
+        std::vector<int8_t> keep(h->h_series_topo);
+        int rc = series_plans(h, keep.data());
+        if (rc) return rc;
+    }
     {
         const DevGrid &gg = h->g;
         const bool small_ok = gg.n_slot <= 32 && gg.n_line <= 32 && gg.n_unit <= 32 && gg.n_load <= 32 && gg.n_sto <= 32 && gg.n_shunt <= 32 &&
@@ -1322,6 +1357,12 @@ extern "C" int b200pf_set_debug(b200pf_handle *h, int planned_div_mod, int redo_
 }
 
 extern "C" int64_t b200pf_redo_launch_count(const b200pf_handle *h) { return h ? h->redo_launches : 0; }
+
+extern "C" int b200pf_plan_counters(const b200pf_handle *h, int64_t *out4) {
+    if (!h || !out4) return fail(B200PF_E_ARG, "null pointer");
+    out4[0] = h->plan_lookups; out4[1] = h->plan_hits; out4[2] = h->plans_built; out4[3] = h->plan_cache_resets;
+    return 0;
+}
 
 extern "C" int b200pf_sync(b200pf_handle *h) {
     if (!h) return fail(B200PF_E_ARG, "null handle");

@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free", "b200pf_rows_group_launch", "b200pf_rows_group_wait",
     "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats", "b200pf_run_device_topo",
     "b200pf_set_debug", "b200pf_redo_launch_count",
-    "b200pf_device_alloc", "b200pf_device_free", "b200pf_ipc_export", "b200pf_ipc_open", "b200pf_ipc_close", "b200pf_device_read",
+    "b200pf_device_alloc", "b200pf_device_free", "b200pf_ipc_export", "b200pf_ipc_open", "b200pf_ipc_close", "b200pf_device_read", "b200pf_plan_counters",
 )
 
 
@@ -121,6 +121,8 @@ def load_library():
     lib.b200pf_set_kernel_policy.argtypes = [vp, i32]
     lib.b200pf_plan_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]
     lib.b200pf_set_debug.argtypes = [vp, i32, i32]
+    lib.b200pf_plan_counters.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.b200pf_plan_counters.restype = i32
     lib.b200pf_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.b200pf_device_free.argtypes = [vp]
     lib.b200pf_ipc_export.argtypes = [vp, vp]
@@ -529,6 +531,11 @@ class PowerFlowEngine:
         n, b, k = C.c_int64(), C.c_int64(), C.c_int()
         self._check(self.lib.b200pf_plan_stats(self.h, C.byref(n), C.byref(b), C.byref(k)), "b200pf_plan_stats")
         return dict(n_plans=n.value, plan_bytes=b.value, last_kernel={0: "none", 1: "warp_pivoting", 2: "cta_pivoting", 3: "planned_sparse", 4: "planned_block"}[k.value])
+
+    def plan_counters(self):
+        v = (C.c_int64 * 4)()
+        self._check(self.lib.b200pf_plan_counters(self.h, v), "b200pf_plan_counters")
+        return dict(lookups=int(v[0]), hits=int(v[1]), built=int(v[2]), cache_resets=int(v[3]))
 
     def view(self, out: np.ndarray) -> OutputView:
         return OutputView(self.gm, out)

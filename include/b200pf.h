@@ -244,6 +244,10 @@ int b200pf_set_stream(b200pf_handle *h, uint64_t stream);
 int b200pf_set_kernel_policy(b200pf_handle *h, int policy);
 /* number of cached plans, their bytes, and the kernel of the last launch (1 warp/pivoting, 2 CTA/pivoting, 3 planned sparse) */
 int b200pf_plan_stats(const b200pf_handle *h, int64_t *n_plans, int64_t *plan_bytes, int *last_kernel);
+/* out4 = { topology rows looked up in the plan cache, of which found, plans built, cache resets (the cache is append-only and
+ * starts over when it is full: 32768 plans / 1 GiB) } since b200pf_create.  New plans of one call are built in parallel on the
+ * host threads (env B200PF_PLAN_THREADS caps them). */
+int b200pf_plan_counters(const b200pf_handle *h, int64_t *out4);
 
 /* Multi-GPU result collection (instances shard across GPUs, the step results go to the agent's rank).  Instead
  * of one collective launch per 60-microsecond step, the agent's rank allocates the result buffer with b200pf_device_alloc
