@@ -18,3 +18,5 @@ echo "== bench wcci N=1"; timeout 600 python bench.py --workload wcci --steps 50
 python -c "import json;d=json.load(open('gpurun_out/bench_wcci_n1.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['parity_check'],d['config']['launch'])"
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 20 --warmup 2 2>&1 | tail -1 > gpurun_out/bench_ref.json; python -c "import json;d=json.load(open('gpurun_out/bench_ref.json'));print(d['value'],d['spread'],d['cpu_baseline']['sample'])"
 timeout 600 python bench.py --impl reference --steps 20 --warmup 2 2>&1 | tail -1 > gpurun_out/bench_ref2.json; python -c "import json;d=json.load(open('gpurun_out/bench_ref2.json'));print(d['value'],d['spread'])"
+echo "== config 3"; timeout 900 python scripts/bench_config3.py --steps 30 > gpurun_out/config3.json 2> gpurun_out/config3.log; tail -3 gpurun_out/config3.log | cut -c1-600
+echo "== single env latency"; NB_TS=300 timeout 900 python scripts/single_env_latency.py > gpurun_out/single_env_latency.json 2> gpurun_out/single_env_latency.log; grep l2rpn gpurun_out/single_env_latency.log | cut -c1-500
