@@ -77,6 +77,7 @@ class BatchedEnv(BatchedDoNothing):
             self.sub_pos[s, :len(p)] = p
         self.line_or_pos, self.line_ex_pos = np.asarray(gm.line_or_pos, dtype=np.int64), np.asarray(gm.line_ex_pos, dtype=np.int64)
         self._topo_dirty = False
+        self.nb_cap = 0                 # bus splits add active buses: launches are sized for every bus slot, not for the plain topology
         self.n_illegal = 0
         self.n_steps = 0
 

@@ -76,13 +76,15 @@ struct b200pf_handle {
     int *d_series_plan = nullptr; int series_plan_state = 0; // 0 none, 1 per-instance plans, 2 all instances on one plan
     int series_plan_single = 0, series_plan_smem = 0;
     int plan_policy = 0;                                    // 0 auto, 1 never, 2 whenever a host copy of the topology exists
-    int plan_max_smem = 0;
+    int plan_max_smem = 0, plan_max_nb = 0, plan_max_nblkA = 0;
+    int series_lay_nb = 0, series_lay_nblkA = 0;
     int sparse_occ_smem = -1, sparse_occ = 0, sparse_occ_variant = 0;
     int sparse_cta_cap = 0;                                 // > 0: resident CTAs per SM of the planned kernel are capped (rest of the SM's memory = L1); < 0: never
     int sparse_minb = 32;                                   // tuning: one-warp CTAs per SM the small-workspace variant is compiled for (32 or 28)
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
+    int blk_wpc = 1, blk_stage = 0;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
     bool series_plans_stale = false;                        // the cache was reset under the series' plan ids: re-resolve before the next step
@@ -232,11 +234,18 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         const char *capv = getenv("B200PF_SPARSE_CTAS");        // tuning: cap of resident CTAs per SM (planned kernel)
         if (capv) h->sparse_cta_cap = atoi(capv);
         // block kernel: lanes per instance x operations per lane and row (B200PF_BLOCK=0: scalar planned kernel)
-        h->blk_T = g.n_line <= 32 ? 4 : (g.n_line <= 64 ? 8 : 32);
-        h->blk_U = g.n_line <= 64 ? 2 : 1;
+        // measured (profiles/round2_sweep_block_*.json): 8 lanes x 1 operation wins on the 5 / 14-substation grids at every batch
+        // size; on the 36 / 118-substation grids the scalar planned kernel is still ahead, so it stays their default
+        h->blk_T = g.n_line <= 32 ? 8 : (g.n_line <= 64 ? 32 : 64);
+        h->blk_U = 1;
+        h->blk = g.n_line <= 32 ? 1 : 0;
         const char *bk = getenv("B200PF_BLOCK"), *bt = getenv("B200PF_BLOCK_T"), *bu = getenv("B200PF_BLOCK_U");
         if (bk && bk[0] == '0') h->blk = 0;
+        if (bk && bk[0] == '1') h->blk = 1;
         if (bt && bu && block_variant_exists(atoi(bt), atoi(bu))) { h->blk_T = atoi(bt); h->blk_U = atoi(bu); }
+        const char *bw = getenv("B200PF_BLOCK_WPC"), *bs = getenv("B200PF_BLOCK_STAGE");
+        if (bw && atoi(bw) == 4) h->blk_wpc = 4;
+        if (bs && bs[0] == '1') { h->blk_stage = 1; h->blk_wpc = 4; }
         const char *nr = getenv("B200PF_NO_REDO");              // measurement only: planned kernel without its safety net
         if (nr && nr[0] == '1') h->redo_enabled = 0;
         const char *var = getenv("B200PF_SPARSE_T");            // tuning: threads per instance of the planned kernel
@@ -343,7 +352,8 @@ static const int PLAN_BUILD_BUDGET = 512;   // new plans one call may build in a
 struct PlanSel {
     const int *d_inst_plan;   // device, per instance of the launch; nullptr = every instance uses plan `single`
     int single;
-    int smem;
+    int smem;                 // per-instance workspace bytes the launch must provide
+    int lay_nb = 0, lay_nblkA = 0;   // block kernel: layout strides of the launch (one plan: its sizes; several: the handle's maxima)
 };
 
 // plan builder of the handle's kernel family (scalar stream laid out for plan_T threads, or block stream for blk_T x blk_U)
@@ -353,6 +363,19 @@ static PlanBuilder make_builder(const b200pf_handle *h, bool optimize_layout = f
     return pb;
 }
 static inline int blk_G(const b200pf_handle *h) { return (h->blk && h->blk_T < 32) ? 32 / h->blk_T : 1; }
+
+// workspace bytes + layout strides of a launch: one plan -> that plan's; several -> the maxima over the cached plans
+static void sel_layout(const b200pf_handle *h, PlanSel *sel, bool single) {
+    const DevGrid &g = h->g;
+    if (single) {
+        const PlanHeader *H = reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel->single]);
+        sel->smem = h->plan_smem[sel->single]; sel->lay_nb = H->nb; sel->lay_nblkA = H->nblkA;
+    } else if (h->blk) {
+        sel->lay_nb = h->plan_max_nb; sel->lay_nblkA = h->plan_max_nblkA;
+        sel->smem = plan_block_smem_bytes(h->plan_max_nb, g.n_line, h->plan_max_nblkA, 2 * g.n_load + 2 * g.n_gen, g.n_shunt);
+        if (sel->smem < h->plan_max_smem) sel->smem = h->plan_max_smem;
+    } else sel->smem = h->plan_max_smem;
+}
 
 // 64-bit hash of a topology row (8 bytes at a time)
 static inline uint64_t topo_hash(const int8_t *tv, size_t n) {
@@ -402,6 +425,8 @@ static int plan_insert(b200pf_handle *h, const int8_t *tv, uint64_t row_hash, in
     h->plan_next.push_back(it != h->plan_index.end() ? it->second : -1);
     h->plan_index[key] = id;
     if (H->smem_bytes > h->plan_max_smem) h->plan_max_smem = H->smem_bytes;
+    if (H->nb > h->plan_max_nb) h->plan_max_nb = H->nb;
+    if (H->nblkA > h->plan_max_nblkA) h->plan_max_nblkA = H->nblkA;
     h->plans_built++;
     return id;
 }
@@ -438,7 +463,7 @@ static int plan_cache_clear(b200pf_handle *h) {
     CU(cudaDeviceSynchronize());
     h->plan_index.clear(); h->plan_keys.clear(); h->plan_outage.clear(); h->plan_next.clear();
     h->plan_off.clear(); h->plan_smem.clear(); h->plan_blobs.clear();
-    h->d_plan_used = 0; h->d_plan_off_n = 0; h->plan_max_smem = 0;
+    h->d_plan_used = 0; h->d_plan_off_n = 0; h->plan_max_smem = 0; h->plan_max_nb = 0; h->plan_max_nblkA = 0;
     h->plan_cache_resets++;
     if (h->series_plan_state) h->series_plans_stale = true;
     return 0;
@@ -493,7 +518,11 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     }
     // ... built in parallel on the host threads (the builder is pure), inserted in order
     if (!miss.empty()) {
-        if (h->plan_policy == 0 && (int)miss.size() > PLAN_BUILD_BUDGET) return 0;
+        // automatic mode: planning pays when plans are re-used.  A call that would have to plan more than an eighth of its
+        // instances from scratch (agents walking through ever new topologies) runs on the pivoting kernels, which discover the
+        // topology on the device (measured, 36 substations, batch 1024, one random substation change per instance and step:
+        // profiles/round2_config3.json)
+        if (h->plan_policy == 0 && ((int)miss.size() > PLAN_BUILD_BUDGET || (n_src >= 64 && miss.size() * 8 > (size_t)n_src * per))) return 0;
         std::vector<std::vector<unsigned char>> blobs(miss.size());
         // a handful of new plans of a batched launch: they will be re-used by many solves (rollouts, N-1 sweeps) -> searched
         // elimination order + bank-conflict-optimised layout (not for single environments: there the build time of a new
@@ -507,6 +536,18 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
         };
         unsigned nthr = std::thread::hardware_concurrency();
         if (nthr > 64) nthr = 64;
+        {   // containers: a cgroup CPU quota below the visible CPUs (the GPU boxes: 128 visible, quota 16) — more threads only thrash
+            static int quota = -1;
+            if (quota < 0) {
+                quota = 0;
+                if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+                    char q[32] = {0}; long per = 0;
+                    if (fscanf(f, "%31s %ld", q, &per) == 2 && q[0] != 'm' && per > 0) quota = (int)((atol(q) + per - 1) / per);
+                    fclose(f);
+                }
+            }
+            if (quota > 0 && (unsigned)quota < nthr) nthr = (unsigned)quota;
+        }
         {   // (a cgroup CPU quota smaller than the visible CPUs: B200PF_PLAN_THREADS caps the builder threads)
             const char *pt = getenv("B200PF_PLAN_THREADS");
             if (pt && atoi(pt) > 0 && (unsigned)atoi(pt) < nthr) nthr = (unsigned)atoi(pt);
@@ -533,7 +574,8 @@ static int plan_select(b200pf_handle *h, const int8_t *host_topo, int n_src, int
     const size_t n = (size_t)n_src * per;
     bool single = true;
     for (size_t k = 1; k < n && single; ++k) single = ids[k] == ids[0];
-    sel->single = ids[0]; sel->smem = single ? h->plan_smem[ids[0]] : h->plan_max_smem; sel->d_inst_plan = nullptr;
+    sel->single = ids[0]; sel->d_inst_plan = nullptr;
+    sel_layout(h, sel, single);
     if (!single) {
         CU(cudaMemcpyAsync(h->d_inst_plan + first, ids, n * 4, cudaMemcpyHostToDevice, st));
         if (!h->inst_plan_ev) CU(cudaEventCreateWithFlags(&h->inst_plan_ev, cudaEventDisableTiming));
@@ -570,6 +612,7 @@ static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &se
     pa.blobs = h->d_plan_blobs;
     pa.plan_off = h->d_plan_off + (sel.d_inst_plan ? 0 : sel.single);
     pa.inst_plan = sel.d_inst_plan;
+    pa.lay_nb = 0; pa.lay_nblkA = 0;
     const int resident = h->sm_count * h->sparse_occ;
     const int rounds = (a.batch + resident - 1) / resident;
     int grid = (a.batch + rounds - 1) / rounds;
@@ -684,14 +727,17 @@ static int launch_redo(b200pf_handle *h, RunArgs a, int nb_cap_req) {
 // ------------------------------------------------------------------------------------------------
 // block-planned kernel (b200pf_block.cuh)
 // ------------------------------------------------------------------------------------------------
-template <int T, int U, int MINB, bool PROT>
+template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false>
 static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
     const DevGrid &g = h->g;
     constexpr int G = T < 32 ? 32 / T : 1;
-    constexpr int BLOCK = T < 32 ? 32 : T;
-    auto kern = pf_kernel_block<T, U, MINB, PROT>;
-    const int smem = sel.smem * G;                       // workspace of one warp / CTA
-    const int variant = 1000 + T * 16 + U * 2 + (PROT ? 1 : 0);
+    constexpr int BLOCK = (T < 32 ? 32 : T) * WPC;
+    auto kern = pf_kernel_block<T, U, MINB, PROT, WPC, STAGE>;
+    const int ws = sel.smem * G;                         // workspace of one warp / CTA
+    int plan_bytes = 0;
+    if (STAGE) plan_bytes = reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes;
+    const int smem = ws * WPC + plan_bytes;
+    const int variant = 1000 + T * 64 + U * 8 + (PROT ? 1 : 0) + (STAGE ? 2 : 0) + (WPC > 1 ? 4 : 0);
     if (h->sparse_occ_smem != smem || h->sparse_occ_variant != variant) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
         int occ = 1;
@@ -711,12 +757,13 @@ static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel
     pa.blobs = h->d_plan_blobs;
     pa.plan_off = h->d_plan_off + (sel.d_inst_plan ? 0 : sel.single);
     pa.inst_plan = sel.d_inst_plan;
-    const int n_grp = (a.batch + G - 1) / G;
+    pa.lay_nb = sel.lay_nb; pa.lay_nblkA = sel.lay_nblkA;
+    const int n_cta_work = ((a.batch + G - 1) / G + WPC - 1) / WPC;
     const int resident = h->sm_count * h->sparse_occ;
-    const int rounds = (n_grp + resident - 1) / resident;
-    int grid = (n_grp + rounds - 1) / rounds;
+    const int rounds = (n_cta_work + resident - 1) / resident;
+    int grid = (n_cta_work + rounds - 1) / rounds;
     if (grid < 1) grid = 1;
-    kern<<<grid, BLOCK, (size_t)smem, h->stream>>>(g, a, pa);
+    kern<<<grid, BLOCK, (size_t)smem, h->stream>>>(g, a, pa, ws, plan_bytes);
     CU(cudaGetLastError());
     h->launches++;
     h->last_smem = smem; h->last_T = T; h->last_grid = grid; h->last_block = BLOCK; h->last_kernel = 4;
@@ -733,6 +780,14 @@ static bool block_variant_exists(int T, int U) {
 
 static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
     const int T = h->blk_T, U = h->blk_U;
+    // experiment knobs: B200PF_BLOCK_WPC=4 -> CTAs of 4 warps; B200PF_BLOCK_STAGE=1 -> the launch's single plan is
+    // staged into shared memory by one bulk asynchronous copy (TMA) per CTA.  Only for the default (4, 2) / (8, 2) variants.
+    if (!a.prot && h->blk_wpc == 4 && !(h->blk_stage && sel.d_inst_plan)) {
+        const bool stage = h->blk_stage && !sel.d_inst_plan &&
+                           reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes <= 32 * 1024;
+        if (T == 4 && U == 2) return stage ? launch_block_t<4, 2, 2, false, 4, true>(h, a, sel) : launch_block_t<4, 2, 2, false, 4, false>(h, a, sel);
+        if (T == 8 && U == 1) return stage ? launch_block_t<8, 1, 2, false, 4, true>(h, a, sel) : launch_block_t<8, 1, 2, false, 4, false>(h, a, sel);
+    }
     if (a.prot) {
 #define X(t, u) if (T == t && U == u) return launch_block_t<t, u, (t <= 32 ? 8 : 4), true>(h, a, sel);
         B200PF_BLOCK_VARIANTS(X)
@@ -908,7 +963,7 @@ static int series_plans(b200pf_handle *h, const int8_t *topo) {
     const int use = plan_select(h, topo, h->series_batch, 0, 0, h->stream, &sel, -1);
     if (use < 0) return use;
     if (!use) return 0;
-    h->series_plan_single = sel.single; h->series_plan_smem = sel.smem;
+    h->series_plan_single = sel.single; h->series_plan_smem = sel.smem; h->series_lay_nb = sel.lay_nb; h->series_lay_nblkA = sel.lay_nblkA;
     h->h_series_topo.assign(topo, topo + (size_t)h->series_batch * h->g.n_topo_in);
     h->h_series_plan.assign(h->h_inst_plan, h->h_inst_plan + h->series_batch);
     if (sel.d_inst_plan) {
@@ -948,7 +1003,8 @@ static int series_step_planned_prot(b200pf_handle *h, RunArgs a) {
         CU(cudaMemsetAsync(h->d_nflag, 0, 4, h->stream));
         a.casc = casc; a.inst_list = list; a.batch = n;
         PlanSel sel;
-        sel.single = 0; sel.smem = h->plan_max_smem; sel.d_inst_plan = h->d_series_plan;
+        sel.single = 0; sel.d_inst_plan = h->d_series_plan;
+        sel_layout(h, &sel, false);
         int rc = launch_sparse(h, a, sel);
         if (rc) return rc;
         if ((rc = launch_redo(h, a, 0))) return rc;       // pivoting re-solve (+ the protection rules) of what ended as ST_DIV
@@ -1014,7 +1070,7 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
     }
     if (h->series_plan_state && !h->prot && h->plan_policy != 1) {
         PlanSel sel;
-        sel.single = h->series_plan_single; sel.smem = h->series_plan_smem;
+        sel.single = h->series_plan_single; sel.smem = h->series_plan_smem; sel.lay_nb = h->series_lay_nb; sel.lay_nblkA = h->series_lay_nblkA;
         sel.d_inst_plan = h->series_plan_state == 1 ? h->d_series_plan : nullptr;
         return launch(h, a, nb_cap, &sel);
     }

