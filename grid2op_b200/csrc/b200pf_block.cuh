@@ -395,6 +395,11 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
     }
     // ---- 4. results (same float32 rounding rules as the reference's read-back, pPB:1159-1183) ------------------
     PB_SYNC();
+    if (!a.is_dc) {
+        // pandapower reports Va = angle(V), i.e. angles in (-180, 180]; the Newton iteration accumulates them unwrapped
+        PF_PHASE { for (int i = tid; i < nb; i += T) { const double x = va[IX(i)]; va[IX(i)] = x - 6.283185307179586477 * rint(x * 0.15915494309189533577); } }
+        PB_SYNC();
+    }
     const double RAD2DEG = 57.295779513082320877, SQRT3 = 1.7320508075688772935;
     {
         const uint16_t *unit_bus = U16(o_unit_bus), *load_bus = U16(o_load_bus), *sto_bus = U16(o_sto_bus), *sh_bus = U16(o_sh_bus);

@@ -875,6 +875,10 @@ __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, uns
     }
     const double RAD2DEG = 57.295779513082320877;
     const double SQRT3 = 1.7320508075688772935;
+    if (!a.is_dc) {        // pandapower reports Va = angle(V), i.e. angles in (-180, 180]
+        for (int i = tid; i < nb; i += T) { const double x = w.va[i]; w.va[i] = x - 6.283185307179586477 * rint(x * 0.15915494309189533577); }
+        gsync<T>();
+    }
     if (a.is_dc) {
         // DC: injections at every bus from the angles (needed for the slack share)
         for (int i = tid; i < nb; i += T) {

@@ -531,6 +531,7 @@ __device__ void solve_small(const DevGrid &g, const RunArgs &a, const SmallLayou
     }
 
     // ---- 7. results -------------------------------------------------------------------------------------
+    if (!a.is_dc) va = va - 6.283185307179586477 * rint(va * 0.15915494309189533577);     // pandapower reports angle(V): (-180, 180]
     if (lane == 0) { a.status[inst] = ST_OK; a.iters[inst] = iters; }
     float r[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     {   // lines (lane = line): flows from the currents of the last mismatch evaluation

@@ -233,6 +233,8 @@ static int solve_one(const b200pf_grid_desc *g, work_t *w, const int8_t *tv, con
     }
     /* results (same float32 rounding rules as the reference's read-back, pPB:1159-1183) */
     const double R2D = 57.295779513082320877, S3 = 1.7320508075688772935;
+    /* pandapower reports Va = angle(V) after the Newton solve: angles in (-180, 180] (pandapower newtonpf / pfsoln) */
+    if (!is_dc) for (int i = 0; i < nb; ++i) w->va[i] = w->va[i] - 6.283185307179586477 * rint(w->va[i] * 0.15915494309189533577);
     float *o = out;
     for (int l = 0; l < nl; ++l) {
         int f = w->brf[l], t = w->brt[l];

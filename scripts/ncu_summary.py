@@ -2,7 +2,9 @@
 """Condense an ncu report (.ncu-rep of the dominant kernel, `ncu --set full --import-source on`) into the small
 tracked artefacts under profiles/: <out>_summary.json (raw-page metrics incl. DRAM bytes per launch, stall
 sampling, top source lines) and <out>_details.txt (details page).  Usage:
-    python scripts/ncu_summary.py gpurun_out/prof5.ncu-rep profiles/round1_ncu "description" [instances_per_launch]"""
+    python scripts/ncu_summary.py gpurun_out/prof5.ncu-rep profiles/round1_ncu "description" [instances_per_launch] [kernel_tag]
+kernel_tag: what bench.py's config.kernel_tag says for the run the profile belongs to (bench.py only quotes `traffic` from a
+summary whose tag matches the kernel it launched)."""
 import collections
 import csv
 import json
@@ -54,6 +56,7 @@ def source_page(rep):
 def main():
     rep, outp, what = sys.argv[1], sys.argv[2], sys.argv[3]
     n_inst = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
+    tag = sys.argv[5] if len(sys.argv) > 5 else None
     m = raw_metrics(rep)
     mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
@@ -64,9 +67,9 @@ def main():
     wr = f("dram__bytes_write.sum") * mul[m["dram__bytes_write.sum"][1]]
     agg, src, stalls, n_sass = source_page(rep)
     tot_i = sum(v[0] for v in agg.values()); tot_s = sum(v[1] for v in agg.values()); st = sum(stalls.values())
-    top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:15]
+    top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]
     summ = {
-        "what": what,
+        "what": what, "kernel_tag": tag,
         "gpu_time_us": f("gpu__time_duration.sum") * (1e3 if m["gpu__time_duration.sum"][1] == "ms" else 1.0),
         "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
         "registers_per_thread": f("launch__registers_per_thread"),

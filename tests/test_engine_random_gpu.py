@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _compare(gm, out, ref, ok):
+def _compare(gm, out, ref, ok, theta_tol=1e-3):
     from grid2op_b200.engine import OutputView
     a, b = OutputView(gm, out[ok]), OutputView(gm, ref[ok])
     tol_mw = 1e-4 * gm.sn_mva
@@ -27,7 +27,7 @@ def _compare(gm, out, ref, ok):
         x, y = getattr(a, k), getattr(b, k)
         assert np.max(np.abs(x - y) / vn, initial=0.0) <= 1e-4, k                            # p.u.
     for k in ("theta_or", "theta_ex", "load_theta", "unit_theta"):
-        assert np.max(np.abs(getattr(a, k) - getattr(b, k)), initial=0.0) <= 1e-3, k         # degrees
+        assert np.max(np.abs(getattr(a, k) - getattr(b, k)), initial=0.0) <= theta_tol, k    # degrees
     x, y = a.a_or, b.a_or
     assert np.max(np.abs(x - y) - 1e-5 * np.abs(y), initial=0.0) <= 1e-2
 
