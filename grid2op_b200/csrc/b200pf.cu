@@ -84,7 +84,7 @@ struct b200pf_handle {
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
-    int blk_wpc = 1, blk_stage = 0;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
+    int blk_wpc = 1, blk_stage = 0, blk_minb = 8;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
     bool series_plans_stale = false;                        // the cache was reset under the series' plan ids: re-resolve before the next step
@@ -92,6 +92,7 @@ struct b200pf_handle {
     int redo_enabled = 1;                                   // pivoting re-solve of what the planned kernel leaves as ST_DIV (B200PF_NO_REDO=1 turns it off)
     int dbg_div_mod = 0;                                    // test knob, see b200pf_set_debug
     int64_t redo_launches = 0;
+    unsigned char *d_redo_mat = nullptr; size_t redo_mat_stride = 0; int redo_mat_ctas = 0;   // global-memory matrices of the safety net (large grids)
     cudaEvent_t inst_plan_ev = nullptr; bool inst_plan_pending = false;   // last H2D copy out of h_inst_plan
     int last_smem = 0, last_T = 0, last_grid = 0, last_block = 0;
 };
@@ -243,6 +244,8 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         if (bk && bk[0] == '0') h->blk = 0;
         if (bk && bk[0] == '1') h->blk = 1;
         if (bt && bu && block_variant_exists(atoi(bt), atoi(bu))) { h->blk_T = atoi(bt); h->blk_U = atoi(bu); }
+        const char *bm = getenv("B200PF_BLOCK_MINB");
+        if (bm && (atoi(bm) == 12 || atoi(bm) == 16 || atoi(bm) == 20)) h->blk_minb = atoi(bm);
         const char *bw = getenv("B200PF_BLOCK_WPC"), *bs = getenv("B200PF_BLOCK_STAGE");
         if (bw && atoi(bw) == 4) h->blk_wpc = 4;
         if (bs && bs[0] == '1') { h->blk_stage = 1; h->blk_wpc = 4; }
@@ -262,6 +265,7 @@ extern "C" int b200pf_destroy(b200pf_handle *h) {
     for (void *p : h->dev_allocs) cudaFree(p);
     if (h->d_plan_blobs) cudaFree(h->d_plan_blobs);
     if (h->d_plan_off) cudaFree(h->d_plan_off);
+    if (h->d_redo_mat) cudaFree(h->d_redo_mat);
     void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv, h->h_rows, h->h_inst_plan};
     for (void *p : pinned) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -675,16 +679,16 @@ static int generic_config(b200pf_handle *h, int cap, int jt, int *T_out, size_t 
 // status reads ST_DIV.  Same stream, no host round trip.  fp64 Jacobian whenever the actual systems fit the workspace with
 // it (5 / 14 / 36 substations), fp32 band LU otherwise (118 substations).
 template <int T, typename JT>
-static int launch_redo_t(b200pf_handle *h, const RunArgs &a) {
+static int launch_redo_t(b200pf_handle *h, const RunArgs &a, int max_ctas) {
     const DevGrid &g = h->g;
-    WsLayout L = ws_layout(a.nb_cap, g.n_slot, g.n_line, g.n_inj, (size_t)a.mat_bytes);
+    // (matrix in global memory: the shared-memory workspace only holds the bus arrays)
+    WsLayout L = ws_layout(a.nb_cap, g.n_slot, g.n_line, g.n_inj, a.redo_mat ? (size_t)16 : (size_t)a.mat_bytes);
     const size_t smem = L.total;
     if (smem > (size_t)h->max_smem_optin) return fail(B200PF_E_CAPACITY, "workspace does not fit in shared memory");
     auto kern = pf_kernel_redo<T, JT>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (a.batch + 31) / 32;
-    const int cap = h->sm_count * 8;
-    if (grid > cap) grid = cap;
+    if (grid > max_ctas) grid = max_ctas;
     if (grid < 1) grid = 1;
     kern<<<grid, T, smem, h->stream>>>(g, a, (int)smem);
     CU(cudaGetLastError());
@@ -697,30 +701,38 @@ static int launch_redo(b200pf_handle *h, RunArgs a, int nb_cap_req) {
     const DevGrid &g = h->g;
     int cap = nb_cap_req;
     if (cap <= 0 || cap > g.n_slot) cap = g.n_slot;
-    // fp64 Jacobian when the system of the plain topology plus a margin of 8 split buses fits; fp32 otherwise
-    int jt = 8, T = 32;
+    // always an fp64 Jacobian with partial pivoting, like the reference's solver.  Where the worst-case system (every bus slot
+    // active) fits the shared-memory workspace it lives there; on the large grids (118 substations: 472 x 474 x 8 B) every
+    // CTA of the launch gets a matrix in global memory instead
+    int T = 32;
     size_t want = 0;
-    {
-        const size_t d_typ = 2 * (size_t)g.n_sub + 16;
-        const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
-        if (fixed + d_typ * (d_typ + 2) * 8 > (size_t)h->max_smem_optin) jt = 4;
-    }
-    int rc = generic_config(h, cap, jt, &T, &want);
-    if (rc) return rc;
-    a.redo = 1; a.nb_cap = cap; a.mat_bytes = (int)want;
-    if (jt == 8) {
-        switch (T) {
-            case 32: return launch_redo_t<32, double>(h, a);
-            case 128: return launch_redo_t<128, double>(h, a);
-            case 256: return launch_redo_t<256, double>(h, a);
-            default: return launch_redo_t<512, double>(h, a);
+    const size_t fixed = ws_fixed_bytes(cap, g.n_slot, g.n_line, g.n_inj);
+    const size_t worst = ws_mat_worst(cap, 8);
+    int max_ctas = h->sm_count * 8;
+    a.redo_mat = nullptr; a.redo_mat_stride = 0;
+    if (fixed + worst > (size_t)h->max_smem_optin) {
+        max_ctas = h->sm_count;
+        if (!h->d_redo_mat || h->redo_mat_stride < worst || h->redo_mat_ctas < max_ctas) {
+            CU(cudaStreamSynchronize(h->stream));
+            if (h->d_redo_mat) CU(cudaFree(h->d_redo_mat));
+            h->d_redo_mat = nullptr;
+            CU(cudaMalloc(&h->d_redo_mat, worst * (size_t)max_ctas));
+            h->redo_mat_stride = worst; h->redo_mat_ctas = max_ctas;
         }
+        a.redo_mat = h->d_redo_mat; a.redo_mat_stride = h->redo_mat_stride;
+        want = worst;
+        const size_t d = 2 * (size_t)cap;
+        T = d <= 64 ? 32 : (d <= 128 ? 128 : (d <= 256 ? 256 : 512));
+    } else {
+        int rc = generic_config(h, cap, 8, &T, &want);
+        if (rc) return rc;
     }
+    a.redo = 1; a.nb_cap = cap; a.mat_bytes = (int)want;
     switch (T) {
-        case 32: return launch_redo_t<32, float>(h, a);
-        case 128: return launch_redo_t<128, float>(h, a);
-        case 256: return launch_redo_t<256, float>(h, a);
-        default: return launch_redo_t<512, float>(h, a);
+        case 32: return launch_redo_t<32, double>(h, a, max_ctas);
+        case 128: return launch_redo_t<128, double>(h, a, max_ctas);
+        case 256: return launch_redo_t<256, double>(h, a, max_ctas);
+        default: return launch_redo_t<512, double>(h, a, max_ctas);
     }
 }
 
@@ -739,7 +751,8 @@ static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel
     const int smem = ws * WPC + plan_bytes;
     const int variant = 1000 + T * 64 + U * 8 + (PROT ? 1 : 0) + (STAGE ? 2 : 0) + (WPC > 1 ? 4 : 0);
     if (h->sparse_occ_smem != smem || h->sparse_occ_variant != variant) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        // (the staged variant owns a few bytes of static shared memory: dynamic + static must stay within the opt-in limit)
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin - 256));
         int occ = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, (size_t)smem));
         if (occ < 1) occ = 1;
@@ -787,6 +800,11 @@ static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) 
                            reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes <= 32 * 1024;
         if (T == 4 && U == 2) return stage ? launch_block_t<4, 2, 2, false, 4, true>(h, a, sel) : launch_block_t<4, 2, 2, false, 4, false>(h, a, sel);
         if (T == 8 && U == 1) return stage ? launch_block_t<8, 1, 2, false, 4, true>(h, a, sel) : launch_block_t<8, 1, 2, false, 4, false>(h, a, sel);
+    }
+    if (!a.prot && T == 8 && U == 1) {            // register budget of the default variant (resident warps per SM): tuning knob
+        if (h->blk_minb == 12) return launch_block_t<8, 1, 12, false>(h, a, sel);
+        if (h->blk_minb == 16) return launch_block_t<8, 1, 16, false>(h, a, sel);
+        if (h->blk_minb == 20) return launch_block_t<8, 1, 20, false>(h, a, sel);
     }
     if (a.prot) {
 #define X(t, u) if (T == t && U == u) return launch_block_t<t, u, (t <= 32 ? 8 : 4), true>(h, a, sel);

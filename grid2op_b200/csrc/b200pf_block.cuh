@@ -27,7 +27,9 @@ namespace b200pf {
 #ifdef B200PF_EMULATE
 #define PB_SYNC() ((void)0)
 #define PB_ANY(x) (x)
+#define PB_LOOP
 #else
+#define PB_LOOP _Pragma("unroll 1")      // the lane loops run 1-3 times: unrolled copies only cost instruction-cache misses (ncu: no_inst 15 %)
 template <int T, int G> __device__ __forceinline__ void pb_sync(unsigned mask) {
     if (T < 32) __syncwarp(mask); else if (T == 32) __syncwarp(); else __syncthreads();
 }
@@ -119,7 +121,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         const uint16_t *vmunit = U16(o_vmunit);
         const double *dcshift = F64(o_dcshift);
         PF_PHASE {
-            for (int i = tid; i < nb; i += T) {
+            PB_LOOP for (int i = tid; i < nb; i += T) {
                 double pg = 0.0, pd = 0.0, qd = 0.0, gs = 0.0, bsu = 0.0;
                 for (int e = bu_ptr[i]; e < bu_ptr[i + 1]; ++e) { const int u = bu[e]; pg += GEN_P(u); }
                 for (int e = bl_ptr[i]; e < bl_ptr[i + 1]; ++e) { const int k = bl[e]; pd += LOAD_P(k); qd += LOAD_Q(k); }
@@ -142,7 +144,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         const double *inv = F64(o_dcinv);
         const int n1 = H.n1;
         PF_PHASE {
-            for (int i = tid; i < n1; i += T) {
+            PB_LOOP for (int i = tid; i < n1; i += T) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 const double *col = inv + i;
                 int j = 0;
@@ -160,7 +162,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
     {
         int bad = 0;
         PF_PHASE {
-            for (int i = tid; i < nb; i += T) {
+            PB_LOOP for (int i = tid; i < nb; i += T) {
                 const int c = p_dcidx[i];
                 const double th = c != 0xFFFF ? Qc[IX(c)] : 0.0;
                 va[IX(i)] = th;
@@ -212,7 +214,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         }
         for (int it = 0;; ++it) {
             PF_PHASE {                                         // lane = line: currents at both ends, off-diagonal blocks (round 0)
-                for (int l = tid; l < nl; l += T) {
+                PB_LOOP for (int l = tid; l < nl; l += T) {
                     const int f = p_brf[l];
                     if (f == 0xFFFF) continue;
                     const int t = p_brt[l];
@@ -228,7 +230,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
             PB_SYNC();
             int viol = 0, wild = 0;
             PF_PHASE {                                         // lane = bus: S = V conj(I), mismatch, diagonal block, right-hand side
-                for (int i = tid; i < nb; i += T) {
+                PB_LOOP for (int i = tid; i < nb; i += T) {
                     const double2 Vi = V[IX(i)];
                     double ir = 0.0, ii = 0.0, gs = 0.0, bs = 0.0;
                     const int sx = shidx[i];
@@ -337,7 +339,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
 #undef PB_AT
             }
             PF_PHASE {                                         // lane = bus: state update from the solved right-hand-side blocks
-                for (int i = tid; i < nb; i += T) {
+                PB_LOOP for (int i = tid; i < nb; i += T) {
                     const int c = p_dcidx[i];
                     double vmi = vm[IX(i)], vai = va[IX(i)];
                     float4 X = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -366,7 +368,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                     }
                 }
                 // (the bus lanes above read right-hand-side blocks only; the cleared set holds off-diagonal blocks)
-                for (int k = tid; k < n_bzero; k += T) A4[IX(bzero[k])] = make_float4(0.f, 0.f, 0.f, 0.f);
+                PB_LOOP for (int k = tid; k < n_bzero; k += T) A4[IX(bzero[k])] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             PB_SYNC();
         }
@@ -375,7 +377,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
     } else {
         // DC: line lanes compute flows from the angles, bus lanes sum them for the slack share
         PF_PHASE {
-            for (int l = tid; l < nl; l += T) {
+            PB_LOOP for (int l = tid; l < nl; l += T) {
                 const int f = p_brf[l];
                 if (f == 0xFFFF) continue;
                 const double pfl = g.line_bdc[l] * (V[IX(f)].x - V[IX(p_brt[l])].x) + g.line_pshift[l];
@@ -384,7 +386,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         }
         PB_SYNC();
         PF_PHASE {
-            for (int i = tid; i < nb; i += T) {
+            PB_LOOP for (int i = tid; i < nb; i += T) {
                 const int sx = shidx[i];
                 double p = sx != 0xFFFF ? gsh[IX(sx)] : 0.0;
                 for (int e = adj_ptr[i]; e < adj_ptr[i + 1]; ++e) p += cur[IX(adj[e])].x;
@@ -408,7 +410,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         const double *qmins = F64(o_qmins), *qmaxs = F64(o_qmaxs);
         PF_PHASE {
             if (tid == 0) { a.status[inst] = ST_OK; a.iters[inst] = iters; }
-            for (int l = tid; l < nl; l += T) {
+            PB_LOOP for (int l = tid; l < nl; l += T) {
                 float r[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 const int f = p_brf[l];
                 if (f != 0xFFFF) {
@@ -434,7 +436,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
             }
             if (out) {
                 float *o = out + 10 * nl;
-                for (int u = tid; u < nu; u += T) {
+                PB_LOOP for (int u = tid; u < nu; u += T) {
                     float p = 0.f, q = 0.f, v = 0.f, th = 0.f;
                     const int i = unit_bus[u];
                     if (i != 0xFFFF) {
@@ -456,15 +458,15 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                     o[u] = p; o[nu + u] = q; o[2 * nu + u] = v; o[3 * nu + u] = th;
                 }
                 o += 4 * nu;
-                for (int k = tid; k < nld; k += T) {
+                PB_LOOP for (int k = tid; k < nld; k += T) {
                     const int i = load_bus[k];
                     o[k] = i != 0xFFFF ? PF_FMUL((float)vm[IX(i)], g.load_vn[k]) : 0.f;
                     o[nld + k] = i != 0xFFFF ? (float)(va[IX(i)] * RAD2DEG) : 0.f;
                 }
                 o += 2 * nld;
-                for (int k = tid; k < nst; k += T) { const int i = sto_bus[k]; o[k] = i != 0xFFFF ? PF_FMUL((float)vm[IX(i)], g.sto_vn[k]) : 0.f; }
+                PB_LOOP for (int k = tid; k < nst; k += T) { const int i = sto_bus[k]; o[k] = i != 0xFFFF ? PF_FMUL((float)vm[IX(i)], g.sto_vn[k]) : 0.f; }
                 o += nst;
-                for (int k = tid; k < nsh; k += T) {
+                PB_LOOP for (int k = tid; k < nsh; k += T) {
                     const int i = sh_bus[k];
                     float p = 0.f, q = 0.f, v = 0.f;
                     if (i != 0xFFFF) {
@@ -478,7 +480,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
             }
             if (a.busv) {
                 double *bv = a.busv + (size_t)inst * 2 * g.n_slot;
-                for (int s = tid; s < 2 * g.n_slot; s += T) bv[s] = PF_QNAN();
+                PB_LOOP for (int s = tid; s < 2 * g.n_slot; s += T) bv[s] = PF_QNAN();
             }
         }
         PB_SYNC();
@@ -494,7 +496,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         const size_t base_l = (size_t)inst * nl;
         int any_trip = 0;
         PF_PHASE {
-            for (int l = tid; l < nl; l += T) {
+            PB_LOOP for (int l = tid; l < nl; l += T) {
                 const bool on = p_brf[l] != 0xFFFF;
                 const float aor = out[3 * nl + l], lim = a.th_lim[l];
                 int inc = a.casc > 0 ? (int)a.incdone[base_l + l] : 0;
@@ -519,7 +521,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                     a.flag_list[slot] = inst;
                 }
             } else {
-                for (int l = tid; l < nl; l += T) {
+                PB_LOOP for (int l = tid; l < nl; l += T) {
                     const float aor = out[3 * nl + l], lim = a.th_lim[l];
                     int *pcp = a.pcount + base_l, *tsp = a.ts_over + base_l;
                     pcp[l] = (!a.from_reset && aor > PF_FMUL(a.soft_thr, lim)) ? pcp[l] + 1 : 0;

@@ -83,6 +83,8 @@ struct RunArgs {
     // safety net of the non-pivoting planned kernel (b200pf_redo.cuh): 1 = this launch re-solves, with partial pivoting,
     // the instances the planned kernel left as ST_DIV; the series row of such an instance was already advanced
     int redo;
+    unsigned char *redo_mat;  // safety net on large grids: per-CTA matrix region in GLOBAL memory (an fp64 Jacobian of the 118-substation
+    size_t redo_mat_stride;   // grid does not fit on chip; the path is rare, its speed does not matter), nullptr = shared memory
     int dbg_div_mod;         // test knob: > 0 makes the planned kernel give up (ST_DIV) on every instance with inst % mod == 0
 };
 
@@ -498,6 +500,7 @@ template <int T, typename JT>
 __device__ void solve_instance(const DevGrid &g, const RunArgs &a, int inst, unsigned char *wsbase, int tid) {
     const int nbc = a.nb_cap;
     Ws w = ws_bind(wsbase, nbc, g.n_slot, g.n_line, g.n_inj, (size_t)a.mat_bytes);
+    if (a.redo_mat) w.mat = a.redo_mat + (size_t)blockIdx.x * a.redo_mat_stride;
     const int src = a.n1_lines > 0 ? inst / a.n1_lines : inst;          // record the inputs come from
     const int outage = a.n1_lines > 0 ? inst % a.n1_lines : -1;         // line forced out of service (N-1 sweep)
     const int8_t *tv = a.topo + (size_t)src * g.n_topo_in;

@@ -100,6 +100,7 @@ struct RunArgs {
     int8_t *trip, *incdone;
     int *n_flag, *flag_list;
     int redo, dbg_div_mod;
+    unsigned char *redo_mat; size_t redo_mat_stride;
 };
 enum { ST_OK = 0, ST_DIV = 1, ST_UNSUP = 2, ST_NOREF = 3, ST_LARGE = 4, ST_DONE = 5 };
 enum { BT_PQ = 1, BT_PV = 2, BT_REF = 3 };

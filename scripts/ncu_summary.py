@@ -91,6 +91,8 @@ def main():
         "top_source_lines_by_samples": [{"line": f"{k[0]}:{k[1]}", "samples_pct": round(100.0 * v[1] / tot_s, 1),
                                          "inst_pct": round(100.0 * v[0] / tot_i, 1), "source": src[k].strip()[:100]} for k, v in top],
     }
+    summ["all_source_lines"] = [[f"{k[0]}:{k[1]}", round(100.0 * v[0] / tot_i, 2), round(100.0 * v[1] / tot_s, 2)]
+                                for k, v in sorted(agg.items()) if v[1] * 1000 >= tot_s or v[0] * 1000 >= tot_i]     # [line, inst %, samples %]
     json.dump(summ, open(outp + "_summary.json", "w"), indent=1)
     det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
     open(outp + "_details.txt", "w").write("\n".join(det.splitlines()[:170]) + "\n")

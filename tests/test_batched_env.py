@@ -24,8 +24,10 @@ def _scripted(k, rng, obs_topo, line_status, line_cd, sub_cd, sub_pos, sub_size,
     Substation actions put two of the connected line ends on busbar 2 (a pass-through node: nothing gets isolated) or
     everything back on busbar 1."""
     act = dict(sub=-1, bus=None, line=-1, status=0)
-    if k % 3 == 0:
+    if k % 3 == 0 or k % 10 == 4:
         s = int(rng.integers(0, len(sub_size)))
+        if k % 10 == 4 and (sub_cd > 0).any():
+            s = int(np.flatnonzero(sub_cd > 0)[0])          # on purpose: a substation that is still in cooldown -> illegal
         pos = sub_pos[s, :sub_size[s]]
         live = obs_topo[pos] > 0
         bus = np.where(live, 1, 0)

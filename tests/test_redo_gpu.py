@@ -148,13 +148,14 @@ def test_forced_breakdowns_in_series_rows_and_n1_modes(cuda_required):
         assert np.array_equal(o1[1::2], o2[1::2])              # untouched instances: same kernel, bit-equal
     assert env.engine.redo_launch_count >= 4
     # host rows path (pipelined chunks) and the group path with zero-copy inputs
+    ref_h = BatchedDoNothing(gm, chron, B)             # (the host path keeps its own row counter: k-th call = k-th row)
     for _ in range(2):
-        ref.step_device()
-        o1, s1, _, _ = ref.fetch()
+        ref_h.step_device()
+        o1, s1, _, _ = ref_h.fetch()
         o2, s2 = env.step_host()
         assert (s2 == 0).all()
         _compare(gm, o2.copy(), o1, s1 == 0)
-    ref.close(); env.close()
+    ref.close(); env.close(); ref_h.close()
     # N-1 sweep
     z = np.load(os.path.join(GOLD, "oracle_case14_steps.npz"))
     topo, inj = z["topo"][:8], z["inj"][:8]
