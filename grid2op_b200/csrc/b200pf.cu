@@ -84,7 +84,7 @@ struct b200pf_handle {
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
-    int blk_wpc = 1, blk_stage = 0, blk_minb = 8;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
+    int blk_wpc = 1, blk_stage = 0, blk_minb = 8, blk_uni = 1;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
     bool series_plans_stale = false;                        // the cache was reset under the series' plan ids: re-resolve before the next step
@@ -245,7 +245,9 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         if (bk && bk[0] == '1') h->blk = 1;
         if (bt && bu && block_variant_exists(atoi(bt), atoi(bu))) { h->blk_T = atoi(bt); h->blk_U = atoi(bu); }
         const char *bm = getenv("B200PF_BLOCK_MINB");
-        if (bm && (atoi(bm) == 12 || atoi(bm) == 16 || atoi(bm) == 20)) h->blk_minb = atoi(bm);
+        if (bm && (atoi(bm) == 8 || atoi(bm) == 16 || atoi(bm) == 20)) h->blk_minb = atoi(bm);
+        const char *bun = getenv("B200PF_BLOCK_UNI");
+        if (bun && bun[0] == '0') h->blk_uni = 0;
         const char *bw = getenv("B200PF_BLOCK_WPC"), *bs = getenv("B200PF_BLOCK_STAGE");
         if (bw && atoi(bw) == 4) h->blk_wpc = 4;
         if (bs && bs[0] == '1') { h->blk_stage = 1; h->blk_wpc = 4; }
@@ -739,17 +741,17 @@ static int launch_redo(b200pf_handle *h, RunArgs a, int nb_cap_req) {
 // ------------------------------------------------------------------------------------------------
 // block-planned kernel (b200pf_block.cuh)
 // ------------------------------------------------------------------------------------------------
-template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false>
+template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false, bool UNI = false>
 static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
     const DevGrid &g = h->g;
     constexpr int G = T < 32 ? 32 / T : 1;
     constexpr int BLOCK = (T < 32 ? 32 : T) * WPC;
-    auto kern = pf_kernel_block<T, U, MINB, PROT, WPC, STAGE>;
+    auto kern = pf_kernel_block<T, U, MINB, PROT, WPC, STAGE, UNI>;
     const int ws = sel.smem * G;                         // workspace of one warp / CTA
     int plan_bytes = 0;
     if (STAGE) plan_bytes = reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes;
     const int smem = ws * WPC + plan_bytes;
-    const int variant = 1000 + T * 64 + U * 8 + (PROT ? 1 : 0) + (STAGE ? 2 : 0) + (WPC > 1 ? 4 : 0);
+    const int variant = 1000 + MINB * 4096 + T * 64 + U * 8 + (PROT ? 1 : 0) + (STAGE ? 2 : 0) + (WPC > 1 ? 4 : 0) + (UNI ? 100000 : 0);
     if (h->sparse_occ_smem != smem || h->sparse_occ_variant != variant) {
         // (the staged variant owns a few bytes of static shared memory: dynamic + static must stay within the opt-in limit)
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin - 256));
@@ -801,8 +803,15 @@ static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) 
         if (T == 4 && U == 2) return stage ? launch_block_t<4, 2, 2, false, 4, true>(h, a, sel) : launch_block_t<4, 2, 2, false, 4, false>(h, a, sel);
         if (T == 8 && U == 1) return stage ? launch_block_t<8, 1, 2, false, 4, true>(h, a, sel) : launch_block_t<8, 1, 2, false, 4, false>(h, a, sel);
     }
-    if (!a.prot && T == 8 && U == 1) {            // register budget of the default variant (resident warps per SM): tuning knob
-        if (h->blk_minb == 12) return launch_block_t<8, 1, 12, false>(h, a, sel);
+    if (!a.prot && T == 8 && U == 1) {
+        // lockstep warps (one plan for the whole launch, whole warps): full-mask barriers / votes instead of per-instance collectives
+        const bool uni = h->blk_uni && !sel.d_inst_plan && a.batch % 4 == 0;
+        // register budget (resident warps per SM): 20 warps x 94 registers is the default, B200PF_BLOCK_MINB = 8 / 16 to compare
+        if (uni) {
+            if (h->blk_minb == 8) return launch_block_t<8, 1, 8, false, 1, false, true>(h, a, sel);
+            if (h->blk_minb == 16) return launch_block_t<8, 1, 16, false, 1, false, true>(h, a, sel);
+            return launch_block_t<8, 1, 20, false, 1, false, true>(h, a, sel);
+        }
         if (h->blk_minb == 16) return launch_block_t<8, 1, 16, false>(h, a, sel);
         if (h->blk_minb == 20) return launch_block_t<8, 1, 20, false>(h, a, sel);
     }

@@ -30,18 +30,21 @@ namespace b200pf {
 #define PB_LOOP
 #else
 #define PB_LOOP _Pragma("unroll 1")      // the lane loops run 1-3 times: unrolled copies only cost instruction-cache misses (ncu: no_inst 15 %)
-template <int T, int G> __device__ __forceinline__ void pb_sync(unsigned mask) {
-    if (T < 32) __syncwarp(mask); else if (T == 32) __syncwarp(); else __syncthreads();
+// UNI ("lockstep"): all instances of the warp share one plan and run the same control flow, so the whole warp
+// synchronises with the plain full-mask primitives.  A per-lane mask (instances free to diverge) makes every barrier / vote a
+// MATCH-based collective — 12 % of the samples in profiles/round2_ncu_block_case14_summary.json.
+template <int T, int G, bool UNI> __device__ __forceinline__ void pb_sync(unsigned mask) {
+    if (T < 32) { if (UNI) __syncwarp(); else __syncwarp(mask); } else if (T == 32) __syncwarp(); else __syncthreads();
 }
-template <int T, int G> __device__ __forceinline__ int pb_any(unsigned mask, int p) {
-    if (T < 32) return __any_sync(mask, p);
+template <int T, int G, bool UNI> __device__ __forceinline__ int pb_any(unsigned mask, int p) {
+    if (T < 32) return UNI ? ((__ballot_sync(0xffffffffu, p) & mask) != 0u) : __any_sync(mask, p);
     return (T == 32) ? __any_sync(0xffffffffu, p) : __syncthreads_or(p);
 }
-#define PB_SYNC() pb_sync<T, G>(imask)
-#define PB_ANY(x) pb_any<T, G>(imask, (x))
+#define PB_SYNC() pb_sync<T, G, UNI>(imask)
+#define PB_ANY(x) pb_any<T, G, UNI>(imask, (x))
 #endif
 
-template <int T, int G>
+template <int T, int G, bool UNI = false>
 PF_DEV void block_fail(const DevGrid &g, const RunArgs &a, int inst, int status, int iters, int tid0, unsigned imask) {
 #ifndef B200PF_EMULATE
     const int tid = tid0;
@@ -59,7 +62,7 @@ PF_DEV void block_fail(const DevGrid &g, const RunArgs &a, int inst, int status,
 }
 
 // sm: workspace of the WARP (G instances, interleaved); gi: instance slot of this lane in the warp; tid0: lane of the instance
-template <int T, int U, int G, bool PROT>
+template <int T, int U, int G, bool PROT, bool UNI = false>
 PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, int inst, unsigned char *sm, int gi, int tid0, unsigned imask) {
 #ifndef B200PF_EMULATE
     const int tid = tid0;
@@ -74,9 +77,13 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         if (PROT && a.casc > 0) trow = trow == 0 ? a.n_rows - 1 : trow - 1;       // later cascade rounds re-solve the SAME row
         PF_PHASE { if (tid == 0 && a.n1_lines <= 0 && !(PROT && a.casc > 0)) a.t[inst] = (trow + 1 >= a.n_rows) ? 0 : trow + 1; }
     }
-    if (PROT && a.done[inst] && a.casc == 0) { block_fail<T, G>(g, a, inst, ST_DONE, 0, tid0, imask); return; }
-    if (H.status != PLAN_ST_OK) { block_fail<T, G>(g, a, inst, H.status, 0, tid0, imask); return; }
-    if (a.dbg_div_mod > 0 && inst % a.dbg_div_mod == 0) { block_fail<T, G>(g, a, inst, ST_DIV, 0, tid0, imask); return; }   // test knob
+    // fstat >= 0: the instance has failed with this status.  Free-running instances (UNI = false) leave at once; in lockstep
+    // the lanes keep executing with the warp (their state is garbage from then on) and store the failure record at the end.
+    int fstat = -1, fiters = 0;
+#define PB_FAIL(st, its) { if (UNI) { if (fstat < 0) { fstat = (st); fiters = (its); } } else { block_fail<T, G, UNI>(g, a, inst, (st), (its), tid0, imask); return; } }
+    if (PROT && a.done[inst] && a.casc == 0) { block_fail<T, G, UNI>(g, a, inst, ST_DONE, 0, tid0, imask); return; }
+    if (H.status != PLAN_ST_OK) { block_fail<T, G, UNI>(g, a, inst, H.status, 0, tid0, imask); return; }      // (lockstep: one plan -> the whole warp leaves)
+    if (a.dbg_div_mod > 0 && inst % a.dbg_div_mod == 0) PB_FAIL(ST_DIV, 0)   // test knob
     const int nb = H.nb, nl = g.n_line, nu = g.n_unit, nh = g.n_hidden, ng = g.n_gen, nld = g.n_load, nst = g.n_sto, nsh = g.n_shunt;
     const int nblk = H.nblk, nblkA = H.nblkA;
     const double base = g.base_mva;
@@ -173,7 +180,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
             }
         }
         bad = PB_ANY(bad);
-        if (bad) { block_fail<T, G>(g, a, inst, ST_DIV, 0, tid0, imask); return; }
+        if (bad) PB_FAIL(ST_DIV, 0)
     }
     // ---- 3. Newton-Raphson ---------------------------------------------------------------------------------
     // Four phases per iteration: [lane = line: branch currents + off-diagonal blocks] [lane = bus: S(V), mismatch, diagonal
@@ -184,7 +191,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         const double *ydiag = F64(o_ydiag);
         const uint2 *bops = reinterpret_cast<const uint2 *>(blob + H.o_bops);
         const int n_brow = H.n_brow, n_round = H.n_round, n_bzero = H.n_bzero, n_late = H.n_late;
-        bool conv = false;
+        bool conv = false, running = fstat < 0;
         PF_PHASE { for (int k = tid; k < n_bzero; k += T) A4[IX(bzero[k])] = make_float4(0.f, 0.f, 0.f, 0.f); }
         PB_SYNC();
         // off-diagonal blocks of line l: block (f, t) += [ti tr; -tr ti] with T = Vf conj(yft Vt), rows of a PV bus f keep only
@@ -257,9 +264,23 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                 }
             }
             viol = PB_ANY(viol);
-            if (!viol) { conv = true; iters = it; break; }
-            wild = PB_ANY(wild);
-            if (it >= a.max_iter || wild) { iters = it; break; }
+#ifndef B200PF_EMULATE
+            if (UNI) {
+                // lockstep: an instance that is through (converged / given up) keeps running with the warp until all are; its
+                // state is frozen (no update below), so the repeated evaluations reproduce the same currents and powers
+                wild = PB_ANY(wild);
+                if (running) {
+                    if (!viol) { conv = true; iters = it; running = false; }
+                    else if (it >= a.max_iter || wild) { iters = it; running = false; }
+                }
+                if (!__any_sync(0xffffffffu, running)) break;
+            } else
+#endif
+            {
+                if (!viol) { conv = true; iters = it; break; }
+                wild = PB_ANY(wild);
+                if (it >= a.max_iter || wild) { iters = it; break; }
+            }
             for (int r = 1, q = 0; r < n_round; ++r) {         // parallel lines / lines inside one bus: later rounds, one barrier each (rare)
                 PF_PHASE {
                     for (int k = q + tid; k < n_late && late[2 * k + 1] == r; k += T) {
@@ -339,7 +360,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
 #undef PB_AT
             }
             PF_PHASE {                                         // lane = bus: state update from the solved right-hand-side blocks
-                PB_LOOP for (int i = tid; i < nb; i += T) {
+                PB_LOOP for (int i = tid; i < ((!UNI || running) ? nb : 0); i += T) {
                     const int c = p_dcidx[i];
                     double vmi = vm[IX(i)], vai = va[IX(i)];
                     float4 X = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -373,7 +394,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
             PB_SYNC();
         }
 #undef PB_OFFDIAG
-        if (!conv) { block_fail<T, G>(g, a, inst, ST_DIV, iters, tid0, imask); return; }
+        if (!conv) PB_FAIL(ST_DIV, iters)
     } else {
         // DC: line lanes compute flows from the angles, bus lanes sum them for the slack share
         PF_PHASE {
@@ -409,6 +430,12 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         const uint16_t *bs_ptr = U16(o_bs_ptr), *bs = U16(o_bs), *p_cnt = U16(o_cnt), *p_nref = U16(o_nref), *p_slot = U16(o_slot);
         const double *qmins = F64(o_qmins), *qmaxs = F64(o_qmaxs);
         PF_PHASE {
+          if (UNI && fstat >= 0) {                             // lockstep: the failure record, stored without leaving the warp
+            if (tid == 0) { a.status[inst] = fstat; a.iters[inst] = fiters; }
+            if (out) for (int k = tid; k < g.n_out; k += T) out[k] = PF_QNANF();
+            if (a.busv) for (int k = tid; k < 2 * g.n_slot; k += T) a.busv[(size_t)inst * 2 * g.n_slot + k] = PF_QNAN();
+            if (a.rho) for (int k = tid; k < g.n_line; k += T) a.rho[(size_t)inst * g.n_line + k] = PF_QNANF();
+          } else {
             if (tid == 0) { a.status[inst] = ST_OK; a.iters[inst] = iters; }
             PB_LOOP for (int l = tid; l < nl; l += T) {
                 float r[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -482,11 +509,12 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                 double *bv = a.busv + (size_t)inst * 2 * g.n_slot;
                 PB_LOOP for (int s = tid; s < 2 * g.n_slot; s += T) bv[s] = PF_QNAN();
             }
+          }
         }
         PB_SYNC();
         if (a.busv) {
             double *bv = a.busv + (size_t)inst * 2 * g.n_slot;
-            PF_PHASE { for (int i = tid; i < nb; i += T) { bv[p_slot[i]] = vm[IX(i)]; bv[g.n_slot + p_slot[i]] = va[IX(i)]; } }
+            PF_PHASE { if (!(UNI && fstat >= 0)) for (int i = tid; i < nb; i += T) { bv[p_slot[i]] = vm[IX(i)]; bv[g.n_slot + p_slot[i]] = va[IX(i)]; } }
             PB_SYNC();
         }
     }
@@ -533,6 +561,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         PB_SYNC();
     }
     (void)imask;
+#undef PB_FAIL
 #undef U16
 #undef F64
 #undef IX
@@ -575,7 +604,8 @@ __device__ __forceinline__ void pb_stage_plan(unsigned char *dst, const unsigned
 // WPC warps per CTA for T <= 32 (each warp: G = 32 / T instances interleaved), one CTA of T threads per instance beyond.
 // Persistent: warp slot w of CTA c takes the instance groups c * WPC + w, + gridDim * WPC, ...
 // ws_bytes: workspace of one warp; STAGE: the launch's single plan is copied behind the workspaces first (plan_bytes).
-template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false>
+// UNI (T < 32 only): lockstep warps — requires ONE plan for the launch and batch % G == 0 (the host checks both).
+template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false, bool UNI = false>
 __global__ void __launch_bounds__((T < 32 ? 32 : T) * WPC, MINB)
 pf_kernel_block(const DevGrid g, const RunArgs a, const PlanArgs pa_in, const int ws_bytes, const int plan_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -608,7 +638,7 @@ pf_kernel_block(const DevGrid g, const RunArgs a, const PlanArgs pa_in, const in
         const int k = w * G + gi;
         if (k < a.batch) {
             const int inst = (PROT && a.inst_list) ? a.inst_list[k] : k;
-            solve_block<T, U, G, PROT>(g, a, pa, inst, ws, gi, j, imask);
+            solve_block<T, U, G, PROT, UNI>(g, a, pa, inst, ws, gi, j, imask);
         }
         if (T <= 32) __syncwarp(); else __syncthreads();
     }

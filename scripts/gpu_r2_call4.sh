@@ -9,9 +9,11 @@ run() { # name, batch, env...
   python -c "import json;d=json.load(open('gpurun_out/var.json'));print('$name B=$batch',round(d['value']/1e6,2),'M/s',round(1e3*d['ms_per_step'],2),'us',d['config']['launch'],d['parity_check']['ok'])" 2>/dev/null || tail -3 gpurun_out/var_err.txt
 }
 for B in 4096 16384 65536; do
-  run "minb8" $B B200PF_BLOCK_MINB=8
-  run "minb16" $B B200PF_BLOCK_MINB=16
-  run "minb20" $B B200PF_BLOCK_MINB=20
+  run "free minb8" $B B200PF_BLOCK_MINB=8 B200PF_BLOCK_UNI=0
+  run "free minb20" $B B200PF_BLOCK_MINB=20 B200PF_BLOCK_UNI=0
+  run "lockstep minb8" $B B200PF_BLOCK_MINB=8
+  run "lockstep minb16" $B B200PF_BLOCK_MINB=16
+  run "lockstep minb20" $B B200PF_BLOCK_MINB=20
   run "wpc4" $B B200PF_BLOCK_WPC=4
   run "wpc4+stage" $B B200PF_BLOCK_STAGE=1
   run "noredo" $B B200PF_NO_REDO=1
@@ -19,7 +21,7 @@ done
 run "scalar" 4096 B200PF_BLOCK=0
 run "scalar" 65536 B200PF_BLOCK=0
 echo "== ncu block case14 minb20 batch 65536"
-B200PF_BLOCK_MINB=20 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pf_kernel_block -s 6 -c 1 -o gpurun_out/prof_b python bench.py --batch 65536 --steps 8 --warmup 3 --no-cpu --e2e-groups 0 > gpurun_out/ncu2.log 2>&1
+B200PF_BLOCK_MINB=20 B200PF_BLOCK_UNI=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pf_kernel_block -s 6 -c 1 -o gpurun_out/prof_b python bench.py --batch 65536 --steps 8 --warmup 3 --no-cpu --e2e-groups 0 > gpurun_out/ncu2.log 2>&1
 python scripts/ncu_summary.py gpurun_out/prof_b.ncu-rep gpurun_out/round2_ncu_block_case14_minb20_b65536 "pf_kernel_block<8,1,MINB=20> l2rpn_case14_sandbox batch 65536 (ncu --set full --clock-control none)" 65536 "planned_block:case14:T8:minb20:b65536"
 rm -f gpurun_out/prof_b.ncu-rep
 echo "== ncu launches"

@@ -134,3 +134,30 @@ def test_block_kernel_series_rows_n1_and_shared_plan_batches(cuda_required):
     ok = st0 == 0
     assert np.allclose(rho0[ok], rho1[ok], rtol=2e-5, atol=1e-6)
     e0.close(); e1.close()
+
+
+def test_lockstep_warps_equal_free_running_warps(cuda_required):
+    """Shared-plan launches run the block kernel with lockstep warps (full-mask barriers); the free-running variant
+    (B200PF_BLOCK_UNI=0) must give bit-identical records — also for instances that fail inside a warp (test knob) while their
+    warp mates go on, and with iteration counts that differ inside a warp."""
+    from grid2op_b200.rollout import BatchedDoNothing
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"].copy()
+    chron[1, :, :2 * gm.n_load] *= 1.6                    # scenario 1 heavier: other iteration counts inside the same warps
+    B = 1024
+    with _env(B200PF_BLOCK_UNI=0):
+        free = BatchedDoNothing(gm, chron, B)
+    lock = BatchedDoNothing(gm, chron, B)
+    for knob in (0, 3):
+        free.engine.set_debug(knob, redo_enabled=False); lock.engine.set_debug(knob, redo_enabled=False)
+        for _ in range(3):
+            free.step_device(); lock.step_device()
+            o1, s1, i1, r1 = free.fetch()
+            o2, s2, i2, r2 = lock.fetch()
+            assert lock.engine.plan_stats()["last_kernel"] == "planned_block"
+            assert np.array_equal(s1, s2) and np.array_equal(i1, i2)
+            assert len(np.unique(i1[s1 == 0])) >= 2
+            assert np.array_equal(o1, o2, equal_nan=True) and np.array_equal(r1, r2, equal_nan=True)
+            if knob:
+                assert (s1[::3] == 1).all() and (s1[1::3] == 0).all()
+    free.close(); lock.close()
