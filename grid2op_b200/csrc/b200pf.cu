@@ -84,11 +84,12 @@ struct b200pf_handle {
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
-    int blk_wpc = 1, blk_stage = 0, blk_minb = 8, blk_uni = 1;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
+    int blk_wpc = 1, blk_stage = 0, blk_minb = 16, blk_uni = 1;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
     bool series_plans_stale = false;                        // the cache was reset under the series' plan ids: re-resolve before the next step
     int64_t launches = 0;
+    int redo_pdl = 1;                                       // B200PF_REDO_PDL=0: plain stream-ordered launch of the safety net
     int redo_enabled = 1;                                   // pivoting re-solve of what the planned kernel leaves as ST_DIV (B200PF_NO_REDO=1 turns it off)
     int dbg_div_mod = 0;                                    // test knob, see b200pf_set_debug
     int64_t redo_launches = 0;
@@ -251,6 +252,8 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         const char *bw = getenv("B200PF_BLOCK_WPC"), *bs = getenv("B200PF_BLOCK_STAGE");
         if (bw && atoi(bw) == 4) h->blk_wpc = 4;
         if (bs && bs[0] == '1') { h->blk_stage = 1; h->blk_wpc = 4; }
+        const char *rp = getenv("B200PF_REDO_PDL");
+        if (rp && rp[0] == '0') h->redo_pdl = 0;
         const char *nr = getenv("B200PF_NO_REDO");              // measurement only: planned kernel without its safety net
         if (nr && nr[0] == '1') h->redo_enabled = 0;
         const char *var = getenv("B200PF_SPARSE_T");            // tuning: threads per instance of the planned kernel
@@ -614,7 +617,7 @@ static int launch_sparse_t(b200pf_handle *h, const RunArgs &a, const PlanSel &se
         }
         h->sparse_occ = occ; h->sparse_occ_smem = smem; h->sparse_occ_variant = variant;
     }
-    PlanArgs pa;
+    PlanArgs pa{};
     pa.blobs = h->d_plan_blobs;
     pa.plan_off = h->d_plan_off + (sel.d_inst_plan ? 0 : sel.single);
     pa.inst_plan = sel.d_inst_plan;
@@ -692,7 +695,16 @@ static int launch_redo_t(b200pf_handle *h, const RunArgs &a, int max_ctas) {
     int grid = (a.batch + 31) / 32;
     if (grid > max_ctas) grid = max_ctas;
     if (grid < 1) grid = 1;
-    kern<<<grid, T, smem, h->stream>>>(g, a, (int)smem);
+    {   // programmatic dependent launch: the launch latency of this (almost always idle) kernel overlaps the planned kernel's tail
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)T); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = h->redo_pdl ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const int wsb = (int)smem;
+        CU(cudaLaunchKernelEx(&cfg, kern, g, a, wsb));
+    }
     CU(cudaGetLastError());
     h->redo_launches++;
     return 0;
@@ -768,7 +780,7 @@ static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel
         }
         h->sparse_occ = occ; h->sparse_occ_smem = smem; h->sparse_occ_variant = variant;
     }
-    PlanArgs pa;
+    PlanArgs pa{};
     pa.blobs = h->d_plan_blobs;
     pa.plan_off = h->d_plan_off + (sel.d_inst_plan ? 0 : sel.single);
     pa.inst_plan = sel.d_inst_plan;
@@ -806,14 +818,15 @@ static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) 
     if (!a.prot && T == 8 && U == 1) {
         // lockstep warps (one plan for the whole launch, whole warps): full-mask barriers / votes instead of per-instance collectives
         const bool uni = h->blk_uni && !sel.d_inst_plan && a.batch % 4 == 0;
-        // register budget (resident warps per SM): 20 warps x 94 registers is the default, B200PF_BLOCK_MINB = 8 / 16 to compare
+        // register budget (resident warps per SM): 16 warps x 128 registers measured best at every batch size
+        // (profiles/round2_block_variants.txt), B200PF_BLOCK_MINB = 8 / 20 to compare
         if (uni) {
             if (h->blk_minb == 8) return launch_block_t<8, 1, 8, false, 1, false, true>(h, a, sel);
-            if (h->blk_minb == 16) return launch_block_t<8, 1, 16, false, 1, false, true>(h, a, sel);
-            return launch_block_t<8, 1, 20, false, 1, false, true>(h, a, sel);
+            if (h->blk_minb == 20) return launch_block_t<8, 1, 20, false, 1, false, true>(h, a, sel);
+            return launch_block_t<8, 1, 16, false, 1, false, true>(h, a, sel);
         }
-        if (h->blk_minb == 16) return launch_block_t<8, 1, 16, false>(h, a, sel);
         if (h->blk_minb == 20) return launch_block_t<8, 1, 20, false>(h, a, sel);
+        if (h->blk_minb == 16) return launch_block_t<8, 1, 16, false>(h, a, sel);
     }
     if (a.prot) {
 #define X(t, u) if (T == t && U == u) return launch_block_t<t, u, (t <= 32 ? 8 : 4), true>(h, a, sel);

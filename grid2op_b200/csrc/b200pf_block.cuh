@@ -148,7 +148,8 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
     }
     // ---- 2. DC angles: theta = Bdc^-1 b with the plan's fp64 inverse (lane = row; Pc = right-hand side, Qc = result) ------
     {
-        const double *inv = F64(o_dcinv);
+        // (the inverse is streamed from global memory with evict-first loads even when the plan itself is staged in shared memory)
+        const double *inv = reinterpret_cast<const double *>((pa.stage_src ? pa.stage_src : blob) + H.o_dcinv);
         const int n1 = H.n1;
         PF_PHASE {
             PB_LOOP for (int i = tid; i < n1; i += T) {
@@ -630,6 +631,7 @@ pf_kernel_block(const DevGrid g, const RunArgs a, const PlanArgs pa_in, const in
         pb_stage_plan(dst, pa_in.blobs + pa_in.plan_off[0], (uint32_t)plan_bytes, &mbar);
         if (threadIdx.x == 0) zero_off = 0;
         __syncthreads();
+        pa.stage_src = pa_in.blobs + pa_in.plan_off[0];
         pa.blobs = dst; pa.plan_off = &zero_off; pa.inst_plan = nullptr;
     }
     unsigned char *ws = smem + (size_t)warp * ws_bytes;

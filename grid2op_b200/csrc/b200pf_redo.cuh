@@ -58,6 +58,9 @@ pf_kernel_redo(const DevGrid g, const RunArgs a, const int ws_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     (void)ws_bytes;
     const int tid = threadIdx.x;
+    // launched with programmatic stream serialisation right behind the planned kernel: this grid is set up while that one
+    // drains, and waits here until it has completed and its results are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int first = blockIdx.x * 32; first < a.batch; first += gridDim.x * 32) {
         // every warp of the CTA computes the same mask (the status words are only written at the very end of a
         // re-solve, behind group barriers that all warps pass)

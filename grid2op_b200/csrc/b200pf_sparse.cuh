@@ -117,6 +117,7 @@ struct PlanArgs {
     // block kernel: the instances interleaved in one warp must agree on the workspace layout whatever their plans are ->
     // array strides of the LAUNCH (maxima over its plans): buses, value blocks
     int lay_nb, lay_nblkA;
+    const unsigned char *stage_src;   // block kernel with a TMA-staged plan: the plan's copy in global memory (streaming loads need it)
 };
 
 template <int T>
