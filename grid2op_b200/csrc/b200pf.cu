@@ -84,7 +84,7 @@ struct b200pf_handle {
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
-    int blk_wpc = 1, blk_stage = 0, blk_minb = 16, blk_uni = 1;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
+    int blk_wpc = 4, blk_stage = 1, blk_minb = 16, blk_uni = 1;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
     bool series_plans_stale = false;                        // the cache was reset under the series' plan ids: re-resolve before the next step
@@ -250,8 +250,8 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         const char *bun = getenv("B200PF_BLOCK_UNI");
         if (bun && bun[0] == '0') h->blk_uni = 0;
         const char *bw = getenv("B200PF_BLOCK_WPC"), *bs = getenv("B200PF_BLOCK_STAGE");
-        if (bw && atoi(bw) == 4) h->blk_wpc = 4;
-        if (bs && bs[0] == '1') { h->blk_stage = 1; h->blk_wpc = 4; }
+        if (bw && (atoi(bw) == 1 || atoi(bw) == 2 || atoi(bw) == 4)) h->blk_wpc = atoi(bw);
+        if (bs && (bs[0] == '0' || bs[0] == '1')) h->blk_stage = bs[0] - '0';
         const char *rp = getenv("B200PF_REDO_PDL");
         if (rp && rp[0] == '0') h->redo_pdl = 0;
         const char *nr = getenv("B200PF_NO_REDO");              // measurement only: planned kernel without its safety net
@@ -807,14 +807,19 @@ static bool block_variant_exists(int T, int U) {
 
 static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
     const int T = h->blk_T, U = h->blk_U;
-    // experiment knobs: B200PF_BLOCK_WPC=4 -> CTAs of 4 warps; B200PF_BLOCK_STAGE=1 -> the launch's single plan is
-    // staged into shared memory by one bulk asynchronous copy (TMA) per CTA.  Only for the default (4, 2) / (8, 2) variants.
-    if (!a.prot && h->blk_wpc == 4 && !(h->blk_stage && sel.d_inst_plan)) {
-        const bool stage = h->blk_stage && !sel.d_inst_plan &&
-                           reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes <= 32 * 1024;
-        if (T == 4 && U == 2) return stage ? launch_block_t<4, 2, 2, false, 4, true>(h, a, sel) : launch_block_t<4, 2, 2, false, 4, false>(h, a, sel);
-        if (T == 8 && U == 1) return stage ? launch_block_t<8, 1, 2, false, 4, true>(h, a, sel) : launch_block_t<8, 1, 2, false, 4, false>(h, a, sel);
+    // Shared-plan launches of the default (8 x 1) variant: CTAs of WPC warps that fetch the plan ONCE into shared memory with a bulk
+    // asynchronous copy (TMA) and run in lockstep — measured best at every batch size (profiles/round2_block_variants.txt;
+    // DESIGN.md 4.4).  Knobs to compare: B200PF_BLOCK_STAGE=0 (plan through L1), B200PF_BLOCK_WPC=1/2/4, B200PF_BLOCK_UNI=0.
+    if (!a.prot && T == 8 && U == 1 && !sel.d_inst_plan && h->blk_stage && a.batch % 4 == 0 &&
+        reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes <= 32 * 1024) {
+        if (h->blk_uni) {
+            if (h->blk_wpc == 1) return launch_block_t<8, 1, 16, false, 1, true, true>(h, a, sel);
+            if (h->blk_wpc == 2) return launch_block_t<8, 1, 8, false, 2, true, true>(h, a, sel);
+            return launch_block_t<8, 1, 4, false, 4, true, true>(h, a, sel);
+        }
+        return launch_block_t<8, 1, 4, false, 4, true, false>(h, a, sel);
     }
+    if (!a.prot && T == 8 && U == 1 && h->blk_wpc == 4 && !h->blk_stage) return launch_block_t<8, 1, 4, false, 4, false, false>(h, a, sel);
     if (!a.prot && T == 8 && U == 1) {
         // lockstep warps (one plan for the whole launch, whole warps): full-mask barriers / votes instead of per-instance collectives
         const bool uni = h->blk_uni && !sel.d_inst_plan && a.batch % 4 == 0;

@@ -610,6 +610,9 @@ template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false, bo
 __global__ void __launch_bounds__((T < 32 ? 32 : T) * WPC, MINB)
 pf_kernel_block(const DevGrid g, const RunArgs a, const PlanArgs pa_in, const int ws_bytes, const int plan_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
+    // the safety-net kernel behind this launch (programmatic dependent launch) may be set up right away: it parks at its
+    // griddepcontrol.wait until this grid has completed, so its launch latency is off the critical path
+    asm volatile("griddepcontrol.launch_dependents;");
     constexpr int G = T < 32 ? 32 / T : 1;
     static_assert(WPC == 1 || T <= 32, "several instances groups per CTA only for warp-sized groups");
     const int lane = T <= 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;

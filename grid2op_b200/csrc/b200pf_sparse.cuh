@@ -590,6 +590,7 @@ template <int T, int MINB, bool PROT>
 __global__ void __launch_bounds__(T, MINB)
 pf_kernel_sparse(const DevGrid g, const RunArgs a, const PlanArgs pa) {
     extern __shared__ __align__(16) unsigned char smem[];
+    asm volatile("griddepcontrol.launch_dependents;");      // (the safety-net kernel behind this launch may be set up right away)
     for (int k = blockIdx.x; k < a.batch; k += gridDim.x) {
         const int inst = (PROT && a.inst_list) ? a.inst_list[k] : k;
         solve_sparse<T, PROT>(g, a, pa, inst, smem, threadIdx.x);

@@ -91,7 +91,7 @@ def test_stress_planned_kernel_vs_pivoting_oracle(cuda_required, name):
         assert np.isnan(out[~ok]).all()
         # (angles: a weakly coupled bus of a state close to collapse is determined to ~1e-2 degree only by a 1e-8 MVA mismatch
         # tolerance — flows and voltages of such a state still agree to 1e-4 p.u.)
-        _compare(gm, out, ref, ok, theta_tol=5e-2)
+        _compare(gm, out, ref, ok, theta_tol=5e-2, theta_vmin=0.5)
         d = iters[ok] - riters[ok]
         assert d.min() >= -1 and d.max() <= 1, (d.min(), d.max())       # the fp64 residual test can flip either way at the threshold
         worst_it = max(worst_it, int(d.max()))
