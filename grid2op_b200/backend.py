@@ -422,8 +422,12 @@ class B200Backend(Backend):
     def save_file(self, full_path) -> None:                                     # pPB:1425-1437 (pp.to_json)
         """Write the current grid state as a pandapower-JSON file: the source ``grid.json`` with the set points,
         element buses (global id = sub + (busbar-1)*n_sub, like the reference's tables) and in-service flags of
-        this backend.  Buses of the extra busbars are not materialised (a file loaded back puts every element on
-        the substation of its bus id modulo n_sub), exactly one grid2op ``load_grid`` away from this state."""
+        this backend.  Like the reference's ``pp.to_json`` of its running net, elements on busbar k > 1 carry the bus id
+        ``sub + (k-1)*n_sub``; the bus rows of those extra busbars are NOT appended to the file's bus table, so a file saved
+        while some element sits on busbar 2 documents the state but is not loadable as a grid (``GridModel`` rejects bus ids
+        beyond the table — the reference's own saved files are not re-loadable as the same environment either: its
+        ``load_grid`` would take the duplicated buses for substations).  With everything on busbar 1 the file re-loads to the
+        same state (tests/test_save_file.py)."""
         from .ppjson import update_pp_json
         gm = self._gm
         nl, nf = gm.n_powerline, gm.n_gen_file

@@ -13,7 +13,8 @@ from test_c_oracle import random_cases
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,nbase", [("l2rpn_case14_sandbox", 48), ("rte_case5_example", 32), ("l2rpn_neurips_2020_track1", 6)])
+@pytest.mark.parametrize("name,nbase", [("l2rpn_case14_sandbox", 48), ("rte_case5_example", 32), ("l2rpn_neurips_2020_track1", 6),
+                                        ("l2rpn_wcci_2022_dev", 3)])
 @pytest.mark.parametrize("policy", [1, 2])
 def test_n1_sweep_matches_oracle(cuda_required, name, nbase, policy):
     from grid2op_b200.engine import PowerFlowEngine
