@@ -393,7 +393,7 @@ def run_ours(args):
             gather_lists = [[torch.empty((K, batch, nl), dtype=torch.float32, device="cuda") for _ in range(world)] for _ in range(2)]
     signal = torch.zeros(1, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-    state = {"k": 0, "works": []}
+    state = {"k": 0, "works": [], "gathered_upto": 0}
 
     def rho_ptr(slot):
         if peer is not None:
@@ -409,18 +409,20 @@ def run_ours(args):
             half = slot // K
             if collect == "p2p":
                 # arrival signal: once it completes on rank 0, every rank's kernels of this half have finished, i.e. their
-                # stores sit in rank 0's HBM
+                # stores sit in rank 0's HBM.  Nobody waits for it inside the loop: the compute stream never stalls on NCCL.
                 state["works"].append(dist.all_reduce(signal, async_op=True))
             else:
-                state["works"].append(dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None,
-                                                  dst=0, async_op=True))
-            while len(state["works"]) > 1:          # keep one in flight: the other half of the ring is being filled meanwhile
-                state["works"].pop(0).wait()
+                dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None, dst=0)
+                state["gathered_upto"] = k + 1
         state["k"] = k + 1
 
     def drain():
         while state["works"]:
             state["works"].pop(0).wait()
+        if world > 1 and collect == "nccl" and state.get("gathered_upto", 0) < state["k"]:
+            half = ((state["k"] - 1) % (2 * K)) // K          # the half that is being filled: gather what it holds so far
+            dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None, dst=0)
+            state["gathered_upto"] = state["k"]
 
     n_warm = max(args.warmup, 3)
     for _ in range(n_warm):

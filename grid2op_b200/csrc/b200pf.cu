@@ -84,7 +84,8 @@ struct b200pf_handle {
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
-    int blk_wpc = 4, blk_stage = 1, blk_minb = 16, blk_uni = 1;                         // experiment knobs: warps per CTA, TMA staging of a shared plan
+    int blk_wpc = 4, blk_stage = 1, blk_minb = 16, blk_uni = 1;
+    unsigned char *d_stat = nullptr; PlanArgs::StatOff stat_off{}; bool stat_dirty = true;   // packed static arrays for staged launches                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
     bool series_plans_stale = false;                        // the cache was reset under the series' plan ids: re-resolve before the next step
@@ -753,6 +754,35 @@ static int launch_redo(b200pf_handle *h, RunArgs a, int nb_cap_req) {
 // ------------------------------------------------------------------------------------------------
 // block-planned kernel (b200pf_block.cuh)
 // ------------------------------------------------------------------------------------------------
+// One device blob with the static arrays a staged block launch reads (D2D copies of the handle's own arrays; rebuilt when the
+// static injections / thermal limits change).  Every section 16-byte aligned (bulk copy + vector loads).
+static int stat_sync(b200pf_handle *h) {
+    if (h->d_stat && !h->stat_dirty) return 0;
+    const DevGrid &g = h->g;
+    PlanArgs::StatOff &o = h->stat_off;
+    size_t off = 0;
+    auto sec = [&](int *field, size_t bytes) { *field = (int)off; off += (bytes + 15) & ~size_t(15); };
+    sec(&o.line_y, (size_t)g.n_line * 64); sec(&o.line_bdc, (size_t)g.n_line * 8); sec(&o.line_pshift, (size_t)g.n_line * 8);
+    sec(&o.line_or_vn, (size_t)g.n_line * 4); sec(&o.line_ex_vn, (size_t)g.n_line * 4); sec(&o.unit_is_ref, (size_t)g.n_unit * 4);
+    sec(&o.unit_qmin, (size_t)g.n_unit * 8); sec(&o.unit_qmax, (size_t)g.n_unit * 8); sec(&o.unit_vn, (size_t)g.n_unit * 4);
+    sec(&o.load_vn, (size_t)g.n_load * 4); sec(&o.sto_vn, (size_t)g.n_sto * 4); sec(&o.sto_q, (size_t)g.n_sto * 8);
+    sec(&o.sh_vn, (size_t)g.n_shunt * 4); sec(&o.sh_vratio, (size_t)g.n_shunt * 8); sec(&o.static_inj, (size_t)g.n_inj * 8);
+    sec(&o.th_lim, (size_t)g.n_line * 4);
+    o.total = (int)off;
+    if (!h->d_stat) { CU(cudaMalloc(&h->d_stat, off)); h->dev_allocs.push_back(h->d_stat); CU(cudaMemset(h->d_stat, 0, off)); }
+    cudaStream_t st = h->stream;
+#define CPY(field, src, bytes) if ((bytes) > 0) CU(cudaMemcpyAsync(h->d_stat + o.field, (src), (bytes), cudaMemcpyDeviceToDevice, st));
+    CPY(line_y, g.line_y, (size_t)g.n_line * 64) CPY(line_bdc, g.line_bdc, (size_t)g.n_line * 8) CPY(line_pshift, g.line_pshift, (size_t)g.n_line * 8)
+    CPY(line_or_vn, g.line_or_vn, (size_t)g.n_line * 4) CPY(line_ex_vn, g.line_ex_vn, (size_t)g.n_line * 4) CPY(unit_is_ref, g.unit_is_ref, (size_t)g.n_unit * 4)
+    CPY(unit_qmin, g.unit_qmin, (size_t)g.n_unit * 8) CPY(unit_qmax, g.unit_qmax, (size_t)g.n_unit * 8) CPY(unit_vn, g.unit_vn, (size_t)g.n_unit * 4)
+    CPY(load_vn, g.load_vn, (size_t)g.n_load * 4) CPY(sto_vn, g.sto_vn, (size_t)g.n_sto * 4) CPY(sto_q, g.sto_q, (size_t)g.n_sto * 8)
+    CPY(sh_vn, g.sh_vn, (size_t)g.n_shunt * 4) CPY(sh_vratio, g.sh_vratio, (size_t)g.n_shunt * 8)
+    CPY(static_inj, h->d_static_inj, (size_t)g.n_inj * 8) CPY(th_lim, h->d_thlim, (size_t)g.n_line * 4)
+#undef CPY
+    h->stat_dirty = false;
+    return 0;
+}
+
 template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false, bool UNI = false>
 static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
     const DevGrid &g = h->g;
@@ -762,7 +792,8 @@ static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel
     const int ws = sel.smem * G;                         // workspace of one warp / CTA
     int plan_bytes = 0;
     if (STAGE) plan_bytes = reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes;
-    const int smem = ws * WPC + plan_bytes;
+    if (STAGE) { int rc = stat_sync(h); if (rc) return rc; }
+    const int smem = ws * WPC + plan_bytes + (STAGE ? h->stat_off.total : 0);
     const int variant = 1000 + MINB * 4096 + T * 64 + U * 8 + (PROT ? 1 : 0) + (STAGE ? 2 : 0) + (WPC > 1 ? 4 : 0) + (UNI ? 100000 : 0);
     if (h->sparse_occ_smem != smem || h->sparse_occ_variant != variant) {
         // (the staged variant owns a few bytes of static shared memory: dynamic + static must stay within the opt-in limit)
@@ -785,6 +816,7 @@ static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel
     pa.plan_off = h->d_plan_off + (sel.d_inst_plan ? 0 : sel.single);
     pa.inst_plan = sel.d_inst_plan;
     pa.lay_nb = sel.lay_nb; pa.lay_nblkA = sel.lay_nblkA;
+    pa.stat = STAGE ? h->d_stat : nullptr; pa.so = h->stat_off;
     const int n_cta_work = ((a.batch + G - 1) / G + WPC - 1) / WPC;
     const int resident = h->sm_count * h->sparse_occ;
     const int rounds = (n_cta_work + resident - 1) / resident;
@@ -986,6 +1018,7 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
     CU(cudaMemcpy(h->d_t, t0, (size_t)batch * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_static_inj, static_inj, (size_t)g.n_inj * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_thlim, thermal_limit_a, (size_t)g.n_line * 4, cudaMemcpyHostToDevice));
+    h->stat_dirty = true;
     CU(cudaMemset(h->d_series_topo, 1, (size_t)batch * g.n_topo_in));
     h->series_batch = batch; h->n_scen = n_scen; h->n_rows = n_rows;
     if ((rc = dmal((void **)&h->d_series_plan, (size_t)batch * 4)) || (rc = dmal((void **)&h->d_trip, (size_t)batch * g.n_line + 4)) ||
@@ -1206,6 +1239,7 @@ extern "C" int b200pf_set_thermal_limit(b200pf_handle *h, const float *thermal_l
     if (!h || !thermal_limit_a) return fail(B200PF_E_ARG, "null pointer");
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpy(h->d_thlim, thermal_limit_a, (size_t)h->g.n_line * 4, cudaMemcpyHostToDevice));
+    h->stat_dirty = true;
     return 0;
 }
 
@@ -1236,6 +1270,7 @@ extern "C" int b200pf_set_static_inj(b200pf_handle *h, const double *static_inj)
     if (!h || !static_inj) return fail(B200PF_E_ARG, "null pointer");
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpy(h->d_static_inj, static_inj, (size_t)h->g.n_inj * 8, cudaMemcpyHostToDevice));
+    h->stat_dirty = true;
     return 0;
 }
 

@@ -28,7 +28,9 @@ namespace b200pf {
 #define PB_SYNC() ((void)0)
 #define PB_ANY(x) (x)
 #define PB_LOOP
+#define PB_UNROLL
 #else
+#define PB_UNROLL _Pragma("unroll")
 #define PB_LOOP _Pragma("unroll 1")      // the lane loops run 1-3 times: unrolled copies only cost instruction-cache misses (ncu: no_inst 15 %)
 // UNI ("lockstep"): all instances of the warp share one plan and run the same control flow, so the whole warp
 // synchronises with the plain full-mask primitives.  A per-lane mask (instances free to diverge) makes every barrier / vote a
@@ -86,11 +88,18 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
     if (a.dbg_div_mod > 0 && inst % a.dbg_div_mod == 0) PB_FAIL(ST_DIV, 0)   // test knob
     const int nb = H.nb, nl = g.n_line, nu = g.n_unit, nh = g.n_hidden, ng = g.n_gen, nld = g.n_load, nst = g.n_sto, nsh = g.n_shunt;
     const int nblk = H.nblk, nblkA = H.nblkA;
-    const double base = g.base_mva;
+    const double base = g.base_mva, inv_base = 1.0 / base;
     float *out = a.out ? a.out + (size_t)inst * g.n_out : nullptr;
 #define U16(off) reinterpret_cast<const uint16_t *>(blob + H.off)
 #define F64(off) reinterpret_cast<const double *>(blob + H.off)
 #define IX(i) ((i) * G + gi)
+#define PB_STAT(name, type) const type *name##_ = pa.stat ? reinterpret_cast<const type *>(pa.stat + pa.so.name) : g.name;
+    PB_STAT(line_y, double) PB_STAT(line_bdc, double) PB_STAT(line_pshift, double) PB_STAT(line_or_vn, float) PB_STAT(line_ex_vn, float)
+    PB_STAT(unit_is_ref, int) PB_STAT(unit_qmin, double) PB_STAT(unit_qmax, double) PB_STAT(unit_vn, float) PB_STAT(load_vn, float)
+    PB_STAT(sto_vn, float) PB_STAT(sto_q, double) PB_STAT(sh_vn, float) PB_STAT(sh_vratio, double)
+#undef PB_STAT
+    const float *th_lim_ = pa.stat ? reinterpret_cast<const float *>(pa.stat + pa.so.th_lim) : a.th_lim;
+    const double *line_y = line_y_;
     const uint16_t *p_colth = U16(o_colth), *p_colv = U16(o_colv), *p_dcidx = U16(o_dcidx);
     const uint16_t *p_brf = U16(o_brf), *p_brt = U16(o_brt);
     const uint16_t *adj_ptr = U16(o_adj_ptr), *adj = U16(o_adj), *shidx = U16(o_shidx);
@@ -105,7 +114,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
     float *srow = reinterpret_cast<float *>(cur + (size_t)2 * nl * G);
     // ---- injections of this instance ----------------------------------------------------------------------
     const bool has_row = a.series != 0;
-    const double *rec = nullptr, *si = a.static_inj;
+    const double *rec = nullptr, *si = pa.stat ? reinterpret_cast<const double *>(pa.stat + pa.so.static_inj) : a.static_inj;
     if (has_row) {
         const float *grow = a.rows ? a.rows + (size_t)src * (size_t)(2 * nld + 2 * ng)
                                    : a.chron + ((size_t)sc * a.n_rows + trow) * (size_t)(2 * nld + 2 * ng);
@@ -114,7 +123,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
     } else rec = a.inj + (size_t)src * g.n_inj;
 #define ROW(k) srow[IX(k)]
 #define GEN_P(u) ((u) < nh ? 0.0 : (has_row ? (double)ROW(2 * nld + (u) - nh) : rec[(u) - nh]))
-#define UNIT_VM(u) (has_row ? ((u) >= nh ? (double)PF_FDIV(ROW(2 * nld + ng + (u) - nh), g.unit_vn[u]) : si[ng + (u)]) : rec[ng + (u)])
+#define UNIT_VM(u) (has_row ? ((u) >= nh ? (double)PF_FDIV(ROW(2 * nld + ng + (u) - nh), unit_vn_[u]) : si[ng + (u)]) : rec[ng + (u)])
 #define LOAD_P(k) (has_row ? (double)ROW(k) : rec[ng + nu + (k)])
 #define LOAD_Q(k) (has_row ? (double)ROW(nld + (k)) : rec[ng + nu + nld + (k)])
 #define STO_P(k) (has_row ? si[ng + nu + 2 * nld + (k)] : rec[ng + nu + 2 * nld + (k)])
@@ -132,14 +141,14 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                 double pg = 0.0, pd = 0.0, qd = 0.0, gs = 0.0, bsu = 0.0;
                 for (int e = bu_ptr[i]; e < bu_ptr[i + 1]; ++e) { const int u = bu[e]; pg += GEN_P(u); }
                 for (int e = bl_ptr[i]; e < bl_ptr[i + 1]; ++e) { const int k = bl[e]; pd += LOAD_P(k); qd += LOAD_Q(k); }
-                for (int e = bs_ptr[i]; e < bs_ptr[i + 1]; ++e) { const int k = bs[e]; pd += STO_P(k); qd += g.sto_q[k]; }
-                for (int e = bh_ptr[i]; e < bh_ptr[i + 1]; ++e) { const int k = bh[e]; gs += SH_P(k) * g.sh_vratio[k]; bsu -= SH_Q(k) * g.sh_vratio[k]; }
+                for (int e = bs_ptr[i]; e < bs_ptr[i + 1]; ++e) { const int k = bs[e]; pd += STO_P(k); qd += sto_q_[k]; }
+                for (int e = bh_ptr[i]; e < bh_ptr[i + 1]; ++e) { const int k = bh[e]; gs += SH_P(k) * sh_vratio_[k]; bsu -= SH_Q(k) * sh_vratio_[k]; }
                 const int vu = vmunit[i];
                 vm[IX(i)] = vu != 0xFFFF ? UNIT_VM(vu) : 1.0;
-                const double ps = (pg - pd) / base, gpu = gs / base;
-                psp[IX(i)] = ps; qsp[IX(i)] = -qd / base;
+                const double ps = (pg - pd) * inv_base, gpu = gs * inv_base;      // (one division per lane instead of four per bus)
+                psp[IX(i)] = ps; qsp[IX(i)] = -qd * inv_base;
                 const int sx = shidx[i];
-                if (sx != 0xFFFF) { gsh[IX(sx)] = gpu; bsh[IX(sx)] = bsu / base; }
+                if (sx != 0xFFFF) { gsh[IX(sx)] = gpu; bsh[IX(sx)] = bsu * inv_base; }
                 const int c = p_dcidx[i];
                 if (c != 0xFFFF) Pc[IX(c)] = ps - gpu - dcshift[i];
             }
@@ -227,7 +236,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                     if (f == 0xFFFF) continue;
                     const int t = p_brt[l];
                     const double2 Vf = V[IX(f)], Vt = V[IX(t)];
-                    const double *y = g.line_y + (size_t)l * 8;
+                    const double *y = line_y + (size_t)l * 8;
                     cur[IX(2 * l)] = make_double2(y[0] * Vf.x - y[1] * Vf.y + y[2] * Vt.x - y[3] * Vt.y,
                                                   y[0] * Vf.y + y[1] * Vf.x + y[2] * Vt.y + y[3] * Vt.x);
                     cur[IX(2 * l + 1)] = make_double2(y[4] * Vf.x - y[5] * Vf.y + y[6] * Vt.x - y[7] * Vt.y,
@@ -288,7 +297,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                         const int l = late[2 * k];
                         const int f = p_brf[l], t = p_brt[l];
                         const double2 Vf = V[IX(f)], Vt = V[IX(t)];
-                        const double *y = g.line_y + (size_t)l * 8;
+                        const double *y = line_y + (size_t)l * 8;
                         PB_OFFDIAG(l, Vf, Vt, y, f, t)
                     }
                 }
@@ -402,7 +411,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
             PB_LOOP for (int l = tid; l < nl; l += T) {
                 const int f = p_brf[l];
                 if (f == 0xFFFF) continue;
-                const double pfl = g.line_bdc[l] * (V[IX(f)].x - V[IX(p_brt[l])].x) + g.line_pshift[l];
+                const double pfl = line_bdc_[l] * (V[IX(f)].x - V[IX(p_brt[l])].x) + line_pshift_[l];
                 cur[IX(2 * l)] = make_double2(pfl, 0.0); cur[IX(2 * l + 1)] = make_double2(-pfl, 0.0);
             }
         }
@@ -452,15 +461,15 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                         pt = (Bb.x * It.x + Bb.y * It.y) * base; qt = (Bb.y * It.x - Bb.x * It.y) * base;
                         sf = sqrt(pf * pf + qf * qf); st = sqrt(pt * pt + qt * qt);
                     }
-                    const float vnf = g.line_or_vn[l], vnt = g.line_ex_vn[l];
+                    const float vnf = line_or_vn_[l], vnt = line_ex_vn_[l];
                     float a1 = (float)(sf / (SQRT3 * (vmf * (double)vnf)) * 1000.0), a2 = (float)(st / (SQRT3 * (vmt * (double)vnt)) * 1000.0);
                     if (!(fabsf(a1) <= 3.4e38f)) a1 = 0.f;
                     if (!(fabsf(a2) <= 3.4e38f)) a2 = 0.f;
                     r[0] = (float)pf; r[1] = (float)qf; r[2] = PF_FMUL((float)vmf, vnf); r[3] = a1; r[4] = (float)(va[IX(f)] * RAD2DEG);
                     r[5] = (float)pt; r[6] = (float)qt; r[7] = PF_FMUL((float)vmt, vnt); r[8] = a2; r[9] = (float)(va[IX(t)] * RAD2DEG);
                 }
-                if (out) for (int k = 0; k < 10; ++k) out[k * nl + l] = r[k];
-                if (a.rho) a.rho[(size_t)inst * nl + l] = r[3] / a.th_lim[l];
+                if (out) { PB_UNROLL for (int k = 0; k < 10; ++k) out[k * nl + l] = r[k]; }
+                if (a.rho) a.rho[(size_t)inst * nl + l] = r[3] / th_lim_[l];
             }
             if (out) {
                 float *o = out + 10 * nl;
@@ -470,38 +479,38 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                     if (i != 0xFFFF) {
                         double pd = 0.0, qd = 0.0, pnonref = 0.0;
                         for (int e = bl_ptr[i]; e < bl_ptr[i + 1]; ++e) { const int k = bl[e]; pd += LOAD_P(k); qd += LOAD_Q(k); }
-                        for (int e = bs_ptr[i]; e < bs_ptr[i + 1]; ++e) { const int k = bs[e]; pd += STO_P(k); qd += g.sto_q[k]; }
-                        for (int e = bu_ptr[i]; e < bu_ptr[i + 1]; ++e) { const int u2 = bu[e]; if (!g.unit_is_ref[u2]) pnonref += GEN_P(u2); }
+                        for (int e = bs_ptr[i]; e < bs_ptr[i + 1]; ++e) { const int k = bs[e]; pd += STO_P(k); qd += sto_q_[k]; }
+                        for (int e = bu_ptr[i]; e < bu_ptr[i + 1]; ++e) { const int u2 = bu[e]; if (!unit_is_ref_[u2]) pnonref += GEN_P(u2); }
                         double pu = GEN_P(u);
-                        if (g.unit_is_ref[u]) pu = (Pc[IX(i)] * base + pd - pnonref) / (double)p_nref[i];     // slack share (pandapower pfsoln)
+                        if (unit_is_ref_[u]) pu = (Pc[IX(i)] * base + pd - pnonref) / (double)p_nref[i];     // slack share (pandapower pfsoln)
                         double qu = 0.0;
                         if (!a.is_dc) {
                             const double qtot = Qc[IX(i)] * base + qd, qmn = qmins[i], qmx = qmaxs[i];
                             const int cb = p_cnt[i];
                             if (cb <= 1 || qmn == qmx) qu = qtot / (double)cb;
-                            else qu = g.unit_qmin[u] + (qtot - qmn) / (qmx - qmn + 2.220446049250313e-16) * (g.unit_qmax[u] - g.unit_qmin[u]);
+                            else qu = unit_qmin_[u] + (qtot - qmn) / (qmx - qmn + 2.220446049250313e-16) * (unit_qmax_[u] - unit_qmin_[u]);
                         }
-                        p = (float)pu; q = (float)qu; v = PF_FMUL((float)vm[IX(i)], g.unit_vn[u]); th = (float)(va[IX(i)] * RAD2DEG);
+                        p = (float)pu; q = (float)qu; v = PF_FMUL((float)vm[IX(i)], unit_vn_[u]); th = (float)(va[IX(i)] * RAD2DEG);
                     }
                     o[u] = p; o[nu + u] = q; o[2 * nu + u] = v; o[3 * nu + u] = th;
                 }
                 o += 4 * nu;
                 PB_LOOP for (int k = tid; k < nld; k += T) {
                     const int i = load_bus[k];
-                    o[k] = i != 0xFFFF ? PF_FMUL((float)vm[IX(i)], g.load_vn[k]) : 0.f;
+                    o[k] = i != 0xFFFF ? PF_FMUL((float)vm[IX(i)], load_vn_[k]) : 0.f;
                     o[nld + k] = i != 0xFFFF ? (float)(va[IX(i)] * RAD2DEG) : 0.f;
                 }
                 o += 2 * nld;
-                PB_LOOP for (int k = tid; k < nst; k += T) { const int i = sto_bus[k]; o[k] = i != 0xFFFF ? PF_FMUL((float)vm[IX(i)], g.sto_vn[k]) : 0.f; }
+                PB_LOOP for (int k = tid; k < nst; k += T) { const int i = sto_bus[k]; o[k] = i != 0xFFFF ? PF_FMUL((float)vm[IX(i)], sto_vn_[k]) : 0.f; }
                 o += nst;
                 PB_LOOP for (int k = tid; k < nsh; k += T) {
                     const int i = sh_bus[k];
                     float p = 0.f, q = 0.f, v = 0.f;
                     if (i != 0xFFFF) {
                         const double v2 = a.is_dc ? 1.0 : vm[IX(i)] * vm[IX(i)];
-                        p = (float)(SH_P(k) * g.sh_vratio[k] * v2);
-                        q = a.is_dc ? 0.f : (float)(SH_Q(k) * g.sh_vratio[k] * v2);
-                        v = PF_FMUL((float)vm[IX(i)], g.sh_vn[k]);
+                        p = (float)(SH_P(k) * sh_vratio_[k] * v2);
+                        q = a.is_dc ? 0.f : (float)(SH_Q(k) * sh_vratio_[k] * v2);
+                        v = PF_FMUL((float)vm[IX(i)], sh_vn_[k]);
                     }
                     o[k] = p; o[nsh + k] = q; o[2 * nsh + k] = v;
                 }
@@ -527,7 +536,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
         PF_PHASE {
             PB_LOOP for (int l = tid; l < nl; l += T) {
                 const bool on = p_brf[l] != 0xFFFF;
-                const float aor = out[3 * nl + l], lim = a.th_lim[l];
+                const float aor = out[3 * nl + l], lim = th_lim_[l];
                 int inc = a.casc > 0 ? (int)a.incdone[base_l + l] : 0;
                 int pc = a.pcount[base_l + l] + inc;
                 bool to_disc = on && (aor > PF_FMUL(a.hard_thr, lim));
@@ -551,7 +560,7 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
                 }
             } else {
                 PB_LOOP for (int l = tid; l < nl; l += T) {
-                    const float aor = out[3 * nl + l], lim = a.th_lim[l];
+                    const float aor = out[3 * nl + l], lim = th_lim_[l];
                     int *pcp = a.pcount + base_l, *tsp = a.ts_over + base_l;
                     pcp[l] = (!a.from_reset && aor > PF_FMUL(a.soft_thr, lim)) ? pcp[l] + 1 : 0;
                     tsp[l] = (!a.from_reset && aor > lim) ? tsp[l] + 1 : 0;
@@ -583,7 +592,8 @@ PF_DEV void solve_block(const DevGrid &g, const RunArgs &a, const PlanArgs &pa, 
 // re-reading the index arrays and the operation stream through L1 for every instance.  Measured against the L1 path in
 // profiles/round2_* (DESIGN.md 4.4).
 __device__ __forceinline__ uint32_t pb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void pb_stage_plan(unsigned char *dst, const unsigned char *src, uint32_t bytes, uint64_t *mbar) {
+__device__ __forceinline__ void pb_stage(unsigned char *dst, const unsigned char *src, uint32_t bytes, unsigned char *dst2, const unsigned char *src2,
+                                         uint32_t bytes2, uint64_t *mbar) {
     const uint32_t mb = pb_smem_addr(mbar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(1) : "memory");
@@ -591,9 +601,11 @@ __device__ __forceinline__ void pb_stage_plan(unsigned char *dst, const unsigned
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes + bytes2) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(pb_smem_addr(dst)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(pb_smem_addr(dst2)), "l"(src2), "r"(bytes2), "r"(mb) : "memory");
     }
     uint32_t ok = 0;
     while (!ok) {
@@ -627,11 +639,15 @@ pf_kernel_block(const DevGrid g, const RunArgs a, const PlanArgs pa_in, const in
         imask = m << gi;
     }
     PlanArgs pa = pa_in;
+    if (!STAGE) pa.stat = nullptr;
     __shared__ int zero_off;
     __shared__ __align__(8) uint64_t mbar;
     if (STAGE) {
+        // behind the workspaces: the plan blob, then the blob of static grid arrays (pa_in.stat: its copy in global memory)
         unsigned char *dst = smem + (size_t)WPC * ws_bytes;
-        pb_stage_plan(dst, pa_in.blobs + pa_in.plan_off[0], (uint32_t)plan_bytes, &mbar);
+        unsigned char *dst2 = dst + plan_bytes;
+        pb_stage(dst, pa_in.blobs + pa_in.plan_off[0], (uint32_t)plan_bytes, dst2, pa_in.stat, (uint32_t)pa_in.so.total, &mbar);
+        pa.stat = dst2;
         if (threadIdx.x == 0) zero_off = 0;
         __syncthreads();
         pa.stage_src = pa_in.blobs + pa_in.plan_off[0];

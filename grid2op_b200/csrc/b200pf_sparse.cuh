@@ -118,6 +118,12 @@ struct PlanArgs {
     // array strides of the LAUNCH (maxima over its plans): buses, value blocks
     int lay_nb, lay_nblkA;
     const unsigned char *stage_src;   // block kernel with a TMA-staged plan: the plan's copy in global memory (streaming loads need it)
+    // block kernel, staged launches: the static grid arrays the solve reads (line admittances, nominal voltages, unit limits, the
+    // static injections, the thermal limits), packed into one blob that is staged next to the plan; nullptr: DevGrid's own
+    // pointers (through L1 / L2 — cold after every L2 flush: ~15 dependent misses per warp in a one-wave launch)
+    const unsigned char *stat;
+    struct StatOff { int line_y, line_bdc, line_pshift, line_or_vn, line_ex_vn, unit_is_ref, unit_qmin, unit_qmax, unit_vn, load_vn, sto_vn, sto_q,
+                         sh_vn, sh_vratio, static_inj, th_lim, total; } so;
 };
 
 template <int T>
