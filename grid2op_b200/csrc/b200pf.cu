@@ -88,6 +88,7 @@ struct b200pf_handle {
     unsigned char *d_stat = nullptr; PlanArgs::StatOff stat_off{}; bool stat_dirty = true;   // packed static arrays for staged launches                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
+    bool series_dev_topo_ahead = false;                     // the warp kernel tripped lines in d_series_topo on the device: the host mirror / plans lag
     bool series_plans_stale = false;                        // the cache was reset under the series' plan ids: re-resolve before the next step
     int64_t launches = 0;
     int redo_pdl = 1;                                       // B200PF_REDO_PDL=0: plain stream-ordered launch of the safety net
@@ -1057,6 +1058,7 @@ extern "C" int b200pf_series_set_topo(b200pf_handle *h, const int8_t *topo) {
     if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpy(h->d_series_topo, topo, (size_t)h->series_batch * h->g.n_topo_in, cudaMemcpyHostToDevice));
+    h->series_dev_topo_ahead = false;
     return series_plans(h, topo);
 }
 
@@ -1131,6 +1133,22 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
         a.pcount = h->d_pcount; a.ts_over = h->d_tsover; a.disc = h->d_disc; a.done = h->d_done;
     }
     h->next_reset = 0;
+    if (h->series_dev_topo_ahead && h->plan_policy != 1) {
+        // protections ran on the device (warp kernel: trips written into d_series_topo); whoever uses plans next — protections
+        // switched off, policy switched to the planned kernel — must see those outages: refresh the host mirror and the plans
+        const DevGrid &gg = h->g;
+        const bool small_ok = gg.n_slot <= 32 && gg.n_line <= 32 && gg.n_unit <= 32 && gg.n_load <= 32 && gg.n_sto <= 32 && gg.n_shunt <= 32 &&
+                              nb_cap > 0 && nb_cap <= 17;
+        const bool warp_again = h->prot && small_ok && h->plan_policy != 2 && !is_dc;
+        if (!warp_again) {
+            std::vector<int8_t> cur((size_t)h->series_batch * gg.n_topo_in);
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaMemcpy(cur.data(), h->d_series_topo, cur.size(), cudaMemcpyDeviceToHost));
+            int rc = series_plans(h, cur.data());
+            if (rc) return rc;
+            h->series_dev_topo_ahead = false;
+        }
+    }
     if (h->series_plans_stale) {
         h->series_plans_stale = false;
         std::vector<int8_t> keep(h->h_series_topo);
@@ -1152,6 +1170,7 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
         sel.d_inst_plan = h->series_plan_state == 1 ? h->d_series_plan : nullptr;
         return launch(h, a, nb_cap, &sel);
     }
+    if (h->prot) h->series_dev_topo_ahead = true;          // (device-side cascade of the warp kernel)
     return launch(h, a, nb_cap);
 }
 

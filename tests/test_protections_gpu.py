@@ -132,3 +132,39 @@ def test_planned_protections_on_a_large_grid_match_the_emulated_kernel(cuda_requ
         n_trip += int((ref.disc[live] >= 0).sum())
     assert n_trip > 0
     env.close()
+
+
+def test_lines_tripped_on_the_device_stay_out_when_the_planned_kernel_takes_over(cuda_required):
+    """Device-side cascade of the warp kernel writes the outages into the device copy of the topology only; switching the
+    protections off (-> planned kernel, host-side plans) must not bring the lines back."""
+    from grid2op_b200.engine import OutputView
+    from grid2op_b200.rollout import BatchedDoNothing
+    gm = GridModel.from_npz(os.path.join(GOLD, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(GOLD, "case14_sandbox_chronics.npz"))["chron"]
+    B = 64
+    probe = BatchedDoNothing(gm, chron, B)
+    probe.step_device()
+    out, status, _, _ = probe.fetch()
+    probe.close()
+    a_all = OutputView(gm, out).a_or
+    a0 = a_all.max(axis=0)
+    th = np.maximum(a0 * 1.5, 1.0).astype(np.float32)
+    victim = int(np.argsort(-a0)[2])
+    th[victim] = a_all[:, victim].min() * 0.4                                 # far above its limit in EVERY instance: trips at once
+    env = BatchedDoNothing(gm, chron, B, protections=True, thermal_limit_a=th)
+    env.reset_step()
+    env.step_device()
+    out, status, _, _ = env.fetch()
+    assert env.engine.plan_stats()["last_kernel"] == "warp_pivoting"
+    live = status == 0
+    assert live.sum() >= B // 2
+    off = OutputView(gm, out).a_or == 0.0
+    assert off[live].any(axis=1).all()                                         # every live instance lost at least that line
+    env.engine.series_protections(False)
+    env.step_device()
+    out2, status2, _, _ = env.fetch()
+    assert env.engine.plan_stats()["last_kernel"].startswith("planned")
+    both = live & (status2 == 0)
+    off2 = OutputView(gm, out2).a_or == 0.0
+    assert np.array_equal(off2[both], off[both])
+    env.close()
