@@ -635,7 +635,7 @@ def main():
     ap.add_argument("--cpu-min-seconds", type=float, default=4.0, help="--impl reference: run at least this long whatever --steps")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-redo", action="store_true", help="measurement only: planned kernel without its pivoting safety net")
-    ap.add_argument("--gather-every", type=int, default=16, help="N>1: steps per arrival signal / gather")
+    ap.add_argument("--gather-every", type=int, default=64, help="N>1: steps per arrival signal / gather")
     ap.add_argument("--collect", default="p2p", choices=["p2p", "nccl"], help="N>1: how rho reaches rank 0")
     ap.add_argument("--policy", type=int, default=0, choices=[0, 1, 2],
                     help="kernel policy (include/b200pf.h): 0 auto = planned kernel, 1 pivoting kernels only, 2 planned always")

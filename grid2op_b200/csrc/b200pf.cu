@@ -84,7 +84,7 @@ struct b200pf_handle {
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
-    int blk_wpc = 4, blk_stage = 1, blk_minb = 16, blk_uni = 1;
+    int blk_wpc = 4, blk_stage = 1, blk_minb = 16, blk_uni = 1, blk_wpc_pinned = 0;
     unsigned char *d_stat = nullptr; PlanArgs::StatOff stat_off{}; bool stat_dirty = true;   // packed static arrays for staged launches                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
@@ -252,7 +252,7 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         const char *bun = getenv("B200PF_BLOCK_UNI");
         if (bun && bun[0] == '0') h->blk_uni = 0;
         const char *bw = getenv("B200PF_BLOCK_WPC"), *bs = getenv("B200PF_BLOCK_STAGE");
-        if (bw && (atoi(bw) == 1 || atoi(bw) == 2 || atoi(bw) == 4)) h->blk_wpc = atoi(bw);
+        if (bw && (atoi(bw) == 1 || atoi(bw) == 2 || atoi(bw) == 4)) { h->blk_wpc = atoi(bw); h->blk_wpc_pinned = 1; }
         if (bs && (bs[0] == '0' || bs[0] == '1')) h->blk_stage = bs[0] - '0';
         const char *rp = getenv("B200PF_REDO_PDL");
         if (rp && rp[0] == '0') h->redo_pdl = 0;
@@ -846,8 +846,11 @@ static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) 
     if (!a.prot && T == 8 && U == 1 && !sel.d_inst_plan && h->blk_stage && a.batch % 4 == 0 &&
         reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes <= 32 * 1024) {
         if (h->blk_uni) {
-            if (h->blk_wpc == 1) return launch_block_t<8, 1, 16, false, 1, true, true>(h, a, sel);
-            if (h->blk_wpc == 2) return launch_block_t<8, 1, 8, false, 2, true, true>(h, a, sel);
+            // warps per CTA: 2 up to 32 k instances (finer SM balance: 167 vs 158 M/s at batch 16 384), 4 beyond (197 vs 189 M/s at
+            // 65 536: one staged copy serves more instances); B200PF_BLOCK_WPC pins it
+            const int wpc = h->blk_wpc_pinned ? h->blk_wpc : (a.batch <= 32768 ? 2 : 4);
+            if (wpc == 1) return launch_block_t<8, 1, 16, false, 1, true, true>(h, a, sel);
+            if (wpc == 2) return launch_block_t<8, 1, 8, false, 2, true, true>(h, a, sel);
             return launch_block_t<8, 1, 4, false, 4, true, true>(h, a, sel);
         }
         return launch_block_t<8, 1, 4, false, 4, true, false>(h, a, sel);
