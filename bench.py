@@ -14,8 +14,8 @@ A "step" is one pass of the hot path over the whole batch = batch env.step() cal
 
 N > 1: independent instances, no collective inside the solve.  The step results every rank owes the agent's rank (rho, 4 bytes
 per line and instance) are stored BY THE KERNEL ITSELF into rank 0's HBM through a peer mapping over NVLink (CUDA IPC,
-include/b200pf.h "Multi-GPU result collection"): no collective launch per 60-microsecond step.  NCCL carries the set-up, the
-arrival signal every --gather-every steps (one 4-byte all-reduce) and the timing reduction; `--collect nccl` selects the plain
+include/b200pf.h "Multi-GPU result collection"), followed by a per-rank completion word (b200pf_series_bind_flag): no
+collective in the stepping loop at all.  NCCL carries the set-up and the timing reduction; `--collect nccl` selects the plain
 alternative (device ring + one NCCL gather every --gather-every steps), also the fallback when peer mapping is unavailable.
 
 One JSON line on stdout (rank 0).  Keys documented in DESIGN.md section "Measurement".
@@ -369,7 +369,7 @@ def run_ours(args):
         handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
         try:
             if rank == 0:
-                peer = PeerBuffer(ring_bytes)
+                peer = PeerBuffer(ring_bytes + 256)           # + one completion word per rank behind the ring
                 handle.copy_(torch.frombuffer(bytearray(peer.handle), dtype=torch.uint8))
         except Exception as exc:      # noqa: BLE001
             ok = 0
@@ -391,7 +391,10 @@ def run_ours(args):
         ring_local = torch.zeros((2 * K, batch, nl), dtype=torch.float32, device="cuda")
         if collect == "nccl" and rank == 0:
             gather_lists = [[torch.empty((K, batch, nl), dtype=torch.float32, device="cuda") for _ in range(world)] for _ in range(2)]
-    signal = torch.zeros(1, dtype=torch.int32, device="cuda")
+    if peer is not None:
+        # every rank's kernels publish "steps done" into rank 0's buffer behind each step (b200pf_series_bind_flag): the agent
+        # reads a 4-byte word per rank to know that a step has fully arrived — no collective anywhere in the stepping loop
+        eng.series_bind_flag(peer.ptr + ring_bytes + 4 * rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     state = {"k": 0, "works": [], "gathered_upto": 0}
 
@@ -408,9 +411,7 @@ def run_ours(args):
         if world > 1 and (k + 1) % K == 0:
             half = slot // K
             if collect == "p2p":
-                # arrival signal: once it completes on rank 0, every rank's kernels of this half have finished, i.e. their
-                # stores sit in rank 0's HBM.  Nobody waits for it inside the loop: the compute stream never stalls on NCCL.
-                state["works"].append(dist.all_reduce(signal, async_op=True))
+                pass          # nothing to launch: results and the completion word are stored by the step's own kernels
             else:
                 dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None, dst=0)
                 state["gathered_upto"] = k + 1
@@ -483,6 +484,10 @@ def run_ours(args):
         dist.all_gather(sums, mine)
         if rank == 0:
             last = (state["k"] - 1) % (2 * K)
+            if peer is not None:
+                flags = peer.read(ring_bytes, world).view(np.int32)
+                if not (flags == state["k"]).all():          # every rank's completion word must read "all steps done"
+                    collected_ok = False
             for r in range(world):
                 if peer is not None:
                     got = peer.read(4 * ((r * 2 * K + last) * slot_elems), slot_elems)
@@ -576,8 +581,8 @@ def run_ours(args):
                                     "whatever the planned kernel leaves unsolved" + (" (OFF in this run)" if args.no_redo else ""),
                        "launch": info, "kernel": kstats, "kernel_tag": kernel_tag, "mean_newton_iterations": mean_iters, "diverged": n_bad,
                        "result_collection": {"local": "single GPU: rho stays in this GPU's HBM",
-                                             "p2p": f"kernels store rho straight into rank 0's HBM (CUDA IPC peer mapping over NVLink), "
-                                                    f"one 4-byte NCCL all-reduce as arrival signal every {K} steps",
+                                             "p2p": "kernels store rho AND a per-rank completion word straight into rank 0's HBM (CUDA IPC peer mapping "
+                                                    "over NVLink); no collective in the stepping loop (NCCL: set-up and timing reduction only)",
                                              "nccl": f"device ring, one NCCL gather to rank 0 every {K} steps"}[collect],
                        "collected_equals_results": collected_ok,
                        "wall_s_incl_flush": t_wall},

@@ -95,6 +95,7 @@ struct b200pf_handle {
     int redo_enabled = 1;                                   // pivoting re-solve of what the planned kernel leaves as ST_DIV (B200PF_NO_REDO=1 turns it off)
     int dbg_div_mod = 0;                                    // test knob, see b200pf_set_debug
     int64_t redo_launches = 0;
+    int *series_flag = nullptr; int series_step_no = 0; int *d_ticket = nullptr; bool flag_in_redo = false;   // completion flag of series steps
     unsigned char *d_redo_mat = nullptr; size_t redo_mat_stride = 0; int redo_mat_ctas = 0;   // global-memory matrices of the safety net (large grids)
     cudaEvent_t inst_plan_ev = nullptr; bool inst_plan_pending = false;   // last H2D copy out of h_inst_plan
     int last_smem = 0, last_T = 0, last_grid = 0, last_block = 0;
@@ -706,6 +707,7 @@ static int launch_redo_t(b200pf_handle *h, const RunArgs &a, int max_ctas) {
         cfg.attrs = at; cfg.numAttrs = 1;
         const int wsb = (int)smem;
         CU(cudaLaunchKernelEx(&cfg, kern, g, a, wsb));
+        if (a.done_flag) h->flag_in_redo = true;
     }
     CU(cudaGetLastError());
     h->redo_launches++;
@@ -1122,15 +1124,38 @@ static int series_step_planned_prot(b200pf_handle *h, RunArgs a) {
     return 0;
 }
 
+static int series_step_impl(b200pf_handle *h, int is_dc, int max_iter, double tol_mva, int nb_cap);
+
 extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, double tol_mva, int nb_cap) {
     if (!h) return fail(B200PF_E_ARG, "null handle");
     if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
     CU(cudaSetDevice(h->device));
+    h->flag_in_redo = false;
+    if (h->series_flag) h->series_step_no++;
+    int rc = series_step_impl(h, is_dc, max_iter, tol_mva, nb_cap);
+    if (rc) return rc;
+    if (h->series_flag && !h->flag_in_redo) {        // no safety-net launch carried the flag: publish it with a one-thread kernel
+        pf_kernel_flag<<<1, 1, 0, h->stream>>>(h->series_flag, h->series_step_no);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int b200pf_series_bind_flag(b200pf_handle *h, int32_t *d_flag) {
+    if (!h) return fail(B200PF_E_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    if (!h->d_ticket) { CU(cudaMalloc(&h->d_ticket, 16)); h->dev_allocs.push_back(h->d_ticket); CU(cudaMemset(h->d_ticket, 0, 16)); }
+    h->series_flag = d_flag; h->series_step_no = 0;
+    return 0;
+}
+
+static int series_step_impl(b200pf_handle *h, int is_dc, int max_iter, double tol_mva, int nb_cap) {
     RunArgs a = base_args(h, h->series_batch, is_dc, max_iter, tol_mva);
     a.topo = h->d_series_topo; a.inj = nullptr; a.out = h->x_out ? h->x_out : h->d_out; a.status = h->x_status ? h->x_status : h->d_status;
     a.iters = h->x_iters ? h->x_iters : h->d_iters; a.busv = nullptr;
     a.series = 1; a.chron = h->d_chron; a.n_scen = h->n_scen; a.n_rows = h->n_rows; a.scen = h->d_scen; a.t = h->d_t;
     a.static_inj = h->d_static_inj; a.th_lim = h->d_thlim; a.rho = h->x_rho ? h->x_rho : h->d_rho;
+    if (h->series_flag && !h->prot) { a.done_flag = h->series_flag; a.done_value = h->series_step_no; a.done_ticket = h->d_ticket; }
     if (h->prot) {
         a.prot = 1; a.from_reset = h->next_reset; a.max_pc = h->max_pc; a.hard_thr = h->hard_thr; a.soft_thr = h->soft_thr;
         a.pcount = h->d_pcount; a.ts_over = h->d_tsover; a.disc = h->d_disc; a.done = h->d_done;

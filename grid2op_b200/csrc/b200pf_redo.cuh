@@ -83,6 +83,27 @@ pf_kernel_redo(const DevGrid g, const RunArgs a, const int ws_bytes) {
             gsync<T>();
         }
     }
+    if (a.done_flag) {
+        // the step is complete when the LAST CTA of this (last) kernel of the step is: it publishes the step number, system-wide
+        // (the flag may sit in the agent rank's HBM, next to the results the planned kernel stored there)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const int t = atomicAdd(a.done_ticket, 1);
+            if (t == (int)gridDim.x - 1) {
+                *a.done_ticket = 0;
+                __threadfence_system();
+                *reinterpret_cast<volatile int *>(a.done_flag) = a.done_value;
+            }
+        }
+    }
+}
+
+// paths without a safety-net launch: one thread publishes the step number behind the step's kernels
+__global__ void pf_kernel_flag(int *flag, int value) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __threadfence_system();
+    *reinterpret_cast<volatile int *>(flag) = value;
 }
 
 }  // namespace b200pf

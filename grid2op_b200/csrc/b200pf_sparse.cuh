@@ -101,6 +101,7 @@ struct RunArgs {
     int *n_flag, *flag_list;
     int redo, dbg_div_mod;
     unsigned char *redo_mat; size_t redo_mat_stride;
+    int *done_flag; int done_value; int *done_ticket;
 };
 enum { ST_OK = 0, ST_DIV = 1, ST_UNSUP = 2, ST_NOREF = 3, ST_LARGE = 4, ST_DONE = 5 };
 enum { BT_PQ = 1, BT_PV = 2, BT_REF = 3 };

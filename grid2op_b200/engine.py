@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "b200pf_rows_chunk_launch_from", "b200pf_pinned_alloc", "b200pf_pinned_free", "b200pf_rows_group_launch", "b200pf_rows_group_wait",
     "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats", "b200pf_run_device_topo",
     "b200pf_set_debug", "b200pf_redo_launch_count",
-    "b200pf_device_alloc", "b200pf_device_free", "b200pf_ipc_export", "b200pf_ipc_open", "b200pf_ipc_close", "b200pf_device_read", "b200pf_plan_counters",
+    "b200pf_device_alloc", "b200pf_device_free", "b200pf_ipc_export", "b200pf_ipc_open", "b200pf_ipc_close", "b200pf_device_read", "b200pf_plan_counters", "b200pf_series_bind_flag",
 )
 
 
@@ -122,6 +122,8 @@ def load_library():
     lib.b200pf_plan_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]
     lib.b200pf_set_debug.argtypes = [vp, i32, i32]
     lib.b200pf_plan_counters.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.b200pf_series_bind_flag.argtypes = [vp, vp]
+    lib.b200pf_series_bind_flag.restype = i32
     lib.b200pf_plan_counters.restype = i32
     lib.b200pf_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.b200pf_device_free.argtypes = [vp]
@@ -472,6 +474,10 @@ class PowerFlowEngine:
         rho = np.empty((B, gm.n_line), dtype=np.float32) if want_rho else None
         self._check(self.lib.b200pf_series_fetch(self.h, _ptr(out), _ptr(status), _ptr(iters), _ptr(rho)), "b200pf_series_fetch")
         return out, status, iters, rho
+
+    def series_bind_flag(self, d_flag: int = 0):
+        """the device stores the number of series steps done to ``*d_flag`` (device / peer pointer) behind every step"""
+        self._check(self.lib.b200pf_series_bind_flag(self.h, C.c_void_p(d_flag or None)), "b200pf_series_bind_flag")
 
     def series_protections(self, enabled: bool = True, hard_overflow_threshold: float = 2.0,
                            soft_overflow_threshold: float = 1.0, nb_timestep_overflow_allowed: int = 2):

@@ -255,6 +255,10 @@ int b200pf_plan_counters(const b200pf_handle *h, int64_t *out4);
  * NVLink — and binds a slice of it as its `rho` output (b200pf_series_bind_outputs): the kernel's own result stores land in
  * the agent's HBM, fused with the solve, no extra launch.  Completion is signalled by whatever orders the streams (a tiny
  * NCCL all-reduce every K steps in bench.py).  handle64: 64 bytes (cudaIpcMemHandle_t). */
+/* b200pf_series_bind_flag: after every b200pf_series_step the device stores the number of steps done so far to *d_flag (behind
+ * all the step's kernels, system-wide visible) — d_flag may point into the agent rank's buffer, next to the results: the agent
+ * learns that a rank's step k has fully arrived by reading a 4-byte word, no collective involved.  NULL unbinds. */
+int b200pf_series_bind_flag(b200pf_handle *h, int32_t *d_flag);
 int b200pf_device_alloc(size_t bytes, void **d_ptr);
 int b200pf_device_free(void *d_ptr);
 int b200pf_device_read(const void *d_src, void *host_dst, size_t bytes);   /* synchronous D2H copy (checks) */
