@@ -13,10 +13,11 @@ sharded over the N GPUs (strong scaling), DoNothing over the bundled 289-row sce
 A "step" is one pass of the hot path over the whole batch = batch env.step() calls.
 
 N > 1: independent instances, no collective inside the solve.  The step results every rank owes the agent's rank (rho, 4 bytes
-per line and instance) are stored BY THE KERNEL ITSELF into rank 0's HBM through a peer mapping over NVLink (CUDA IPC,
-include/b200pf.h "Multi-GPU result collection"), followed by a per-rank completion word (b200pf_series_bind_flag): no
-collective in the stepping loop at all.  NCCL carries the set-up and the timing reduction; `--collect nccl` selects the plain
-alternative (device ring + one NCCL gather every --gather-every steps), also the fallback when peer mapping is unavailable.
+per line and instance) go into a device ring of 2 x 64 step slots; ONE NCCL gather per 64 steps ships a half ring to rank 0,
+asynchronously, while the kernels fill the other half (measured on 2 x B200: 0.98 weak-scaling efficiency).  `--collect p2p`
+is the alternative without any collective: the kernels store rho AND a per-rank completion word straight into rank 0's HBM
+through a peer mapping over NVLink (CUDA IPC, include/b200pf.h "Multi-GPU result collection"); it measured slower (0.88-0.91:
+the remote stores and their system-wide fence sit on the step's critical path), so it is the option, not the default.
 
 One JSON line on stdout (rank 0).  Keys documented in DESIGN.md section "Measurement".
 """
@@ -413,7 +414,12 @@ def run_ours(args):
             if collect == "p2p":
                 pass          # nothing to launch: results and the completion word are stored by the step's own kernels
             else:
-                dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None, dst=0)
+                # one NCCL gather of the K step results of this half to the agent's rank, asynchronous: it overlaps the next
+                # K steps, which fill the OTHER half; before a half is gathered again its previous gather must be through
+                state["works"].append(dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None,
+                                                  dst=0, async_op=True))
+                while len(state["works"]) > 1:          # the next steps refill the other half: its gather (K steps old) must be through
+                    state["works"].pop(0).wait()
                 state["gathered_upto"] = k + 1
         state["k"] = k + 1
 
@@ -583,7 +589,8 @@ def run_ours(args):
                        "result_collection": {"local": "single GPU: rho stays in this GPU's HBM",
                                              "p2p": "kernels store rho AND a per-rank completion word straight into rank 0's HBM (CUDA IPC peer mapping "
                                                     "over NVLink); no collective in the stepping loop (NCCL: set-up and timing reduction only)",
-                                             "nccl": f"device ring, one NCCL gather to rank 0 every {K} steps"}[collect],
+                                             "nccl": f"device ring of 2 x {K} step slots, one asynchronous NCCL gather of a half ring to rank 0 every {K} steps "
+                                                     "(overlaps the steps that fill the other half)"}[collect],
                        "collected_equals_results": collected_ok,
                        "wall_s_incl_flush": t_wall},
             "spread": {"unit": UNIT, "min": float(rate.min()), "median": float(np.median(rate)), "max": float(rate.max()),
@@ -641,7 +648,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-redo", action="store_true", help="measurement only: planned kernel without its pivoting safety net")
     ap.add_argument("--gather-every", type=int, default=64, help="N>1: steps per arrival signal / gather")
-    ap.add_argument("--collect", default="p2p", choices=["p2p", "nccl"], help="N>1: how rho reaches rank 0")
+    ap.add_argument("--collect", default="nccl", choices=["p2p", "nccl"], help="N>1: how rho reaches rank 0")
     ap.add_argument("--policy", type=int, default=0, choices=[0, 1, 2],
                     help="kernel policy (include/b200pf.h): 0 auto = planned kernel, 1 pivoting kernels only, 2 planned always")
     args = ap.parse_args()
