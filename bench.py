@@ -337,6 +337,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from grid2op_b200.collect import RingCollector
     from grid2op_b200.engine import PeerBuffer
     from grid2op_b200.rollout import BatchedDoNothing
     os.environ["B200PF_PLAN_POLICY"] = str(args.policy)
@@ -388,48 +389,33 @@ def run_ours(args):
             if peer is not None:
                 peer.close(); peer = None
             collect = "nccl"
+    collector = None
     if collect in ("nccl", "local"):
-        ring_local = torch.zeros((2 * K, batch, nl), dtype=torch.float32, device="cuda")
-        if collect == "nccl" and rank == 0:
-            gather_lists = [[torch.empty((K, batch, nl), dtype=torch.float32, device="cuda") for _ in range(world)] for _ in range(2)]
+        collector = RingCollector(rank, world, K, (batch, nl), "cuda")
     if peer is not None:
         # every rank's kernels publish "steps done" into rank 0's buffer behind each step (b200pf_series_bind_flag): the agent
         # reads a 4-byte word per rank to know that a step has fully arrived — no collective anywhere in the stepping loop
         eng.series_bind_flag(peer.ptr + ring_bytes + 4 * rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-    state = {"k": 0, "works": [], "gathered_upto": 0}
+    state = {"k": 0}
 
     def rho_ptr(slot):
         if peer is not None:
             return peer.ptr + 4 * ((rank * 2 * K + slot) * slot_elems)
-        return ring_local[slot].data_ptr()
+        return collector.ring[slot].data_ptr()
 
     def one_step():
         k = state["k"]
         slot = k % (2 * K)
         eng.series_bind_outputs(0, status.data_ptr(), iters.data_ptr(), rho_ptr(slot))
         env.step_device()
-        if world > 1 and (k + 1) % K == 0:
-            half = slot // K
-            if collect == "p2p":
-                pass          # nothing to launch: results and the completion word are stored by the step's own kernels
-            else:
-                # one NCCL gather of the K step results of this half to the agent's rank, asynchronous: it overlaps the next
-                # K steps, which fill the OTHER half; before a half is gathered again its previous gather must be through
-                state["works"].append(dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None,
-                                                  dst=0, async_op=True))
-                while len(state["works"]) > 1:          # the next steps refill the other half: its gather (K steps old) must be through
-                    state["works"].pop(0).wait()
-                state["gathered_upto"] = k + 1
+        if collector is not None:
+            collector.step_done(k)          # (p2p: nothing to launch — results and the completion word are stored by the step's kernels)
         state["k"] = k + 1
 
     def drain():
-        while state["works"]:
-            state["works"].pop(0).wait()
-        if world > 1 and collect == "nccl" and state.get("gathered_upto", 0) < state["k"]:
-            half = ((state["k"] - 1) % (2 * K)) // K          # the half that is being filled: gather what it holds so far
-            dist.gather(ring_local[half * K:(half + 1) * K], gather_lists[half] if rank == 0 else None, dst=0)
-            state["gathered_upto"] = state["k"]
+        if collector is not None:
+            collector.drain()
 
     n_warm = max(args.warmup, 3)
     for _ in range(n_warm):
@@ -498,7 +484,7 @@ def run_ours(args):
                 if peer is not None:
                     got = peer.read(4 * ((r * 2 * K + last) * slot_elems), slot_elems)
                 else:
-                    got = gather_lists[last // K][r][last % K].cpu().numpy().ravel()
+                    got = collector.gathered(r, state["k"] - 1).cpu().numpy().ravel()
                 if not np.isclose(float(np.nansum(got.astype(np.float64))), float(sums[r].item()), rtol=1e-9):
                     collected_ok = False
 

@@ -80,6 +80,43 @@ def test_two_ranks_equal_one_rank():
     assert np.array_equal(got, want)              # sharding must not change a single bit
 
 
+def _ring_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from grid2op_b200.collect import RingCollector
+    K, n_steps, shape = 4, 23, (5, 3)
+    col = RingCollector(rank, world, K, shape, "cpu")
+    for k in range(n_steps):
+        col.slot(k).copy_(torch.full(shape, float(1000 * rank + k)))      # what the step's kernel would store
+        col.step_done(k)
+    col.drain()
+    if rank == 0:
+        ok = True
+        for r in range(world):
+            for k in range(n_steps - K, n_steps):           # the last K steps are always available on the agent's rank
+                ok = ok and bool((col.gathered(r, k) == float(1000 * r + k)).all())
+        q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ring_collector_two_ranks():
+    """RingCollector (bench.py's N > 1 result collection: device ring, one asynchronous gather per K steps, partial gather at the
+    end) with gloo on CPU tensors"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=180) is True
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+
 def test_schedule_is_a_partition():
     s_all, t_all = instance_schedule(4096 * 8, 3, 576)
     for r in range(8):
