@@ -80,6 +80,30 @@ class BatchedDoNothing:
     def step_device(self) -> None:
         """Asynchronous: one fused kernel for the whole batch; results stay in HBM."""
         self.engine.series_step(is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva, nb_cap=self.nb_cap)
+        self._n_dev_steps = getattr(self, "_n_dev_steps", 0) + 1
+
+    def simulate_forecast(self, forecast: np.ndarray, forecast_has_prod_v: bool = True, topo: Optional[np.ndarray] = None):
+        """Batched ``obs.simulate(do_nothing, time_step=1)`` (reference grid2op/Observation/baseObservation.py:3365-3669 fed by
+        ``GridStateFromFileWithForecasts.forecasts``, gridStateFromFileWithForecasts.py:311-353): ONE launch solves, for every
+        instance, the forecast row that belongs to the step it has just done (``forecast[scen, current row]``, float32
+        [n_scen, n_rows, 2 n_load + 2 n_gen] from :func:`grid2op_b200.chronics.load_forecasts`) on its current topology
+        (``topo``: int8 [batch, n_topo_in] for a what-if on another topology).  A forecast folder without ``prod_v_forecasted``
+        keeps the current voltage set points, like the reference.  Does not advance the series; the device-side result buffers of
+        the last step are overwritten (fetch them first).  Returns ``(out, status, rho)`` on the host."""
+        gm, B = self.gm, self.batch
+        n_rows = self.chron.shape[1]
+        cur = (self.t0.astype(np.int64) + getattr(self, "_n_dev_steps", 0) - 1) % n_rows
+        rows = np.ascontiguousarray(forecast[self.scen, cur], dtype=np.float32)
+        if not forecast_has_prod_v:
+            rows[:, 2 * gm.n_load + gm.n_gen:] = self.chron[self.scen, cur][:, 2 * gm.n_load + gm.n_gen:]
+        st = self.engine.staging()
+        st["topo"][:B] = self.topo0 if topo is None else np.ascontiguousarray(topo, dtype=np.int8).reshape(B, gm.n_topo_in)
+        self.engine.rows_staging()[:B] = rows
+        self.engine.set_static_inj(self._inj0)
+        self.engine.run_rows_staged(B, is_dc=self.is_dc, max_iter=self.max_iter, tol_mva=self.tol_mva, nb_cap=0 if topo is not None else self.nb_cap)
+        out, status = st["out"][:B].copy(), st["status"][:B].copy()
+        rho = self.engine.view(out).a_or / self.thermal_limit_a[None, :]
+        return out, status, rho
 
     def reset_step(self) -> None:
         """The step an environment performs inside ``reset()``: same solve, but no soft-overflow counting

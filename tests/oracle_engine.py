@@ -254,6 +254,37 @@ class COracleSeriesEngine:
     def series_fetch_state(self):
         raise NotImplementedError
 
+    # rows entry point (what-if launches): pinned staging buffers are plain arrays here
+    def staging(self):
+        if not hasattr(self, "_stage"):
+            gm = self.gm
+            self._stage = dict(topo=np.zeros((self.B, gm.n_topo_in), dtype=np.int8), inj=np.zeros((self.B, gm.n_inj)),
+                               out=np.zeros((self.B, gm.n_out), dtype=np.float32), status=np.zeros(self.B, dtype=np.int32),
+                               iters=np.zeros(self.B, dtype=np.int32))
+            self._rows = np.zeros((self.B, 2 * gm.n_load + 2 * gm.n_gen), dtype=np.float32)
+        return self._stage
+
+    def rows_staging(self):
+        self.staging()
+        return self._rows
+
+    def set_static_inj(self, static_inj):
+        self.static_inj = np.asarray(static_inj, dtype=np.float64)
+
+    def run_rows_staged(self, batch, is_dc=False, max_iter=10, tol_mva=1e-8, nb_cap=0):
+        gm = self.gm
+        rows = self._rows[:batch]
+        sl, nl, ng = gm.inj_slices(), gm.n_load, gm.n_gen
+        inj = np.tile(self.static_inj, (batch, 1))
+        inj[:, sl["load_p"]] = rows[:, :nl]; inj[:, sl["load_q"]] = rows[:, nl:2 * nl]
+        inj[:, sl["gen_p"]] = rows[:, 2 * nl:2 * nl + ng]
+        inj[:, sl["gen_vm"]] = (rows[:, 2 * nl + ng:] / gm.prod_pu_to_kv[None, :]).astype(np.float32)
+        out, status, iters, _ = self.orc.run(self._stage["topo"][:batch], inj, is_dc=is_dc, max_iter=max_iter, tol_mva=tol_mva)
+        self._stage["out"][:batch] = out; self._stage["status"][:batch] = status; self._stage["iters"][:batch] = iters
+
+    def view(self, out):
+        return OutputView(self.gm, out)
+
     def plan_stats(self):
         return {"last_kernel": "oracle"}
 
