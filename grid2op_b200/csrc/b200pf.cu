@@ -248,8 +248,6 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         if (bk && bk[0] == '0') h->blk = 0;
         if (bk && bk[0] == '1') h->blk = 1;
         if (bt && bu && block_variant_exists(atoi(bt), atoi(bu))) { h->blk_T = atoi(bt); h->blk_U = atoi(bu); }
-        const char *bm = getenv("B200PF_BLOCK_MINB");
-        if (bm && (atoi(bm) == 8 || atoi(bm) == 16 || atoi(bm) == 20)) h->blk_minb = atoi(bm);
         const char *bun = getenv("B200PF_BLOCK_UNI");
         if (bun && bun[0] == '0') h->blk_uni = 0;
         const char *bw = getenv("B200PF_BLOCK_WPC"), *bs = getenv("B200PF_BLOCK_STAGE");
@@ -832,7 +830,9 @@ static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel
     return 0;
 }
 
-#define B200PF_BLOCK_VARIANTS(X) X(2, 4) X(4, 1) X(4, 2) X(4, 4) X(8, 1) X(8, 2) X(16, 1) X(16, 2) X(32, 1) X(32, 2) X(64, 1)
+// compiled (lanes, operations per lane and row) variants — the round-2 sweep (profiles/round2_sweep_block_*.json) covered more of
+// them; U > 1 never won and 2 lanes per instance lost everywhere, so they are not built any more
+#define B200PF_BLOCK_VARIANTS(X) X(4, 1) X(4, 2) X(8, 1) X(16, 1) X(32, 1) X(64, 1)
 static bool block_variant_exists(int T, int U) {
 #define X(t, u) if (T == t && U == u) return true;
     B200PF_BLOCK_VARIANTS(X)
@@ -857,19 +857,13 @@ static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) 
         }
         return launch_block_t<8, 1, 4, false, 4, true, false>(h, a, sel);
     }
-    if (!a.prot && T == 8 && U == 1 && h->blk_wpc == 4 && !h->blk_stage) return launch_block_t<8, 1, 4, false, 4, false, false>(h, a, sel);
+    if (!a.prot && T == 8 && U == 1 && h->blk_wpc == 4 && h->blk_wpc_pinned && !h->blk_stage) return launch_block_t<8, 1, 4, false, 4, false, false>(h, a, sel);
     if (!a.prot && T == 8 && U == 1) {
         // lockstep warps (one plan for the whole launch, whole warps): full-mask barriers / votes instead of per-instance collectives
         const bool uni = h->blk_uni && !sel.d_inst_plan && a.batch % 4 == 0;
-        // register budget (resident warps per SM): 16 warps x 128 registers measured best at every batch size
-        // (profiles/round2_block_variants.txt), B200PF_BLOCK_MINB = 8 / 20 to compare
-        if (uni) {
-            if (h->blk_minb == 8) return launch_block_t<8, 1, 8, false, 1, false, true>(h, a, sel);
-            if (h->blk_minb == 20) return launch_block_t<8, 1, 20, false, 1, false, true>(h, a, sel);
-            return launch_block_t<8, 1, 16, false, 1, false, true>(h, a, sel);
-        }
-        if (h->blk_minb == 20) return launch_block_t<8, 1, 20, false>(h, a, sel);
-        if (h->blk_minb == 16) return launch_block_t<8, 1, 16, false>(h, a, sel);
+        // register budget: 16 warps x 128 registers per SM measured best at every batch size (profiles/round2_block_variants.txt)
+        if (uni) return launch_block_t<8, 1, 16, false, 1, false, true>(h, a, sel);
+        return launch_block_t<8, 1, 16, false>(h, a, sel);
     }
     if (a.prot) {
 #define X(t, u) if (T == t && U == u) return launch_block_t<t, u, (t <= 32 ? 8 : 4), true>(h, a, sel);
