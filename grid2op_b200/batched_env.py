@@ -212,6 +212,21 @@ class BatchedEnv(BatchedDoNothing):
         self.n_steps += 1
         return rho, self.done.copy(), {"status": status, "iters": iters, "disc_lines": disc, "newly_done": newly_done}
 
+    def reset_instances(self, idx, rows=None):
+        """``env.reset()`` of the instances ``idx`` (typically the finished ones): plain topology, cooldowns / counters / done flag
+        cleared on the host and on the device, next chronics row ``rows`` (default: the row each instance started from).  Their
+        next :meth:`step` is an ordinary step on that row (use ``rows - 1`` semantics of your agent loop accordingly)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        if len(idx) == 0:
+            return
+        rows = self.t0[idx].astype(np.int64) if rows is None else np.asarray(rows, dtype=np.int64)
+        self.topo[idx] = self.topo0[idx]
+        self.last_bus[idx] = np.where(self.topo0[idx, :self.gm.dim_topo] > 0, self.topo0[idx, :self.gm.dim_topo], 1)
+        self.line_cooldown[idx] = 0; self.sub_cooldown[idx] = 0
+        self.done[idx] = False
+        self.row[idx] = rows
+        self.engine.series_reset_instances(idx, t_new=rows % self.chron.shape[1], topo_rows=self.topo[idx])
+
     def reset_step(self):
         """the solve ``env.reset()`` performs on the first row (no soft-overflow counting, no cooldown from actions)"""
         return self.step(from_reset=True)

@@ -84,7 +84,7 @@ struct b200pf_handle {
     int plan_T = 32;                                        // threads per instance of the planned kernel (32, 64, 128)
     int blk = 1;                                            // 1: BLOCK plans + pf_kernel_block (default), 0: scalar plans + pf_kernel_sparse
     int blk_T = 4, blk_U = 2;                               // lanes per instance / operations per lane and row of the block kernel
-    int blk_wpc = 4, blk_stage = 1, blk_minb = 16, blk_uni = 1, blk_wpc_pinned = 0;
+    int blk_wpc = 4, blk_stage = 1, blk_minb = 16, blk_uni = 1, blk_wpc_pinned = 0, blk_spec = 1;
     unsigned char *d_stat = nullptr; PlanArgs::StatOff stat_off{}; bool stat_dirty = true;   // packed static arrays for staged launches                         // experiment knobs: warps per CTA, TMA staging of a shared plan
     int last_kernel = 0;                                    // 1 small, 2 generic, 3 sparse
     int64_t plans_built = 0, plan_cache_resets = 0, plan_lookups = 0, plan_hits = 0;
@@ -248,6 +248,8 @@ extern "C" int b200pf_create(const b200pf_grid_desc *gd, int max_batch, int devi
         if (bk && bk[0] == '0') h->blk = 0;
         if (bk && bk[0] == '1') h->blk = 1;
         if (bt && bu && block_variant_exists(atoi(bt), atoi(bu))) { h->blk_T = atoi(bt); h->blk_U = atoi(bu); }
+        const char *bsp = getenv("B200PF_BLOCK_SPEC");
+        if (bsp && bsp[0] == '0') h->blk_spec = 0;
         const char *bun = getenv("B200PF_BLOCK_UNI");
         if (bun && bun[0] == '0') h->blk_uni = 0;
         const char *bw = getenv("B200PF_BLOCK_WPC"), *bs = getenv("B200PF_BLOCK_STAGE");
@@ -784,18 +786,18 @@ static int stat_sync(b200pf_handle *h) {
     return 0;
 }
 
-template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false, bool UNI = false>
+template <int T, int U, int MINB, bool PROT, int WPC = 1, bool STAGE = false, bool UNI = false, int MODE = 0>
 static int launch_block_t(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) {
     const DevGrid &g = h->g;
     constexpr int G = T < 32 ? 32 / T : 1;
     constexpr int BLOCK = (T < 32 ? 32 : T) * WPC;
-    auto kern = pf_kernel_block<T, U, MINB, PROT, WPC, STAGE, UNI>;
+    auto kern = pf_kernel_block<T, U, MINB, PROT, WPC, STAGE, UNI, MODE>;
     const int ws = sel.smem * G;                         // workspace of one warp / CTA
     int plan_bytes = 0;
     if (STAGE) plan_bytes = reinterpret_cast<const PlanHeader *>(h->plan_blobs.data() + h->plan_off[sel.single])->total_bytes;
     if (STAGE) { int rc = stat_sync(h); if (rc) return rc; }
     const int smem = ws * WPC + plan_bytes + (STAGE ? h->stat_off.total : 0);
-    const int variant = 1000 + MINB * 4096 + T * 64 + U * 8 + (PROT ? 1 : 0) + (STAGE ? 2 : 0) + (WPC > 1 ? 4 : 0) + (UNI ? 100000 : 0);
+    const int variant = 1000 + MINB * 4096 + T * 64 + U * 8 + (PROT ? 1 : 0) + (STAGE ? 2 : 0) + (WPC > 1 ? 4 : 0) + (UNI ? 100000 : 0) + MODE * 200000;
     if (h->sparse_occ_smem != smem || h->sparse_occ_variant != variant) {
         // (the staged variant owns a few bytes of static shared memory: dynamic + static must stay within the opt-in limit)
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin - 256));
@@ -852,8 +854,10 @@ static int launch_block(b200pf_handle *h, const RunArgs &a, const PlanSel &sel) 
             // 65 536: one staged copy serves more instances); B200PF_BLOCK_WPC pins it
             const int wpc = h->blk_wpc_pinned ? h->blk_wpc : (a.batch <= 32768 ? 2 : 4);
             if (wpc == 1) return launch_block_t<8, 1, 16, false, 1, true, true>(h, a, sel);
-            if (wpc == 2) return launch_block_t<8, 1, 8, false, 2, true, true>(h, a, sel);
-            return launch_block_t<8, 1, 4, false, 4, true, true>(h, a, sel);
+            // the stepping paths (AC, inputs = chronics rows) run the variant specialised for exactly that
+            const bool ac_rows = !a.is_dc && a.series && h->blk_spec;
+            if (wpc == 2) return ac_rows ? launch_block_t<8, 1, 8, false, 2, true, true, 1>(h, a, sel) : launch_block_t<8, 1, 8, false, 2, true, true>(h, a, sel);
+            return ac_rows ? launch_block_t<8, 1, 4, false, 4, true, true, 1>(h, a, sel) : launch_block_t<8, 1, 4, false, 4, true, true>(h, a, sel);
         }
         return launch_block_t<8, 1, 4, false, 4, true, false>(h, a, sel);
     }
@@ -1003,6 +1007,17 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
     for (int i = 0; i < batch; ++i)
         if (scen[i] < 0 || scen[i] >= n_scen || t0[i] < 0 || t0[i] >= n_rows) return fail(B200PF_E_ARG, "scenario / row index out of range");
     const size_t ncol = 2 * (size_t)g.n_load + 2 * (size_t)g.n_gen;
+    if (h->series_batch) {      // re-bind: the previous series' buffers go back first
+        CU(cudaStreamSynchronize(h->stream));
+        void *old[] = {h->d_chron, h->d_scen, h->d_t, h->d_series_topo, h->d_pcount, h->d_tsover, h->d_disc, h->d_done, h->d_series_plan, h->d_trip,
+                       h->d_incdone, h->d_nflag, h->d_flaglist, h->d_casclist};
+        for (void *p : old) {
+            if (!p) continue;
+            for (size_t q = 0; q < h->dev_allocs.size(); ++q) if (h->dev_allocs[q] == p) { h->dev_allocs.erase(h->dev_allocs.begin() + q); break; }
+            cudaFree(p);
+        }
+        h->series_batch = 0; h->series_plan_state = 0; h->series_dev_topo_ahead = false;
+    }
     auto dmal = [&](void **p, size_t bytes) -> int { CU(cudaMalloc(p, bytes ? bytes : 1)); h->dev_allocs.push_back(*p); return 0; };
     int rc;
     if ((rc = dmal((void **)&h->d_chron, (size_t)n_scen * n_rows * ncol * 4)) || (rc = dmal((void **)&h->d_scen, (size_t)batch * 4)) ||
@@ -1194,6 +1209,43 @@ static int series_step_impl(b200pf_handle *h, int is_dc, int max_iter, double to
     }
     if (h->prot) h->series_dev_topo_ahead = true;          // (device-side cascade of the warp kernel)
     return launch(h, a, nb_cap);
+}
+
+extern "C" int b200pf_series_reset_instances(b200pf_handle *h, int n, const int32_t *idx, const int32_t *t_new, const int8_t *topo_rows) {
+    if (!h || (n > 0 && !idx)) return fail(B200PF_E_ARG, "null pointer");
+    if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
+    if (n <= 0) return 0;
+    if (n > h->series_batch) return fail(B200PF_E_ARG, "more instances than the series holds");
+    CU(cudaSetDevice(h->device));
+    const DevGrid &g = h->g;
+    const size_t nt = (size_t)g.n_topo_in;
+    for (int k = 0; k < n; ++k) {
+        if (idx[k] < 0 || idx[k] >= h->series_batch) return fail(B200PF_E_ARG, "instance index out of range");
+        if (t_new && (t_new[k] < 0 || t_new[k] >= h->n_rows)) return fail(B200PF_E_ARG, "row index out of range");
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    // d_casclist / d_flaglist: scratch of batch ints each (idle between steps)
+    CU(cudaMemcpy(h->d_casclist, idx, (size_t)n * 4, cudaMemcpyHostToDevice));
+    if (t_new) CU(cudaMemcpy(h->d_flaglist, t_new, (size_t)n * 4, cudaMemcpyHostToDevice));
+    pf_kernel_series_reset<<<n, 64, 0, h->stream>>>(n, h->d_casclist, t_new ? h->d_flaglist : nullptr, g.n_line, h->d_t, h->d_done, h->d_pcount,
+                                                     h->d_tsover, h->d_disc, h->d_trip, h->d_incdone);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    if (topo_rows) {
+        // the instances' topology: device copy, host mirror, plans
+        std::vector<int8_t> all;
+        if (h->series_dev_topo_ahead || h->h_series_topo.size() != (size_t)h->series_batch * nt) {
+            all.resize((size_t)h->series_batch * nt);
+            CU(cudaMemcpy(all.data(), h->d_series_topo, all.size(), cudaMemcpyDeviceToHost));
+        } else all = h->h_series_topo;
+        for (int k = 0; k < n; ++k) {
+            memcpy(all.data() + (size_t)idx[k] * nt, topo_rows + (size_t)k * nt, nt);
+            CU(cudaMemcpy(h->d_series_topo + (size_t)idx[k] * nt, topo_rows + (size_t)k * nt, nt, cudaMemcpyHostToDevice));
+        }
+        h->series_dev_topo_ahead = false;
+        return series_plans(h, all.data());
+    }
+    return 0;
 }
 
 extern "C" int b200pf_series_protections(b200pf_handle *h, int enabled, float hard_thr, float soft_thr, int max_allowed) {

@@ -99,6 +99,19 @@ pf_kernel_redo(const DevGrid g, const RunArgs a, const int ws_bytes) {
     }
 }
 
+// env.reset() of single instances of a bound series: counters, flags and the row pointer back to a fresh episode
+__global__ void pf_kernel_series_reset(int n, const int *idx, const int *t_new, int n_line, int *t, int *done, int *pcount, int *ts_over, int *disc,
+                                       int8_t *trip, int8_t *incdone) {
+    const int k = blockIdx.x;
+    if (k >= n) return;
+    const int inst = idx[k];
+    if (threadIdx.x == 0) { done[inst] = 0; if (t_new) t[inst] = t_new[k]; }
+    for (int l = threadIdx.x; l < n_line; l += blockDim.x) {
+        const size_t o = (size_t)inst * n_line + l;
+        pcount[o] = 0; ts_over[o] = 0; disc[o] = -1; trip[o] = 0; incdone[o] = 0;
+    }
+}
+
 // paths without a safety-net launch: one thread publishes the step number behind the step's kernels
 __global__ void pf_kernel_flag(int *flag, int value) {
     asm volatile("griddepcontrol.wait;" ::: "memory");

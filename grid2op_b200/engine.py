@@ -36,6 +36,7 @@ ABI_SYMBOLS = (
     "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats", "b200pf_run_device_topo",
     "b200pf_set_debug", "b200pf_redo_launch_count",
     "b200pf_device_alloc", "b200pf_device_free", "b200pf_ipc_export", "b200pf_ipc_open", "b200pf_ipc_close", "b200pf_device_read", "b200pf_plan_counters", "b200pf_series_bind_flag",
+    "b200pf_series_reset_instances",
 )
 
 
@@ -123,6 +124,8 @@ def load_library():
     lib.b200pf_set_debug.argtypes = [vp, i32, i32]
     lib.b200pf_plan_counters.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.b200pf_series_bind_flag.argtypes = [vp, vp]
+    lib.b200pf_series_reset_instances.argtypes = [vp, i32, vp, vp, vp]
+    lib.b200pf_series_reset_instances.restype = i32
     lib.b200pf_series_bind_flag.restype = i32
     lib.b200pf_plan_counters.restype = i32
     lib.b200pf_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -474,6 +477,14 @@ class PowerFlowEngine:
         rho = np.empty((B, gm.n_line), dtype=np.float32) if want_rho else None
         self._check(self.lib.b200pf_series_fetch(self.h, _ptr(out), _ptr(status), _ptr(iters), _ptr(rho)), "b200pf_series_fetch")
         return out, status, iters, rho
+
+    def series_reset_instances(self, idx, t_new=None, topo_rows=None):
+        """``env.reset()`` of single instances of the bound series: flags / counters cleared, next chronics row ``t_new``, topology
+        ``topo_rows`` (int8 [n, n_topo_in])."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        t = None if t_new is None else np.ascontiguousarray(t_new, dtype=np.int32)
+        tr = None if topo_rows is None else np.ascontiguousarray(topo_rows, dtype=np.int8).reshape(len(idx), self.gm.n_topo_in)
+        self._check(self.lib.b200pf_series_reset_instances(self.h, len(idx), _ptr(idx), _ptr(t), _ptr(tr)), "b200pf_series_reset_instances")
 
     def series_bind_flag(self, d_flag: int = 0):
         """the device stores the number of series steps done to ``*d_flag`` (device / peer pointer) behind every step"""

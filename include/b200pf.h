@@ -255,6 +255,10 @@ int b200pf_plan_counters(const b200pf_handle *h, int64_t *out4);
  * NVLink — and binds a slice of it as its `rho` output (b200pf_series_bind_outputs): the kernel's own result stores land in
  * the agent's HBM, fused with the solve, no extra launch.  Completion is signalled by whatever orders the streams (a tiny
  * NCCL all-reduce every K steps in bench.py).  handle64: 64 bytes (cudaIpcMemHandle_t). */
+/* env.reset() of single instances of a bound series (reference Environment.reset, environment.py; BaseEnv counters
+ * baseEnv.py:3352-3393): done flag, protection counters, overflow counters and disc_lines back to a fresh episode; t_new (may be
+ * NULL): the chronics row the instance's next solve uses; topo_rows (may be NULL): int8 [n][n_topo_in], its topology. */
+int b200pf_series_reset_instances(b200pf_handle *h, int n, const int32_t *idx, const int32_t *t_new, const int8_t *topo_rows);
 /* b200pf_series_bind_flag: after every b200pf_series_step the device stores the number of steps done so far to *d_flag (behind
  * all the step's kernels, system-wide visible) — d_flag may point into the agent rank's buffer, next to the results: the agent
  * learns that a rank's step k has fully arrived by reading a 4-byte word, no collective involved.  NULL unbinds. */

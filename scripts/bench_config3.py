@@ -47,9 +47,7 @@ def run(policy, batch, steps, grid, chronf, seed=1):
         if done.any():                                   # game over -> that environment restarts from the plain topology
             who = np.flatnonzero(done)
             restarts += len(who)
-            env.topo[who] = env.topo0[who]
-            env.done[who] = False
-            env._topo_dirty = True
+            env.reset_instances(who, rows=env.row[who])      # fresh episode on the plain topology, chronics go on
     ts = np.array(ts)
     steady = ts[len(ts) // 2:]
     look = sum(p["lookups"] for p in per_step[len(ts) // 2:]); hits = sum(p["hits"] for p in per_step[len(ts) // 2:])

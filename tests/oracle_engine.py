@@ -254,6 +254,13 @@ class COracleSeriesEngine:
     def series_fetch_state(self):
         raise NotImplementedError
 
+    def series_reset_instances(self, idx, t_new=None, topo_rows=None):
+        idx = np.asarray(idx, dtype=np.int64)
+        if t_new is not None:
+            self.t[idx] = np.asarray(t_new, dtype=np.int64)
+        if topo_rows is not None:
+            self.topo[idx] = np.asarray(topo_rows, dtype=np.int8).reshape(len(idx), self.gm.n_topo_in)
+
     # rows entry point (what-if launches): pinned staging buffers are plain arrays here
     def staging(self):
         if not hasattr(self, "_stage"):

@@ -161,3 +161,70 @@ def test_batched_env_vs_reference_env_gpu(cuda_required, protections):
     from grid2op_b200.backend import B200Backend
     saw = _run(130, 96, B200Backend, lambda gm: None, protections=protections, seeds=(0, 1, 2, 3))
     assert saw["maint"] and saw["sub"] and saw["line"] and saw["illegal"]
+
+
+@pytest.mark.gpu
+def test_reset_of_single_instances(cuda_required):
+    """game over -> BatchedEnv.reset_instances: flags / counters cleared on the device too, the instances step again"""
+    from grid2op_b200.batched_env import BatchedEnv
+    from grid2op_b200.engine import OutputView
+    from grid2op_b200.gridmodel import GridModel
+    from grid2op_b200.rollout import BatchedDoNothing
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    gm = GridModel.from_npz(os.path.join(gold, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(gold, "case14_sandbox_chronics.npz"))["chron"]
+    B = 64
+    probe = BatchedDoNothing(gm, chron, B)
+    probe.step_device()
+    out, _, _, _ = probe.fetch()
+    probe.close()
+    a_all = OutputView(gm, out).a_or
+    th = np.maximum(a_all.max(axis=0) * 1.5, 1.0).astype(np.float32)
+    env = BatchedEnv(gm, chron, B, protections=True, thermal_limit_a=th)
+    env.reset_step()
+    # make half of the instances game over: disconnect lines until the grid falls apart (scripted through the action API)
+    victims = np.arange(0, B, 2)
+    for l in range(gm.n_line):
+        lid = np.full(B, -1); lst = np.zeros(B, dtype=np.int64)
+        lid[victims] = l; lst[victims] = -1
+        rho, done, info = env.step(line_id=lid, line_status=lst)
+        if done[victims].all():
+            break
+    assert done[victims].all() and not done[1::2].any()
+    st = env.engine.series_fetch_state()
+    assert (st["done"][victims] == 1).all()
+    env.reset_instances(victims)
+    st = env.engine.series_fetch_state()
+    assert (st["done"] == 0).all() and (st["protection_counter"][victims] == 0).all() and (st["disc_lines"][victims] == -1).all()
+    rho, done, info = env.step()
+    assert not done.any() and (info["status"] == 0).all()
+    assert np.isfinite(rho).all()
+    env.close()
+
+
+def test_reset_of_single_instances_host_logic():
+    """reset_instances on the oracle stand-in engine: the reset instance replays exactly what a fresh driver produces, the others go on"""
+    from grid2op_b200.batched_env import BatchedEnv
+    from grid2op_b200.gridmodel import GridModel
+    from oracle_engine import COracleSeriesEngine
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    gm = GridModel.from_npz(os.path.join(gold, "gridmodel_l2rpn_case14_sandbox.npz"))
+    chron = np.load(os.path.join(gold, "case14_sandbox_chronics.npz"))["chron"]
+    B = 4
+    t0 = np.array([3, 3, 7, 7], dtype=np.int32)
+    mk = lambda: BatchedEnv(gm, chron, B, scen=np.zeros(B, dtype=np.int32), t0=t0, nb_timestep_cooldown_line=3,        # noqa: E731
+                            engine=COracleSeriesEngine(gm))
+    env, fresh = mk(), mk()
+    first, _, _ = fresh.step()
+    lid = np.array([2, -1, 5, -1]); lst = np.array([-1, 0, -1, 0])
+    rho1, _, _ = env.step(line_id=lid, line_status=lst)
+    assert rho1[0, 2] == 0 and env.line_cooldown[0, 2] == 3
+    rho2, _, _ = env.step()
+    env.reset_instances([0, 2])
+    assert (env.line_cooldown[[0, 2]] == 0).all() and (env.topo[[0, 2]] == env.topo0[[0, 2]]).all()
+    assert env.row[0] == 3 and env.row[2] == 7 and env.row[1] == 5
+    rho3, done, _ = env.step()
+    assert not done.any()
+    assert np.array_equal(rho3[[0, 2]], first[[0, 2]])                 # a fresh episode from the same rows
+    third, _, _ = (fresh.step(), fresh.step())[1]
+    assert np.array_equal(rho3[[1, 3]], third[[1, 3]])                 # the others: third step of an undisturbed run
