@@ -39,7 +39,7 @@ __all__ = ["BatchedEnv", "random_substation_actions"]
 class BatchedEnv(BatchedDoNothing):
     def __init__(self, gm: GridModel, chron: np.ndarray, batch: int, *, maintenance: Optional[np.ndarray] = None,
                  hazards: Optional[np.ndarray] = None, nb_timestep_cooldown_line: int = 0, nb_timestep_cooldown_sub: int = 0,
-                 nb_timestep_reconnection: int = 10, engine=None, **kw):
+                 nb_timestep_reconnection: int = 10, engine=None, tight_cap: bool = True, **kw):
         """``maintenance`` / ``hazards``: bool [n_scen, n_rows, n_line] (:func:`grid2op_b200.chronics.load_line_events` per
         scenario), row-aligned with ``chron``.  Cooldown parameters: grid2op.Parameters NB_TIMESTEP_COOLDOWN_LINE /
         NB_TIMESTEP_COOLDOWN_SUB / NB_TIMESTEP_RECONNECTION (Parameters.py:255-300)."""
@@ -77,11 +77,23 @@ class BatchedEnv(BatchedDoNothing):
             self.sub_pos[s, :len(p)] = p
         self.line_or_pos, self.line_ex_pos = np.asarray(gm.line_or_pos, dtype=np.int64), np.asarray(gm.line_ex_pos, dtype=np.int64)
         self._topo_dirty = False
-        self.nb_cap = 0                 # bus splits add active buses: launches are sized for every bus slot, not for the plain topology
+        # Bus splits add active buses: the kernels that discover the topology on the device size their workspace (and the
+        # threads per instance) for ``nb_cap`` active buses.  The host knows every instance's topology, so the cap is the
+        # bus count of the fullest instance (:meth:`_bus_cap`: host code of the library, recomputed when a topology changed) instead of every bus slot.
+        self.tight_cap = bool(tight_cap)
+        self.nb_cap = self._bus_cap() if self.tight_cap else 0
         self.n_illegal = 0
         self.n_steps = 0
 
     # ------------------------------------------------------------------------------------------------------------
+    def _bus_cap(self) -> int:
+        """Active buses (bus slots with a connected element) of the fullest instance, rounded up to a multiple of 8 above 17
+        (<= 17: exact — the warp-per-instance kernel takes systems up to 17 buses), at most every bus slot."""
+        n = int(self.engine.max_active_buses(self.topo))
+        if n > 17:
+            n = (n + 7) // 8 * 8
+        return min(n, self.gm.n_slot)
+
     def line_status(self) -> np.ndarray:
         return (self.topo[:, self.line_or_pos] > 0) & (self.topo[:, self.line_ex_pos] > 0)
 
@@ -170,6 +182,8 @@ class BatchedEnv(BatchedDoNothing):
         if self._topo_dirty:
             self.engine.series_set_topo(self.topo)
             self._topo_dirty = False
+            if self.tight_cap:
+                self.nb_cap = self._bus_cap()
         if from_reset:
             self.engine.series_next_is_reset()
         self.step_device()
@@ -226,6 +240,8 @@ class BatchedEnv(BatchedDoNothing):
         self.done[idx] = False
         self.row[idx] = rows
         self.engine.series_reset_instances(idx, t_new=rows % self.chron.shape[1], topo_rows=self.topo[idx])
+        if self.tight_cap:
+            self.nb_cap = self._bus_cap()
 
     def reset_step(self):
         """the solve ``env.reset()`` performs on the first row (no soft-overflow counting, no cooldown from actions)"""

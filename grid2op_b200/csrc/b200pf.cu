@@ -294,6 +294,43 @@ extern "C" int b200pf_sizes(const b200pf_handle *h, int *n_topo_in, int *n_inj, 
     return 0;
 }
 
+// Active buses (bus slots with at least one connected element; the count the on-device-topology kernels arrive at, b200pf_kernel.cuh
+// step 1) of n topology records: the tight nb_cap of a launch.  Pure host function of the grid description (no device, no handle).
+extern "C" int b200pf_grid_max_active_buses(const b200pf_grid_desc *gd, int n, const int8_t *topo, int32_t *per_instance, int32_t *max_out) {
+    if (!gd || !max_out || (n > 0 && !topo)) return fail(B200PF_E_ARG, "null pointer");
+    if (gd->abi_version != B200PF_ABI_VERSION) return fail(B200PF_E_ARG, "grid description: ABI version mismatch");
+    const int nbb = gd->n_busbar, n_unit = gd->n_hidden + gd->n_gen;
+    const size_t nt = (size_t)gd->dim_topo + gd->n_shunt + gd->n_hidden;
+    if (nbb < 1 || nbb > 8) return fail(B200PF_E_ARG, "1 to 8 busbars per substation");
+    // (position in the record, substation) of every element
+    std::vector<int> pos, sub;
+    auto add = [&](const int32_t *p, const int32_t *s, int cnt, int base) {
+        for (int k = 0; k < cnt; ++k) { pos.push_back(p ? p[k] : base + k); sub.push_back(s[k]); }
+    };
+    add(gd->line_or_pos, gd->line_or_sub, gd->n_line, 0); add(gd->line_ex_pos, gd->line_ex_sub, gd->n_line, 0);
+    add(gd->unit_pos, gd->unit_sub, n_unit, 0); add(gd->load_pos, gd->load_sub, gd->n_load, 0);
+    add(gd->storage_pos, gd->storage_sub, gd->n_storage, 0); add(nullptr, gd->shunt_sub, gd->n_shunt, gd->dim_topo);
+    for (size_t e = 0; e < pos.size(); ++e)
+        if (pos[e] < 0 || (size_t)pos[e] >= nt || sub[e] < 0 || sub[e] >= gd->n_sub) return fail(B200PF_E_ARG, "grid description: position / substation out of range");
+    std::vector<uint8_t> bars(gd->n_sub);        // bit b-1: busbar b of the substation carries a connected element
+    int best = 0;
+    const size_t ne = pos.size();
+    for (int r = 0; r < n; ++r) {
+        const int8_t *tv = topo + (size_t)r * nt;
+        std::fill(bars.begin(), bars.end(), (uint8_t)0);
+        for (size_t e = 0; e < ne; ++e) {
+            const int b = tv[pos[e]];
+            if (b > 0 && b <= nbb) bars[sub[e]] |= (uint8_t)(1u << (b - 1));
+        }
+        int cnt = 0;
+        for (int s2 = 0; s2 < gd->n_sub; ++s2) cnt += __builtin_popcount(bars[s2]);
+        if (per_instance) per_instance[r] = cnt;
+        if (cnt > best) best = cnt;
+    }
+    *max_out = best;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch configuration
 // ------------------------------------------------------------------------------------------------

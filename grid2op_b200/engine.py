@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "b200pf_rows_group_config", "b200pf_set_kernel_policy", "b200pf_plan_stats", "b200pf_run_device_topo",
     "b200pf_set_debug", "b200pf_redo_launch_count",
     "b200pf_device_alloc", "b200pf_device_free", "b200pf_ipc_export", "b200pf_ipc_open", "b200pf_ipc_close", "b200pf_device_read", "b200pf_plan_counters", "b200pf_series_bind_flag",
-    "b200pf_series_reset_instances",
+    "b200pf_series_reset_instances", "b200pf_grid_max_active_buses",
 )
 
 
@@ -126,6 +126,8 @@ def load_library():
     lib.b200pf_series_bind_flag.argtypes = [vp, vp]
     lib.b200pf_series_reset_instances.argtypes = [vp, i32, vp, vp, vp]
     lib.b200pf_series_reset_instances.restype = i32
+    lib.b200pf_grid_max_active_buses.argtypes = [C.POINTER(_GridDesc), i32, vp, vp, C.POINTER(i32)]
+    lib.b200pf_grid_max_active_buses.restype = i32
     lib.b200pf_series_bind_flag.restype = i32
     lib.b200pf_plan_counters.restype = i32
     lib.b200pf_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -216,6 +218,56 @@ class OutputView:
         assert o == gm.n_out
 
 
+def make_grid_desc(gm: GridModel):
+    """-> (``b200pf_grid_desc`` of include/b200pf.h, the arrays it points to — keep them alive as long as the descriptor)"""
+    keep = []
+    d = _GridDesc()
+    d.abi_version = 2
+    d.n_sub, d.n_busbar = gm.n_sub, gm.n_busbar
+    d.n_line, d.n_gen, d.n_hidden, d.n_load = gm.n_line, gm.n_gen, gm.n_hidden, gm.n_load
+    d.n_storage, d.n_shunt, d.dim_topo = gm.n_storage, gm.n_shunt, gm.dim_topo
+    d.sn_mva = gm.sn_mva
+
+    def put(name, arr, dtype):
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dtype)
+        keep.append(a)
+        setattr(d, name, a.ctypes.data)
+
+    i32, f64, f32 = np.int32, np.float64, np.float32
+    put("line_or_sub", gm.line_or_sub, i32); put("line_ex_sub", gm.line_ex_sub, i32)
+    put("line_or_pos", gm.line_or_pos, i32); put("line_ex_pos", gm.line_ex_pos, i32)
+    put("line_y", gm.line_y, f64); put("line_bdc", gm.line_bdc, f64); put("line_pshift", gm.line_pshift, f64)
+    put("line_or_vn", gm.line_or_vn, f32); put("line_ex_vn", gm.line_ex_vn, f32)
+    put("unit_sub", gm.unit_sub, i32); put("unit_pos", gm.unit_pos, i32); put("unit_is_ref", gm.unit_is_ref, i32)
+    put("unit_qmin", gm.unit_qmin, f64); put("unit_qmax", gm.unit_qmax, f64); put("unit_vn", gm.unit_vn, f32)
+    put("load_sub", gm.load_sub, i32); put("load_pos", gm.load_pos, i32); put("load_vn", gm.load_vn, f32)
+    put("storage_sub", gm.storage_sub, i32); put("storage_pos", gm.storage_pos, i32)
+    put("storage_vn", gm.storage_vn, f32); put("storage_q", gm.storage_q, f64)
+    put("shunt_sub", gm.shunt_sub, i32); put("shunt_vn", gm.shunt_vn, f32); put("shunt_vratio", gm.shunt_vratio, f64)
+    put("sub_rank", getattr(gm, "sub_rank", np.arange(gm.n_sub)), i32)
+    return d, keep
+
+
+def grid_max_active_buses(gm: GridModel, topo: np.ndarray, desc=None):
+    """Active buses (bus slots with a connected element) of every topology record, int8 [B, n_topo_in] -> (max, int32 [B]).
+    Host code of the library (``b200pf_grid_max_active_buses``): needs no device."""
+    lib = load_library()
+    keep = None
+    if desc is None:
+        desc, keep = make_grid_desc(gm)
+    topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(-1, gm.n_topo_in)
+    cnt = np.empty(topo.shape[0], dtype=np.int32)
+    best = C.c_int32(0)
+    if topo.shape[0]:
+        rc = lib.b200pf_grid_max_active_buses(C.byref(desc), topo.shape[0], _ptr(topo), _ptr(cnt), C.byref(best))
+        if rc != 0:
+            raise RuntimeError(f"b200pf_grid_max_active_buses failed ({rc}): {lib.b200pf_last_error().decode()}")
+    del keep
+    return int(best.value), cnt
+
+
 class PowerFlowEngine:
     """One device handle: static grid on the GPU + staging for up to ``max_batch`` instances."""
 
@@ -225,33 +277,8 @@ class PowerFlowEngine:
         if self.lib.b200pf_abi_version() != 2:
             raise EngineUnavailable("libb200pf ABI version mismatch")
         self.max_batch = int(max_batch)
-        self._keep = []
-        d = _GridDesc()
-        d.abi_version = 2
-        d.n_sub, d.n_busbar = gm.n_sub, gm.n_busbar
-        d.n_line, d.n_gen, d.n_hidden, d.n_load = gm.n_line, gm.n_gen, gm.n_hidden, gm.n_load
-        d.n_storage, d.n_shunt, d.dim_topo = gm.n_storage, gm.n_shunt, gm.dim_topo
-        d.sn_mva = gm.sn_mva
-
-        def put(name, arr, dtype):
-            a = np.ascontiguousarray(arr, dtype=dtype)
-            if a.size == 0:
-                a = np.zeros(1, dtype=dtype)
-            self._keep.append(a)
-            setattr(d, name, a.ctypes.data)
-
-        i32, f64, f32 = np.int32, np.float64, np.float32
-        put("line_or_sub", gm.line_or_sub, i32); put("line_ex_sub", gm.line_ex_sub, i32)
-        put("line_or_pos", gm.line_or_pos, i32); put("line_ex_pos", gm.line_ex_pos, i32)
-        put("line_y", gm.line_y, f64); put("line_bdc", gm.line_bdc, f64); put("line_pshift", gm.line_pshift, f64)
-        put("line_or_vn", gm.line_or_vn, f32); put("line_ex_vn", gm.line_ex_vn, f32)
-        put("unit_sub", gm.unit_sub, i32); put("unit_pos", gm.unit_pos, i32); put("unit_is_ref", gm.unit_is_ref, i32)
-        put("unit_qmin", gm.unit_qmin, f64); put("unit_qmax", gm.unit_qmax, f64); put("unit_vn", gm.unit_vn, f32)
-        put("load_sub", gm.load_sub, i32); put("load_pos", gm.load_pos, i32); put("load_vn", gm.load_vn, f32)
-        put("storage_sub", gm.storage_sub, i32); put("storage_pos", gm.storage_pos, i32)
-        put("storage_vn", gm.storage_vn, f32); put("storage_q", gm.storage_q, f64)
-        put("shunt_sub", gm.shunt_sub, i32); put("shunt_vn", gm.shunt_vn, f32); put("shunt_vratio", gm.shunt_vratio, f64)
-        put("sub_rank", getattr(gm, "sub_rank", np.arange(gm.n_sub)), i32)
+        d, self._keep = make_grid_desc(gm)
+        self._desc = d                      # (its arrays live in self._keep)
         h = C.c_void_p()
         rc = self.lib.b200pf_create(C.byref(d), self.max_batch, int(device), C.byref(h))
         if rc != 0:
@@ -280,26 +307,19 @@ class PowerFlowEngine:
         except Exception:
             pass
 
-    def max_active_buses(self, topo: np.ndarray) -> int:
-        """Largest number of active buses (bus slots with at least one connected element) over a batch
-        of topology records: the tight ``nb_cap`` for a launch (0 = unknown -> size for every slot)."""
+    def max_active_buses(self, topo: np.ndarray, per_instance: bool = False):
+        """Largest number of active buses (bus slots with at least one connected element) over a batch of topology records: the
+        tight ``nb_cap`` for a launch (0 = unknown -> size for every slot).  ``per_instance``: -> (max, int32 [B]).  Host code of
+        the library (``b200pf_grid_max_active_buses``)."""
         gm = self.gm
-        if getattr(self, "_slot_tbl", None) is None:
-            sub = np.zeros(gm.n_topo_in, dtype=np.int64)
-            sub[gm.line_or_pos] = gm.line_or_sub; sub[gm.line_ex_pos] = gm.line_ex_sub
-            sub[gm.gen_pos] = gm.gen_sub; sub[gm.load_pos] = gm.load_sub
-            if gm.n_storage:
-                sub[gm.storage_pos] = gm.storage_sub
-            sub[gm.dim_topo:gm.dim_topo + gm.n_shunt] = gm.shunt_sub
-            sub[gm.dim_topo + gm.n_shunt:] = gm.hidden_sub
-            self._slot_tbl = sub
-        topo = np.asarray(topo).reshape(-1, gm.n_topo_in).astype(np.int64)
-        if topo.shape[0] == 0:
-            return 0
-        slot = self._slot_tbl[None, :] + (topo - 1) * gm.n_sub
-        active = np.zeros((topo.shape[0], gm.n_slot + 1), dtype=bool)
-        np.put_along_axis(active, np.where(topo > 0, slot, gm.n_slot), True, axis=1)     # column n_slot = dump
-        return int(active[:, :gm.n_slot].sum(axis=1).max())
+        topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(-1, gm.n_topo_in)
+        n = topo.shape[0]
+        cnt = np.empty(n, dtype=np.int32) if per_instance else None
+        best = C.c_int32(0)
+        if n:
+            self._check(self.lib.b200pf_grid_max_active_buses(C.byref(self._desc), n, _ptr(topo), _ptr(cnt), C.byref(best)),
+                        "b200pf_grid_max_active_buses")
+        return (int(best.value), cnt) if per_instance else int(best.value)
 
     def run(self, topo: np.ndarray, inj: np.ndarray, is_dc: bool = False, max_iter: int = 10,
             tol_mva: float = 1e-8, nb_cap: int = -1, want_busv: bool = False

@@ -104,6 +104,12 @@ int b200pf_device_count(void);
 int b200pf_create(const b200pf_grid_desc *grid, int max_batch, int device, b200pf_handle **out);
 int b200pf_destroy(b200pf_handle *h);
 
+/* Active buses (bus slots with at least one connected element) of n topology records int8 [n][n_topo_in]: per_instance (may be
+ * NULL) int32 [n], *max_out their maximum = the tight nb_cap of a launch on these records (the bound the callers of the reference's
+ * backend never need because pandapower re-derives the bus set per call, pPB:1097-1105 -> pandapower pd2ppc).  Pure host function
+ * of the grid description: no device, no handle. */
+int b200pf_grid_max_active_buses(const b200pf_grid_desc *grid, int n, const int8_t *topo, int32_t *per_instance, int32_t *max_out);
+
 /* sizes derived from the grid description */
 int b200pf_sizes(const b200pf_handle *h, int *n_topo_in, int *n_inj, int *n_out, int *n_slot);
 

@@ -25,15 +25,15 @@ from grid2op_b200.gridmodel import GridModel  # noqa: E402
 GOLD = os.path.join(REPO, "tests", "golden")
 
 
-def run(policy, batch, steps, grid, chronf, seed=1):
+def run(policy, batch, steps, grid, chronf, seed=1, tight_cap=True):
     gm = GridModel.from_npz(os.path.join(GOLD, grid))
     chron = np.load(os.path.join(GOLD, chronf))["chron"]
     os.environ["B200PF_PLAN_POLICY"] = str(policy)
-    env = BatchedEnv(gm, chron, batch)
+    env = BatchedEnv(gm, chron, batch, tight_cap=tight_cap)
     env.engine.set_kernel_policy(policy)
     rng = np.random.default_rng(seed)
     env.reset_step()
-    ts, conv, restarts = [], [], 0
+    ts, conv, restarts, caps = [], [], 0, []
     c0 = env.engine.plan_counters()
     per_step = []
     for k in range(steps):
@@ -41,6 +41,7 @@ def run(policy, batch, steps, grid, chronf, seed=1):
         t = time.perf_counter()
         rho, done, info = env.step(sub, bus)
         ts.append(time.perf_counter() - t)
+        caps.append(int(env.nb_cap))
         conv.append(float((info["status"] == 0).mean()))
         c1 = env.engine.plan_counters()
         per_step.append({k2: c1[k2] - c0[k2] for k2 in c1}); c0 = c1
@@ -60,6 +61,7 @@ def run(policy, batch, steps, grid, chronf, seed=1):
            "plans_built_per_step_steady": float(np.mean([p["built"] for p in per_step[len(ts) // 2:]])),
            "cache_resets": env.engine.plan_counters()["cache_resets"],
            "converged_fraction_mean": float(np.mean(conv)), "game_over_restarts": restarts,
+           "bus_cap": {"tight": bool(tight_cap), "min": min(caps), "max": max(caps), "every_slot": int(gm.n_slot)},
            "host_threads_visible": os.cpu_count(), "plan_threads_cap": os.environ.get("B200PF_PLAN_THREADS", "min(64, hardware)")}
     env.close()
     return res
@@ -77,4 +79,7 @@ if __name__ == "__main__":
     for pol in (2, 1, 0):
         out[f"policy{pol}"] = run(pol, a.batch, a.steps, a.grid, a.chron)
         print(pol, json.dumps(out[f"policy{pol}"]), file=sys.stderr, flush=True)
+    # the pivoting kernels with their workspace sized for every bus slot (round-2 state before the bus cap followed the topology)
+    out["policy1_every_slot"] = run(1, a.batch, a.steps, a.grid, a.chron, tight_cap=False)
+    print("1 (every slot)", json.dumps(out["policy1_every_slot"]), file=sys.stderr, flush=True)
     print(json.dumps(out, indent=1))

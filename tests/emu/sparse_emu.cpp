@@ -461,3 +461,25 @@ extern "C" int block_emu_validate_plan(const b200pf_grid_desc *gd, const int8_t 
     if (max_err) *max_err = err;
     return err < 1e-9 ? 0 : 8;
 }
+
+// Timing aid of the plan builder (scripts/time_plan_builder.py): builds the plans of n topology rows, one thread, returns the
+// seconds spent and the bytes produced; statuses that are not OK are counted in *n_bad.
+#include <chrono>
+extern "C" int plan_emu_build_many(const b200pf_grid_desc *gd, int n, const int8_t *topo_rows, int op_width, int blk_T, int blk_U, double *seconds,
+                                   long long *bytes, int *n_bad) {
+    HostGrid hg = host_grid(gd);
+    PlanBuilder pb(hg, op_width);
+    if (blk_T > 0) pb.block_mode(blk_T, blk_U);
+    const size_t nt = (size_t)hg.n_topo_in;
+    long long tot = 0; int bad = 0;
+    double sec_ok = 0.0;                     // (plans of topologies with isolated elements end early: timed apart)
+    for (int k = 0; k < n; ++k) {
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<unsigned char> blob = pb.build(topo_rows + (size_t)k * nt, -1);
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (((const PlanHeader *)blob.data())->status != PLAN_ST_OK) { ++bad; continue; }
+        tot += (long long)blob.size(); sec_ok += dt;
+    }
+    *seconds = sec_ok; *bytes = tot; *n_bad = bad;
+    return 0;
+}

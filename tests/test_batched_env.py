@@ -228,3 +228,74 @@ def test_reset_of_single_instances_host_logic():
     assert np.array_equal(rho3[[0, 2]], first[[0, 2]])                 # a fresh episode from the same rows
     third, _, _ = (fresh.step(), fresh.step())[1]
     assert np.array_equal(rho3[[1, 3]], third[[1, 3]])                 # the others: third step of an undisturbed run
+
+
+def test_bus_cap_follows_the_topology():
+    """BatchedEnv.nb_cap = active buses of the fullest instance (exact up to 17, then rounded up to a multiple of 8)"""
+    from grid2op_b200.batched_env import BatchedEnv
+    from grid2op_b200.gridmodel import GridModel
+    from grid2op_b200.rollout import BatchedDoNothing
+    from oracle_engine import COracleSeriesEngine
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    for name, chr_ in (("l2rpn_case14_sandbox", "case14_sandbox_chronics.npz"), ("l2rpn_neurips_2020_track1", "neurips_2020_track1_chronics.npz")):
+        gm = GridModel.from_npz(os.path.join(gold, f"gridmodel_{name}.npz"))
+        chron = np.load(os.path.join(gold, chr_))["chron"]
+        env = BatchedEnv(gm, chron, 3, engine=COracleSeriesEngine(gm))
+        plain = BatchedDoNothing(gm, chron, 3, engine=COracleSeriesEngine(gm)).nb_cap
+        rnd = lambda n: n if n <= 17 else min((n + 7) // 8 * 8, gm.n_slot)          # noqa: E731
+        assert env.nb_cap == rnd(plain)
+        # split substation 1 of instance 2 (two elements to busbar 2): one more active bus
+        bus = np.zeros((3, env.max_sub_size), dtype=np.int8)
+        bus[2, :env.sub_size[1]] = 1; bus[2, :2] = 2
+        env.step(sub_id=np.array([-1, -1, 1]), sub_bus=bus)
+        assert env.nb_cap == rnd(plain + 1)
+        # brute force on the topology records
+        def count(tv):
+            return len(set(env._slots(tv).tolist()))
+        assert max(count(env.topo[i]) for i in range(3)) == plain + 1
+        env.reset_instances([2])
+        assert env.nb_cap == rnd(plain)
+        off = BatchedEnv(gm, chron, 3, engine=COracleSeriesEngine(gm), tight_cap=False)
+        assert off.nb_cap == 0
+
+
+@pytest.mark.gpu
+def test_pivoting_kernels_with_tight_cap_equal_planned(cuda_required):
+    """random-walk topologies (BASELINE configs[2]) through the kernels that discover the topology on the device, workspace sized by
+    BatchedEnv's bus cap, against the planned kernel (plans built on the host) and against the same kernels sized for every bus
+    slot: same statuses (no ST_LARGE ever), same flows"""
+    from grid2op_b200.batched_env import BatchedEnv, random_substation_actions
+    from grid2op_b200.gridmodel import GridModel
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    gm = GridModel.from_npz(os.path.join(gold, "gridmodel_l2rpn_neurips_2020_track1.npz"))
+    chron = np.load(os.path.join(gold, "neurips_2020_track1_chronics.npz"))["chron"]
+    B = 192
+    envs = [BatchedEnv(gm, chron, B), BatchedEnv(gm, chron, B, tight_cap=False), BatchedEnv(gm, chron, B)]
+    for e, pol in zip(envs, (1, 1, 2)):
+        e.engine.set_kernel_policy(pol)
+        e.reset_step()
+    rng = np.random.default_rng(5)
+    caps = []
+    n_conv = 0
+    for k in range(10):
+        sub, bus = random_substation_actions(envs[0], rng)
+        res = [e.step(sub, bus) for e in envs]
+        caps.append(envs[0].nb_cap)
+        st = [r[2]["status"] for r in res]
+        assert not (st[0] == 4).any() and not (st[1] == 4).any()                      # ST_LARGE
+        assert np.array_equal(st[0], st[1])
+        assert int((st[0] != st[2]).sum()) <= 1, (k, np.flatnonzero(st[0] != st[2]))   # (pivoting vs planned + safety net: borderline states)
+        ok = (st[0] == 0) & (st[2] == 0) & ~res[0][1] & ~res[2][1]
+        n_conv += int(ok.sum())
+        assert np.allclose(res[0][0][ok], res[1][0][ok], rtol=1e-5, atol=1e-6)
+        assert np.allclose(res[0][0][ok], res[2][0][ok], rtol=2e-3, atol=2e-4), float(np.max(np.abs(res[0][0][ok] - res[2][0][ok])))
+        done = res[0][1] | res[2][1]
+        if done.any():
+            who = np.flatnonzero(done)
+            for e in envs:
+                e.reset_instances(who, rows=e.row[who])
+    assert envs[0].engine.plan_stats()["last_kernel"] != "planned_sparse" and envs[2].engine.plan_stats()["last_kernel"].startswith("planned")
+    assert 36 < max(caps) < gm.n_slot          # above the plain topology's bus count, below "every slot"
+    assert n_conv > 5 * B
+    for e in envs:
+        e.close()
