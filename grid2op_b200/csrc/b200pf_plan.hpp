@@ -336,47 +336,52 @@ public:
                     if (S[(size_t)i * d + k]) seq.push_back({(uint16_t)(nnzF + i), (uint16_t)P(i, k), (uint16_t)(nnzF + k), (uint16_t)kk});
             }
             std::vector<int> wlev(nA + 1, 0), rlev(nA + 1, 0), lev(seq.size(), 0);
-            // successor edges of the dependency graph (RAW, WAW, WAR), for the row balancing below
-            std::vector<std::vector<int>> succ(seq.size()), readers(nA + 1);
-            std::vector<int> lastw(nA + 1, -1);
+            // For the row balancing below: the earliest pass of any successor of an operation in the dependency graph (RAW, WAW,
+            // WAR edges).  Flat arrays only (this is the builder's hot loop: the cost of a new topology in a single environment):
+            // the readers of an entry since its last write are a linked list threaded through the three read slots of every
+            // operation.
+            const int NOSUCC = 1 << 30;
+            std::vector<int> minsucc(seq.size(), NOSUCC), lastw(nA + 1, -1), rd_head(nA + 1, -1), rd_next(seq.size() * 3, -1);
             int nlev = 0;
             for (size_t q = 0; q < seq.size(); ++q) {
                 const Op &o = seq[q];
-                int lv = std::max(std::max(wlev[o.ik], wlev[o.kj]), std::max(wlev[o.kk], std::max(wlev[o.ij], rlev[o.ij]))) + 1;
+                const int lv = std::max(std::max(wlev[o.ik], wlev[o.kj]), std::max(wlev[o.kk], std::max(wlev[o.ij], rlev[o.ij]))) + 1;
                 lev[q] = lv; nlev = std::max(nlev, lv);
                 wlev[o.ij] = lv;
                 rlev[o.ik] = std::max(rlev[o.ik], lv); rlev[o.kj] = std::max(rlev[o.kj], lv); rlev[o.kk] = std::max(rlev[o.kk], lv);
                 const int rd[3] = {o.ik, o.kj, o.kk};
-                for (int r : rd) if (lastw[r] >= 0) succ[lastw[r]].push_back((int)q);
-                if (lastw[o.ij] >= 0) succ[lastw[o.ij]].push_back((int)q);
-                for (int r : readers[o.ij]) succ[r].push_back((int)q);
-                readers[o.ij].clear();
-                for (int r : rd) readers[r].push_back((int)q);
+                for (int r : rd) { const int p = lastw[r]; if (p >= 0 && lv < minsucc[p]) minsucc[p] = lv; }            // RAW
+                { const int p = lastw[o.ij]; if (p >= 0 && lv < minsucc[p]) minsucc[p] = lv; }                          // WAW
+                for (int nd = rd_head[o.ij]; nd >= 0; nd = rd_next[nd]) { const int p = nd / 3; if (lv < minsucc[p]) minsucc[p] = lv; }   // WAR
+                rd_head[o.ij] = -1;
+                for (int s3 = 0; s3 < 3; ++s3) { const int nd = (int)q * 3 + s3; rd_next[nd] = rd_head[rd[s3]]; rd_head[rd[s3]] = nd; }
                 lastw[o.ij] = (int)q;
             }
             const int W = op_width_;
             {   // Row balancing: a pass costs ceil(n / W) rows.  Going down the passes, the operations of the last, partly
                 // filled row move to the next pass when they have slack (every successor at least two passes later; those with
                 // the most slack first): that saves a row here and costs at most one there, where the remainder rolls on.
-                // Dependencies are untouched by construction (tests/ validate every stream).
-                std::vector<std::vector<int>> at(nlev + 2);
-                for (size_t q = 0; q < seq.size(); ++q) at[lev[q]].push_back((int)q);
+                // Dependencies are untouched by construction (tests/ validate every stream).  (The successors of the operations of
+                // pass l sit in later passes, which have not been touched yet when l is balanced: their passes are still the ones
+                // of the scan above, which is what minsucc holds.)
+                std::vector<int> cnt(nlev + 2, 0), off(nlev + 3, 0);
+                for (int lv : lev) cnt[lv]++;
+                for (int l = 0; l <= nlev + 1; ++l) off[l + 1] = off[l] + cnt[l] + W;      // room for what moves in from the pass before
+                std::vector<int> at((size_t)off[nlev + 2]), fill(off.begin(), off.end() - 1);
+                for (size_t q = 0; q < seq.size(); ++q) at[fill[lev[q]]++] = (int)q;
                 std::vector<std::pair<int, int>> cand;
                 for (int l = 1; l < nlev; ++l) {
-                    const int r = (int)at[l].size() % W;
+                    const int n_here = fill[l] - off[l];
+                    const int r = n_here % W;
                     if (r == 0) continue;
                     cand.clear();
-                    for (int q : at[l]) {
-                        int ms = 1 << 30;
-                        for (int sq : succ[q]) ms = std::min(ms, lev[sq]);
-                        if (ms >= l + 2) cand.push_back({-ms, q});
-                    }
+                    for (int k = off[l]; k < fill[l]; ++k) { const int q = at[k]; if (minsucc[q] >= l + 2) cand.push_back({-minsucc[q], q}); }
                     if ((int)cand.size() < r) continue;
                     std::sort(cand.begin(), cand.end());
-                    for (int c = 0; c < r; ++c) { const int q = cand[c].second; lev[q] = l + 1; at[l + 1].push_back(q); }
-                    std::vector<int> keep;
-                    for (int q : at[l]) if (lev[q] == l) keep.push_back(q);
-                    at[l].swap(keep);
+                    for (int c = 0; c < r; ++c) { const int q = cand[c].second; lev[q] = l + 1; at[fill[l + 1]++] = q; }
+                    int w = off[l];
+                    for (int k = off[l]; k < fill[l]; ++k) if (lev[at[k]] == l) at[w++] = at[k];
+                    fill[l] = w;
                 }
             }
             // passes padded to whole rows of op_width slots; the last row of a pass carries the barrier flag

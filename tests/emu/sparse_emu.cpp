@@ -483,3 +483,17 @@ extern "C" int plan_emu_build_many(const b200pf_grid_desc *gd, int n, const int8
     *seconds = sec_ok; *bytes = tot; *n_bad = bad;
     return 0;
 }
+
+// FNV-1a hash + size of the plan blob of one topology record (tests: the builder is deterministic; refactorings of the builder
+// are checked for bit-identical blobs against hashes of the previous build).  n_seeds > 0: the searched plan.
+extern "C" unsigned long long plan_emu_blob_hash(const b200pf_grid_desc *gd, const int8_t *topo, int outage, int op_width, int blk_T, int blk_U,
+                                                 int n_seeds, int *size_out) {
+    HostGrid hg = host_grid(gd);
+    std::vector<unsigned char> blob;
+    if (n_seeds > 0) blob = build_plan_searched(hg, op_width, topo, outage, n_seeds, blk_T, blk_U);
+    else { PlanBuilder pb(hg, op_width); if (blk_T > 0) pb.block_mode(blk_T, blk_U); blob = pb.build(topo, outage); }
+    unsigned long long hsh = 1469598103934665603ull;
+    for (unsigned char c : blob) { hsh ^= c; hsh *= 1099511628211ull; }
+    if (size_out) *size_out = (int)blob.size();
+    return hsh;
+}

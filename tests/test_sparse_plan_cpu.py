@@ -200,3 +200,27 @@ def test_plan_search_is_deterministic_and_never_worse(name, width):
         b = emu.lib.sparse_emu_plan_rows(*args, C.c_int(1), C.byref(c2))
         assert a == b and c1.value == c2.value          # same plan, byte for byte
         assert (base < 0 and a < 0) or (0 < a <= base)  # rows of the operation stream
+
+
+def test_plan_blobs_are_deterministic():
+    """the builder is a pure function of (grid, topology record, outage, kernel shape): same input -> byte-identical blob
+    (tests/emu: plan_emu_blob_hash; how builder refactorings are checked against the previous build)"""
+    import ctypes as C
+    import sparse_emu
+    from grid2op_b200.gridmodel import GridModel
+    gm = GridModel.from_npz(os.path.join(os.path.dirname(__file__), "golden", "gridmodel_l2rpn_neurips_2020_track1.npz"))
+    emu = sparse_emu.SparseEmu(gm)
+    emu.lib.plan_emu_blob_hash.restype = C.c_ulonglong
+    t0 = np.ascontiguousarray(gm.default_topo(), dtype=np.int8)
+    t1 = t0.copy(); t1[gm.line_or_pos[3]] = 2; t1[gm.line_ex_pos[5]] = 2
+
+    def h(tv, w, T, U, seeds=0, outage=-1):
+        sz = C.c_int()
+        v = emu.lib.plan_emu_blob_hash(C.byref(emu.desc), tv.ctypes.data_as(C.c_void_p), outage, w, T, U, seeds, C.byref(sz))
+        return int(v), sz.value
+
+    for shape in ((64, 0, 0), (32, 0, 0), (32, 8, 1), (32, 32, 1)):
+        a, b = h(t0, *shape), h(t0, *shape)
+        assert a == b and a[1] > 0
+        assert h(t1, *shape) != a and h(t0, *shape, outage=2) != a
+    assert h(t0, 64, 0, 0, seeds=4) == h(t0, 64, 0, 0, seeds=4)
