@@ -1,7 +1,8 @@
 """Locate an importable ``grid2op`` (the host framework we plug into; NOT re-implemented here).
 
 Search order: an already importable ``grid2op`` -> ``$GRID2OP_B200_REF`` -> ``<repo>/baseline/_ref``
-(the unmodified reference installed with ``pip install --target``; git-ignored) -> ``/root/reference``.
+(the unmodified reference installed with ``pip install --target``; git-ignored).  Nothing else is searched: a checkout
+elsewhere is named through the environment variable (tests/conftest.py does that for the build container).
 
 grid2op imports ``pandapower`` at package-import time (reference:
 grid2op/Backend/__init__.py:4 -> grid2op/Backend/pandaPowerBackend.py:18) even when only the
@@ -22,7 +23,6 @@ _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _CANDIDATES = [
     os.environ.get("GRID2OP_B200_REF", ""),
     os.path.join(_REPO, "baseline", "_ref"),
-    "/root/reference",
 ]
 
 _state = {"done": False, "ok": False, "why": ""}

@@ -420,14 +420,13 @@ class B200Backend(Backend):
         self._gm = None
 
     def save_file(self, full_path) -> None:                                     # pPB:1425-1437 (pp.to_json)
-        """Write the current grid state as a pandapower-JSON file: the source ``grid.json`` with the set points,
-        element buses (global id = sub + (busbar-1)*n_sub, like the reference's tables) and in-service flags of
-        this backend.  Like the reference's ``pp.to_json`` of its running net, elements on busbar k > 1 carry the bus id
-        ``sub + (k-1)*n_sub``; the bus rows of those extra busbars are NOT appended to the file's bus table, so a file saved
-        while some element sits on busbar 2 documents the state but is not loadable as a grid (``GridModel`` rejects bus ids
-        beyond the table — the reference's own saved files are not re-loadable as the same environment either: its
-        ``load_grid`` would take the duplicated buses for substations).  With everything on busbar 1 the file re-loads to the
-        same state (tests/test_save_file.py)."""
+        """Write the current grid state as a pandapower-JSON file: the source ``grid.json`` with the set points, element buses
+        and in-service flags of this backend.  Like the reference's running net (``load_grid`` duplicates every bus once per extra
+        busbar, pPB:548-566, and ``pp.to_json`` writes them), the bus table carries ``n_busbar_per_sub * n_sub`` rows: busbar k of
+        substation s is bus ``s + (k-1) * n_sub``, in service when a connected element sits on it (pPB:920-922) — the file is a
+        complete pandapower net of the CURRENT topology (tests/test_save_file.py solves it with the oracle's pandapower
+        restatement and finds the backend's flows).  Loaded back as an environment grid it shows ``n_busbar_per_sub * n_sub``
+        substations, exactly like a file saved by the reference."""
         from .ppjson import update_pp_json
         gm = self._gm
         nl, nf = gm.n_powerline, gm.n_gen_file
@@ -451,4 +450,18 @@ class B200Backend(Backend):
                             "bus": glob(gm.shunt_sub, self._sh_bus)}
         if gm.n_storage:
             upd["storage"] = {"p_mw": list(self._sto_p), "in_service": list(self._sto_on), "bus": glob(gm.storage_sub, self._sto_bus)}
-        update_pp_json(gm.path, str(full_path), upd)
+        if gm.n_hidden:
+            upd["ext_grid"] = {"bus": glob(gm.hidden_sub, self._hid_bus) + [int(b) for b in gm.ext_grid_bus_file[gm.n_hidden:]]}
+        # bus table: one row per (substation, busbar); active = a connected element sits on it
+        active = np.zeros(gm.n_sub * gm.n_busbar, dtype=bool)
+        for sub, bar, on in ((gm.line_or_sub, self._lor_bus, self._line_on), (gm.line_ex_sub, self._lex_bus, self._line_on),
+                             (gm.load_sub, self._load_bus, self._load_on), (gm.gen_sub, self._gen_bus, self._gen_on),
+                             (gm.storage_sub, self._sto_bus, self._sto_on), (gm.shunt_sub, self._sh_bus, self._sh_on),
+                             (gm.hidden_sub, self._hid_bus, self._hid_on)):
+            on = np.asarray(on, dtype=bool)
+            if len(on):
+                active[np.asarray(sub, dtype=np.int64)[on] + (np.asarray(bar, dtype=np.int64)[on] - 1) * gm.n_sub] = True
+        row_of_label = {int(lab): r for r, lab in enumerate(gm.bus_labels_file)}
+        dup = [(row_of_label[s], s + k * gm.n_sub) for k in range(1, gm.n_busbar) for s in sorted(row_of_label)]
+        upd["bus"] = {"in_service": [bool(active[lab]) for lab in gm.bus_labels_file] + [bool(active[lab]) for _, lab in dup]}
+        update_pp_json(gm.path, str(full_path), upd, duplicate_rows={"bus": dup})

@@ -57,6 +57,7 @@ class GridModel:
         self.name_sub = np.array([f"sub_{int(i)}" for i in labels])
         self.bus_in_service0 = np.zeros(self.n_sub, dtype=bool)
         self.bus_in_service0[labels] = bus.col("in_service", 1.0) != 0
+        self.bus_labels_file = labels.copy()                 # file row order (Backend.save_file)
 
         # ------------------------------------------------------------------ lines then trafos
         nl, nt = len(line), len(trafo)
@@ -112,6 +113,7 @@ class GridModel:
         if len(gen) and "name" in gen and not gen.has_nulls("name"):
             g_names = [str(v) for v in gen.strings("name")]
         e_bus = eg.col("bus", 0).astype(np.int64)
+        self.ext_grid_bus_file = e_bus.copy()                # file row order (Backend.save_file)
         e_vm = eg.col("vm_pu", 1.0)
         e_qmin = eg.col("min_q_mvar", -1e9)
         e_qmax = eg.col("max_q_mvar", 1e9)

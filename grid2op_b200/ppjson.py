@@ -168,12 +168,17 @@ def read_pp_json(path: str, tables: Iterable[str] = _ELEMENT_TABLES) -> PPNet:
     return PPNet(fields, out)
 
 
-def update_pp_json(src_path: str, dst_path: str, updates: Dict[str, Dict[str, Any]]) -> None:
+def update_pp_json(src_path: str, dst_path: str, updates: Dict[str, Dict[str, Any]],
+                   duplicate_rows: Optional[Dict[str, List[Any]]] = None) -> None:
     """Write a copy of the pandapower-JSON file ``src_path`` to ``dst_path`` with some table columns replaced
     (``updates[table][column] = sequence of new values, file row order``) - the part of ``pp.to_json`` that
     ``Backend.save_file`` needs (reference: grid2op/Backend/pandaPowerBackend.py:1425-1437).  Everything else
     (other tables, std_types, geodata, options) is carried over byte-for-byte; result tables are emptied of
-    nothing - they simply keep the values stored in the source file."""
+    nothing - they simply keep the values stored in the source file.
+
+    ``duplicate_rows[table] = [(source row number, new index label), ...]``: copies of existing rows appended to the table
+    BEFORE the column updates (``updates`` then names values for the old and the appended rows) — the busbar buses the
+    reference creates at load time (pPB:548-566) and therefore writes with ``pp.to_json``."""
     with open(src_path, "r", encoding="utf-8") as f:
         top = json.load(f)
     obj = top["_object"] if isinstance(top, dict) and "_object" in top else top
@@ -197,6 +202,10 @@ def update_pp_json(src_path: str, dst_path: str, updates: Dict[str, Dict[str, An
             data = [[tab[nm].get(k) for nm in names] for k in (index or [])]
             tab = {"columns": names, "index": index or [], "data": data}
             spec["orient"] = "split"
+        for src_row, label in (duplicate_rows or {}).get(tname, []):
+            tab["data"].append(list(tab["data"][int(src_row)]))
+            if "index" in tab and tab["index"] is not None:
+                tab["index"].append(int(label))
         for cname, values in cols.items():
             values = list(values)
             if cname not in tab["columns"]:
