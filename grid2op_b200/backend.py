@@ -39,10 +39,16 @@ _K_LOAD, _K_GEN, _K_LOR, _K_LEX, _K_STO = 0, 1, 2, 3, 4
 class B200Backend(Backend):
     shunts_data_available = True
 
-    def __init__(self, detailed_infos_for_cascading_failures: bool = False, can_be_copied: bool = True,
-                 max_iter: int = 10, tol_mva: float = 1e-8, device: int = 0):
+    def __init__(self, detailed_infos_for_cascading_failures: bool = False, lightsim2grid: bool = False, dist_slack: bool = False,
+                 max_iter: int = 10, can_be_copied: bool = True, with_numba: bool = False, *, tol_mva: float = 1e-8, device: int = 0):
+        """Positional arguments as ``PandaPowerBackend.__init__`` (pPB:119-127) so that subclasses written for it keep working
+        (reference tests/test_no_backend_copy.py:25-35).  ``lightsim2grid`` / ``with_numba`` select pandapower's inner solver
+        there and mean nothing here; ``dist_slack`` (distributed slack) is not implemented."""
+        if dist_slack:
+            raise NotImplementedError("B200Backend: distributed slack (dist_slack=True) is not implemented")
         Backend.__init__(self, detailed_infos_for_cascading_failures=detailed_infos_for_cascading_failures,
-                         can_be_copied=can_be_copied, max_iter=max_iter, tol_mva=tol_mva, device=device)
+                         can_be_copied=can_be_copied, lightsim2grid=lightsim2grid, dist_slack=dist_slack, max_iter=max_iter,
+                         with_numba=with_numba, tol_mva=tol_mva, device=device)
         self._max_iter = int(max_iter)
         self._tol_mva = float(tol_mva)
         self._device = int(device)
@@ -100,10 +106,13 @@ class B200Backend(Backend):
         self.gen_to_sub_pos = gm.gen_to_sub_pos.astype(dt_int)
         self.line_or_to_sub_pos = gm.line_or_to_sub_pos.astype(dt_int)
         self.line_ex_to_sub_pos = gm.line_ex_to_sub_pos.astype(dt_int)
-        self.n_shunt = gm.n_shunt
-        self.shunt_to_subid = gm.shunt_sub.astype(dt_int)
-        self.name_shunt = gm.name_shunt.copy()
-        self._sh_vnkv = gm.sh_vnkv.copy()
+        if type(self).shunts_data_available:                                    # pPB:556-559, 755-766
+            self.n_shunt = gm.n_shunt
+            self.shunt_to_subid = gm.shunt_sub.astype(dt_int)
+            self.name_shunt = gm.name_shunt.copy()
+            self._sh_vnkv = gm.sh_vnkv.copy()
+        else:
+            self.n_shunt = None         # (the shunts of the file still take part in the power flow, as set in the file)
         self._compute_pos_big_topo()
         self.thermal_limit_a = gm.thermal_limit_a.astype(dt_float)
 
