@@ -116,16 +116,10 @@ class B200Backend(Backend):
         self._compute_pos_big_topo()
         self.thermal_limit_a = gm.thermal_limit_a.astype(dt_float)
 
-        # position -> (kind, element) dispatch for apply_action               pPB:630-653
-        kind = np.full(gm.dim_topo, -1, dtype=np.int8)
-        idx = np.zeros(gm.dim_topo, dtype=np.int32)
-        kind[gm.load_pos] = _K_LOAD; idx[gm.load_pos] = np.arange(gm.n_load)
-        kind[gm.gen_pos] = _K_GEN; idx[gm.gen_pos] = np.arange(gm.n_gen)
-        kind[gm.line_or_pos] = _K_LOR; idx[gm.line_or_pos] = np.arange(gm.n_line)
-        kind[gm.line_ex_pos] = _K_LEX; idx[gm.line_ex_pos] = np.arange(gm.n_line)
-        if gm.n_storage:
-            kind[gm.storage_pos] = _K_STO; idx[gm.storage_pos] = np.arange(gm.n_storage)
-        self._pos_kind, self._pos_idx = kind, idx
+        # the topology vector grid2op sees (normally the grid file's layout; without the storage units in a "compatibility"
+        # environment, see storage_deact_for_backward_comaptibility)
+        self._set_public_layout(gm.dim_topo, gm.line_or_pos, gm.line_ex_pos, gm.load_pos, gm.gen_pos,
+                                gm.storage_pos if gm.n_storage else np.zeros(0, dtype=np.int64))
 
         # --- mutable state (what PandaPowerBackend keeps in its DataFrames)
         self._gen_p = gm.gen_p0.copy()
@@ -163,7 +157,7 @@ class B200Backend(Backend):
                                                                               buf(gm.n_storage), buf(gm.n_storage))
         self._shunt_p, self._shunt_q, self._shunt_v = buf(gm.n_shunt), buf(gm.n_shunt), buf(gm.n_shunt)
         self.line_status = np.zeros(gm.n_line, dtype=dt_bool)
-        self._topo_vect = np.full(gm.dim_topo, -1, dtype=dt_int)
+        self._compat_no_storage = False
         self._refresh_status_topo()
         self.comp_time = 0.0
 
@@ -178,6 +172,36 @@ class B200Backend(Backend):
         self._state0 = self._snapshot()
 
     # ------------------------------------------------------------------------------------------
+    def _set_public_layout(self, dim_topo, p_lor, p_lex, p_load, p_gen, p_sto):
+        """positions of the elements in the topology vector exchanged with grid2op + the position -> (kind, element)
+        dispatch of apply_action (pPB:630-668)"""
+        as_i = lambda a: np.asarray(a, dtype=np.int64)          # noqa: E731
+        self._pub_dim = int(dim_topo)
+        self._pub_lor, self._pub_lex, self._pub_load, self._pub_gen, self._pub_sto = as_i(p_lor), as_i(p_lex), as_i(p_load), as_i(p_gen), as_i(p_sto)
+        kind = np.full(self._pub_dim, -1, dtype=np.int8)
+        idx = np.zeros(self._pub_dim, dtype=np.int32)
+        kind[self._pub_load] = _K_LOAD; idx[self._pub_load] = np.arange(len(self._pub_load))
+        kind[self._pub_gen] = _K_GEN; idx[self._pub_gen] = np.arange(len(self._pub_gen))
+        kind[self._pub_lor] = _K_LOR; idx[self._pub_lor] = np.arange(len(self._pub_lor))
+        kind[self._pub_lex] = _K_LEX; idx[self._pub_lex] = np.arange(len(self._pub_lex))
+        if len(self._pub_sto):
+            kind[self._pub_sto] = _K_STO; idx[self._pub_sto] = np.arange(len(self._pub_sto))
+        self._pos_kind, self._pos_idx = kind, idx
+
+    def storage_deact_for_backward_comaptibility(self) -> None:                 # pPB:876-886 (called by Environment.py:690)
+        """An environment in "compatibility" mode (``_compat_glop_version`` of a grid2op without storage units) has stripped
+        the storage units from the class: results and topology vector take the class's sizes / positions.  The units stay in
+        the power flow with the set points of the grid file, like in the reference's pandapower grid."""
+        cls = type(self)
+        self._compat_no_storage = cls.n_storage == 0 and self._gm.n_storage > 0
+        if not self._compat_no_storage:
+            return
+        self._set_public_layout(cls.dim_topo, cls.line_or_pos_topo_vect, cls.line_ex_pos_topo_vect, cls.load_pos_topo_vect,
+                                cls.gen_pos_topo_vect, np.zeros(0, dtype=np.int64))
+        self.n_storage = 0
+        self.dim_topo = int(cls.dim_topo)
+        self._refresh_status_topo()
+
     def _snapshot(self):
         names = ("_gen_p", "_gen_vm", "_hid_vm", "_load_p", "_load_q", "_sto_p", "_sh_p", "_sh_q", "_line_on",
                  "_lor_bus", "_lex_bus", "_gen_on", "_gen_bus", "_load_on", "_load_bus", "_sto_on", "_sto_bus",
@@ -195,13 +219,13 @@ class B200Backend(Backend):
     def _refresh_status_topo(self):
         gm = self._gm
         self.line_status = self._line_on.astype(dt_bool)
-        tv = np.full(gm.dim_topo, -1, dtype=dt_int)
-        tv[gm.line_or_pos] = np.where(self._line_on, self._lor_bus, -1)
-        tv[gm.line_ex_pos] = np.where(self._line_on, self._lex_bus, -1)
-        tv[gm.load_pos] = np.where(self._load_on, self._load_bus, -1)
-        tv[gm.gen_pos] = np.where(self._gen_on, self._gen_bus, -1)
-        if gm.n_storage:
-            tv[gm.storage_pos] = np.where(self._sto_on, self._sto_bus, -1)
+        tv = np.full(self._pub_dim, -1, dtype=dt_int)
+        tv[self._pub_lor] = np.where(self._line_on, self._lor_bus, -1)
+        tv[self._pub_lex] = np.where(self._line_on, self._lex_bus, -1)
+        tv[self._pub_load] = np.where(self._load_on, self._load_bus, -1)
+        tv[self._pub_gen] = np.where(self._gen_on, self._gen_bus, -1)
+        if len(self._pub_sto):
+            tv[self._pub_sto] = np.where(self._sto_on, self._sto_bus, -1)
         self._topo_vect = tv
 
     # ------------------------------------------------------------------------------------------
@@ -223,7 +247,7 @@ class B200Backend(Backend):
         self._load_p[ch] = load_p.values[ch]
         ch = load_q.changed
         self._load_q[ch] = load_q.values[ch]
-        if gm.n_storage > 0:
+        if gm.n_storage > 0 and not self._compat_no_storage:
             ch = storage.changed
             self._sto_p[ch] = storage.values[ch]
             stor_bus = backend_action.get_storages_bus()                        # pPB:941-951
@@ -282,7 +306,12 @@ class B200Backend(Backend):
     def _device_records(self):
         gm = self._gm
         topo = np.empty(gm.n_topo_in, dtype=np.int8)
-        topo[:gm.dim_topo] = self._topo_vect
+        topo[gm.line_or_pos] = np.where(self._line_on, self._lor_bus, -1)
+        topo[gm.line_ex_pos] = np.where(self._line_on, self._lex_bus, -1)
+        topo[gm.load_pos] = np.where(self._load_on, self._load_bus, -1)
+        topo[gm.gen_pos] = np.where(self._gen_on, self._gen_bus, -1)
+        if gm.n_storage:
+            topo[gm.storage_pos] = np.where(self._sto_on, self._sto_bus, -1)
         topo[gm.dim_topo:gm.dim_topo + gm.n_shunt] = np.where(self._sh_on, self._sh_bus, -1)
         topo[gm.dim_topo + gm.n_shunt:] = np.where(self._hid_on, self._hid_bus, -1)
         inj = np.concatenate([self._gen_p, self._hid_vm, self._gen_vm, self._load_p, self._load_q,
@@ -358,7 +387,7 @@ class B200Backend(Backend):
                    "load_p", "load_q", "load_v", "storage_p", "storage_q", "storage_v", "theta_or", "theta_ex",
                    "load_theta", "gen_theta", "storage_theta", "_shunt_p", "_shunt_q", "_shunt_v"):
             getattr(self, nm)[:] = np.nan
-        self._topo_vect = np.full(self._gm.dim_topo, -1, dtype=dt_int)
+        self._topo_vect = np.full(self._pub_dim, -1, dtype=dt_int)
         self.line_status = np.zeros(self._gm.n_line, dtype=dt_bool)
 
     # ------------------------------------------------------------------------------------------
@@ -386,6 +415,9 @@ class B200Backend(Backend):
         return self.p_ex.copy(), self.q_ex.copy(), self.v_ex.copy(), self.a_ex.copy()
 
     def storages_info(self):
+        if self._compat_no_storage:
+            e = np.zeros(0, dtype=dt_float)
+            return e, e.copy(), e.copy()
         return self.storage_p.copy(), self.storage_q.copy(), self.storage_v.copy()
 
     def shunt_info(self):
@@ -394,7 +426,7 @@ class B200Backend(Backend):
 
     def get_theta(self):
         return (1.0 * self.theta_or, 1.0 * self.theta_ex, 1.0 * self.load_theta, 1.0 * self.gen_theta,
-                1.0 * self.storage_theta)
+                1.0 * self.storage_theta if not self._compat_no_storage else np.zeros(0, dtype=dt_float))
 
     def sub_from_bus_id(self, bus_id: int) -> int:
         n = self._gm.n_sub
@@ -415,13 +447,15 @@ class B200Backend(Backend):
         self.comp_time = 0.0
 
     def copy(self) -> "B200Backend":                                            # pPB:1289-1409
-        gm, eng, st0 = self._gm, self._engine, self._state0
+        gm, eng, st0, kw = self._gm, self._engine, self._state0, self._my_kwargs
         self._gm = self._engine = self._state0 = None
+        self._my_kwargs = None
         try:
             res = copy.deepcopy(self)
         finally:
-            self._gm, self._engine, self._state0 = gm, eng, st0
+            self._gm, self._engine, self._state0, self._my_kwargs = gm, eng, st0, kw
         res._gm, res._engine, res._state0 = gm, eng, st0      # immutable / shared device handle
+        res._my_kwargs = kw         # the constructor arguments are handed on as they are, not copied (pPB:1296: type(self)(**self._my_kwargs))
         return res
 
     def close(self) -> None:
