@@ -1,8 +1,8 @@
 """The reference's OWN test modules (``grid2op/tests/test_*.py``, unmodified, from the reference tree) with ``B200Backend`` standing
 where they expect ``PandaPowerBackend`` (tests/ref_modules_runner.py): environment-, runner-, simulator-, observation- and
 rule-level regression tests that exercise the backend through the public API.  CPU: the backend's host logic over the oracle
-adapter.  A run over ALL 192 modules of the reference is summarised in ``profiles/round2_reference_test_modules.json`` (132 modules
-fully green; the rest reach into PandaPowerBackend's private pandapower grid, need gymnasium / matplotlib / the network, or compare
+adapter.  A run over ALL 192 modules of the reference is summarised in ``profiles/round2_reference_test_modules.json`` (133 modules
+fully green, 3443 tests run; the rest reach into PandaPowerBackend's private pandapower grid, need gymnasium / matplotlib / the network, or compare
 class names that contain "PandaPowerBackend"); this file keeps a curated, fast subset in the suite."""
 import json
 import os
