@@ -96,10 +96,26 @@ struct b200pf_handle {
     int dbg_div_mod = 0;                                    // test knob, see b200pf_set_debug
     int64_t redo_launches = 0;
     int *series_flag = nullptr; int series_step_no = 0; int *d_ticket = nullptr; bool flag_in_redo = false;   // completion flag of series steps
-    unsigned char *d_redo_mat = nullptr; size_t redo_mat_stride = 0; int redo_mat_ctas = 0;   // global-memory matrices of the safety net (large grids)
+    // global-memory matrices of the safety net (large grids), one region per launching stream: chunk / group launches of one
+    // handle run concurrently, and two safety-net launches in flight must never share a CTA's matrix
+    struct RedoMat { unsigned char *d = nullptr; size_t stride = 0; int ctas = 0; };
+    std::unordered_map<cudaStream_t, RedoMat> redo_mats;
+    bool on_side_stream = false;                            // a chunk / group launch is being issued (h->stream is swapped for it)
     cudaEvent_t inst_plan_ev = nullptr; bool inst_plan_pending = false;   // last H2D copy out of h_inst_plan
     int last_smem = 0, last_T = 0, last_grid = 0, last_block = 0;
 };
+
+// Host -> device copy of caller memory (pageable as a rule) that launches on ANY stream of the handle may read afterwards.  A plain
+// cudaMemcpy may return before its DMA has finished and the handle's non-blocking streams are not ordered against the legacy
+// stream; so the copy is issued on the handle's stream and the stream drained before returning.  Set-up calls only (never per step
+// of the device-resident paths).
+static int h2d_sync(b200pf_handle *h, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return 0;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+#define H2D(dst, src, bytes) do { int rc__ = h2d_sync(h, (dst), (src), (bytes)); if (rc__) return rc__; } while (0)
 
 template <typename Tp>
 static int upload(b200pf_handle *h, const Tp *src, size_t n, const Tp **dst) {
@@ -107,7 +123,7 @@ static int upload(b200pf_handle *h, const Tp *src, size_t n, const Tp **dst) {
     size_t bytes = (n ? n : 1) * sizeof(Tp);
     CU(cudaMalloc(&d, bytes));
     h->dev_allocs.push_back(d);
-    if (n) CU(cudaMemcpy(d, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+    if (n) H2D(d, src, n * sizeof(Tp));
     *dst = d;
     return 0;
 }
@@ -273,7 +289,7 @@ extern "C" int b200pf_destroy(b200pf_handle *h) {
     for (void *p : h->dev_allocs) cudaFree(p);
     if (h->d_plan_blobs) cudaFree(h->d_plan_blobs);
     if (h->d_plan_off) cudaFree(h->d_plan_off);
-    if (h->d_redo_mat) cudaFree(h->d_redo_mat);
+    for (auto &kv : h->redo_mats) if (kv.second.d) cudaFree(kv.second.d);
     void *pinned[] = {h->h_topo, h->h_inj, h->h_out, h->h_status, h->h_iters, h->h_busv, h->h_rows, h->h_inst_plan};
     for (void *p : pinned) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -766,15 +782,17 @@ static int launch_redo(b200pf_handle *h, RunArgs a, int nb_cap_req) {
     int max_ctas = h->sm_count * 8;
     a.redo_mat = nullptr; a.redo_mat_stride = 0;
     if (fixed + worst > (size_t)h->max_smem_optin) {
-        max_ctas = h->sm_count;
-        if (!h->d_redo_mat || h->redo_mat_stride < worst || h->redo_mat_ctas < max_ctas) {
+        // (the handle's main stream gets one matrix per SM; the chunk / group streams a smaller set each: the path is rare)
+        max_ctas = h->on_side_stream ? 32 : h->sm_count;
+        b200pf_handle::RedoMat &rm = h->redo_mats[h->stream];
+        if (!rm.d || rm.stride < worst || rm.ctas < max_ctas) {
             CU(cudaStreamSynchronize(h->stream));
-            if (h->d_redo_mat) CU(cudaFree(h->d_redo_mat));
-            h->d_redo_mat = nullptr;
-            CU(cudaMalloc(&h->d_redo_mat, worst * (size_t)max_ctas));
-            h->redo_mat_stride = worst; h->redo_mat_ctas = max_ctas;
+            if (rm.d) CU(cudaFree(rm.d));
+            rm.d = nullptr;
+            CU(cudaMalloc(&rm.d, worst * (size_t)max_ctas));
+            rm.stride = worst; rm.ctas = max_ctas;
         }
-        a.redo_mat = h->d_redo_mat; a.redo_mat_stride = h->redo_mat_stride;
+        a.redo_mat = rm.d; a.redo_mat_stride = rm.stride;
         want = worst;
         const size_t d = 2 * (size_t)cap;
         T = d <= 64 ? 32 : (d <= 128 ? 128 : (d <= 256 ? 256 : 512));
@@ -809,7 +827,7 @@ static int stat_sync(b200pf_handle *h) {
     sec(&o.sh_vn, (size_t)g.n_shunt * 4); sec(&o.sh_vratio, (size_t)g.n_shunt * 8); sec(&o.static_inj, (size_t)g.n_inj * 8);
     sec(&o.th_lim, (size_t)g.n_line * 4);
     o.total = (int)off;
-    if (!h->d_stat) { CU(cudaMalloc(&h->d_stat, off)); h->dev_allocs.push_back(h->d_stat); CU(cudaMemset(h->d_stat, 0, off)); }
+    if (!h->d_stat) { CU(cudaMalloc(&h->d_stat, off)); h->dev_allocs.push_back(h->d_stat); CU(cudaMemsetAsync(h->d_stat, 0, off, h->stream)); }
     cudaStream_t st = h->stream;
 #define CPY(field, src, bytes) if ((bytes) > 0) CU(cudaMemcpyAsync(h->d_stat + o.field, (src), (bytes), cudaMemcpyDeviceToDevice, st));
     CPY(line_y, g.line_y, (size_t)g.n_line * 64) CPY(line_bdc, g.line_bdc, (size_t)g.n_line * 8) CPY(line_pshift, g.line_pshift, (size_t)g.n_line * 8)
@@ -819,6 +837,7 @@ static int stat_sync(b200pf_handle *h) {
     CPY(sh_vn, g.sh_vn, (size_t)g.n_shunt * 4) CPY(sh_vratio, g.sh_vratio, (size_t)g.n_shunt * 8)
     CPY(static_inj, h->d_static_inj, (size_t)g.n_inj * 8) CPY(th_lim, h->d_thlim, (size_t)g.n_line * 4)
 #undef CPY
+    CU(cudaStreamSynchronize(st));      // rare (first launch, new static injections / limits); every stream of the handle reads the blob afterwards
     h->stat_dirty = false;
     return 0;
 }
@@ -1063,20 +1082,20 @@ extern "C" int b200pf_series_bind(b200pf_handle *h, const float *chron_host, int
         (rc = dmal((void **)&h->d_pcount, (size_t)batch * g.n_line * 4)) || (rc = dmal((void **)&h->d_tsover, (size_t)batch * g.n_line * 4)) ||
         (rc = dmal((void **)&h->d_disc, (size_t)batch * g.n_line * 4)) || (rc = dmal((void **)&h->d_done, (size_t)batch * 4)))
         return rc;
-    CU(cudaMemset(h->d_pcount, 0, (size_t)batch * g.n_line * 4)); CU(cudaMemset(h->d_tsover, 0, (size_t)batch * g.n_line * 4));
-    CU(cudaMemset(h->d_disc, 0xff, (size_t)batch * g.n_line * 4)); CU(cudaMemset(h->d_done, 0, (size_t)batch * 4));
-    CU(cudaMemcpy(h->d_chron, chron_host, (size_t)n_scen * n_rows * ncol * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_scen, scen, (size_t)batch * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_t, t0, (size_t)batch * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_static_inj, static_inj, (size_t)g.n_inj * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_thlim, thermal_limit_a, (size_t)g.n_line * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemsetAsync(h->d_pcount, 0, (size_t)batch * g.n_line * 4, h->stream)); CU(cudaMemsetAsync(h->d_tsover, 0, (size_t)batch * g.n_line * 4, h->stream));
+    CU(cudaMemsetAsync(h->d_disc, 0xff, (size_t)batch * g.n_line * 4, h->stream)); CU(cudaMemsetAsync(h->d_done, 0, (size_t)batch * 4, h->stream));
+    H2D(h->d_chron, chron_host, (size_t)n_scen * n_rows * ncol * 4);
+    H2D(h->d_scen, scen, (size_t)batch * 4);
+    H2D(h->d_t, t0, (size_t)batch * 4);
+    H2D(h->d_static_inj, static_inj, (size_t)g.n_inj * 8);
+    H2D(h->d_thlim, thermal_limit_a, (size_t)g.n_line * 4);
     h->stat_dirty = true;
-    CU(cudaMemset(h->d_series_topo, 1, (size_t)batch * g.n_topo_in));
+    CU(cudaMemsetAsync(h->d_series_topo, 1, (size_t)batch * g.n_topo_in, h->stream));
     h->series_batch = batch; h->n_scen = n_scen; h->n_rows = n_rows;
     if ((rc = dmal((void **)&h->d_series_plan, (size_t)batch * 4)) || (rc = dmal((void **)&h->d_trip, (size_t)batch * g.n_line + 4)) ||
         (rc = dmal((void **)&h->d_incdone, (size_t)batch * g.n_line + 4)) || (rc = dmal((void **)&h->d_nflag, 16)) ||
         (rc = dmal((void **)&h->d_flaglist, (size_t)batch * 4)) || (rc = dmal((void **)&h->d_casclist, (size_t)batch * 4))) return rc;
-    CU(cudaMemset(h->d_trip, 0, (size_t)batch * g.n_line + 4)); CU(cudaMemset(h->d_incdone, 0, (size_t)batch * g.n_line + 4));
+    CU(cudaMemsetAsync(h->d_trip, 0, (size_t)batch * g.n_line + 4, h->stream)); CU(cudaMemsetAsync(h->d_incdone, 0, (size_t)batch * g.n_line + 4, h->stream));
     {
         std::vector<int8_t> ones((size_t)batch * g.n_topo_in, 1);
         return series_plans(h, ones.data());
@@ -1108,7 +1127,7 @@ extern "C" int b200pf_series_set_topo(b200pf_handle *h, const int8_t *topo) {
     if (!h || !topo) return fail(B200PF_E_ARG, "null pointer");
     if (!h->series_batch) return fail(B200PF_E_STATE, "series not bound");
     CU(cudaSetDevice(h->device));
-    CU(cudaMemcpy(h->d_series_topo, topo, (size_t)h->series_batch * h->g.n_topo_in, cudaMemcpyHostToDevice));
+    H2D(h->d_series_topo, topo, (size_t)h->series_batch * h->g.n_topo_in);
     h->series_dev_topo_ahead = false;
     return series_plans(h, topo);
 }
@@ -1190,7 +1209,7 @@ extern "C" int b200pf_series_step(b200pf_handle *h, int is_dc, int max_iter, dou
 extern "C" int b200pf_series_bind_flag(b200pf_handle *h, int32_t *d_flag) {
     if (!h) return fail(B200PF_E_ARG, "null handle");
     CU(cudaSetDevice(h->device));
-    if (!h->d_ticket) { CU(cudaMalloc(&h->d_ticket, 16)); h->dev_allocs.push_back(h->d_ticket); CU(cudaMemset(h->d_ticket, 0, 16)); }
+    if (!h->d_ticket) { CU(cudaMalloc(&h->d_ticket, 16)); h->dev_allocs.push_back(h->d_ticket); CU(cudaMemsetAsync(h->d_ticket, 0, 16, h->stream)); }
     h->series_flag = d_flag; h->series_step_no = 0;
     return 0;
 }
@@ -1262,8 +1281,8 @@ extern "C" int b200pf_series_reset_instances(b200pf_handle *h, int n, const int3
     }
     CU(cudaStreamSynchronize(h->stream));
     // d_casclist / d_flaglist: scratch of batch ints each (idle between steps)
-    CU(cudaMemcpy(h->d_casclist, idx, (size_t)n * 4, cudaMemcpyHostToDevice));
-    if (t_new) CU(cudaMemcpy(h->d_flaglist, t_new, (size_t)n * 4, cudaMemcpyHostToDevice));
+    H2D(h->d_casclist, idx, (size_t)n * 4);
+    if (t_new) H2D(h->d_flaglist, t_new, (size_t)n * 4);
     pf_kernel_series_reset<<<n, 64, 0, h->stream>>>(n, h->d_casclist, t_new ? h->d_flaglist : nullptr, g.n_line, h->d_t, h->d_done, h->d_pcount,
                                                      h->d_tsover, h->d_disc, h->d_trip, h->d_incdone);
     CU(cudaGetLastError());
@@ -1277,7 +1296,8 @@ extern "C" int b200pf_series_reset_instances(b200pf_handle *h, int n, const int3
         } else all = h->h_series_topo;
         for (int k = 0; k < n; ++k) {
             memcpy(all.data() + (size_t)idx[k] * nt, topo_rows + (size_t)k * nt, nt);
-            CU(cudaMemcpy(h->d_series_topo + (size_t)idx[k] * nt, topo_rows + (size_t)k * nt, nt, cudaMemcpyHostToDevice));
+            // (stream-ordered; the stream is drained once, at the start of series_plans below)
+            CU(cudaMemcpyAsync(h->d_series_topo + (size_t)idx[k] * nt, topo_rows + (size_t)k * nt, nt, cudaMemcpyHostToDevice, h->stream));
         }
         h->series_dev_topo_ahead = false;
         return series_plans(h, all.data());
@@ -1368,7 +1388,7 @@ extern "C" int b200pf_run_staged(b200pf_handle *h, int batch, int is_dc, int max
 extern "C" int b200pf_set_thermal_limit(b200pf_handle *h, const float *thermal_limit_a) {
     if (!h || !thermal_limit_a) return fail(B200PF_E_ARG, "null pointer");
     CU(cudaSetDevice(h->device));
-    CU(cudaMemcpy(h->d_thlim, thermal_limit_a, (size_t)h->g.n_line * 4, cudaMemcpyHostToDevice));
+    H2D(h->d_thlim, thermal_limit_a, (size_t)h->g.n_line * 4);
     h->stat_dirty = true;
     return 0;
 }
@@ -1399,7 +1419,7 @@ extern "C" int b200pf_n1_host(b200pf_handle *h, int batch, const int8_t *topo, c
 extern "C" int b200pf_set_static_inj(b200pf_handle *h, const double *static_inj) {
     if (!h || !static_inj) return fail(B200PF_E_ARG, "null pointer");
     CU(cudaSetDevice(h->device));
-    CU(cudaMemcpy(h->d_static_inj, static_inj, (size_t)h->g.n_inj * 8, cudaMemcpyHostToDevice));
+    H2D(h->d_static_inj, static_inj, (size_t)h->g.n_inj * 8);
     h->stat_dirty = true;
     return 0;
 }
@@ -1501,9 +1521,9 @@ static int rows_chunk_launch_impl(b200pf_handle *h, int first, int count, const 
     if (direct) a.out = h->h_out + F * g.n_out;   // pinned host memory is device-addressable (unified addressing): posted PCIe writes
     if (direct_st) { a.status = h->h_status + F; a.iters = h->h_iters + F; }
     cudaStream_t keep = h->stream;
-    h->stream = st;
+    h->stream = st; h->on_side_stream = true;
     int rc = launch(h, a, nb_cap, use ? &sel : nullptr);
-    h->stream = keep;
+    h->stream = keep; h->on_side_stream = false;
     if (rc) return rc;
     if (!direct) CU(cudaMemcpyAsync(h->h_out + F * g.n_out, h->d_out + F * g.n_out, C * g.n_out * 4, cudaMemcpyDeviceToHost, st));
     if (!direct_st) {
@@ -1583,6 +1603,7 @@ extern "C" int b200pf_device_alloc(size_t bytes, void **d_ptr) {
     if (!d_ptr) return fail(B200PF_E_ARG, "null pointer");
     CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
     CU(cudaMemset(*d_ptr, 0, bytes ? bytes : 1));
+    CU(cudaDeviceSynchronize());      // (the legacy stream is not ordered against the handles' non-blocking streams)
     return 0;
 }
 extern "C" int b200pf_device_free(void *d_ptr) {
