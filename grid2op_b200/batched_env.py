@@ -81,6 +81,8 @@ class BatchedEnv(BatchedDoNothing):
         # threads per instance) for ``nb_cap`` active buses.  The host knows every instance's topology, so the cap is the
         # bus count of the fullest instance (:meth:`_bus_cap`: host code of the library, recomputed when a topology changed) instead of every bus slot.
         self.tight_cap = bool(tight_cap)
+        self._nb_inst = np.zeros(B, dtype=np.int32)                        # active buses per instance (kept incrementally)
+        self._cap_dirty = np.ones(B, dtype=bool)                           # instances whose topology changed since it was counted
         self.nb_cap = self._bus_cap() if self.tight_cap else 0
         self.n_illegal = 0
         self.n_steps = 0
@@ -88,8 +90,16 @@ class BatchedEnv(BatchedDoNothing):
     # ------------------------------------------------------------------------------------------------------------
     def _bus_cap(self) -> int:
         """Active buses (bus slots with a connected element) of the fullest instance, rounded up to a multiple of 8 above 17
-        (<= 17: exact — the warp-per-instance kernel takes systems up to 17 buses), at most every bus slot."""
-        n = int(self.engine.max_active_buses(self.topo))
+        (<= 17: exact — the warp-per-instance kernel takes systems up to 17 buses), at most every bus slot.  Per-instance counts are
+        kept; only the instances whose topology changed since the last call are counted again (lines tripped by the protections
+        only remove buses: the kept count stays an upper bound)."""
+        rows = np.flatnonzero(self._cap_dirty)
+        if len(rows) == self.batch:
+            self._nb_inst[:] = self.engine.max_active_buses(self.topo, per_instance=True)[1]
+        elif len(rows):                   # only the instances whose topology changed are counted again
+            self._nb_inst[rows] = self.engine.max_active_buses(self.topo[rows], per_instance=True)[1]
+        self._cap_dirty[:] = False
+        n = int(self._nb_inst.max())
         if n > 17:
             n = (n + 7) // 8 * 8
         return min(n, self.gm.n_slot)
@@ -135,6 +145,7 @@ class BatchedEnv(BatchedDoNothing):
                 self.last_bus[ii[live], pp[live]] = val[m][live]
                 aff_s[who, sub_id[who]] = True
                 self._topo_dirty = True
+                self._cap_dirty[who] = True
         if has_line.any():
             who = np.flatnonzero(has_line & ok)
             if len(who):
@@ -147,6 +158,7 @@ class BatchedEnv(BatchedDoNothing):
                 self.topo[who[on], pe[on]] = self.last_bus[who[on], pe[on]]
                 aff_l[who, l] = True
                 self._topo_dirty = True
+                self._cap_dirty[who] = True
         return aff_l, aff_s
 
     def _apply_environment(self):
@@ -169,6 +181,7 @@ class BatchedEnv(BatchedDoNothing):
             self.topo[ii, self.line_ex_pos[ll]] = -1
             if was_on.any():
                 self._topo_dirty = True
+                self._cap_dirty[ii[was_on]] = True
 
     def step(self, sub_id=None, sub_bus=None, line_id=None, line_status=None, from_reset: bool = False):
         """One env.step of every instance.  ``sub_id`` int [B] (-1: none) with ``sub_bus`` int8 [B, >= max_sub_size] (busbar per
@@ -240,6 +253,7 @@ class BatchedEnv(BatchedDoNothing):
         self.done[idx] = False
         self.row[idx] = rows
         self.engine.series_reset_instances(idx, t_new=rows % self.chron.shape[1], topo_rows=self.topo[idx])
+        self._cap_dirty[idx] = True
         if self.tight_cap:
             self.nb_cap = self._bus_cap()
 

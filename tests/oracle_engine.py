@@ -254,17 +254,18 @@ class COracleSeriesEngine:
     def series_fetch_state(self):
         raise NotImplementedError
 
-    def max_active_buses(self, topo):
+    def max_active_buses(self, topo, per_instance=False):
         """brute force (the product engine: b200pf_grid_max_active_buses)"""
         gm = self.gm
         subs = np.concatenate([gm.line_or_sub, gm.line_ex_sub, gm.gen_sub, gm.load_sub, gm.storage_sub, gm.shunt_sub, gm.hidden_sub])
         pos = np.concatenate([gm.line_or_pos, gm.line_ex_pos, gm.gen_pos, gm.load_pos, gm.storage_pos,
                               gm.dim_topo + np.arange(gm.n_shunt), gm.dim_topo + gm.n_shunt + np.arange(gm.n_hidden)])
-        best = 0
+        cnt = []
         for tv in np.asarray(topo).reshape(-1, gm.n_topo_in):
             b = tv[pos].astype(np.int64)
-            best = max(best, len(set((subs[b > 0] * 8 + b[b > 0]).tolist())))
-        return best
+            cnt.append(len(set((subs[b > 0] * 8 + b[b > 0]).tolist())))
+        best = max(cnt) if cnt else 0
+        return (best, np.asarray(cnt, dtype=np.int32)) if per_instance else best
 
     def series_reset_instances(self, idx, t_new=None, topo_rows=None):
         idx = np.asarray(idx, dtype=np.int64)
