@@ -36,12 +36,8 @@ MODULES = [
 ]
 
 
-@pytest.fixture(scope="module")
-def results():
-    if not os.path.isdir(REF_TESTS) or not os.path.isdir("/root/reference/grid2op/data_test"):
-        pytest.skip("reference test tree (with its data_test fixtures) not available")
-    env = dict(os.environ)
-    r = subprocess.run([sys.executable, os.path.join(HERE, "ref_modules_runner.py"), "hostlogic"] + MODULES, cwd=HERE, env=env,
+def _run_modules():
+    r = subprocess.run([sys.executable, os.path.join(HERE, "ref_modules_runner.py"), "hostlogic"] + MODULES, cwd=HERE, env=dict(os.environ),
                        capture_output=True, text=True, timeout=1500)
     out = {}
     for ln in r.stdout.splitlines():
@@ -51,6 +47,28 @@ def results():
     if not out:
         pytest.fail("runner produced nothing: " + r.stderr[-1500:])
     return out
+
+
+@pytest.fixture(scope="module")
+def results(request, tmp_path_factory):
+    if not os.path.isdir(REF_TESTS) or not os.path.isdir("/root/reference/grid2op/data_test"):
+        pytest.skip("reference test tree (with its data_test fixtures) not available")
+    uid = getattr(request.config, "workerinput", {}).get("testrunuid")
+    if uid is None:                      # plain (serial) run
+        return _run_modules()
+    # pytest-xdist: every worker that receives one of the parametrised tests would run the modules again — concurrently, and
+    # some of them write into shared scratch directories of the reference tree.  One worker runs them, the others read its result.
+    import fcntl
+    path = os.path.join(str(tmp_path_factory.getbasetemp().parent), f"reference_modules_{uid}.json")
+    with open(path + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f)
+        out = _run_modules()
+        with open(path, "w") as f:
+            json.dump(out, f)
+        return out
 
 
 @pytest.mark.parametrize("module", MODULES)
