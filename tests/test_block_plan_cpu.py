@@ -93,3 +93,32 @@ def test_block_operation_stream_is_valid(name):
             assert rc in (0, -1), (name, T, U, i, rc, err)           # -1: the topology has no plan (islanded / no reference)
     rc, err, info = validate_block_plan(gm, gm.default_topo(), 0 if gm.n_line > 8 else -1, 32, 1)
     assert rc in (0, -1)
+
+
+@pytest.mark.parametrize("name", ["l2rpn_case14_sandbox", "l2rpn_neurips_2020_track1"])
+def test_three_busbars_per_substation(name):
+    """``n_busbar_per_sub = 3`` (reference: Backend.can_handle_more_than_2_busbar, grid2op/Backend/backend.py:212-260; exercised through
+    the backend by aaa_test_backend_interface.py:1632 test_30_n_busbar_per_sub_ok): topology plans and both planned kernels (host
+    builds) on records that use busbar 3, against the fp64 oracle."""
+    from sparse_emu import SparseEmu
+    from test_c_oracle import _sub_of
+    path = env_grid(name)
+    if path is None:
+        pytest.skip("reference grid files not available")
+    gm = GridModel(path, n_busbar=3)
+    rng = np.random.default_rng(7)
+    n = 120
+    topo = np.tile(gm.default_topo(), (n, 1))
+    inj = np.tile(gm.default_inj(), (n, 1))
+    for i in range(1, n):
+        for s in rng.choice(gm.n_sub, size=rng.integers(0, 3), replace=False):
+            for p in range(gm.dim_topo):
+                if _sub_of(gm, p) == s and topo[i, p] > 0:
+                    topo[i, p] = rng.integers(1, 4)
+    assert (topo == 3).any()
+    ref, rstatus, _, _ = COracle(gm).run(topo, inj)
+    assert (rstatus == 0).sum() >= n // 4 and (rstatus != 0).any()
+    for emu in (SparseEmu(gm), BlockEmu(gm, 8, 1)):
+        out, status, _, _ = emu.run(topo, inj)
+        assert np.array_equal(status, rstatus)
+        compare(gm, out, ref, status == 0)
