@@ -356,6 +356,8 @@ class B200Backend(Backend):
         self.p_or[:] = v.p_or[0]; self.q_or[:] = v.q_or[0]; self.v_or[:] = v.v_or[0]; self.a_or[:] = v.a_or[0]
         self.p_ex[:] = v.p_ex[0]; self.q_ex[:] = v.q_ex[0]; self.v_ex[:] = v.v_ex[0]; self.a_ex[:] = v.a_ex[0]
         self.theta_or[:] = v.theta_or[0]; self.theta_ex[:] = v.theta_ex[0]
+        if not self._line_on.all():
+            self._theta_of_open_lines(v)
         self.prod_p[:] = v.unit_p[0, nh:]; self.prod_q[:] = v.unit_q[0, nh:]
         self.prod_v[:] = v.unit_v[0, nh:]; self.gen_theta[:] = v.unit_theta[0, nh:]
         if gm.id_gen_added is not None and nh:
@@ -380,6 +382,29 @@ class B200Backend(Backend):
         if is_dc:                                                               # pPB:1212-1218
             self.prod_q[:] = 0.0; self.load_q[:] = 0.0; self.storage_q[:] = 0.0
             self.q_or[:] = 0.0; self.q_ex[:] = 0.0
+
+    def _theta_of_open_lines(self, v):
+        """Reference quirk (pPB:1163-1187): the voltage of an out-of-service line / transformer is forced to 0 (pPB:1180-1181:
+        "pandapower does not take into account disconnected powerline for their voltage") but its ANGLE is not — ``theta_or`` /
+        ``theta_ex`` keep what pandapower's result table holds, the angle of the bus the end was last attached to
+        (``line.from_bus`` is not touched by a disconnection, pPB:1040-1067), or 0 when that bus has no element left (NaN -> 0,
+        pPB:1186-1187).  The kernels' result record carries 0 for open lines; the angle of the (substation, busbar) pair is the
+        one any connected line end / generator / load on it reports (the same float32 value)."""
+        gm = self._gm
+        ns, nh = gm.n_sub, gm.n_hidden
+        slot_theta = np.full(gm.n_slot, np.nan, dtype=np.float64)
+        on = self._line_on
+        slot_theta[gm.line_or_sub[on] + (self._lor_bus[on].astype(np.int64) - 1) * ns] = v.theta_or[0][on]
+        slot_theta[gm.line_ex_sub[on] + (self._lex_bus[on].astype(np.int64) - 1) * ns] = v.theta_ex[0][on]
+        g = self._gen_on
+        slot_theta[gm.gen_sub[g] + (self._gen_bus[g].astype(np.int64) - 1) * ns] = v.unit_theta[0, nh:][g]
+        ld = self._load_on
+        slot_theta[gm.load_sub[ld] + (self._load_bus[ld].astype(np.int64) - 1) * ns] = v.load_theta[0][ld]
+        off = ~on
+        th_or = slot_theta[gm.line_or_sub[off] + (self._lor_bus[off].astype(np.int64) - 1) * ns]
+        th_ex = slot_theta[gm.line_ex_sub[off] + (self._lex_bus[off].astype(np.int64) - 1) * ns]
+        self.theta_or[off] = np.where(np.isfinite(th_or), th_or, 0.0)
+        self.theta_ex[off] = np.where(np.isfinite(th_ex), th_ex, 0.0)
 
     # pPB:1257-1287
     def _reset_all_nan(self):

@@ -1,0 +1,87 @@
+"""Random-agent fuzz of the drop-in boundary, CPU: two unmodified grid2op environments side by side — ``B200Backend`` (its HOST logic:
+apply_action / topology bookkeeping / result slicing / copy / reset, engine replaced by the oracle adapter = test infrastructure) and
+the oracle's restatement of ``PandaPowerBackend`` — fed the same ``action_space.sample()`` stream (set_bus / change_bus / line status
+/ redispatch / curtailment / storage, whatever the environment's action class allows) with the same seeds.  After every step the
+observations must agree (integers exactly), game overs must coincide; after a game over both reset and go on.
+Reference: the sequence ``BaseEnv.step`` -> ``_backend_action += action`` -> ``apply_action_public`` -> ``next_grid_state``
+(grid2op/Environment/baseEnv.py:3778-3872, grid2op/Backend/backend.py:450-496, :1433-1521)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import env_grid
+
+
+def _close(a, b, tol, what):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, what
+    assert np.array_equal(np.isfinite(a), np.isfinite(b)), what
+    m = np.isfinite(a)
+    if m.any():
+        err = float(np.max(np.abs(a[m] - b[m])))
+        assert err <= tol, (what, err)
+
+
+def _compare(o1, o2, sn_mva, step):
+    tol_mw = 1e-4 * sn_mva + 4e-6 * 2000.0
+    for k in ("p_or", "q_or", "p_ex", "q_ex", "gen_p", "gen_q", "load_p", "load_q", "storage_power", "actual_dispatch", "target_dispatch"):
+        _close(getattr(o1, k), getattr(o2, k), tol_mw, (k, step))
+    vmax = max(1.0, float(np.nanmax(np.abs(o2.v_or))))
+    for k in ("v_or", "v_ex", "gen_v", "load_v"):
+        _close(getattr(o1, k), getattr(o2, k), 1e-4 * vmax, (k, step))
+    _close(o1.rho, o2.rho, 2e-4, ("rho", step))
+    _close(o1.storage_charge, o2.storage_charge, 1e-3, ("storage_charge", step))
+    for k in ("theta_or", "theta_ex", "gen_theta", "load_theta"):
+        _close(getattr(o1, k), getattr(o2, k), 2e-3, (k, step))
+    for k in ("topo_vect", "line_status", "timestep_overflow", "time_before_cooldown_line", "time_before_cooldown_sub",
+              "time_next_maintenance", "duration_next_maintenance"):
+        assert np.array_equal(getattr(o1, k), getattr(o2, k)), (k, step)
+
+
+@pytest.mark.parametrize("name,n_steps,sn_mva", [("l2rpn_case14_sandbox", 120, 100.0), ("educ_case14_storage", 120, 100.0),
+                                                 ("l2rpn_neurips_2020_track1", 60, 1.0), ("l2rpn_wcci_2022_dev", 30, 1.0)])
+def test_random_agent_side_by_side(name, n_steps, sn_mva):
+    if env_grid(name) is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    from oracle_engine import OracleEngine
+    import grid2op
+    from oracle.ppbackend_ref import PandaPowerBackendRef
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e1 = grid2op.make(name, test=True, backend=HostLogicBackend(), _add_to_name="fuzz_b200")
+        e2 = grid2op.make(name, test=True, backend=PandaPowerBackendRef(), _add_to_name="fuzz_ref")
+    try:
+        for e in (e1, e2):
+            e.seed(3); e.set_id(0)
+        o1, o2 = e1.reset(), e2.reset()
+        _compare(o1, o2, sn_mva, "reset")
+        e1.action_space.seed(11); e2.action_space.seed(11)
+        n_over = n_acted = 0
+        for i in range(n_steps):
+            # every other step a do-nothing, so that the grid lives long enough for cooldowns / storage / dispatch to matter
+            a1 = e1.action_space.sample() if i % 2 == 0 else e1.action_space()
+            a2 = e2.action_space.sample() if i % 2 == 0 else e2.action_space()
+            assert np.array_equal(a1.to_vect(), a2.to_vect(), equal_nan=True)
+            o1, r1, d1, i1 = e1.step(a1)
+            o2, r2, d2, i2 = e2.step(a2)
+            assert d1 == d2, (i, i1["exception"], i2["exception"])
+            assert i1["is_illegal"] == i2["is_illegal"] and i1["is_ambiguous"] == i2["is_ambiguous"], i
+            assert np.array_equal(i1["disc_lines"], i2["disc_lines"]), i
+            if d1:
+                n_over += 1
+                o1, o2 = e1.reset(), e2.reset()
+                _compare(o1, o2, sn_mva, ("reset after game over", i))
+                continue
+            n_acted += 1
+            _compare(o1, o2, sn_mva, i)
+            assert abs(r1 - r2) <= 1e-3 * max(1.0, abs(r2)), (i, r1, r2)
+        assert n_acted >= n_steps // 4, (n_acted, n_over)
+    finally:
+        e1.close(); e2.close()

@@ -28,6 +28,9 @@ def _compare_obs(o1, o2, sn_mva, vn_max):
     for k in ("v_or", "v_ex", "gen_v", "load_v"):
         _close(getattr(o1, k), getattr(o2, k), 1e-4 * vn_max, k)
     _close(o1.rho, o2.rho, 1e-4, "rho")
+    # angles, incl. the reference's quirk for OPEN lines (the angle of the bus the end was last attached to, pPB:1163-1187)
+    for k in ("theta_or", "theta_ex", "gen_theta", "load_theta"):
+        _close(getattr(o1, k), getattr(o2, k), 1e-2, k)
     for k in ("topo_vect", "line_status", "timestep_overflow"):
         assert np.array_equal(getattr(o1, k), getattr(o2, k)), k
 
