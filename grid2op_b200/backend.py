@@ -375,9 +375,13 @@ class B200Backend(Backend):
             if is_dc:
                 # res_bus.vm_pu is NaN in DC -> the reference zeroes p, q, v        pPB:1203-1206
                 # (only for connected units: a disconnected one already has v = 0, keeps its set point)
-                on = self._sto_on
+                on = self._sto_on.copy()
                 self.storage_p[on] = 0.0; self.storage_q[on] = 0.0; self.storage_v[:] = 0.0
                 self.storage_theta[:] = np.nan
+                # ... and switches those units OFF in its grid (pPB:1207 `storage["in_service"].values[deact_storage] = False`):
+                # this step's topology vector was taken before the solve (pPB:1236-1237) and still shows them connected, the next
+                # one shows -1 and the units stay out until an action re-attaches them.  Reproduced as is.
+                self._sto_on[on] = False
         self._shunt_p[:] = v.shunt_p[0]; self._shunt_q[:] = v.shunt_q[0]; self._shunt_v[:] = v.shunt_v[0]
         if is_dc:                                                               # pPB:1212-1218
             self.prod_q[:] = 0.0; self.load_q[:] = 0.0; self.storage_q[:] = 0.0
