@@ -28,7 +28,7 @@ from grid2op.Backend.backend import Backend  # noqa: E402
 from grid2op.dtypes import dt_bool, dt_float, dt_int  # noqa: E402
 from grid2op.Exceptions import BackendError  # noqa: E402
 
-from .engine import STATUS_TEXT, PowerFlowEngine  # noqa: E402
+from .engine import ST_UNSUPPLIED, STATUS_TEXT, PowerFlowEngine  # noqa: E402
 from .gridmodel import GridModel  # noqa: E402
 
 __all__ = ["B200Backend"]
@@ -53,6 +53,7 @@ class B200Backend(Backend):
         self._tol_mva = float(tol_mva)
         self._device = int(device)
         self.can_output_theta = True
+        self._needs_active_bus = True                       # like pPB:144: apply_action reads the action's active_bus (bus.in_service of the reference)
         self._gm: Optional[GridModel] = None
         self._engine = None
         self._topo_vect: Optional[np.ndarray] = None
@@ -130,6 +131,10 @@ class B200Backend(Backend):
         self._sto_p = gm.storage_p0.copy()
         self._sh_p = gm.shunt_p0.copy()
         self._sh_q = gm.shunt_q0.copy()
+        # bus.in_service of the reference's net (pPB:920-922 rewrites it from the action's active_bus on every apply_action; the file
+        # state — and so the state after reset() — has busbar 1 of every substation in service, the duplicated busbars out, pPB:548-566)
+        self._active_bus = np.zeros((gm.n_sub, gm.n_busbar), dtype=bool)
+        self._active_bus[:, 0] = True
         self._line_on = gm.line_in_service0.copy()
         self._lor_bus = np.ones(gm.n_line, dtype=np.int8)
         self._lex_bus = np.ones(gm.n_line, dtype=np.int8)
@@ -203,7 +208,7 @@ class B200Backend(Backend):
         self._refresh_status_topo()
 
     def _snapshot(self):
-        names = ("_gen_p", "_gen_vm", "_hid_vm", "_load_p", "_load_q", "_sto_p", "_sh_p", "_sh_q", "_line_on",
+        names = ("_active_bus", "_gen_p", "_gen_vm", "_hid_vm", "_load_p", "_load_q", "_sto_p", "_sh_p", "_sh_q", "_line_on",
                  "_lor_bus", "_lex_bus", "_gen_on", "_gen_bus", "_load_on", "_load_bus", "_sto_on", "_sto_bus",
                  "_sh_on", "_sh_bus", "_hid_on", "_hid_bus",
                  "p_or", "q_or", "v_or", "a_or", "p_ex", "q_ex", "v_ex", "a_ex", "theta_or", "theta_ex",
@@ -235,7 +240,10 @@ class B200Backend(Backend):
         if backend_action is None:
             return
         gm = self._gm
-        _, (prod_p, prod_v, load_p, load_q, storage), topo__, shunts__ = backend_action()
+        active_bus, (prod_p, prod_v, load_p, load_q, storage), topo__, shunts__ = backend_action()
+        ab = np.asarray(active_bus, dtype=bool)                                 # pPB:920-922
+        if ab.shape == self._active_bus.shape:
+            self._active_bus[:, :] = ab
         ch = prod_p.changed
         self._gen_p[ch] = prod_p.values[ch]
         ch = prod_v.changed
@@ -323,7 +331,23 @@ class B200Backend(Backend):
         t0 = time.perf_counter()
         self._refresh_status_topo()                                             # pPB:1236-1237
         topo, inj = self._device_records()
-        nb_cap = int(min(gm.n_slot, np.unique(self._active_slots(topo)).size))     # exact number of active buses
+        slots = np.unique(self._active_slots(topo))
+        nb_cap = int(min(gm.n_slot, slots.size))                                   # exact number of active buses
+        # A busbar the ENVIRONMENT holds for active (``active_bus``: it carries an element of the environment's topology vector or a
+        # shunt the environment believes connected, _backendAction.py:1519-1531) is an in-service bus of the reference's net.  When no
+        # element of the backend actually sits on it — a shunt that is out of service in the grid file while the environment counts it
+        # in (l2rpn_neurips_2020_track1), once every other element of its substation has moved to the other busbar — pandapower leaves
+        # that bus without a voltage and the reference reports a divergence (pPB:1241-1244 "Isolated bus").  Same here, before any
+        # launch.
+        has_el = np.zeros(gm.n_slot, dtype=bool)
+        has_el[slots] = True
+        if (self._active_bus.T.reshape(-1) & ~has_el).any():
+            self.comp_time += time.perf_counter() - t0
+            msg = STATUS_TEXT[ST_UNSUPPLIED]
+            self._last_status, self._last_iters = ST_UNSUPPLIED, 0
+            self.div_exception = BackendError(msg)
+            self._reset_all_nan()
+            return False, BackendError(f'powerflow diverged with error :"{msg}"')
         out, status, iters, _ = self._engine.run(topo[None, :], inj[None, :], is_dc=is_dc, max_iter=self._max_iter,
                                                  tol_mva=self._tol_mva, nb_cap=nb_cap)
         self.comp_time += time.perf_counter() - t0
@@ -386,6 +410,9 @@ class B200Backend(Backend):
         if is_dc:                                                               # pPB:1212-1218
             self.prod_q[:] = 0.0; self.load_q[:] = 0.0; self.storage_q[:] = 0.0
             self.q_or[:] = 0.0; self.q_ex[:] = 0.0
+            # shunt_info reads res_bus.vm_pu (pPB:1599-1608), which pandapower leaves NaN after a DC solve: connected shunts report
+            # v = NaN (disconnected ones 0, pPB:1610)
+            self._shunt_v[self._sh_on] = np.nan
 
     def _theta_of_open_lines(self, v):
         """Reference quirk (pPB:1163-1187): the voltage of an out-of-service line / transformer is forced to 0 (pPB:1180-1181:
