@@ -77,6 +77,16 @@ class BatchedEnv(BatchedDoNothing):
             self.sub_pos[s, :len(p)] = p
         self.line_or_pos, self.line_ex_pos = np.asarray(gm.line_or_pos, dtype=np.int64), np.asarray(gm.line_ex_pos, dtype=np.int64)
         self._topo_dirty = False
+        # Shunts: this driver never acts on them, so the environment of the reference holds every shunt for connected to busbar 1
+        # (_BackendAction.current_shunt_bus, grid2op/Action/_backendAction.py:513-514) and counts that busbar as active
+        # (:1519-1531 -> bus.in_service, pandaPowerBackend.py:920-922) — also when the grid file has the shunt out of service (all six of
+        # l2rpn_neurips_2020_track1).  Busbar 1 of such a substation must keep an element: :meth:`_isolated_shunt_busbar`.
+        self._shunt_off = np.flatnonzero(self.topo0[0, gm.dim_topo:gm.dim_topo + gm.n_shunt] <= 0) if gm.n_shunt else np.zeros(0, dtype=np.int64)
+        self._shunt_off_pos = [self.sub_pos[int(gm.shunt_sub[k]), :self.sub_size[int(gm.shunt_sub[k])]] for k in self._shunt_off]
+        hid_sub = np.asarray(gm.hidden_sub, dtype=np.int64) if gm.n_hidden else np.zeros(0, dtype=np.int64)
+        on_sub = np.asarray(gm.shunt_sub, dtype=np.int64)[np.setdiff1d(np.arange(gm.n_shunt), self._shunt_off)] if gm.n_shunt else hid_sub
+        self._iso_cols = self._iso_seg = None
+        self._shunt_off_other = [bool(np.isin(int(gm.shunt_sub[k]), hid_sub) or np.isin(int(gm.shunt_sub[k]), on_sub)) for k in self._shunt_off]
         # Bus splits add active buses: the kernels that discover the topology on the device size their workspace (and the
         # threads per instance) for ``nb_cap`` active buses.  The host knows every instance's topology, so the cap is the
         # bus count of the fullest instance (:meth:`_bus_cap`: host code of the library, recomputed when a topology changed) instead of every bus slot.
@@ -161,6 +171,20 @@ class BatchedEnv(BatchedDoNothing):
                 self._cap_dirty[who] = True
         return aff_l, aff_s
 
+    def _isolated_shunt_busbar(self) -> np.ndarray:
+        """bool [B]: busbar 1 of a substation whose shunt is out of service in the grid file carries no element any more — for the
+        reference an in-service bus without a voltage: ``runpf`` fails with "Isolated bus" (pandaPowerBackend.py:1241-1244) and the
+        episode ends (baseEnv.py:3523-3524)."""
+        if self._iso_cols is None:            # one gather over the positions of those substations + a segmented "any"
+            keep = [pos for pos, other in zip(self._shunt_off_pos, self._shunt_off_other) if not other]
+            # (other: an in-service shunt / the hidden slack unit sits on that substation, never moved by this driver)
+            self._iso_cols = np.concatenate(keep) if keep else np.zeros(0, dtype=np.int64)
+            self._iso_seg = np.cumsum([0] + [len(p) for p in keep])[:-1]
+        if len(self._iso_cols) == 0:
+            return np.zeros(self.batch, dtype=bool)
+        on1 = (self.topo[:, self._iso_cols] == 1).astype(np.uint8)
+        return (np.add.reduceat(on1, self._iso_seg, axis=1) == 0).any(axis=1)
+
     def _apply_environment(self):
         """maintenance / hazards of the row every instance is about to solve: those lines are out"""
         gm = self.gm
@@ -211,6 +235,10 @@ class BatchedEnv(BatchedDoNothing):
                 self.topo[ii, self.line_or_pos[ll]] = -1
                 self.topo[ii, self.line_ex_pos[ll]] = -1
                 # (the engine's own mirror of the series topology already holds them: no re-upload needed)
+        if len(self._shunt_off):              # (after the trips of this step: the cascade's re-solves see them too, backend.py:1466-1521)
+            iso = self._isolated_shunt_busbar()
+            if iso.any():
+                status = np.where(iso, 2, status).astype(status.dtype)          # ST_UNSUPPLIED: the reference's "Isolated bus"
         r = self.row % self.chron.shape[1]
         # ---- cooldowns (baseEnv.py:3352-3393, :2566-2597), in the reference's order --------------------------------------
         live = ~self.done

@@ -299,3 +299,64 @@ def test_pivoting_kernels_with_tight_cap_equal_planned(cuda_required):
     assert n_conv > 5 * B
     for e in envs:
         e.close()
+
+
+def test_busbar_left_with_an_out_of_service_shunt_only_host_logic():
+    """l2rpn_neurips_2020_track1: the grid file has its six shunts out of service, the reference's environment still counts busbar 1 of
+    their substations as active (``active_bus``, _backendAction.py:1519-1531 -> bus.in_service, pPB:920-922).  Moving EVERY element of
+    such a substation to busbar 2 leaves an in-service bus without a voltage: the reference ends the episode ("Isolated bus",
+    pPB:1241-1244); the same move on a substation without a shunt is an ordinary (pass-through) topology.  BatchedEnv and unmodified
+    environments (B200Backend host logic) must agree on both."""
+    if env_grid(ENV) is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    import grid2op
+    from grid2op.Parameters import Parameters
+    from oracle_engine import COracleSeriesEngine, OracleEngine
+    from grid2op_b200.batched_env import BatchedEnv
+    from grid2op_b200.chronics import load_scenarios
+    from grid2op_b200.gridmodel import GridModel
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    grid = env_grid(ENV)
+    gm = GridModel(grid)
+    cdir = os.path.join(os.path.dirname(grid), "chronics")
+    folder = os.path.join(cdir, sorted(os.listdir(cdir))[0])
+    chron = load_scenarios(cdir, gm, scenarios=[folder])
+    shunt_subs = set(int(x) for x in gm.shunt_sub)
+    p = Parameters()
+    p.NO_OVERFLOW_DISCONNECTION = True
+    envs = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(2):
+            e = grid2op.make(ENV, test=True, backend=HostLogicBackend(), param=p, opponent_init_budget=0., opponent_budget_per_ts=0.,
+                             _add_to_name=f"benv_iso{i}")
+            e.set_id(0)
+            e.reset()
+            envs.append(e)
+    th = np.asarray(envs[0].get_thermal_limit(), dtype=np.float32)
+    benv = BatchedEnv(gm, chron, 2, scen=np.zeros(2, dtype=np.int32), t0=np.full(2, 1, dtype=np.int32), thermal_limit_a=th,
+                      protections=False, engine=COracleSeriesEngine(gm))
+    s_shunt = 12
+    assert s_shunt in shunt_subs and benv.sub_size[s_shunt] == 4
+    s_plain = [s for s in range(gm.n_sub) if s not in shunt_subs and 3 <= benv.sub_size[s] <= 5 and not np.isin(s, gm.gen_sub)]
+    assert s_plain
+    subs = [s_shunt, s_plain[0]]
+    sub_id = np.asarray(subs, dtype=np.int64)
+    sub_bus = np.zeros((2, benv.max_sub_size), dtype=np.int8)
+    ref_done = []
+    for i, s in enumerate(subs):
+        n = int(benv.sub_size[s])
+        sub_bus[i, :n] = 2
+        o, r, d, info = envs[i].step(envs[i].action_space({"set_bus": {"substations_id": [(s, [2] * n)]}}))
+        ref_done.append(bool(d))
+    rho, done, info = benv.step(sub_id, sub_bus, np.full(2, -1), np.zeros(2, dtype=np.int64))
+    assert ref_done == [True, False]
+    assert done.tolist() == ref_done, (done, info["status"])
+    for e in envs:
+        e.close()
+    benv.close()
