@@ -360,3 +360,78 @@ def test_busbar_left_with_an_out_of_service_shunt_only_host_logic():
     for e in envs:
         e.close()
     benv.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_substation_actions_host_logic(seed):
+    """BASELINE configs[2] as a parity test: every instance draws one substation and a random busbar for each of its elements, every
+    step (``random_substation_actions``), side by side with unmodified environments fed the same ``set_bus`` actions — game overs
+    (isolated elements, islanded grids, the isolated-busbar rule) must coincide step by step, topology vectors / cooldowns equal,
+    rho within tolerance.  CPU: host logic on both sides (oracle adapters)."""
+    if env_grid(ENV) is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    import grid2op
+    from grid2op.Parameters import Parameters
+    from oracle_engine import COracleSeriesEngine, OracleEngine
+    from grid2op_b200.batched_env import BatchedEnv, random_substation_actions
+    from grid2op_b200.chronics import load_scenarios
+    from grid2op_b200.gridmodel import GridModel
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    grid = env_grid(ENV)
+    gm = GridModel(grid)
+    cdir = os.path.join(os.path.dirname(grid), "chronics")
+    folder = os.path.join(cdir, sorted(os.listdir(cdir))[0])
+    chron = load_scenarios(cdir, gm, scenarios=[folder])
+    B = 6
+    p = Parameters()
+    p.NO_OVERFLOW_DISCONNECTION = True
+    p.NB_TIMESTEP_COOLDOWN_SUB = 1
+    envs = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(B):
+            e = grid2op.make(ENV, test=True, backend=HostLogicBackend(), param=p, opponent_init_budget=0., opponent_budget_per_ts=0.,
+                             _add_to_name=f"benv_rnd{i}")
+            e.set_id(0)
+            e.reset()
+            envs.append(e)
+    th = np.asarray(envs[0].get_thermal_limit(), dtype=np.float32)
+    benv = BatchedEnv(gm, chron, B, scen=np.zeros(B, dtype=np.int32), t0=np.full(B, 1, dtype=np.int32), thermal_limit_a=th,
+                      nb_timestep_cooldown_sub=1, protections=False, engine=COracleSeriesEngine(gm))
+    rng = np.random.default_rng(50 + seed)
+    alive = np.ones(B, dtype=bool)
+    n_over = n_checked = 0
+    for k in range(10):
+        sub, bus = random_substation_actions(benv, rng)
+        ref = []
+        for i, e in enumerate(envs):
+            if not alive[i]:
+                ref.append(None)
+                continue
+            n = int(benv.sub_size[sub[i]])
+            o, r, d, info = e.step(e.action_space({"set_bus": {"substations_id": [(int(sub[i]), bus[i, :n].astype(int).tolist())]}}))
+            ref.append((o, d, info))
+        rho, done, binfo = benv.step(sub, bus)
+        for i in range(B):
+            if not alive[i]:
+                continue
+            o, d, info = ref[i]
+            assert bool(done[i]) == bool(d), (k, i, int(sub[i]), bus[i], info["exception"], binfo["status"][i])
+            if d:
+                alive[i] = False; n_over += 1
+                continue
+            n_checked += 1
+            assert np.array_equal(o.topo_vect, benv.topo[i, :gm.dim_topo]), (k, i)
+            assert np.array_equal(o.time_before_cooldown_sub, benv.sub_cooldown[i]), (k, i)
+            assert np.allclose(o.rho, rho[i], rtol=2e-4, atol=2e-5), (k, i, float(np.max(np.abs(o.rho - rho[i]))))
+        if not alive.any():
+            break
+    assert n_checked >= 6 and n_over >= 1, (n_checked, n_over)
+    for e in envs:
+        e.close()
+    benv.close()
