@@ -107,3 +107,69 @@ def test_random_agent_side_by_side(name, n_steps, sn_mva, dc, n_busbar, with_sim
         assert n_acted >= n_steps // 5, (n_acted, n_over)
     finally:
         e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("name,sn_mva,dc", [("l2rpn_case14_sandbox", 100.0, False), ("l2rpn_case14_sandbox", 100.0, True),
+                                            ("educ_case14_storage", 100.0, False), ("educ_case14_storage", 100.0, True),
+                                            ("rte_case5_example", 1.0, False)])
+def test_random_element_actions_with_detachment(name, sn_mva, dc):
+    """Same side-by-side run with the actions ``action_space.sample()`` never draws: loads / generators / storage units moved between
+    busbars or DETACHED (``allow_detachment=True``, set_bus -1: grid2op/Backend/backend.py:262-329), shunts switched, moved and
+    re-set (``shunt`` key), in AC and DC environments; the shunt part of the observation is compared too."""
+    if env_grid(name) is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    from grid2op.Parameters import Parameters
+    from oracle_engine import OracleEngine
+    import grid2op
+    from oracle.ppbackend_ref import PandaPowerBackendRef
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    p = Parameters()
+    p.ENV_DC = bool(dc)
+    p.MAX_SUB_CHANGED = 99
+    p.MAX_LINE_STATUS_CHANGED = 99
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from grid2op.Action import CompleteAction        # (every key allowed, whatever the environment's own action class is)
+        e1 = grid2op.make(name, test=True, param=p, allow_detachment=True, action_class=CompleteAction, backend=HostLogicBackend(),
+                          _add_to_name="det_b200")
+        e2 = grid2op.make(name, test=True, param=p, allow_detachment=True, action_class=CompleteAction, backend=PandaPowerBackendRef(),
+                          _add_to_name="det_ref")
+    rng = np.random.default_rng(4)
+    try:
+        for e in (e1, e2):
+            e.seed(1); e.set_id(0)
+        o1, o2 = e1.reset(), e2.reset()
+        _compare(o1, o2, sn_mva, "reset")
+        n_ok = 0
+        for i in range(50):
+            r = rng.random()
+            spec = {}
+            if r < 0.3:
+                spec = {"set_bus": {"loads_id": [(int(rng.integers(0, e1.n_load)), int(rng.choice([-1, 1, 2])))]}}
+            elif r < 0.5:
+                spec = {"set_bus": {"generators_id": [(int(rng.integers(0, e1.n_gen)), int(rng.choice([-1, 1, 2])))]}}
+            elif r < 0.6 and e1.n_storage:
+                spec = {"set_bus": {"storages_id": [(int(rng.integers(0, e1.n_storage)), int(rng.choice([-1, 1, 2])))]}}
+            elif r < 0.7 and e1.n_shunt:
+                spec = {"shunt": {"set_bus": [(int(rng.integers(0, e1.n_shunt)), int(rng.choice([-1, 1, 2])))]}}
+            elif r < 0.8 and e1.n_shunt:
+                spec = {"shunt": {"shunt_q": [(int(rng.integers(0, e1.n_shunt)), float(rng.uniform(-30, 30)))]}}
+            o1, r1, d1, i1 = e1.step(e1.action_space(spec))
+            o2, r2, d2, i2 = e2.step(e2.action_space(spec))
+            assert d1 == d2, (i, spec, i1["exception"], i2["exception"])
+            if d1:
+                o1, o2 = e1.reset(), e2.reset()
+                _compare(o1, o2, sn_mva, ("reset after game over", i))
+                continue
+            n_ok += 1
+            _compare(o1, o2, sn_mva, (i, spec))
+            for k in ("_shunt_p", "_shunt_q", "_shunt_v", "_shunt_bus"):
+                assert np.allclose(getattr(o1, k), getattr(o2, k), atol=1e-3, equal_nan=True), (k, i, spec)
+        assert n_ok >= 10
+    finally:
+        e1.close(); e2.close()
