@@ -244,6 +244,8 @@ class B200Backend(Backend):
         ab = np.asarray(active_bus, dtype=bool)                                 # pPB:920-922
         if ab.shape == self._active_bus.shape:
             self._active_bus[:, :] = ab
+        else:                                   # (an action class of another grid shape: no information -> the rule of runpf is off)
+            self._active_bus[:, :] = False
         ch = prod_p.changed
         self._gen_p[ch] = prod_p.values[ch]
         ch = prod_v.changed
