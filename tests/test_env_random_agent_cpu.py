@@ -5,6 +5,7 @@ the oracle's restatement of ``PandaPowerBackend`` — fed the same ``action_spac
 observations must agree (integers exactly), game overs must coincide; after a game over both reset and go on.
 Reference: the sequence ``BaseEnv.step`` -> ``_backend_action += action`` -> ``apply_action_public`` -> ``next_grid_state``
 (grid2op/Environment/baseEnv.py:3778-3872, grid2op/Backend/backend.py:450-496, :1433-1521)."""
+import os
 import warnings
 
 import numpy as np
@@ -171,5 +172,45 @@ def test_random_element_actions_with_detachment(name, sn_mva, dc):
             for k in ("_shunt_p", "_shunt_q", "_shunt_v", "_shunt_bus"):
                 assert np.allclose(getattr(o1, k), getattr(o2, k), atol=1e-3, equal_nan=True), (k, i, spec)
         assert n_ok >= 10
+    finally:
+        e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("name", ["educ_case14_redisp", "l2rpn_case14_sandbox_diff_grid", "l2rpn_icaps_2021", "l2rpn_idf_2023",
+                                  "l2rpn_neurips_2020_track2", "l2rpn_wcci_2020", "rte_case118_example", "rte_case14_opponent",
+                                  "rte_case14_realistic", "rte_case14_redisp", "rte_case14_test"])
+def test_every_other_bundled_environment(name):
+    """A short sampled-action run on every remaining environment the reference bundles (grid2op/data/*: other grid files, trafo
+    parameters, opponents, multi-mix, 118-substation grids): same observations as the oracle backend."""
+    if env_grid(name) is None and not os.path.isdir(os.path.join(os.path.dirname(os.path.dirname(env_grid("l2rpn_case14_sandbox") or "/x/y")), name)):
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    from oracle_engine import OracleEngine
+    import grid2op
+    from oracle.ppbackend_ref import PandaPowerBackendRef
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e1 = grid2op.make(name, test=True, backend=HostLogicBackend(), _add_to_name="all_b200")
+        e2 = grid2op.make(name, test=True, backend=PandaPowerBackendRef(), _add_to_name="all_ref")
+    try:
+        for e in (e1, e2):
+            e.seed(0); e.set_id(0)
+        o1, o2 = e1.reset(), e2.reset()
+        _compare(o1, o2, 100.0, "reset")
+        e1.action_space.seed(7); e2.action_space.seed(7)
+        for i in range(8):
+            a1 = e1.action_space.sample() if i % 2 == 0 else e1.action_space()
+            a2 = e2.action_space.sample() if i % 2 == 0 else e2.action_space()
+            o1, r1, d1, i1 = e1.step(a1)
+            o2, r2, d2, i2 = e2.step(a2)
+            assert d1 == d2, (i, i1["exception"], i2["exception"])
+            if d1:
+                o1, o2 = e1.reset(), e2.reset()
+            _compare(o1, o2, 100.0, i)
     finally:
         e1.close(); e2.close()
