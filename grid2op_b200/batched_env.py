@@ -12,6 +12,8 @@ What one :meth:`BatchedEnv.step` restates for a whole batch of independent envir
    (grid2op/Rules/PreventReconnection.py:33-60, baseEnv.py:3798-3820);
 2. ``_backend_action += action`` (baseEnv.py:3822-3846): busbars of the substation's elements, line disconnection
    (both ends -1) / reconnection (each end back on its last busbar, grid2op/Action/_backendAction.py ``last_topo_registered``);
+   a busbar > 0 for the end of a DISCONNECTED line inside a substation action reconnects that line (the line, not the
+   substation, is what such an entry impacts: grid2op/Action/baseAction.py:1836-1860);
 3. the environment's own modifications of this step: next chronics row (gridStateFromFile.py:766-776), lines in
    ``maintenance`` / ``hazards`` forced out (gridStateFromFile.py:780-797, baseAction ``maintenance`` / ``hazards`` keys);
 4. ``backend.next_grid_state`` — one batched power flow with the protections of backend.py:1433-1521 on the device;
@@ -76,6 +78,11 @@ class BatchedEnv(BatchedDoNothing):
             p = np.flatnonzero(sub_of == s)
             self.sub_pos[s, :len(p)] = p
         self.line_or_pos, self.line_ex_pos = np.asarray(gm.line_or_pos, dtype=np.int64), np.asarray(gm.line_ex_pos, dtype=np.int64)
+        # line whose end sits at a position of the topology vector (-1: not a line end) and the position of its other end
+        self.line_of_pos = np.full(gm.dim_topo, -1, dtype=np.int64)
+        self.other_end_pos = np.full(gm.dim_topo, -1, dtype=np.int64)
+        self.line_of_pos[self.line_or_pos] = np.arange(nl); self.line_of_pos[self.line_ex_pos] = np.arange(nl)
+        self.other_end_pos[self.line_or_pos] = self.line_ex_pos; self.other_end_pos[self.line_ex_pos] = self.line_or_pos
         self._topo_dirty = False
         # Shunts: this driver never acts on them, so the environment of the reference holds every shunt for connected to busbar 1
         # (_BackendAction.current_shunt_bus, grid2op/Action/_backendAction.py:513-514) and counts that busbar as active
@@ -133,27 +140,57 @@ class BatchedEnv(BatchedDoNothing):
             line_id = np.asarray(line_id, dtype=np.int64)
             line_status = np.asarray(line_status, dtype=np.int64)
             has_line = (line_id >= 0) & (line_status != 0)
-        # legality (PreventReconnection on what the action names), finished instances ignore their action
+        # A busbar > 0 for the end of a DISCONNECTED line is a reconnection of that line (reference: BaseAction.get_topological_impact,
+        # grid2op/Action/baseAction.py:1836-1860 — the line counts as impacted, its two ends do not count for the substation; applied by
+        # _BackendAction: the other end goes back to its last busbar)
+        reco = pos = val = m = who_s = None
+        sub_impacted = has_sub.copy()
+        n_reco = np.zeros(B, dtype=np.int64)
+        reco_in_cd = np.zeros(B, dtype=bool)
+        reco_is_line = np.zeros(B, dtype=bool)           # the explicitly named line is one of the reconnected ones
+        if has_sub.any():
+            who_s = np.flatnonzero(has_sub)
+            pos = self.sub_pos[sub_id[who_s]]                                    # [n, max_sub_size]
+            val = sub_bus[who_s][:, :self.max_sub_size]
+            m = (pos >= 0) & (val > 0)
+            psafe = np.where(pos >= 0, pos, 0)
+            lp = np.where(pos >= 0, self.line_of_pos[psafe], -1)
+            cur = self.topo[who_s[:, None], psafe]
+            reco = m & (lp >= 0) & (cur <= 0)
+            if reco.any():
+                lsafe = np.where(lp >= 0, lp, 0)
+                n_reco[who_s] = reco.sum(axis=1)
+                reco_in_cd[who_s] = (reco & (self.line_cooldown[who_s[:, None], lsafe] > 0)).any(axis=1)
+                if line_id is not None:
+                    reco_is_line[who_s] = (reco & (lp == np.where(has_line[who_s], line_id[who_s], -2)[:, None])).any(axis=1)
+                sub_impacted[who_s] = (m & ~reco).any(axis=1)
+        # legality (DefaultRules: LookParam MAX_SUB_CHANGED = MAX_LINE_STATUS_CHANGED = 1, grid2op/Rules/LookParam.py; PreventReconnection on
+        # what the action impacts, grid2op/Rules/PreventReconnection.py:33-60); finished instances ignore their action
         illegal = np.zeros(B, dtype=bool)
         if has_sub.any():
-            illegal |= has_sub & (self.sub_cooldown[idx, np.where(has_sub, sub_id, 0)] > 0)
+            illegal |= sub_impacted & (self.sub_cooldown[idx, np.where(has_sub, sub_id, 0)] > 0)
+            illegal |= reco_in_cd
+            illegal |= (n_reco + (has_line & ~reco_is_line)) > 1
         if has_line.any():
             illegal |= has_line & (self.line_cooldown[idx, np.where(has_line, line_id, 0)] > 0)
         self.n_illegal += int((illegal & ~self.done).sum())
         ok = ~illegal & ~self.done
         if has_sub.any():
-            who = np.flatnonzero(has_sub & ok)
-            if len(who):
-                pos = self.sub_pos[sub_id[who]]                                  # [n, max_sub_size]
-                val = sub_bus[who][:, :self.max_sub_size]
-                m = (pos >= 0) & (val > 0)
-                ii = np.broadcast_to(who[:, None], pos.shape)[m]
-                pp = pos[m]
-                cur = self.topo[ii, pp]
-                live = cur > 0                                                    # (the driver does not reconnect through set_bus)
-                self.topo[ii[live], pp[live]] = val[m][live]
-                self.last_bus[ii[live], pp[live]] = val[m][live]
-                aff_s[who, sub_id[who]] = True
+            keep = ok[who_s]
+            if keep.any():
+                who, pos_k, val_k, m_k, reco_k = who_s[keep], pos[keep], val[keep], m[keep], reco[keep]
+                ii = np.broadcast_to(who[:, None], pos_k.shape)
+                live = m_k & ~reco_k & (self.topo[ii, np.where(pos_k >= 0, pos_k, 0)] > 0)
+                self.topo[ii[live], pos_k[live]] = val_k[live]
+                self.last_bus[ii[live], pos_k[live]] = val_k[live]
+                if reco_k.any():                                                  # reconnections: this end on the named busbar, the other on its last one
+                    ir, pr, vr = ii[reco_k], pos_k[reco_k], val_k[reco_k]
+                    po = self.other_end_pos[pr]
+                    self.topo[ir, pr] = vr; self.last_bus[ir, pr] = vr
+                    self.topo[ir, po] = self.last_bus[ir, po]
+                    aff_l[ir, self.line_of_pos[pr]] = True
+                simp = sub_impacted[who]
+                aff_s[who[simp], sub_id[who[simp]]] = True
                 self._topo_dirty = True
                 self._cap_dirty[who] = True
         if has_line.any():

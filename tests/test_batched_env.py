@@ -435,3 +435,93 @@ def test_random_substation_actions_host_logic(seed):
     for e in envs:
         e.close()
     benv.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 3])
+def test_random_mixed_actions_host_logic(seed):
+    """Random mix of substation re-assignments (a busbar for EVERY element, ends of disconnected lines included), line switching and
+    do-nothing, with line / substation cooldowns: a busbar > 0 for the end of a disconnected line is a reconnection of that line
+    (impact rules of grid2op/Action/baseAction.py:1836-1860: the line counts, its ends do not count for the substation; illegal while
+    the line is in cooldown or when more than MAX_LINE_STATUS_CHANGED lines are touched; the other end returns to its last busbar).
+    Topology vectors, both cooldown vectors, game overs and rho equal to unmodified environments after every step."""
+    if env_grid(ENV) is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    import grid2op
+    from grid2op.Parameters import Parameters
+    from oracle_engine import COracleSeriesEngine, OracleEngine
+    from grid2op_b200.batched_env import BatchedEnv, random_substation_actions
+    from grid2op_b200.chronics import load_scenarios
+    from grid2op_b200.gridmodel import GridModel
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    grid = env_grid(ENV)
+    gm = GridModel(grid)
+    cdir = os.path.join(os.path.dirname(grid), "chronics")
+    folder = os.path.join(cdir, sorted(os.listdir(cdir))[0])
+    chron = load_scenarios(cdir, gm, scenarios=[folder])
+    B = 5
+    p = Parameters()
+    p.NO_OVERFLOW_DISCONNECTION = True
+    p.NB_TIMESTEP_COOLDOWN_SUB = 1
+    p.NB_TIMESTEP_COOLDOWN_LINE = 2
+    envs = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(B):
+            e = grid2op.make(ENV, test=True, backend=HostLogicBackend(), param=p, opponent_init_budget=0., opponent_budget_per_ts=0.,
+                             _add_to_name=f"benv_mix{i}")
+            e.set_id(0)
+            e.reset()
+            envs.append(e)
+    th = np.asarray(envs[0].get_thermal_limit(), dtype=np.float32)
+    benv = BatchedEnv(gm, chron, B, scen=np.zeros(B, dtype=np.int32), t0=np.full(B, 1, dtype=np.int32), thermal_limit_a=th,
+                      nb_timestep_cooldown_sub=1, nb_timestep_cooldown_line=2, protections=False, engine=COracleSeriesEngine(gm))
+    rng = np.random.default_rng(seed)
+    alive = np.ones(B, dtype=bool)
+    n_illegal_ref = n_checked = 0
+    for k in range(14):
+        sub, bus = random_substation_actions(benv, rng)
+        line = np.full(B, -1, dtype=np.int64); lst = np.zeros(B, dtype=np.int64)
+        kind = rng.random(B)
+        ref = []
+        for i, e in enumerate(envs):
+            if not alive[i]:
+                ref.append(None)
+                continue
+            spec = {}
+            if kind[i] < 0.5:
+                n = int(benv.sub_size[sub[i]])
+                spec["set_bus"] = {"substations_id": [(int(sub[i]), bus[i, :n].astype(int).tolist())]}
+            else:
+                sub[i] = -1
+                if kind[i] < 0.8:
+                    l = int(rng.integers(0, gm.n_line))
+                    line[i] = l; lst[i] = -1 if benv.line_status()[i, l] else 1
+                    spec["set_line_status"] = [(l, int(lst[i]))]
+            o, r, d, info = e.step(e.action_space(spec))
+            n_illegal_ref += int(bool(info["is_illegal"]))
+            ref.append((o, d, info, spec))
+        rho, done, binfo = benv.step(sub, bus, line, lst)
+        for i in range(B):
+            if not alive[i]:
+                continue
+            o, d, info, spec = ref[i]
+            assert bool(done[i]) == bool(d), (k, i, spec, info["exception"], binfo["status"][i])
+            if d:
+                alive[i] = False
+                continue
+            n_checked += 1
+            assert np.array_equal(o.topo_vect, benv.topo[i, :gm.dim_topo]), (k, i, spec, info["is_illegal"])
+            assert np.array_equal(o.time_before_cooldown_line, benv.line_cooldown[i]), (k, i, spec)
+            assert np.array_equal(o.time_before_cooldown_sub, benv.sub_cooldown[i]), (k, i, spec)
+            assert np.allclose(o.rho, rho[i], rtol=2e-4, atol=2e-5), (k, i)
+        if not alive.any():
+            break
+    assert benv.n_illegal == n_illegal_ref and n_checked >= 8
+    for e in envs:
+        e.close()
+    benv.close()
