@@ -143,7 +143,7 @@ class BatchedEnv(BatchedDoNothing):
         # A busbar > 0 for the end of a DISCONNECTED line is a reconnection of that line (reference: BaseAction.get_topological_impact,
         # grid2op/Action/baseAction.py:1836-1860 — the line counts as impacted, its two ends do not count for the substation; applied by
         # _BackendAction: the other end goes back to its last busbar)
-        reco = pos = val = m = who_s = None
+        reco = None
         sub_impacted = has_sub.copy()
         n_reco = np.zeros(B, dtype=np.int64)
         reco_in_cd = np.zeros(B, dtype=bool)
@@ -154,23 +154,31 @@ class BatchedEnv(BatchedDoNothing):
             val = sub_bus[who_s][:, :self.max_sub_size]
             m = (pos >= 0) & (val > 0)
             psafe = np.where(pos >= 0, pos, 0)
-            lp = np.where(pos >= 0, self.line_of_pos[psafe], -1)
-            cur = self.topo[who_s[:, None], psafe]
-            reco = m & (lp >= 0) & (cur <= 0)
-            if reco.any():
-                lsafe = np.where(lp >= 0, lp, 0)
-                n_reco[who_s] = reco.sum(axis=1)
-                reco_in_cd[who_s] = (reco & (self.line_cooldown[who_s[:, None], lsafe] > 0)).any(axis=1)
-                if line_id is not None:
-                    reco_is_line[who_s] = (reco & (lp == np.where(has_line[who_s], line_id[who_s], -2)[:, None])).any(axis=1)
-                sub_impacted[who_s] = (m & ~reco).any(axis=1)
+            assert self.topo.flags.c_contiguous and self.last_bus.flags.c_contiguous
+            tflat, lflat = self.topo.reshape(-1), self.last_bus.reshape(-1)       # (views: both arrays are C-contiguous)
+            ft = who_s[:, None] * self.topo.shape[1] + psafe                      # flat indices of the named entries
+            cur = tflat[ft]
+            dead = m & (cur <= 0)
+            if dead.any():                                                        # rare: some named element is disconnected
+                lp = np.where(pos >= 0, self.line_of_pos[psafe], -1)
+                reco = dead & (lp >= 0)
+                if reco.any():
+                    lsafe = np.where(lp >= 0, lp, 0)
+                    n_reco[who_s] = reco.sum(axis=1)
+                    reco_in_cd[who_s] = (reco & (self.line_cooldown[who_s[:, None], lsafe] > 0)).any(axis=1)
+                    if line_id is not None:
+                        reco_is_line[who_s] = (reco & (lp == np.where(has_line[who_s], line_id[who_s], -2)[:, None])).any(axis=1)
+                    sub_impacted[who_s] = (m & ~reco).any(axis=1)
+                else:
+                    reco = None
         # legality (DefaultRules: LookParam MAX_SUB_CHANGED = MAX_LINE_STATUS_CHANGED = 1, grid2op/Rules/LookParam.py; PreventReconnection on
         # what the action impacts, grid2op/Rules/PreventReconnection.py:33-60); finished instances ignore their action
         illegal = np.zeros(B, dtype=bool)
         if has_sub.any():
             illegal |= sub_impacted & (self.sub_cooldown[idx, np.where(has_sub, sub_id, 0)] > 0)
-            illegal |= reco_in_cd
-            illegal |= (n_reco + (has_line & ~reco_is_line)) > 1
+            if reco is not None:
+                illegal |= reco_in_cd
+                illegal |= (n_reco + (has_line & ~reco_is_line)) > 1
         if has_line.any():
             illegal |= has_line & (self.line_cooldown[idx, np.where(has_line, line_id, 0)] > 0)
         self.n_illegal += int((illegal & ~self.done).sum())
@@ -178,21 +186,23 @@ class BatchedEnv(BatchedDoNothing):
         if has_sub.any():
             keep = ok[who_s]
             if keep.any():
-                who, pos_k, val_k, m_k, reco_k = who_s[keep], pos[keep], val[keep], m[keep], reco[keep]
-                ii = np.broadcast_to(who[:, None], pos_k.shape)
-                live = m_k & ~reco_k & (self.topo[ii, np.where(pos_k >= 0, pos_k, 0)] > 0)
-                self.topo[ii[live], pos_k[live]] = val_k[live]
-                self.last_bus[ii[live], pos_k[live]] = val_k[live]
-                if reco_k.any():                                                  # reconnections: this end on the named busbar, the other on its last one
-                    ir, pr, vr = ii[reco_k], pos_k[reco_k], val_k[reco_k]
-                    po = self.other_end_pos[pr]
-                    self.topo[ir, pr] = vr; self.last_bus[ir, pr] = vr
-                    self.topo[ir, po] = self.last_bus[ir, po]
-                    aff_l[ir, self.line_of_pos[pr]] = True
-                simp = sub_impacted[who]
-                aff_s[who[simp], sub_id[who[simp]]] = True
+                sel = m & (cur > 0) & keep[:, None]                                # connected elements of the legal actions
+                fl = who_s[:, None] * self.last_bus.shape[1] + psafe
+                tflat[ft[sel]] = val[sel]
+                lflat[fl[sel]] = val[sel]
+                if reco is not None:                                              # reconnections: this end on the named busbar, the other on its last one
+                    rk = reco & keep[:, None]
+                    if rk.any():
+                        ir = np.broadcast_to(who_s[:, None], pos.shape)[rk]
+                        pr, vr = pos[rk], val[rk]
+                        po = self.other_end_pos[pr]
+                        self.topo[ir, pr] = vr; self.last_bus[ir, pr] = vr
+                        self.topo[ir, po] = self.last_bus[ir, po]
+                        aff_l[ir, self.line_of_pos[pr]] = True
+                who = who_s[keep & sub_impacted[who_s]]
+                aff_s[who, sub_id[who]] = True
                 self._topo_dirty = True
-                self._cap_dirty[who] = True
+                self._cap_dirty[who_s[keep]] = True
         if has_line.any():
             who = np.flatnonzero(has_line & ok)
             if len(who):
