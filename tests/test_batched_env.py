@@ -525,3 +525,77 @@ def test_random_mixed_actions_host_logic(seed):
     for e in envs:
         e.close()
     benv.close()
+
+
+def test_hazards_and_maintenance_tables_host_logic(tmp_path):
+    """Unplanned outages (``hazards``) next to a planned one (``maintenance``): a copy of l2rpn_case14_sandbox gets synthetic tables
+    written into its chronics folder (the bundled data has no hazards), an unmodified environment reads them through
+    ``GridStateFromFile`` (grid2op/Chronics/gridStateFromFile.py:780-797), BatchedEnv through ``chronics.load_line_events``: forced
+    outages, the cooldowns they impose (baseEnv.py:2566-2597) and the illegal reconnection attempts during them must agree."""
+    import bz2
+    import shutil
+    if env_grid("l2rpn_case14_sandbox") is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    import grid2op
+    from grid2op.Parameters import Parameters
+    from oracle_engine import COracleSeriesEngine, OracleEngine
+    from grid2op_b200.batched_env import BatchedEnv
+    from grid2op_b200.chronics import load_line_events, load_scenarios
+    from grid2op_b200.gridmodel import GridModel
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    dst = os.path.join(str(tmp_path), "l2rpn_case14_sandbox")
+    shutil.copytree(os.path.dirname(env_grid("l2rpn_case14_sandbox")), dst)
+    cdir = os.path.join(dst, "chronics")
+    scens = sorted(os.listdir(cdir))
+    folder = os.path.join(cdir, scens[0])
+    for other in scens[1:]:
+        shutil.rmtree(os.path.join(cdir, other))
+    gm = GridModel(os.path.join(dst, "grid.json"))
+    with bz2.open(os.path.join(folder, "load_p.csv.bz2"), "rt") as f:
+        n_rows = sum(1 for _ in f) - 1
+    haz = np.zeros((n_rows, gm.n_line), dtype=int)
+    haz[5:9, 3] = 1; haz[12:14, 7] = 1; haz[13:20, 3] = 1
+    mnt = np.zeros((n_rows, gm.n_line), dtype=int)
+    mnt[25:30, 10] = 1
+    for nm, arr in (("hazards", haz), ("maintenance", mnt)):
+        with bz2.open(os.path.join(folder, nm + ".csv.bz2"), "wt") as f:
+            f.write(";".join(gm.name_line) + "\\n")
+            for r in arr:
+                f.write(";".join(str(int(x)) for x in r) + "\\n")
+    p = Parameters()
+    p.NO_OVERFLOW_DISCONNECTION = True
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e = grid2op.make(dst, backend=HostLogicBackend(), param=p, _add_to_name="haz")
+    e.set_id(0)
+    e.reset()
+    chron = load_scenarios(cdir, gm, scenarios=[folder])
+    H = load_line_events(folder, gm, "hazards")[None]
+    M = load_line_events(folder, gm, "maintenance")[None]
+    th = np.asarray(e.get_thermal_limit(), dtype=np.float32)
+    benv = BatchedEnv(gm, chron, 1, maintenance=M, hazards=H, scen=np.zeros(1, dtype=np.int32), t0=np.full(1, 1, dtype=np.int32),
+                      thermal_limit_a=th, nb_timestep_reconnection=p.NB_TIMESTEP_RECONNECTION, protections=False,
+                      engine=COracleSeriesEngine(gm))
+    attempts = {7: 3, 10: 3, 15: 7, 22: 3, 27: 10, 31: 10}          # reconnection attempts: during the outages (illegal) and after them
+    n_illegal_ref = 0
+    saw_out = set()
+    for k in range(40):
+        lid = np.full(1, -1); lst = np.zeros(1, dtype=np.int64); spec = {}
+        if k in attempts:
+            lid[0] = attempts[k]; lst[0] = 1; spec = {"set_line_status": [(attempts[k], 1)]}
+        o, r, d, info = e.step(e.action_space(spec))
+        n_illegal_ref += int(bool(info["is_illegal"]))
+        rho, done, binfo = benv.step(line_id=lid, line_status=lst)
+        assert bool(done[0]) == bool(d) and not d, (k, info["exception"])
+        assert np.array_equal(o.topo_vect, benv.topo[0, :gm.dim_topo]), (k, np.flatnonzero(o.topo_vect != benv.topo[0, :gm.dim_topo]))
+        assert np.array_equal(o.time_before_cooldown_line, benv.line_cooldown[0]), (k, o.time_before_cooldown_line, benv.line_cooldown[0])
+        assert np.allclose(o.rho, rho[0], rtol=2e-4, atol=2e-5), k
+        saw_out |= set(np.flatnonzero(~o.line_status).tolist())
+    assert benv.n_illegal == n_illegal_ref and n_illegal_ref >= 2 and {3, 7, 10} <= saw_out
+    e.close()
+    benv.close()
