@@ -564,9 +564,9 @@ def test_hazards_and_maintenance_tables_host_logic(tmp_path):
     mnt[25:30, 10] = 1
     for nm, arr in (("hazards", haz), ("maintenance", mnt)):
         with bz2.open(os.path.join(folder, nm + ".csv.bz2"), "wt") as f:
-            f.write(";".join(gm.name_line) + "\\n")
+            f.write(";".join(gm.name_line) + "\n")
             for r in arr:
-                f.write(";".join(str(int(x)) for x in r) + "\\n")
+                f.write(";".join(str(int(x)) for x in r) + "\n")
     p = Parameters()
     p.NO_OVERFLOW_DISCONNECTION = True
     with warnings.catch_warnings():
