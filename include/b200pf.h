@@ -14,6 +14,10 @@
  * negative B200PF_E_* code; b200pf_last_error() gives the message.  A handle is not thread safe;
  * different handles are independent (one CUDA stream each).  No CPU fallback exists: with no
  * CUDA device b200pf_create() fails with B200PF_E_CUDA.
+ * Ordering: every call that takes HOST data which later launches read (grid description, series bind / set_topo /
+ * reset_instances, static injections, thermal limits) copies it on the handle's stream and returns when the copy has
+ * arrived (the caller may reuse its buffer at once, and launches on any stream of the handle — chunk and group launches
+ * run on internal streams — see the data); nothing is issued on the legacy default stream.
  *
  * Data layout (all row-major, instance-major so that one warp/CTA reads one contiguous record):
  *   topo   int8  [batch][n_topo_in]   n_topo_in = dim_topo + n_shunt + n_hidden
