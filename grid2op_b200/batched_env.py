@@ -314,6 +314,36 @@ class BatchedEnv(BatchedDoNothing):
         self.n_steps += 1
         return rho, self.done.copy(), {"status": status, "iters": iters, "disc_lines": disc, "newly_done": newly_done}
 
+    def line_angles(self, out: np.ndarray):
+        """``theta_or, theta_ex`` [B, n_line] of the full result records ``out`` (:meth:`fetch`) as an OBSERVATION of the reference
+        shows them: the kernels' records carry 0 for open lines, PandaPowerBackend reports the angle of the bus the end was last
+        attached to (it zeroes the voltage of open lines, not the angle: pandaPowerBackend.py:1163-1187), 0 when that busbar has no
+        element left.  Same rule as ``B200Backend._theta_of_open_lines``, for the whole batch."""
+        from .engine import OutputView
+        gm, B = self.gm, self.batch
+        v = OutputView(gm, out)
+        th_or, th_ex = np.array(v.theta_or, dtype=np.float32), np.array(v.theta_ex, dtype=np.float32)
+        on = self.line_status()
+        if on.all():
+            return th_or, th_ex
+        ns, nh, dt = gm.n_sub, gm.n_hidden, gm.dim_topo
+        slot_theta = np.full((B, gm.n_slot + 1), np.nan, dtype=np.float64)          # (last column: dump for disconnected elements)
+
+        def scatter(sub, pos, theta):
+            bus = self.topo[:, pos].astype(np.int64)
+            slot = np.where(bus > 0, np.asarray(sub, dtype=np.int64)[None, :] + (bus - 1) * ns, gm.n_slot)
+            np.put_along_axis(slot_theta, slot, np.asarray(theta, dtype=np.float64), axis=1)
+
+        scatter(gm.line_or_sub, self.line_or_pos, v.theta_or); scatter(gm.line_ex_sub, self.line_ex_pos, v.theta_ex)
+        scatter(gm.gen_sub, np.asarray(gm.gen_pos, dtype=np.int64), v.unit_theta[:, nh:])
+        scatter(gm.load_sub, np.asarray(gm.load_pos, dtype=np.int64), v.load_theta)
+        slot_theta[:, gm.n_slot] = np.nan
+        for th, sub, pos in ((th_or, gm.line_or_sub, self.line_or_pos), (th_ex, gm.line_ex_sub, self.line_ex_pos)):
+            last = self.last_bus[:, pos].astype(np.int64)
+            a = np.take_along_axis(slot_theta, np.asarray(sub, dtype=np.int64)[None, :] + (last - 1) * ns, axis=1)
+            th[~on] = np.where(np.isfinite(a), a, 0.0)[~on]
+        return th_or, th_ex
+
     def reset_instances(self, idx, rows=None):
         """``env.reset()`` of the instances ``idx`` (typically the finished ones): plain topology, cooldowns / counters / done flag
         cleared on the host and on the device, next chronics row ``rows`` (default: the row each instance started from).  Their

@@ -482,7 +482,7 @@ def test_random_mixed_actions_host_logic(seed):
                       nb_timestep_cooldown_sub=1, nb_timestep_cooldown_line=2, protections=False, engine=COracleSeriesEngine(gm))
     rng = np.random.default_rng(seed)
     alive = np.ones(B, dtype=bool)
-    n_illegal_ref = n_checked = 0
+    n_illegal_ref = n_checked = n_open = 0
     for k in range(14):
         sub, bus = random_substation_actions(benv, rng)
         line = np.full(B, -1, dtype=np.int64); lst = np.zeros(B, dtype=np.int64)
@@ -506,6 +506,7 @@ def test_random_mixed_actions_host_logic(seed):
             n_illegal_ref += int(bool(info["is_illegal"]))
             ref.append((o, d, info, spec))
         rho, done, binfo = benv.step(sub, bus, line, lst)
+        th = None
         for i in range(B):
             if not alive[i]:
                 continue
@@ -519,8 +520,14 @@ def test_random_mixed_actions_host_logic(seed):
             assert np.array_equal(o.time_before_cooldown_line, benv.line_cooldown[i]), (k, i, spec)
             assert np.array_equal(o.time_before_cooldown_sub, benv.sub_cooldown[i]), (k, i, spec)
             assert np.allclose(o.rho, rho[i], rtol=2e-4, atol=2e-5), (k, i)
+            if th is None:
+                th = benv.line_angles(benv.fetch()[0])
+            # angles as an observation shows them, open lines included (the angle of the bus the end was last attached to)
+            assert np.allclose(o.theta_or, th[0][i], atol=2e-3) and np.allclose(o.theta_ex, th[1][i], atol=2e-3), (k, i, spec)
+            n_open += int((~o.line_status).sum())
         if not alive.any():
             break
+    assert n_open > 0
     assert benv.n_illegal == n_illegal_ref and n_checked >= 8
     for e in envs:
         e.close()
