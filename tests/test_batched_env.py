@@ -452,6 +452,7 @@ def test_random_mixed_actions_host_logic(seed):
     from oracle_engine import COracleSeriesEngine, OracleEngine
     from grid2op_b200.batched_env import BatchedEnv, random_substation_actions
     from grid2op_b200.chronics import load_scenarios
+    from grid2op_b200.engine import OutputView
     from grid2op_b200.gridmodel import GridModel
 
     class HostLogicBackend(bk.B200Backend):
@@ -521,7 +522,16 @@ def test_random_mixed_actions_host_logic(seed):
             assert np.array_equal(o.time_before_cooldown_sub, benv.sub_cooldown[i]), (k, i, spec)
             assert np.allclose(o.rho, rho[i], rtol=2e-4, atol=2e-5), (k, i)
             if th is None:
-                th = benv.line_angles(benv.fetch()[0])
+                rec = benv.fetch()[0]
+                th = benv.line_angles(rec)
+                view = OutputView(gm, rec)
+            # the full result record of the batched step against the observation of the unmodified environment
+            for a_ref, a_rec, tol in ((o.p_or, view.p_or[i], 2e-3), (o.q_or, view.q_or[i], 2e-3), (o.p_ex, view.p_ex[i], 2e-3),
+                                      (o.v_or, view.v_or[i], 2e-3), (o.v_ex, view.v_ex[i], 2e-3), (o.gen_p, view.unit_p[i, gm.n_hidden:], 2e-3),
+                                      (o.gen_q, view.unit_q[i, gm.n_hidden:], 2e-3), (o.gen_v, view.unit_v[i, gm.n_hidden:], 2e-3),
+                                      (o.load_v, view.load_v[i], 2e-3)):
+                assert np.allclose(a_ref, a_rec, rtol=2e-4, atol=tol), (k, i, float(np.max(np.abs(a_ref - a_rec))))
+            assert np.allclose(o.a_or, view.a_or[i], rtol=2e-4, atol=0.05), (k, i)
             # angles as an observation shows them, open lines included (the angle of the bus the end was last attached to)
             assert np.allclose(o.theta_or, th[0][i], atol=2e-3) and np.allclose(o.theta_ex, th[1][i], atol=2e-3), (k, i, spec)
             n_open += int((~o.line_status).sum())
