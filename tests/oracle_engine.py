@@ -310,3 +310,78 @@ class COracleSeriesEngine:
 
     def close(self):
         pass
+
+
+class EmuProtSeriesEngine(COracleSeriesEngine):
+    """TEST INFRASTRUCTURE: the series API WITH protections, on the host build of the planned kernel + its cascade loop
+    (tests/emu/sparse_emu.cpp ``sparse_emu_series_prot_step``: the same kernel source and the same host loop as
+    ``b200pf_series_step`` with protections on the 36 / 118-substation grids).  Lets ``BatchedEnv`` with protections be stepped next to
+    unmodified environments on a machine without a GPU."""
+
+    def __init__(self, gm: GridModel):
+        super().__init__(gm)
+        import ctypes as C
+        from sparse_emu import SparseEmu
+        self._C = C
+        self.emu = SparseEmu(gm)
+        self.emu.lib.sparse_emu_series_prot_step.restype = C.c_int
+        self.next_reset = 0
+        self.hard, self.soft, self.max_allowed = 2.0, 1.0, 2
+
+    def series_bind(self, chron, scen, t0, static_inj, thermal_limit_a):
+        super().series_bind(chron, scen, t0, static_inj, thermal_limit_a)
+        gm, B, nl = self.gm, self.B, self.gm.n_line
+        self.chron32 = np.ascontiguousarray(self.chron, dtype=np.float32)
+        self.scen32 = np.ascontiguousarray(self.scen, dtype=np.int32)
+        self.t32 = np.ascontiguousarray(self.t, dtype=np.int32).copy()
+        self.topo = np.ascontiguousarray(self.topo, dtype=np.int8)
+        self.out = np.zeros((B, gm.n_out), dtype=np.float32)
+        self.status = np.zeros(B, dtype=np.int32); self.iters = np.zeros(B, dtype=np.int32)
+        self.rho = np.zeros((B, nl), dtype=np.float32)
+        self.pcount = np.zeros((B, nl), dtype=np.int32); self.ts_over = np.zeros((B, nl), dtype=np.int32)
+        self.disc = np.full((B, nl), -1, dtype=np.int32); self.done = np.zeros(B, dtype=np.int32)
+        self.rounds = np.zeros(1, dtype=np.int32)
+
+    def series_set_topo(self, topo):
+        self.topo = np.ascontiguousarray(topo, dtype=np.int8).reshape(self.B, self.gm.n_topo_in).copy()
+
+    def series_protections(self, enabled=True, hard_overflow_threshold=2.0, soft_overflow_threshold=1.0, nb_timestep_overflow_allowed=2):
+        self.prot = bool(enabled)
+        self.hard, self.soft, self.max_allowed = float(hard_overflow_threshold), float(soft_overflow_threshold), int(nb_timestep_overflow_allowed)
+
+    def series_next_is_reset(self):
+        self.next_reset = 1
+
+    def series_step(self, is_dc=False, max_iter=10, tol_mva=1e-8, nb_cap=0):
+        if not self.prot or is_dc:
+            self.t = self.t32.astype(np.int64)
+            super().series_step(is_dc=is_dc, max_iter=max_iter, tol_mva=tol_mva, nb_cap=nb_cap)
+            self.t32 = self.t.astype(np.int32)
+            self.rho = (OutputView(self.gm, self.out).a_or / self.th[None, :]).astype(np.float32)
+            return
+        C = self._C
+        p = lambda a: a.ctypes.data_as(C.c_void_p)     # noqa: E731
+        static = np.ascontiguousarray(self.static_inj, dtype=np.float64)
+        th = np.ascontiguousarray(self.th, dtype=np.float32)
+        rc = self.emu.lib.sparse_emu_series_prot_step(
+            C.byref(self.emu.desc), C.c_int(self.B), p(self.topo), p(self.chron32), C.c_int(self.chron32.shape[0]), C.c_int(self.chron32.shape[1]),
+            p(self.scen32), p(self.t32), p(static), p(th), C.c_int(int(self.next_reset)), C.c_float(self.hard), C.c_float(self.soft),
+            C.c_int(self.max_allowed), C.c_int(int(max_iter)), C.c_double(float(tol_mva)), p(self.out), p(self.status), p(self.iters), p(self.rho),
+            p(self.pcount), p(self.ts_over), p(self.disc), p(self.done), p(self.rounds))
+        assert rc == 0, rc
+        self.next_reset = 0
+        self.launch_count += 1
+
+    def series_fetch(self, want_out=True, want_rho=True):
+        return (self.out if want_out else None), self.status, self.iters, (self.rho if want_rho else None)
+
+    def series_fetch_state(self):
+        return dict(protection_counter=self.pcount.copy(), timestep_overflow=self.ts_over.copy(), disc_lines=self.disc.copy(), done=self.done.copy())
+
+    def series_reset_instances(self, idx, t_new=None, topo_rows=None):
+        idx = np.asarray(idx, dtype=np.int64)
+        if t_new is not None:
+            self.t32[idx] = np.asarray(t_new, dtype=np.int32)
+        if topo_rows is not None:
+            self.topo[idx] = np.asarray(topo_rows, dtype=np.int8).reshape(len(idx), self.gm.n_topo_in)
+        self.pcount[idx] = 0; self.ts_over[idx] = 0; self.disc[idx] = -1; self.done[idx] = 0

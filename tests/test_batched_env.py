@@ -437,9 +437,12 @@ def test_random_substation_actions_host_logic(seed):
     benv.close()
 
 
-@pytest.mark.parametrize("seed", [0, 1, 3])
-def test_random_mixed_actions_host_logic(seed):
-    """Random mix of substation re-assignments (a busbar for EVERY element, ends of disconnected lines included), line switching and
+@pytest.mark.parametrize("seed,protections", [(0, False), (1, False), (3, False), (0, True), (2, True), (5, True)])
+def test_random_mixed_actions_host_logic(seed, protections):
+    """(``protections``: with the overflow protections of Backend.next_grid_state, backend.py:1433-1521 — the batched side runs the HOST
+    BUILD of the planned kernel with its cascade loop, tests/oracle_engine.py EmuProtSeriesEngine; tripped lines, their reconnection
+    cooldown and the cascades must coincide with the reference's host loop.)
+    Random mix of substation re-assignments (a busbar for EVERY element, ends of disconnected lines included), line switching and
     do-nothing, with line / substation cooldowns: a busbar > 0 for the end of a disconnected line is a reconnection of that line
     (impact rules of grid2op/Action/baseAction.py:1836-1860: the line counts, its ends do not count for the substation; illegal while
     the line is in cooldown or when more than MAX_LINE_STATUS_CHANGED lines are touched; the other end returns to its last busbar).
@@ -449,7 +452,7 @@ def test_random_mixed_actions_host_logic(seed):
     import grid2op_b200.backend as bk
     import grid2op
     from grid2op.Parameters import Parameters
-    from oracle_engine import COracleSeriesEngine, OracleEngine
+    from oracle_engine import COracleSeriesEngine, EmuProtSeriesEngine, OracleEngine
     from grid2op_b200.batched_env import BatchedEnv, random_substation_actions
     from grid2op_b200.chronics import load_scenarios
     from grid2op_b200.engine import OutputView
@@ -466,7 +469,7 @@ def test_random_mixed_actions_host_logic(seed):
     chron = load_scenarios(cdir, gm, scenarios=[folder])
     B = 5
     p = Parameters()
-    p.NO_OVERFLOW_DISCONNECTION = True
+    p.NO_OVERFLOW_DISCONNECTION = not protections
     p.NB_TIMESTEP_COOLDOWN_SUB = 1
     p.NB_TIMESTEP_COOLDOWN_LINE = 2
     envs = []
@@ -480,10 +483,13 @@ def test_random_mixed_actions_host_logic(seed):
             envs.append(e)
     th = np.asarray(envs[0].get_thermal_limit(), dtype=np.float32)
     benv = BatchedEnv(gm, chron, B, scen=np.zeros(B, dtype=np.int32), t0=np.full(B, 1, dtype=np.int32), thermal_limit_a=th,
-                      nb_timestep_cooldown_sub=1, nb_timestep_cooldown_line=2, protections=False, engine=COracleSeriesEngine(gm))
+                      nb_timestep_cooldown_sub=1, nb_timestep_cooldown_line=2, nb_timestep_reconnection=p.NB_TIMESTEP_RECONNECTION,
+                      protections=protections, hard_overflow_threshold=p.HARD_OVERFLOW_THRESHOLD,
+                      soft_overflow_threshold=p.SOFT_OVERFLOW_THRESHOLD, nb_timestep_overflow_allowed=p.NB_TIMESTEP_OVERFLOW_ALLOWED,
+                      engine=(EmuProtSeriesEngine if protections else COracleSeriesEngine)(gm))
     rng = np.random.default_rng(seed)
     alive = np.ones(B, dtype=bool)
-    n_illegal_ref = n_checked = n_open = 0
+    n_illegal_ref = n_checked = n_open = n_trip = 0
     for k in range(14):
         sub, bus = random_substation_actions(benv, rng)
         line = np.full(B, -1, dtype=np.int64); lst = np.zeros(B, dtype=np.int64)
@@ -507,6 +513,9 @@ def test_random_mixed_actions_host_logic(seed):
             n_illegal_ref += int(bool(info["is_illegal"]))
             ref.append((o, d, info, spec))
         rho, done, binfo = benv.step(sub, bus, line, lst)
+        if binfo["disc_lines"] is not None:
+            n_trip += int((binfo["disc_lines"] >= 0).sum())
+        ts_over = benv.fetch_state()["timestep_overflow"] if protections else None
         th = None
         for i in range(B):
             if not alive[i]:
@@ -521,6 +530,8 @@ def test_random_mixed_actions_host_logic(seed):
             assert np.array_equal(o.time_before_cooldown_line, benv.line_cooldown[i]), (k, i, spec)
             assert np.array_equal(o.time_before_cooldown_sub, benv.sub_cooldown[i]), (k, i, spec)
             assert np.allclose(o.rho, rho[i], rtol=2e-4, atol=2e-5), (k, i)
+            if protections:
+                assert np.array_equal(o.timestep_overflow, ts_over[i]), (k, i)
             if th is None:
                 rec = benv.fetch()[0]
                 th = benv.line_angles(rec)
@@ -537,7 +548,7 @@ def test_random_mixed_actions_host_logic(seed):
             n_open += int((~o.line_status).sum())
         if not alive.any():
             break
-    assert n_open > 0
+    assert n_open > 0 and (n_trip > 0 or not protections), (n_open, n_trip)
     assert benv.n_illegal == n_illegal_ref and n_checked >= 8
     for e in envs:
         e.close()
