@@ -122,3 +122,30 @@ def test_three_busbars_per_substation(name):
         out, status, _, _ = emu.run(topo, inj)
         assert np.array_equal(status, rstatus)
         compare(gm, out, ref, status == 0)
+
+
+@pytest.mark.parametrize("name", ["educ_case14_redisp", "l2rpn_case14_sandbox_diff_grid", "l2rpn_icaps_2021", "l2rpn_idf_2023",
+                                  "l2rpn_neurips_2020_track2", "l2rpn_wcci_2020", "rte_case118_example", "rte_case14_opponent",
+                                  "rte_case14_realistic", "rte_case14_redisp", "rte_case14_test"])
+def test_every_other_bundled_grid_through_the_planned_kernels(name):
+    """the remaining grid files the reference bundles (other line / transformer parameters, 118-substation variants): topology plans +
+    both planned kernels (host builds) against the fp64 oracle on random splits / outages / injections"""
+    from sparse_emu import SparseEmu
+    from conftest import grid2op_root
+    root = grid2op_root()
+    path = None
+    if root is not None:
+        base = os.path.join(root, "data", name)
+        cands = [os.path.join(base, "grid.json")] + ([os.path.join(base, d, "grid.json") for d in sorted(os.listdir(base))] if os.path.isdir(base) else [])
+        path = next((p for p in cands if os.path.exists(p)), None)
+    if path is None:
+        pytest.skip("reference grid files not available")
+    gm = GridModel(path)
+    n = 12 if gm.n_sub > 50 else 32
+    topo, inj = random_cases(gm, n, seed=5)
+    ref, rstatus, _, _ = COracle(gm).run(topo, inj)
+    assert (rstatus == 0).sum() >= n // 4
+    for emu in (SparseEmu(gm), BlockEmu(gm, 8, 1) if gm.n_line <= 32 else BlockEmu(gm, 32, 1)):
+        out, status, _, _ = emu.run(topo, inj)
+        assert np.array_equal(status, rstatus)
+        compare(gm, out, ref, status == 0)
