@@ -366,13 +366,17 @@ class B200Backend(Backend):
 
     def _active_slots(self, topo):
         gm = self._gm
-        subs = np.concatenate([gm.line_or_sub, gm.line_ex_sub, gm.gen_sub, gm.load_sub, gm.storage_sub,
-                               gm.shunt_sub, gm.hidden_sub])
-        pos = np.concatenate([gm.line_or_pos, gm.line_ex_pos, gm.gen_pos, gm.load_pos, gm.storage_pos,
-                              gm.dim_topo + np.arange(gm.n_shunt), gm.dim_topo + gm.n_shunt + np.arange(gm.n_hidden)])
+        cache = getattr(gm, "_slot_index_cache", None)           # (constant per grid: substation and record position of every element)
+        if cache is None:
+            subs = np.concatenate([gm.line_or_sub, gm.line_ex_sub, gm.gen_sub, gm.load_sub, gm.storage_sub,
+                                   gm.shunt_sub, gm.hidden_sub]).astype(np.int64)
+            pos = np.concatenate([gm.line_or_pos, gm.line_ex_pos, gm.gen_pos, gm.load_pos, gm.storage_pos,
+                                  gm.dim_topo + np.arange(gm.n_shunt), gm.dim_topo + gm.n_shunt + np.arange(gm.n_hidden)]).astype(np.int64)
+            cache = gm._slot_index_cache = (subs, pos)
+        subs, pos = cache
         b = topo[pos].astype(np.int64)
         ok = b > 0
-        return subs[ok].astype(np.int64) + (b[ok] - 1) * gm.n_sub
+        return subs[ok] + (b[ok] - 1) * gm.n_sub
 
     # pPB:1122-1218 (+ 1526-1564, 1596-1612, 1621-1647)
     def _fetch(self, out, is_dc):

@@ -199,23 +199,27 @@ def _ptr(a: Optional[np.ndarray]):
 class OutputView:
     """Named float32 views into the packed result record ``out[batch, n_out]`` (include/b200pf.h)."""
 
+    FIELDS = ("p_or", "q_or", "v_or", "a_or", "theta_or", "p_ex", "q_ex", "v_ex", "a_ex", "theta_ex", "unit_p", "unit_q", "unit_v",
+              "unit_theta", "load_v", "load_theta", "storage_v", "shunt_p", "shunt_q", "shunt_v")
+
+    @staticmethod
+    def layout(gm: GridModel):
+        """-> ((field, start, stop), ...) of the packed record (cached on the grid model)"""
+        lay = getattr(gm, "_out_layout_cache", None)
+        if lay is None:
+            nl, nu, nld, ns, nsh = gm.n_line, gm.n_unit, gm.n_load, gm.n_storage, gm.n_shunt
+            sizes = [nl] * 10 + [nu] * 4 + [nld, nld, ns, nsh, nsh, nsh]
+            o, lay = 0, []
+            for name, n in zip(OutputView.FIELDS, sizes):
+                lay.append((name, o, o + n))
+                o += n
+            assert o == gm.n_out
+            lay = gm._out_layout_cache = tuple(lay)
+        return lay
+
     def __init__(self, gm: GridModel, out: np.ndarray):
-        nl, nu, nld, ns, nsh = gm.n_line, gm.n_unit, gm.n_load, gm.n_storage, gm.n_shunt
-        o = 0
-
-        def take(n):
-            nonlocal o
-            v = out[:, o:o + n]
-            o += n
-            return v
-
-        (self.p_or, self.q_or, self.v_or, self.a_or, self.theta_or,
-         self.p_ex, self.q_ex, self.v_ex, self.a_ex, self.theta_ex) = [take(nl) for _ in range(10)]
-        self.unit_p, self.unit_q, self.unit_v, self.unit_theta = [take(nu) for _ in range(4)]
-        self.load_v, self.load_theta = take(nld), take(nld)
-        self.storage_v = take(ns)
-        self.shunt_p, self.shunt_q, self.shunt_v = take(nsh), take(nsh), take(nsh)
-        assert o == gm.n_out
+        for name, a, b in OutputView.layout(gm):
+            setattr(self, name, out[:, a:b])
 
 
 def make_grid_desc(gm: GridModel):
