@@ -56,24 +56,30 @@ def test_random_agent_side_by_side(name, n_steps, sn_mva, dc, n_busbar, with_sim
     if env_grid(name) is None:
         pytest.skip("reference data not available")
     import grid2op_b200.backend as bk           # (locates / bootstraps the grid2op install first)
+    from oracle_engine import OracleEngine
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    run_side_by_side(HostLogicBackend, name, n_steps, sn_mva, dc, n_busbar, with_simulate)
+
+
+def run_side_by_side(backend_class, name, n_steps, sn_mva, dc, n_busbar, with_simulate, tag="fuzz"):
+    """(also the body of the GPU variant, tests/test_env_random_agent_gpu.py, with the CUDA backend as ``backend_class``)"""
+    import grid2op_b200.backend as bk           # noqa: F401  (locates / bootstraps the grid2op install first)
     from grid2op.Parameters import Parameters
     param = Parameters()
     param.ENV_DC = bool(dc)
     kw = {"param": param}
     if n_busbar != 2:
         kw["n_busbar"] = n_busbar
-    from oracle_engine import OracleEngine
     import grid2op
     from oracle.ppbackend_ref import PandaPowerBackendRef
-
-    class HostLogicBackend(bk.B200Backend):
-        def _make_engine(self, gm):
-            return OracleEngine(gm)
-
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        e1 = grid2op.make(name, test=True, backend=HostLogicBackend(), _add_to_name=f"fuzz_b200_{n_busbar}", **kw)
-        e2 = grid2op.make(name, test=True, backend=PandaPowerBackendRef(), _add_to_name=f"fuzz_ref_{n_busbar}", **kw)
+        e1 = grid2op.make(name, test=True, backend=backend_class(), _add_to_name=f"{tag}_b200_{n_busbar}", **kw)
+        e2 = grid2op.make(name, test=True, backend=PandaPowerBackendRef(), _add_to_name=f"{tag}_ref_{n_busbar}", **kw)
     try:
         for e in (e1, e2):
             e.seed(3); e.set_id(0)

@@ -1,0 +1,24 @@
+"""GPU variant of tests/test_env_random_agent_cpu.py: the same sampled-action runs with ``B200Backend`` THROUGH CUDA next to the oracle's
+restatement of ``PandaPowerBackend``.
+
+Written after this round's GPU budget was spent: the function has never run on hardware (its CPU counterpart, which shares the whole
+body, is green).  It is therefore marked ``xfail(strict=False)`` — a pass shows up as XPASS in the driver's round-end GPU run, a
+failure cannot break the suite; drop the marker once it has passed on a B200."""
+import pytest
+
+from conftest import env_grid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet run on hardware")
+@pytest.mark.parametrize("name,n_steps,sn_mva,dc,with_simulate", [("l2rpn_case14_sandbox", 80, 100.0, False, True),
+                                                                  ("educ_case14_storage", 60, 100.0, False, False),
+                                                                  ("l2rpn_case14_sandbox", 40, 100.0, True, False),
+                                                                  ("l2rpn_neurips_2020_track1", 30, 1.0, False, False)])
+def test_random_agent_side_by_side_through_cuda(cuda_required, name, n_steps, sn_mva, dc, with_simulate):
+    if env_grid(name) is None:
+        pytest.skip("reference data not available")
+    from grid2op_b200.backend import B200Backend
+    from test_env_random_agent_cpu import run_side_by_side
+    run_side_by_side(B200Backend, name, n_steps, sn_mva, dc, 2, with_simulate, tag="fuzzgpu")
