@@ -439,6 +439,30 @@ def test_random_substation_actions_host_logic(seed):
 
 @pytest.mark.parametrize("seed,protections", [(0, False), (1, False), (3, False), (0, True), (2, True), (5, True)])
 def test_random_mixed_actions_host_logic(seed, protections):
+    if env_grid(ENV) is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    from oracle_engine import COracleSeriesEngine, EmuProtSeriesEngine, OracleEngine
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    run_random_mixed_actions(seed, protections, HostLogicBackend, EmuProtSeriesEngine if protections else COracleSeriesEngine)
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet run on hardware")
+@pytest.mark.parametrize("seed,protections", [(0, False), (2, True)])
+def test_random_mixed_actions_gpu(cuda_required, seed, protections):
+    """the same run with the CUDA engine on both sides (see tests/test_env_random_agent_gpu.py for the marker)"""
+    if env_grid(ENV) is None:
+        pytest.skip("reference data not available")
+    from grid2op_b200.backend import B200Backend
+    run_random_mixed_actions(seed, protections, B200Backend, lambda gm: None)
+
+
+def run_random_mixed_actions(seed, protections, backend_class, engine_factory):
     """(``protections``: with the overflow protections of Backend.next_grid_state, backend.py:1433-1521 — the batched side runs the HOST
     BUILD of the planned kernel with its cascade loop, tests/oracle_engine.py EmuProtSeriesEngine; tripped lines, their reconnection
     cooldown and the cascades must coincide with the reference's host loop.)
@@ -447,20 +471,13 @@ def test_random_mixed_actions_host_logic(seed, protections):
     (impact rules of grid2op/Action/baseAction.py:1836-1860: the line counts, its ends do not count for the substation; illegal while
     the line is in cooldown or when more than MAX_LINE_STATUS_CHANGED lines are touched; the other end returns to its last busbar).
     Topology vectors, both cooldown vectors, game overs and rho equal to unmodified environments after every step."""
-    if env_grid(ENV) is None:
-        pytest.skip("reference data not available")
-    import grid2op_b200.backend as bk
+    import grid2op_b200.backend as bk           # noqa: F401  (locates / bootstraps the grid2op install first)
     import grid2op
     from grid2op.Parameters import Parameters
-    from oracle_engine import COracleSeriesEngine, EmuProtSeriesEngine, OracleEngine
     from grid2op_b200.batched_env import BatchedEnv, random_substation_actions
     from grid2op_b200.chronics import load_scenarios
     from grid2op_b200.engine import OutputView
     from grid2op_b200.gridmodel import GridModel
-
-    class HostLogicBackend(bk.B200Backend):
-        def _make_engine(self, gm):
-            return OracleEngine(gm)
 
     grid = env_grid(ENV)
     gm = GridModel(grid)
@@ -476,8 +493,8 @@ def test_random_mixed_actions_host_logic(seed, protections):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         for i in range(B):
-            e = grid2op.make(ENV, test=True, backend=HostLogicBackend(), param=p, opponent_init_budget=0., opponent_budget_per_ts=0.,
-                             _add_to_name=f"benv_mix{i}")
+            e = grid2op.make(ENV, test=True, backend=backend_class(), param=p, opponent_init_budget=0., opponent_budget_per_ts=0.,
+                             _add_to_name=f"benv_mix{i}_{int(protections)}")
             e.set_id(0)
             e.reset()
             envs.append(e)
@@ -486,7 +503,7 @@ def test_random_mixed_actions_host_logic(seed, protections):
                       nb_timestep_cooldown_sub=1, nb_timestep_cooldown_line=2, nb_timestep_reconnection=p.NB_TIMESTEP_RECONNECTION,
                       protections=protections, hard_overflow_threshold=p.HARD_OVERFLOW_THRESHOLD,
                       soft_overflow_threshold=p.SOFT_OVERFLOW_THRESHOLD, nb_timestep_overflow_allowed=p.NB_TIMESTEP_OVERFLOW_ALLOWED,
-                      engine=(EmuProtSeriesEngine if protections else COracleSeriesEngine)(gm))
+                      engine=engine_factory(gm))
     rng = np.random.default_rng(seed)
     alive = np.ones(B, dtype=bool)
     n_illegal_ref = n_checked = n_open = n_trip = 0
