@@ -286,7 +286,9 @@ def run_reference(args):
         "impl": "reference", "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": int(len(ts)),
         "warmup": max(args.warmup, 1), "ms_per_step": float(1e3 * np.median(ts)), "higher_is_better": True, "scaling": w["scaling"],
         "vs_baseline": None, "dtype": "f64", "data": f"synthetic (bundled {w['env']} chronics rows replayed, DoNothing)",
-        "config": {"workload": f"{w['env']} AC Newton-Raphson, batch {batch}, DoNothing rollout, host CPU", "batch_per_step": batch,
+        # (the same `workload` text as the GPU arm prints for this workload: the two lines describe one configuration)
+        "config": {"workload": f"{w['env']} AC Newton-Raphson, batch {batch} envs per GPU, DoNothing rollout", "batch_per_step": batch,
+                   "arm": "host CPU: one batch of that size per step, all host threads the cgroup grants",
                    "requested_steps": args.steps,
                    "note": "value = median over the steps of batch / step time; the arm runs at least 2 s whatever --steps says"},
         "spread": {"min": float(rates.min()), "median": value, "max": float(rates.max()), "unit": UNIT, "n": int(len(ts))},
