@@ -451,17 +451,6 @@ def test_random_mixed_actions_host_logic(seed, protections):
     run_random_mixed_actions(seed, protections, HostLogicBackend, EmuProtSeriesEngine if protections else COracleSeriesEngine)
 
 
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet run on hardware")
-@pytest.mark.parametrize("seed,protections", [(0, False), (2, True)])
-def test_random_mixed_actions_gpu(cuda_required, seed, protections):
-    """the same run with the CUDA engine on both sides (see tests/test_env_random_agent_gpu.py for the marker)"""
-    if env_grid(ENV) is None:
-        pytest.skip("reference data not available")
-    from grid2op_b200.backend import B200Backend
-    run_random_mixed_actions(seed, protections, B200Backend, lambda gm: None)
-
-
 def run_random_mixed_actions(seed, protections, backend_class, engine_factory):
     """(``protections``: with the overflow protections of Backend.next_grid_state, backend.py:1433-1521 — the batched side runs the HOST
     BUILD of the planned kernel with its cascade loop, tests/oracle_engine.py EmuProtSeriesEngine; tripped lines, their reconnection

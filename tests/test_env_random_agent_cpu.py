@@ -66,7 +66,7 @@ def test_random_agent_side_by_side(name, n_steps, sn_mva, dc, n_busbar, with_sim
 
 
 def run_side_by_side(backend_class, name, n_steps, sn_mva, dc, n_busbar, with_simulate, tag="fuzz"):
-    """(also the body of the GPU variant, tests/test_env_random_agent_gpu.py, with the CUDA backend as ``backend_class``)"""
+    """(also the body of the GPU variant, tests/test_zz_random_agents_gpu.py, with the CUDA backend as ``backend_class``)"""
     import grid2op_b200.backend as bk           # noqa: F401  (locates / bootstraps the grid2op install first)
     from grid2op.Parameters import Parameters
     param = Parameters()
