@@ -19,4 +19,5 @@ def test_side_by_side_host_logic(monkeypatch):
             return OracleEngine(gm)
 
     monkeypatch.setattr(bk, "B200Backend", HostLogicBackend)
+    monkeypatch.setattr(T, "WITH_THETA", True)          # angles too, incl. the reference's value for open lines (pPB:1163-1187)
     T.test_case14_sandbox_env_side_by_side(None)

@@ -35,3 +35,14 @@ def test_random_mixed_actions_through_cuda(cuda_required, seed, protections):
     from grid2op_b200.backend import B200Backend
     from test_batched_env import run_random_mixed_actions
     run_random_mixed_actions(seed, protections, B200Backend, lambda gm: None)
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet run on hardware")
+def test_side_by_side_environment_with_angles_through_cuda(cuda_required, monkeypatch):
+    """tests/test_env_vs_oracle_env_gpu.py with the voltage angles compared too (open lines: the angle of the bus the end was last
+    attached to, pPB:1163-1187) — green on the CPU with the host logic (tests/test_env_hostlogic_cpu.py)"""
+    if env_grid("l2rpn_case14_sandbox") is None:
+        pytest.skip("reference data not available")
+    import test_env_vs_oracle_env_gpu as T
+    monkeypatch.setattr(T, "WITH_THETA", True)
+    T.test_case14_sandbox_env_side_by_side(None)
