@@ -402,6 +402,8 @@ class B200Backend(Backend):
             self.storage_q[:] = gm.storage_q
             self.storage_v[:] = v.storage_v[0]
             self.storage_theta[:] = v.storage_v[0]                              # sic, pPB:1635-1640
+            if not self._sto_on.all() and not is_dc:
+                self._theta_of_detached_storages(v)
             if is_dc:
                 # res_bus.vm_pu is NaN in DC -> the reference zeroes p, q, v        pPB:1203-1206
                 # (only for connected units: a disconnected one already has v = 0, keeps its set point)
@@ -442,6 +444,25 @@ class B200Backend(Backend):
         th_ex = slot_theta[gm.line_ex_sub[off] + (self._lex_bus[off].astype(np.int64) - 1) * ns]
         self.theta_or[off] = np.where(np.isfinite(th_or), th_or, 0.0)
         self.theta_ex[off] = np.where(np.isfinite(th_ex), th_ex, 0.0)
+
+    def _theta_of_detached_storages(self, v):
+        """The (sic) of pPB:1635-1640 goes one step further: ``storage_theta`` is ``res_bus.vm_pu`` of the bus in the storage TABLE times
+        the storage's nominal voltage, and unlike ``storage_v`` it is not zeroed for units that are out of service (pPB:1641) — a detached
+        unit reports the voltage magnitude [kV] of the busbar it was last attached to (NaN when that busbar has no element left)."""
+        gm = self._gm
+        ns, nh = gm.n_sub, gm.n_hidden
+        slot_vm = np.full(gm.n_slot, np.nan, dtype=np.float64)
+        on = self._line_on
+        slot_vm[gm.line_or_sub[on] + (self._lor_bus[on].astype(np.int64) - 1) * ns] = v.v_or[0][on] / gm.line_or_vn[on]
+        slot_vm[gm.line_ex_sub[on] + (self._lex_bus[on].astype(np.int64) - 1) * ns] = v.v_ex[0][on] / gm.line_ex_vn[on]
+        g = self._gen_on
+        slot_vm[gm.gen_sub[g] + (self._gen_bus[g].astype(np.int64) - 1) * ns] = v.unit_v[0, nh:][g] / gm.unit_vn[nh:][g]
+        ld = self._load_on
+        slot_vm[gm.load_sub[ld] + (self._load_bus[ld].astype(np.int64) - 1) * ns] = v.load_v[0][ld] / gm.load_vn[ld]
+        st = self._sto_on
+        slot_vm[gm.storage_sub[st] + (self._sto_bus[st].astype(np.int64) - 1) * ns] = v.storage_v[0][st] / gm.storage_vn[st]
+        off = ~st
+        self.storage_theta[off] = slot_vm[gm.storage_sub[off] + (self._sto_bus[off].astype(np.int64) - 1) * ns] * gm.storage_vn[off]
 
     # pPB:1257-1287
     def _reset_all_nan(self):

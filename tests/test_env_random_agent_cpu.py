@@ -35,6 +35,7 @@ def _compare(o1, o2, sn_mva, step):
     _close(o1.storage_charge, o2.storage_charge, 1e-3, ("storage_charge", step))
     for k in ("theta_or", "theta_ex", "gen_theta", "load_theta"):
         _close(getattr(o1, k), getattr(o2, k), 2e-3, (k, step))
+    _close(o1.storage_theta, o2.storage_theta, 2e-3, ("storage_theta", step))      # (the reference's "theta" of a storage unit is a voltage)
     for k in ("topo_vect", "line_status", "timestep_overflow", "time_before_cooldown_line", "time_before_cooldown_sub",
               "time_next_maintenance", "duration_next_maintenance"):
         assert np.array_equal(getattr(o1, k), getattr(o2, k)), (k, step)
