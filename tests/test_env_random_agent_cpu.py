@@ -221,3 +221,72 @@ def test_every_other_bundled_environment(name):
             _compare(o1, o2, 100.0, i)
     finally:
         e1.close(); e2.close()
+
+
+def _getters(b):
+    out = {"topo": b.get_topo_vect(), "status": b.get_line_status()}
+    for nm, fn in (("gen", b.generators_info), ("load", b.loads_info), ("or", b.lines_or_info), ("ex", b.lines_ex_info),
+                   ("storage", b.storages_info), ("shunt", b.shunt_info)):
+        for k, a in enumerate(fn()):
+            out[f"{nm}{k}"] = np.asarray(a, dtype=np.float64)
+    for k, a in enumerate(b.get_theta()):
+        out[f"theta{k}"] = np.asarray(a, dtype=np.float64)
+    return out
+
+
+@pytest.mark.parametrize("name", ["l2rpn_case14_sandbox", "educ_case14_storage", "l2rpn_neurips_2020_track1"])
+def test_backend_level_sequences_without_an_environment(name):
+    """The Backend API driven directly (the way aaa_test_backend_interface.py drives it): random sequences of ``apply_action`` with
+    sampled TOPOLOGY actions on a backend action, ``copy()``, and ``runpf`` in AC or DC in any order — every getter of ``B200Backend``
+    (host logic) equal to the oracle backend's after every converged solve.  (Injection-type actions are left out: a fresh
+    ``_BackendAction`` holds uninitialised set points, ``ValueStore`` is ``np.empty``.)"""
+    if env_grid(name) is None:
+        pytest.skip("reference data not available")
+    import grid2op_b200.backend as bk
+    from oracle_engine import OracleEngine
+    import grid2op
+    from grid2op.Action import CompleteAction
+    from oracle.ppbackend_ref import PandaPowerBackendRef
+
+    class HostLogicBackend(bk.B200Backend):
+        def _make_engine(self, gm):
+            return OracleEngine(gm)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e1 = grid2op.make(name, test=True, action_class=CompleteAction, backend=HostLogicBackend(), _add_to_name="bkseq_b200")
+        e2 = grid2op.make(name, test=True, action_class=CompleteAction, backend=PandaPowerBackendRef(), _add_to_name="bkseq_ref")
+    try:
+        n_conv = n_dc = n_fail = 0
+        for seed in range(2):
+            e1.action_space.seed(seed); e2.action_space.seed(seed)
+            b1, b2 = e1.backend.copy(), e2.backend.copy()
+            ba1, ba2 = type(b1).my_bk_act_class(), type(b2).my_bk_act_class()
+            rng = np.random.default_rng(seed)
+            for i in range(40):
+                r = rng.random()
+                if r < 0.5:
+                    a1, a2 = e1.action_space.sample(), e2.action_space.sample()
+                    while a1._modif_inj or a1._modif_redispatch or a1._modif_storage or a1._modif_curtailment or a1._modif_alarm or a1._modif_alert:
+                        a1, a2 = e1.action_space.sample(), e2.action_space.sample()
+                    ba1 += a1; ba2 += a2
+                    b1.apply_action(ba1); b2.apply_action(ba2)
+                    ba1.reset(); ba2.reset()
+                elif r < 0.6:
+                    b1, b2 = b1.copy(), b2.copy()
+                dc = bool(rng.random() < 0.3)
+                c1, x1 = b1.runpf(is_dc=dc)
+                c2, x2 = b2.runpf(is_dc=dc)
+                assert c1 == c2, (seed, i, dc, x1, x2)
+                if not c1:                      # like an environment after a game over: back to the loaded state
+                    n_fail += 1
+                    b1, b2 = e1.backend.copy(), e2.backend.copy()
+                    ba1, ba2 = type(b1).my_bk_act_class(), type(b2).my_bk_act_class()
+                    continue
+                n_conv += 1; n_dc += int(dc)
+                g1, g2 = _getters(b1), _getters(b2)
+                for k in g1:
+                    _close(g1[k], g2[k], 2e-3 * max(1.0, 0.1 * float(np.nanmax(np.abs(g2[k]), initial=0.0))), (k, seed, i, dc))
+        assert n_conv >= 20 and n_dc >= 3 and n_fail >= 1, (n_conv, n_dc, n_fail)
+    finally:
+        e1.close(); e2.close()
