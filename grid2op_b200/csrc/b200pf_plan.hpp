@@ -335,6 +335,7 @@ public:
                 for (int i = k - 1; i >= 0; --i)
                     if (S[(size_t)i * d + k]) seq.push_back({(uint16_t)(nnzF + i), (uint16_t)P(i, k), (uint16_t)(nnzF + k), (uint16_t)kk});
             }
+            PLAN_TICK("ops: seq");
             std::vector<int> wlev(nA + 1, 0), rlev(nA + 1, 0), lev(seq.size(), 0);
             // For the row balancing below: the earliest pass of any successor of an operation in the dependency graph (RAW, WAW,
             // WAR edges).  Flat arrays only (this is the builder's hot loop: the cost of a new topology in a single environment):
@@ -357,6 +358,7 @@ public:
                 for (int s3 = 0; s3 < 3; ++s3) { const int nd = (int)q * 3 + s3; rd_next[nd] = rd_head[rd[s3]]; rd_head[rd[s3]] = nd; }
                 lastw[o.ij] = (int)q;
             }
+            PLAN_TICK("ops: levels");
             const int W = op_width_;
             {   // Row balancing: a pass costs ceil(n / W) rows.  Going down the passes, the operations of the last, partly
                 // filled row move to the next pass when they have slack (every successor at least two passes later; those with
@@ -384,6 +386,7 @@ public:
                     fill[l] = w;
                 }
             }
+            PLAN_TICK("ops: balance");
             // passes padded to whole rows of op_width slots; the last row of a pass carries the barrier flag
             std::vector<int> lv_ptr(nlev + 2, 0);
             for (int lv : lev) lv_ptr[lv + 1]++;
